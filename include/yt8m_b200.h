@@ -1,0 +1,157 @@
+/* yt8m_b200 -- C ABI of libyt8m_b200.so: the B200 (sm_100a) hot path of wangheda/youtube-8m.
+ *
+ * The reference has no FFI: its hot path is TensorFlow-1.0 graph ops built inside the model plugins'
+ * create_model() (youtube-8m-wangheda/models.py:17-21).  Each entry point below replaces the group of
+ * TF ops cited beside it ("wh/" = youtube-8m-wangheda/, "zt/" = youtube-8m-zhangteng/); the Python
+ * plugins in youtube-8m_b200/ bind them with ctypes (see INTEGRATION.md for the stub a maintainer of the
+ * reference would add).
+ *
+ * Conventions
+ *   - every function returns 0 (YT8M_OK) or a negative YT8M_E_* code; yt8m_last_error() returns a
+ *     thread-local, human-readable message for the last failure on the calling thread;
+ *   - all tensor arguments are CALLER-OWNED DEVICE pointers (row-major, explicit sizes / row strides in
+ *     elements); kernels are enqueued on `stream` and the call returns without synchronising;
+ *   - no allocation, no global state: scratch memory is passed in (`workspace`, size from the matching
+ *     *_workspace_bytes query), so calls are re-entrant (one stream per rank);
+ *   - "bf16" pointers are uint16_t-sized IEEE bfloat16; activations that must keep fp32-level precision
+ *     through the tensor cores are passed as a hi/lo bf16 pair (x ~= hi + lo); `lo` may be NULL;
+ *   - weights are PACKED ONCE (yt8m_*_pack_*) from the reference/TensorFlow [in, out] layout into the
+ *     K-contiguous [out, in] bf16 layout the tcgen05 kernels consume.
+ */
+#ifndef YT8M_B200_H_
+#define YT8M_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define YT8M_OK 0
+#define YT8M_E_BADSHAPE (-1)
+#define YT8M_E_BADPTR (-2)
+#define YT8M_E_CUDA (-3)
+#define YT8M_E_UNSUPPORTED (-4)
+
+typedef void* yt8m_stream_t; /* cudaStream_t */
+typedef uint16_t yt8m_bf16;
+
+/* activation codes for yt8m_linear_fwd (slim.fully_connected activation_fn) */
+#define YT8M_ACT_NONE 0
+#define YT8M_ACT_RELU 1
+#define YT8M_ACT_RELU6 2
+#define YT8M_ACT_SIGMOID 3
+#define YT8M_ACT_TANH 4
+
+/* library version (major*10000 + minor*100 + patch) */
+int yt8m_version(void);
+const char* yt8m_last_error(void);
+
+/* ---- frame-row transforms ----------------------------------------------------------------------
+ * wh/all_feature_transform/default_transformer.py:5-8  (tf.nn.l2_normalize over the feature dim) and,
+ * for src_dtype = U8, wh/utils.py:23-38 Dequantize(max=2, min=-2) fused in front of it
+ * (reader path wh/readers.py:178-186).  out = x * rsqrt(max(sum x^2, 1e-12)); all-zero (padding)
+ * rows stay zero.  src_dtype: 0 = fp32, 1 = bf16, 2 = uint8 (de-quantised first; rows at or beyond
+ * num_frames[b] are written as zeros like the reader's padding when num_frames != NULL).
+ * `normalize` = 0 skips the L2 normalisation (plain convert / de-quantise). */
+#define YT8M_SRC_F32 0
+#define YT8M_SRC_BF16 1
+#define YT8M_SRC_U8 2
+int yt8m_l2norm_rows_fwd(const void* x, int src_dtype, long long rows, int dim, int normalize,
+                         const int* num_frames, int frames_per_video, yt8m_bf16* out_bf16, float* out_f32,
+                         yt8m_stream_t stream);
+
+/* ---- dense layer (slim.fully_connected / tf.matmul + bias / folded batch-norm + activation) ----
+ * out[M, N] = act((A[M, K] . W[N, K]^T) * col_scale[N] + col_shift[N]);  A = a_hi (+ a_lo).
+ * Replaces e.g. wh/all_video_models/logistic_model.py:23-25, wh/all_frame_models/dbof_model.py:76-115,
+ * wh/all_video_models/deep_combine_chain_model.py:31-36.  K, lda, ldw must be multiples of 8.
+ * Outputs (any subset non-NULL): fp32, bf16 hi, bf16 lo, all with row stride ld_out.
+ * workspace: optional split-K scratch (>= yt8m_linear_workspace_bytes) -- used when the tile grid
+ * alone cannot fill the GPU. */
+size_t yt8m_linear_workspace_bytes(int M, int N, int K);
+int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, const yt8m_bf16* w,
+                    long long ldw, int M, int N, int K, const float* col_scale, const float* col_shift,
+                    int act, float* out_f32, yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out,
+                    void* workspace, size_t workspace_bytes, yt8m_stream_t stream);
+
+/* fp32 [K, N] (TF layout) -> bf16 [N, ldw] (K contiguous, zero padded to ldw) */
+int yt8m_pack_transpose_bf16(const float* w_kn, int K, int N, yt8m_bf16* w_packed, long long ldw,
+                             yt8m_stream_t stream);
+
+/* ---- MoeModel head: wh/all_video_models/moe_model.py:38-65 -------------------------------------
+ * p[b, v] = sum_{m<M} softmax_{M+1}(x . Wg)[v, m] * sigmoid(x . We + be)[v, m]
+ * Packed weight: rows grouped in tiles of 128; a tile holds CPT = floor(128 / (2M+1)) classes,
+ * class-major, each class = [gate_0..gate_M, expert_0..expert_{M-1}], zero padded to 128 rows.
+ * yt8m_moe_packed_rows() = 128 * ceil(V / CPT).  num_mixtures in {1, 2, 3, 4, 8}. */
+long long yt8m_moe_packed_rows(int vocab, int num_mixtures);
+int yt8m_moe_pack_weights(const float* gate_w, const float* expert_w, const float* expert_b, int D, int vocab,
+                          int num_mixtures, yt8m_bf16* w_packed, long long ldw, float* bias_packed,
+                          yt8m_stream_t stream);
+int yt8m_moe_fwd(const yt8m_bf16* x_hi, const yt8m_bf16* x_lo, long long ldx, const yt8m_bf16* w_packed,
+                 long long ldw, const float* bias_packed, int B, int D, int vocab, int num_mixtures, float* out,
+                 long long ld_out, yt8m_stream_t stream);
+
+/* max over groups of `heads` consecutive rows: out[b, :] = max_a in[b*heads + a, :]
+ * (wh/all_frame_models/lstm_attention_max_pooling_model.py:65-66, zt/video_level_models.py:2327-2328) */
+int yt8m_group_max_rows(const float* in, long long groups, int heads, int cols, float* out, yt8m_stream_t stream);
+
+/* ---- LstmModel / LstmMemoryModel: wh/all_frame_models/lstm_model.py:30-47 ------------------------
+ * MultiRNNCell[BasicLSTMCell(H, forget_bias)] x L under dynamic_rnn(sequence_length = num_frames).
+ * Per layer one packed matrix [4H, in_l + H] (in_0 = D, in_l = H): row 4u+g holds gate g (i, j, f, o) of
+ * unit u, columns = [x | h] as in TF's [in+H, 4H] kernel; b_packed in the same row order.
+ * state_out: [B, L*2*H] = [c0, h0, c1, h1, ...] (lstm_model.py state_is_tuple=False layout).
+ * out_seq / out_seq_bf (nullable): top-layer outputs [B, T, H] (zero for t >= num_frames[b]). */
+int yt8m_lstm_pack_weights(const float* w_tf, const float* b_tf, int in_dim, int H, yt8m_bf16* w_packed,
+                           float* b_packed, yt8m_stream_t stream);
+size_t yt8m_lstm_workspace_bytes(int B, int T, int D, int H, int L);
+int yt8m_lstm_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int H, int L,
+                  const yt8m_bf16* const* w_packed, const float* const* b_packed, float forget_bias,
+                  float* state_out, float* out_seq, yt8m_bf16* out_seq_bf, void* workspace,
+                  size_t workspace_bytes, yt8m_stream_t stream);
+
+/* ---- attention pooling over frames --------------------------------------------------------------
+ * out[b, a, :] = sum_t w[b, t, a] * feats[b, t, :]
+ *   mode 0 (softmax over T, masked, renormalised):
+ *        wh/all_frame_models/lstm_attention_max_pooling_model.py:58-63, zt/frame_level_models.py:4393-4397
+ *   mode 1 (sigmoid gate, masked, / (sum + 1e-8)): wh/all_frame_models/lstm_multi_attention_model.py:66-78
+ * logits: [B, T, ld_logits>=A] fp32 (already includes the bias).  Mask: t < num_frames[b] when
+ * num_frames != NULL, else "frame row has a non-zero entry" (zt/frame_level_models.py:4372-4375).
+ * feats: bf16 [B, T, F]. out: fp32 [B, A, F] (+ optional bf16 hi/lo copies as MoE operands). */
+int yt8m_attn_pool_fwd(const float* logits, long long ld_logits, const yt8m_bf16* feats, const int* num_frames,
+                       int B, int T, int A, int F, int mode, float* out, yt8m_bf16* out_hi, yt8m_bf16* out_lo,
+                       yt8m_stream_t stream);
+
+/* ---- NetVLAD (not in the reference; definition in oracle/yt8m_oracle.py:netvlad_pool) -----------
+ * FUSED soft-assignment GEMM + masked softmax over K + residual aggregation GEMM + intra-norm +
+ * final L2 norm.  x: bf16 [B, T, D]; cw_packed: bf16 [K, D]; scale/shift: [K] (folded BN or bias);
+ * cw2: fp32 [D, K].  out: [B, D*K] (D-major, K-minor).  K in {16..128, multiple of 16}, D % 64 == 0. */
+int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K,
+                     const yt8m_bf16* cw_packed, const float* scale, const float* shift, const float* cw2,
+                     float* out_f32, yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out,
+                     yt8m_stream_t stream);
+
+/* ---- elementwise glue -----------------------------------------------------------------------------
+ * y = x * sigmoid(g * scale + shift)  (context gating; g = x . Wg from yt8m_linear_fwd) */
+int yt8m_context_gate_fwd(const float* x, const float* g, const float* scale, const float* shift, long long rows,
+                          int cols, float* out_f32, yt8m_bf16* out_hi, yt8m_bf16* out_lo, yt8m_stream_t stream);
+
+/* fp32 [rows, cols] -> bf16 hi (+lo) with destination row stride ld_out and column offset already applied
+ * by the caller (used to build concatenated operands, e.g. chain_moe_model.py:16) */
+int yt8m_split_bf16(const float* x, long long rows, int cols, long long ld_in, yt8m_bf16* out_hi,
+                    yt8m_bf16* out_lo, long long ld_out, yt8m_stream_t stream);
+
+/* CrossEntropyLoss (wh/losses.py:114-130): loss = mean_b sum_v -[y log(p+1e-5) + (1-y) log(1-p+1e-5)];
+ * loss_out: 1 float (accumulated; zeroed by the call); dpred (nullable): dLoss/dp * grad_scale. */
+int yt8m_xent_fwd_bwd(const float* pred, const float* labels, int B, int V, float* loss_out, float* dpred,
+                      float grad_scale, yt8m_stream_t stream);
+
+/* top-k per row, descending (wh/inference.py:76-87 format_lines; wh/eval_util.py:164 top_k_triplets).
+ * k <= 32.  idx_out: int32 [rows, k]; val_out: fp32 [rows, k]. */
+int yt8m_topk_rows(const float* x, long long rows, int cols, int k, int* idx_out, float* val_out,
+                   yt8m_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* YT8M_B200_H_ */

@@ -1,0 +1,407 @@
+// yt8m_b200 -- warp-specialised tcgen05 GEMM main loop with fused epilogues (sm_100a).
+//
+//   D[M, N] = epilogue( A[M, K] . W[N, K]^T )        A, W bf16 (K contiguous), fp32 accumulate in TMEM
+//
+// One CTA computes one 128 x BLOCK_N output tile (optionally one K-split of it):
+//   warp 0      : TMA producer  (cp.async.bulk.tensor 2D, SWIZZLE_128B boxes of 64 K-elements)
+//   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16)
+//   warps 2..5  : epilogue -- tcgen05.ld the accumulator row owned by each thread, apply the fused
+//                 epilogue (bias/activation, MoE softmax x sigmoid, LSTM gates) and store.
+// A may be given as a bf16 hi + lo pair (A_SPLIT = 2): both are multiplied against the same W tile
+// and accumulated into the same TMEM tile, which carries ~16 mantissa bits of the activation through
+// the tensor cores (used for recurrent state / chained activations; weights are bf16-exact).
+#pragma once
+#include "yt8m_common.cuh"
+
+namespace yt8m {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;            // 64 bf16 = 128 B = one SWIZZLE_128B row
+constexpr int kUmmaK = 16;
+constexpr int kGemmThreads = 192;
+
+struct GemmShape {
+  int M, N, K;
+  int kb_per_split;                    // K-blocks handled by one blockIdx.z
+};
+
+template <int BLOCK_N, int A_SPLIT>
+struct GemmSmem {
+  static constexpr int kABytes = kBlockM * kBlockK * 2;               // 16 KB
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = A_SPLIT * kABytes + kBBytes;
+  static constexpr int kBudget = 200 * 1024;
+  static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
+  static constexpr int kBarrierBytes = 256;
+  static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024 for alignment slack
+  static_assert(kStages >= 2, "need at least two pipeline stages");
+};
+
+__host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n <= 64 ? 64 : n <= 128 ? 128 : n <= 256 ? 256 : 512; }
+
+// Epilogue concept:
+//   struct Epi { struct Params {...};
+//     template <int BLOCK_N> static __device__ void run(const Params&, const GemmShape&, int row (global M index),
+//                                       int n0 (global N index of tile col 0), uint32_t tmem_row_addr, bool row_valid); }
+// run() is called by every epilogue thread (uniformly per warp: tcgen05.ld is warp-collective).
+
+template <int BLOCK_N, int A_SPLIT, class Epi>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                    const __grid_constant__ CUtensorMap tm_b, const GemmShape shape, const typename Epi::Params ep) {
+  using S = GemmSmem<BLOCK_N, A_SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* tiles = smem;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* empty_bar = full_bar + S::kStages;
+  uint64_t* tmem_full_bar = empty_bar + S::kStages;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
+  const int num_kb_total = (shape.K + kBlockK - 1) / kBlockK;
+  const int kb_begin = split * shape.kb_per_split;
+  const int kb_end = min(kb_begin + shape.kb_per_split, num_kb_total);
+  const int num_kb = kb_end - kb_begin;
+  constexpr uint32_t kTmemCols = tmem_cols_for(BLOCK_N);
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_a_hi);
+    if (A_SPLIT == 2) tma_prefetch_desc(&tm_a_lo);
+    tma_prefetch_desc(&tm_b);
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer -------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* st = tiles + stage * S::kStageBytes;
+        mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
+        tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal);
+        if (A_SPLIT == 2)
+          tma_load_2d(st + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal);
+        tma_load_2d(st + A_SPLIT * S::kABytes, &tm_b, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N,
+                    kEvictNormal);
+        if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer ---------------------------------
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_addr = smem_u32(tiles + stage * S::kStageBytes);
+        const uint32_t b_addr = a_addr + A_SPLIT * S::kABytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          const uint64_t bdesc = make_sdesc_sw128(b_addr + k * (kUmmaK * 2), 16, 1024);
+          const uint64_t adesc = make_sdesc_sw128(a_addr + k * (kUmmaK * 2), 16, 1024);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          if (A_SPLIT == 2) {
+            const uint64_t adesc2 = make_sdesc_sw128(a_addr + S::kABytes + k * (kUmmaK * 2), 16, 1024);
+            umma_bf16(tmem_base, adesc2, bdesc, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // ------------------------------- epilogue -----------------------------------
+    const int q = warp & 3;                          // TMEM lane quadrant this warp may access
+    const int row_in_tile = q * 32 + lane;
+    const int row = m_tile * kBlockM + row_in_tile;
+    if (num_kb > 0) {
+      mbar_wait(tmem_full_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    Epi::template run<BLOCK_N>(ep, shape, row, n_tile * BLOCK_N, taddr, row < shape.M, num_kb > 0, split);
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue 1: linear  -- y = act((acc) * col_scale + col_shift)  [col_shift doubles as the bias]
+//   outputs: fp32 and/or bf16 hi (+ lo).  With split-K > 1 the raw accumulator is atomically added
+//   into a zero-initialised fp32 workspace and a finalize kernel applies the affine/activation.
+// ---------------------------------------------------------------------------------------------
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_RELU6 = 2, ACT_SIGMOID = 3, ACT_TANH = 4 };
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(v, 0.0f);
+    case ACT_RELU6: return fminf(fmaxf(v, 0.0f), 6.0f);
+    case ACT_SIGMOID: return sigmoidf_(v);
+    case ACT_TANH: return tanhf_(v);
+    default: return v;
+  }
+}
+
+struct EpiLinear {
+  struct Params {
+    float* out_f32;            // nullable
+    __nv_bfloat16* out_hi;     // nullable
+    __nv_bfloat16* out_lo;     // nullable
+    long long ld_out;          // row stride (elements) of all outputs
+    const float* col_scale;    // nullable (=> 1)
+    const float* col_shift;    // nullable (=> 0): bias / folded BN shift
+    int act;
+    int split_k;               // > 1: atomicAdd raw partials into out_f32, nothing else
+  };
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, const GemmShape& s, int row, int n0, uint32_t taddr,
+                                             bool row_valid, bool have_acc, int /*split*/) {
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      uint32_t r[32];
+      if (have_acc) {
+        tmem_ld32(taddr + c, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (!row_valid) continue;
+      const int col0 = n0 + c;
+      if (col0 >= s.N) continue;
+      const long long base = static_cast<long long>(row) * p.ld_out + col0;
+      if (p.split_k > 1) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j < s.N) atomicAdd(p.out_f32 + base + j, __uint_as_float(r[j]));
+        continue;
+      }
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]);
+        const int col = col0 + j;
+        if (col < s.N) {
+          if (p.col_scale) x *= __ldg(p.col_scale + col);
+          if (p.col_shift) x += __ldg(p.col_shift + col);
+        }
+        v[j] = apply_act(x, p.act);
+      }
+      const bool full = (col0 + 32 <= s.N) && ((p.ld_out & 7) == 0);
+      if (p.out_f32) {
+        if (full) {
+          float4* dst = reinterpret_cast<float4*>(p.out_f32 + base);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < s.N) p.out_f32[base + j] = v[j];
+        }
+      }
+      if (p.out_hi) {
+        if (full) {
+          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + base);
+          uint4* dl = p.out_lo ? reinterpret_cast<uint4*>(p.out_lo + base) : nullptr;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 h, l;
+            pack8_hi_lo(v + 8 * j, h, l);
+            dh[j] = h;
+            if (dl) dl[j] = l;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < s.N) {
+              __nv_bfloat16 h, l;
+              split_bf16(v[j], h, l);
+              p.out_hi[base + j] = h;
+              if (p.out_lo) p.out_lo[base + j] = l;
+            }
+        }
+      }
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue 2: MoE head (wh/all_video_models/moe_model.py:54-64 of the reference).
+//   Packed weight rows: tile of 128 rows = CPT = floor(128/(2M+1)) classes, class-major, each class
+//   = [gate_0..gate_M, expert_0..expert_{M-1}], zero padded to 128.  The epilogue thread owning batch
+//   row b turns its 128 accumulators into CPT probabilities:
+//       p[b, v] = sum_{m<M} softmax_{M+1}(gate)[m] * sigmoid(expert[m] + bias[m])
+//   The B x V(2M+1) activations never reach HBM.  Optional max over `heads` consecutive rows
+//   (MoeExtendModel / attention-max-pooling) is done by the caller's reduce kernel.
+// ---------------------------------------------------------------------------------------------
+template <int NMIX>
+struct EpiMoe {
+  static constexpr int kPer = 2 * NMIX + 1;
+  static constexpr int kCpt = 128 / kPer;
+  struct Params {
+    float* out;                 // [M, vocab] fp32
+    long long ld_out;
+    const float* bias_packed;   // [n_tiles * 128]: expert biases in packed order (0 for gates / padding)
+    int vocab;
+  };
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, const GemmShape& /*s*/, int row, int n0, uint32_t taddr,
+                                             bool row_valid, bool /*have_acc*/, int /*split*/) {
+    static_assert(BLOCK_N == 128, "MoE epilogue expects 128-column tiles");
+    float acc[128];
+#pragma unroll
+    for (int c = 0; c < 128; c += 32) tmem_ld32(taddr + c, reinterpret_cast<uint32_t*>(acc) + c);
+    tmem_ld_wait();
+    if (!row_valid) return;
+    const int v0 = (n0 / 128) * kCpt;
+    const float* bias = p.bias_packed + n0;
+    float* out = p.out + static_cast<long long>(row) * p.ld_out + v0;
+#pragma unroll
+    for (int c = 0; c < kCpt; ++c) {
+      const int o = c * kPer;
+      float mx = acc[o];
+#pragma unroll
+      for (int m = 1; m <= NMIX; ++m) mx = fmaxf(mx, acc[o + m]);
+      float den = 0.0f, num = 0.0f;
+#pragma unroll
+      for (int m = 0; m <= NMIX; ++m) {
+        const float e = __expf(acc[o + m] - mx);
+        den += e;
+        if (m < NMIX) num += e * sigmoidf_(acc[o + NMIX + 1 + m] + __ldg(bias + o + NMIX + 1 + m));
+      }
+      if (v0 + c < p.vocab) out[c] = num / den;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Epilogue 3: one BasicLSTMCell step (TF 1.0 semantics; call site wh/all_frame_models/lstm_model.py:34-47).
+//   Packed weight rows: unit-major, [i_u, j_u, f_u, o_u] per hidden unit u (128-row tile = 32 units).
+//   acc = [x_t, h_{t-1}] . W   (or only the h part when the x projection was hoisted: then xw holds
+//   x_t . W_x + b in the same packed column order).
+//     c' = c * sigmoid(f + forget_bias) + sigmoid(i) * tanh(j);  h' = tanh(c') * sigmoid(o)
+//   dynamic_rnn(sequence_length): rows with t >= num_frames[b] keep (c, h) and emit 0.
+// ---------------------------------------------------------------------------------------------
+struct EpiLstm {
+  struct Params {
+    const float* xw;            // nullable: [B, 4H] slice for this t (row stride ld_xw), packed order
+    long long ld_xw;
+    const float* bias_packed;   // nullable: [4H] packed order
+    const float* c_in;          // [B, H]
+    const float* h_in;          // [B, H] fp32
+    float* c_out;
+    float* h_out;
+    __nv_bfloat16* a0_hi;       // destination 0 for bf16 hi/lo of h' (own recurrent operand), row stride ld_a0
+    __nv_bfloat16* a0_lo;
+    long long ld_a0;
+    __nv_bfloat16* a1_hi;       // nullable destination 1 (next layer's input operand)
+    __nv_bfloat16* a1_lo;
+    long long ld_a1;
+    float* out_seq;             // nullable: [B, T, H] fp32 outputs (pre-offset to time t), row stride ld_seq
+    __nv_bfloat16* out_seq_bf;  // nullable: bf16 copy of the outputs (operand for attention logits)
+    long long ld_seq;
+    const int* num_frames;      // [B]
+    int t;
+    int hidden;
+    float forget_bias;
+  };
+  template <int BLOCK_N>
+  static __device__ __forceinline__ void run(const Params& p, const GemmShape& /*s*/, int row, int n0, uint32_t taddr,
+                                             bool row_valid, bool /*have_acc*/, int /*split*/) {
+    static_assert(BLOCK_N == 128, "LSTM epilogue expects 128-column tiles (32 units)");
+    const int u0 = n0 / 4;
+    const bool live = row_valid && (p.t < __ldg(p.num_frames + (row_valid ? row : 0)));
+#pragma unroll 1
+    for (int c = 0; c < 128; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c, r);
+      tmem_ld_wait();
+      if (!row_valid) continue;
+      float g[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) g[j] = __uint_as_float(r[j]);
+      if (p.xw) {
+        const float4* xw = reinterpret_cast<const float4*>(p.xw + static_cast<long long>(row) * p.ld_xw + n0 + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 x = __ldg(xw + j);
+          g[4 * j] += x.x; g[4 * j + 1] += x.y; g[4 * j + 2] += x.z; g[4 * j + 3] += x.w;
+        }
+      }
+      if (p.bias_packed) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) g[j] += __ldg(p.bias_packed + n0 + c + j);
+      }
+      const int ub = u0 + c / 4;                          // 8 units in this chunk
+      const long long sbase = static_cast<long long>(row) * p.hidden + ub;
+      float cn[8], hn[8], ho[8];
+      {
+        const float4* ci = reinterpret_cast<const float4*>(p.c_in + sbase);
+        const float4* hi4 = reinterpret_cast<const float4*>(p.h_in + sbase);
+        const float4 c0 = ci[0], c1 = ci[1], h0 = hi4[0], h1 = hi4[1];
+        const float cp[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+        const float hp[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const float gi = g[4 * u], gj = g[4 * u + 1], gf = g[4 * u + 2], go = g[4 * u + 3];
+          const float c2 = cp[u] * sigmoidf_(gf + p.forget_bias) + sigmoidf_(gi) * tanhf_(gj);
+          const float h2 = tanhf_(c2) * sigmoidf_(go);
+          cn[u] = live ? c2 : cp[u];
+          hn[u] = live ? h2 : hp[u];
+          ho[u] = live ? h2 : 0.0f;
+        }
+      }
+      float4* co = reinterpret_cast<float4*>(p.c_out + sbase);
+      float4* hofp = reinterpret_cast<float4*>(p.h_out + sbase);
+      co[0] = make_float4(cn[0], cn[1], cn[2], cn[3]);
+      co[1] = make_float4(cn[4], cn[5], cn[6], cn[7]);
+      hofp[0] = make_float4(hn[0], hn[1], hn[2], hn[3]);
+      hofp[1] = make_float4(hn[4], hn[5], hn[6], hn[7]);
+      uint4 hi, lo;
+      pack8_hi_lo(hn, hi, lo);
+      *reinterpret_cast<uint4*>(p.a0_hi + static_cast<long long>(row) * p.ld_a0 + ub) = hi;
+      *reinterpret_cast<uint4*>(p.a0_lo + static_cast<long long>(row) * p.ld_a0 + ub) = lo;
+      if (p.a1_hi) {
+        // the layer above consumes this step's h' (finished rows are frozen there too, so what they
+        // receive is irrelevant)
+        *reinterpret_cast<uint4*>(p.a1_hi + static_cast<long long>(row) * p.ld_a1 + ub) = hi;
+        *reinterpret_cast<uint4*>(p.a1_lo + static_cast<long long>(row) * p.ld_a1 + ub) = lo;
+      }
+      if (p.out_seq) {
+        float4* os = reinterpret_cast<float4*>(p.out_seq + static_cast<long long>(row) * p.ld_seq + ub);
+        os[0] = make_float4(ho[0], ho[1], ho[2], ho[3]);
+        os[1] = make_float4(ho[4], ho[5], ho[6], ho[7]);
+      }
+      if (p.out_seq_bf) {
+        uint4 oh, ol;
+        pack8_hi_lo(ho, oh, ol);
+        *reinterpret_cast<uint4*>(p.out_seq_bf + static_cast<long long>(row) * p.ld_seq + ub) = oh;
+      }
+    }
+  }
+};
+
+}  // namespace yt8m

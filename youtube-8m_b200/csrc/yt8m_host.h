@@ -1,0 +1,43 @@
+// yt8m_b200 -- host-side helpers shared by the C-ABI translation units.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/yt8m_b200.h"
+
+namespace yt8m {
+
+void set_error(const char* fmt, ...);
+
+// bf16 row-major [rows, cols] (row stride ld_elems) -> 2D tensor map, SWIZZLE_128B, box = box_rows x 64 cols
+int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld_elems,
+                      uint32_t box_rows, uint32_t box_cols = 64);
+// bf16 [d2, d1, d0] (d0 contiguous; strides in elements) -> 3D tensor map, box = 1 x box_d1 x 64
+int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1_elems,
+                      uint64_t ld2_elems, uint32_t box_d1, uint32_t box_d0 = 64);
+
+int check_launch(const char* what);
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace yt8m
+
+#define YT8M_REQUIRE(cond, code, ...)     \
+  do {                                    \
+    if (!(cond)) {                        \
+      ::yt8m::set_error(__VA_ARGS__);     \
+      return (code);                      \
+    }                                     \
+  } while (0)
+
+#define YT8M_CUDA(expr)                                                                \
+  do {                                                                                 \
+    cudaError_t e__ = (expr);                                                          \
+    if (e__ != cudaSuccess) {                                                          \
+      ::yt8m::set_error("%s failed: %s", #expr, cudaGetErrorString(e__));              \
+      return YT8M_E_CUDA;                                                              \
+    }                                                                                  \
+  } while (0)

@@ -1,0 +1,414 @@
+// yt8m_b200 -- fused NetVLAD for sm_100a: soft-assignment GEMM (B.T x D by D x K) + masked softmax over
+// K + residual-aggregation GEMM (assignment^T . X) + intra-normalisation + final L2 norm, one CTA per
+// video.  (NetVLAD is not part of /root/reference; definition: oracle/yt8m_oracle.py:netvlad_pool.)
+//
+// Data flow per video b (T frames, D features, KC clusters, all tiles SWIZZLE_128B in shared memory):
+//   phase 0  S_i[128 frames, KC] = X_i[128, D] . Cw^T     i = 0..NT-1 frame tiles, accumulated in TMEM
+//            while the D axis streams through a TMA ring (each Cw k-block is loaded once and shared by the
+//            NT frame tiles).  X comes from HBM here -- the only HBM read of X.
+//   softmax  4 warps (one TMEM lane = one frame) tcgen05.ld their S rows, apply the folded-BN affine,
+//            softmax over KC in registers, zero padded frames, round to bf16 and store the assignment tile
+//            to shared memory in the MN-major layout the second GEMM wants; column sums a_sum[k] via a
+//            warp transpose-reduce.
+//   phase 1  V^T[D, KC] = X^T[D, frames] . a[frames, KC]: X tiles are streamed AGAIN (L2 hits: the video was
+//            read microseconds ago) as the MN-major A operand; accumulators for 256 TMEM columns at a
+//            time (double buffered) while the epilogue warps subtract a_sum[k]*cw2[d,k], accumulate the
+//            per-cluster sum of squares and stash the un-normalised descriptor.
+//   rescale  after the last group: per-cluster rsqrt (intra-norm) x global rsqrt (final L2 norm) applied
+//            to the stash in place (L2-resident) -> bf16 hi (+lo) / fp32 output, D-major / K-minor.
+#include "yt8m_common.cuh"
+#include "yt8m_host.h"
+
+using namespace yt8m;
+
+namespace {
+
+constexpr int kNvThreads = 192;
+constexpr int kNtMax = 3;                 // up to 384 frames
+constexpr int kSlotBytes = 128 * 64 * 2;  // one TMA box: 128 rows x 64 bf16
+
+template <int KC>
+struct NvCfg {
+  static constexpr int kNBlk = (KC + 63) / 64;                 // 64-cluster blocks of an assignment tile
+  static constexpr int kGM = 256 / KC;                         // M-blocks (128 D rows) per TMEM group
+  static constexpr int kSlots = (KC <= 64) ? 8 : 4;            // X ring slots (even)
+  static constexpr int kCwStages = 3;
+  static constexpr int kCwBytes = KC * 128;                    // KC rows x 64 bf16
+  static constexpr int kATileBytes = kNBlk * kSlotBytes;       // 128 frames x KC (64-wide blocks)
+  static constexpr int kOffX = 0;
+  static constexpr int kOffCw = kOffX + kSlots * kSlotBytes;
+  static constexpr int kOffA = kOffCw + ((kCwStages * kCwBytes + 1023) / 1024) * 1024;
+  static constexpr int kOffSmall = kOffA + kNtMax * kATileBytes;
+  static constexpr int kSmallBytes = 5 * KC * 4 + 512;         // scale, shift, asum, ssq, fscale + barriers
+  static constexpr int kTotal = kOffSmall + kSmallBytes + 1024;
+  static_assert(kTotal <= 227 * 1024, "NetVLAD shared-memory budget exceeded");
+};
+
+// 32 values per lane, 32 lanes -> lane L returns sum over lanes of v[L]   (31 shuffles)
+__device__ __forceinline__ float warp_transpose_reduce32(float* v, int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int j = 0; j < off; ++j) {
+      const float send = upper ? v[j] : v[j + off];
+      const float keep = upper ? v[j + off] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int KC>
+__global__ void __launch_bounds__(kNvThreads, 1)
+netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_cw,
+                     const int* __restrict__ num_frames, int T, int D, const float* __restrict__ scale,
+                     const float* __restrict__ shift, const float* __restrict__ cw2, float* __restrict__ out_f32,
+                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ld_out) {
+  using C = NvCfg<KC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* xs = smem + C::kOffX;
+  uint8_t* cws = smem + C::kOffCw;
+  uint8_t* atile = smem + C::kOffA;
+  float* scale_s = reinterpret_cast<float*>(smem + C::kOffSmall);
+  float* shift_s = scale_s + KC;
+  float* asum_s = shift_s + KC;
+  float* ssq_s = asum_s + KC;
+  float* fscale_s = ssq_s + KC;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fscale_s + KC);
+  uint64_t* cw_full = bars;                       // [3]
+  uint64_t* cw_empty = cw_full + 3;               // [3]
+  uint64_t* x_full0 = cw_empty + 3;               // [8]
+  uint64_t* x_empty0 = x_full0 + 8;               // [8]
+  uint64_t* x_full1 = x_empty0 + 8;               // [4]
+  uint64_t* x_empty1 = x_full1 + 4;               // [4]
+  uint64_t* s_full = x_empty1 + 4;                // [1]
+  uint64_t* a_ready = s_full + 1;                 // [1]
+  uint64_t* v_full = a_ready + 1;                 // [2]
+  uint64_t* v_empty = v_full + 2;                 // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + 2);
+  float* total_s = reinterpret_cast<float*>(tmem_slot + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x;
+  const int NT = (T + 127) / 128;
+  const int NKB = D / 64;
+  const int NMB = D / 128;
+  const int NG = (NMB + C::kGM - 1) / C::kGM;
+  constexpr int kPairs = C::kSlots / 2;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_cw);
+    for (int i = 0; i < 3; ++i) { mbar_init(&cw_full[i], 1); mbar_init(&cw_empty[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&x_full0[i], 1); mbar_init(&x_empty0[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&x_full1[i], 1); mbar_init(&x_empty1[i], 1); }
+    mbar_init(s_full, 1);
+    mbar_init(a_ready, 4);
+    for (int i = 0; i < 2; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  for (int k = threadIdx.x; k < KC; k += kNvThreads) {
+    scale_s[k] = scale ? scale[k] : 1.0f;
+    shift_s[k] = shift ? shift[k] : 0.0f;
+    asum_s[k] = 0.0f;
+    ssq_s[k] = 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // =================================== TMA producer ===================================
+    if (lane == 0) {
+      int slot = 0, cst = 0;
+      uint32_t ph = 0, cph = 0;
+      for (int kb = 0; kb < NKB; ++kb) {
+        mbar_wait(&cw_empty[cst], cph ^ 1u);
+        mbar_arrive_expect_tx(&cw_full[cst], C::kCwBytes);
+        tma_load_2d(cws + cst * C::kCwBytes, &tm_cw, &cw_full[cst], kb * 64, 0, kEvictLast);
+        for (int i = 0; i < NT; ++i) {
+          mbar_wait(&x_empty0[slot], ph ^ 1u);
+          mbar_arrive_expect_tx(&x_full0[slot], kSlotBytes);
+          tma_load_3d(xs + slot * kSlotBytes, &tm_x, &x_full0[slot], kb * 64, i * 128, b, kEvictNormal);
+          if (++slot == C::kSlots) { slot = 0; ph ^= 1u; }
+        }
+        if (++cst == C::kCwStages) { cst = 0; cph ^= 1u; }
+      }
+      // phase 1: every phase-0 MMA has completed once s_full flips -> the whole X ring is free again
+      mbar_wait(s_full, 0);
+      int pair = 0;
+      uint32_t pph = 0;
+      for (int g = 0; g < NG; ++g)
+        for (int i = 0; i < NT; ++i)
+          for (int ml = 0; ml < C::kGM; ++ml) {
+            const int m = g * C::kGM + ml;
+            if (m >= NMB) break;
+            mbar_wait(&x_empty1[pair], pph ^ 1u);
+            mbar_arrive_expect_tx(&x_full1[pair], 2 * kSlotBytes);
+            tma_load_3d(xs + (2 * pair) * kSlotBytes, &tm_x, &x_full1[pair], m * 128, i * 128, b, kEvictFirst);
+            tma_load_3d(xs + (2 * pair + 1) * kSlotBytes, &tm_x, &x_full1[pair], m * 128 + 64, i * 128, b, kEvictFirst);
+            if (++pair == kPairs) { pair = 0; pph ^= 1u; }
+          }
+    }
+  } else if (warp == 1) {
+    // =================================== MMA issuer =====================================
+    constexpr uint32_t idesc0 = make_idesc_bf16(128, KC, 0, 0);     // S = X . Cw^T      (both K-major)
+    constexpr uint32_t idesc1 = make_idesc_bf16(128, KC, 1, 1);     // V^T = X^T . a     (both MN-major)
+    int slot = 0, cst = 0;
+    uint32_t ph = 0, cph = 0;
+    for (int kb = 0; kb < NKB; ++kb) {
+      mbar_wait(&cw_full[cst], cph);
+      for (int i = 0; i < NT; ++i) {
+        mbar_wait(&x_full0[slot], ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = smem_u32(xs + slot * kSlotBytes);
+          const uint32_t b_addr = smem_u32(cws + cst * C::kCwBytes);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_base + i * KC, make_sdesc_sw128(a_addr + k * 32, 16, 1024),
+                      make_sdesc_sw128(b_addr + k * 32, 16, 1024), idesc0, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&x_empty0[slot]);
+        }
+        __syncwarp();
+        if (++slot == C::kSlots) { slot = 0; ph ^= 1u; }
+      }
+      if (lane == 0) umma_commit(&cw_empty[cst]);
+      __syncwarp();
+      if (++cst == C::kCwStages) { cst = 0; cph ^= 1u; }
+    }
+    if (lane == 0) umma_commit(s_full);
+    __syncwarp();
+    // phase 1 (needs every assignment tile: the accumulator groups reuse the S columns)
+    mbar_wait(a_ready, 0);
+    tc_fence_after();
+    int pair = 0;
+    uint32_t pph = 0;
+    for (int g = 0; g < NG; ++g) {
+      const int buf = g & 1;
+      if (g >= 2) {
+        mbar_wait(&v_empty[buf], ((g >> 1) - 1) & 1);
+        tc_fence_after();
+      }
+      for (int i = 0; i < NT; ++i) {
+        const int valid = min(128, T - i * 128);
+        const int nsteps = (valid + 15) >> 4;
+        for (int ml = 0; ml < C::kGM; ++ml) {
+          const int m = g * C::kGM + ml;
+          if (m >= NMB) break;
+          mbar_wait(&x_full1[pair], pph);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_addr = smem_u32(xs + (2 * pair) * kSlotBytes);
+            const uint32_t b_addr = smem_u32(atile + i * C::kATileBytes);
+            for (int s = 0; s < nsteps; ++s)
+              umma_bf16(tmem_base + buf * 256 + ml * KC, make_sdesc_sw128(a_addr + s * 2048, kSlotBytes, 1024),
+                        make_sdesc_sw128(b_addr + s * 2048, kSlotBytes, 1024), idesc1, (i > 0 || s > 0) ? 1u : 0u);
+            umma_commit(&x_empty1[pair]);
+          }
+          __syncwarp();
+          if (++pair == kPairs) { pair = 0; pph ^= 1u; }
+        }
+      }
+      if (lane == 0) umma_commit(&v_full[buf]);
+      __syncwarp();
+    }
+  } else {
+    // ============================ softmax + epilogue warps (128 threads) ============================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int nf = min(max(num_frames[b], 0), T);
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    for (int i = 0; i < NT; ++i) {
+      float l[KC];
+#pragma unroll
+      for (int c = 0; c < KC; c += 32) tmem_ld32(taddr + i * KC + c, reinterpret_cast<uint32_t*>(l) + c);
+      tmem_ld_wait();
+      const bool valid = (i * 128 + row) < nf;
+      float mx = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        l[k] = l[k] * scale_s[k] + shift_s[k];
+        mx = fmaxf(mx, l[k]);
+      }
+      float sum = 0.0f;
+#pragma unroll
+      for (int k = 0; k < KC; ++k) {
+        l[k] = __expf(l[k] - mx);
+        sum += l[k];
+      }
+      const float inv = valid ? 1.0f / sum : 0.0f;
+      uint8_t* at = atile + i * C::kATileBytes;
+#pragma unroll
+      for (int c8 = 0; c8 < KC / 8; ++c8) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(l[c8 * 8 + 2 * j] * inv);
+          const __nv_bfloat16 h1 = __float2bfloat16_rn(l[c8 * 8 + 2 * j + 1] * inv);
+          l[c8 * 8 + 2 * j] = __bfloat162float(h0);         // a_sum uses the rounded assignment too
+          l[c8 * 8 + 2 * j + 1] = __bfloat162float(h1);
+          w[j] = pack_bf16x2(h0, h1);
+        }
+        const int nb = c8 >> 3;
+        *reinterpret_cast<uint4*>(at + nb * kSlotBytes + sw128_offset(row, c8 & 7)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+#pragma unroll
+      for (int c = 0; c < KC; c += 32) {
+        const float tot = warp_transpose_reduce32(l + c, lane);
+        atomicAdd(&asum_s[c + lane], tot);
+      }
+    }
+    tc_fence_before();
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(a_ready);
+    named_bar_sync(1, 128);                               // a_sum complete
+
+    __nv_bfloat16* ohi = out_hi + static_cast<long long>(b) * ld_out;
+    __nv_bfloat16* olo = out_lo ? out_lo + static_cast<long long>(b) * ld_out : nullptr;
+    for (int g = 0; g < NG; ++g) {
+      const int buf = g & 1;
+      mbar_wait(&v_full[buf], (g >> 1) & 1);
+      tc_fence_after();
+      for (int ml = 0; ml < C::kGM; ++ml) {
+        const int m = g * C::kGM + ml;
+        if (m >= NMB) break;
+        const int d = m * 128 + row;
+        const float* c2 = cw2 + static_cast<long long>(d) * KC;
+#pragma unroll 1
+        for (int c = 0; c < KC; c += 32) {
+          float v[32];
+          tmem_ld32(taddr + buf * 256 + ml * KC + c, reinterpret_cast<uint32_t*>(v));
+          tmem_ld_wait();
+          float sq[32];
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 cc = __ldg(reinterpret_cast<const float4*>(c2 + c + j));
+            v[j] -= asum_s[c + j] * cc.x;
+            v[j + 1] -= asum_s[c + j + 1] * cc.y;
+            v[j + 2] -= asum_s[c + j + 2] * cc.z;
+            v[j + 3] -= asum_s[c + j + 3] * cc.w;
+          }
+          // stash un-normalised (bf16 hi [+ lo]); the sum of squares uses the stashed precision
+#pragma unroll
+          for (int j8 = 0; j8 < 4; ++j8) {
+            uint4 hi, lo;
+            pack8_hi_lo(v + 8 * j8, hi, lo);
+            const long long o = static_cast<long long>(d) * KC + c + 8 * j8;
+            *reinterpret_cast<uint4*>(ohi + o) = hi;
+            if (olo) *reinterpret_cast<uint4*>(olo + o) = lo;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
+          const float tot = warp_transpose_reduce32(sq, lane);
+          atomicAdd(&ssq_s[c + lane], tot);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&v_empty[buf]);
+    }
+    // ------------------------------- rescale in place -------------------------------
+    __threadfence_block();
+    named_bar_sync(1, 128);
+    const int et = threadIdx.x - 64;                       // 0..127
+    if (et == 0) *total_s = 0.0f;
+    named_bar_sync(1, 128);
+    if (et < KC) {
+      const float ss = ssq_s[et];
+      const float rs = rsqrtf(fmaxf(ss, 1e-12f));
+      fscale_s[et] = rs;
+      atomicAdd(total_s, ss * rs * rs);
+    }
+    named_bar_sync(1, 128);
+    const float gs = rsqrtf(fmaxf(*total_s, 1e-12f));
+    const long long n = static_cast<long long>(D) * KC;
+    float* of = out_f32 ? out_f32 + static_cast<long long>(b) * ld_out : nullptr;
+    for (long long e = static_cast<long long>(et) * 8; e < n; e += 128 * 8) {
+      const int k0 = static_cast<int>(e % KC);
+      const uint4 h = __ldcg(reinterpret_cast<const uint4*>(ohi + e));
+      uint4 lw = make_uint4(0, 0, 0, 0);
+      if (olo) lw = __ldcg(reinterpret_cast<const uint4*>(olo + e));
+      const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+      const uint32_t lv[4] = {lw.x, lw.y, lw.z, lw.w};
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lv[j] << 16);
+        v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lv[j] & 0xFFFF0000u);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] *= fscale_s[k0 + j] * gs;
+      uint4 nh, nl;
+      pack8_hi_lo(v, nh, nl);
+      *reinterpret_cast<uint4*>(ohi + e) = nh;
+      if (olo) *reinterpret_cast<uint4*>(olo + e) = nl;
+      if (of) {
+        *reinterpret_cast<float4*>(of + e) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(of + e + 4) = make_float4(v[4], v[5], v[6], v[7]);
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int KC>
+int launch_netvlad(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, const yt8m_bf16* cw_packed,
+                   const float* scale, const float* shift, const float* cw2, float* out_f32, yt8m_bf16* out_hi,
+                   yt8m_bf16* out_lo, long long ld_out, cudaStream_t stream) {
+  using C = NvCfg<KC>;
+  CUtensorMap tm_x, tm_cw;
+  int rc;
+  if ((rc = make_tmap_bf16_3d(&tm_x, x, D, T, B, D, static_cast<uint64_t>(T) * D, 128)) != YT8M_OK) return rc;
+  if ((rc = make_tmap_bf16_2d(&tm_cw, cw_packed, KC, D, D, KC)) != YT8M_OK) return rc;
+  auto kern = netvlad_fused_kernel<KC>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    YT8M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
+    attr_done = true;
+  }
+  kern<<<B, kNvThreads, C::kTotal, stream>>>(tm_x, tm_cw, num_frames, T, D, scale, shift, cw2, out_f32,
+                                             reinterpret_cast<__nv_bfloat16*>(out_hi),
+                                             reinterpret_cast<__nv_bfloat16*>(out_lo), ld_out);
+  return check_launch("netvlad_fused_kernel");
+}
+
+}  // namespace
+
+extern "C" int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K,
+                                const yt8m_bf16* cw_packed, const float* scale, const float* shift, const float* cw2,
+                                float* out_f32, yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out,
+                                yt8m_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  YT8M_REQUIRE(x && num_frames && cw_packed && cw2 && out_hi, YT8M_E_BADPTR,
+               "yt8m_netvlad_fwd: null pointer (out_hi is required: it doubles as the stash)");
+  YT8M_REQUIRE(B > 0 && T > 0 && T <= 128 * kNtMax && D > 0 && D % 128 == 0, YT8M_E_BADSHAPE,
+               "yt8m_netvlad_fwd: need 0 < T <= %d and D %% 128 == 0 (T=%d D=%d)", 128 * kNtMax, T, D);
+  YT8M_REQUIRE(ld_out >= static_cast<long long>(D) * K && ld_out % 8 == 0, YT8M_E_BADSHAPE, "yt8m_netvlad_fwd: ld_out");
+  YT8M_REQUIRE(aligned16(out_hi) && (!out_lo || aligned16(out_lo)) && (!out_f32 || aligned16(out_f32)) && aligned16(cw2),
+               YT8M_E_BADPTR, "yt8m_netvlad_fwd: outputs / cw2 must be 16-byte aligned");
+  switch (K) {
+    case 32: return launch_netvlad<32>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, stream);
+    case 64: return launch_netvlad<64>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, stream);
+    case 128: return launch_netvlad<128>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, stream);
+    default:
+      set_error("yt8m_netvlad_fwd: cluster count K=%d unsupported (32, 64, 128)", K);
+      return YT8M_E_UNSUPPORTED;
+  }
+}
