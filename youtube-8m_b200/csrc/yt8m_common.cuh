@@ -100,14 +100,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded spin: a wedged pipeline traps (-> cudaErrorLaunchFailure) instead of hanging the GPU.
-#ifndef YT8M_SPIN_LIMIT
-#define YT8M_SPIN_LIMIT (1u << 26)
+// Bounded wait: a wedged pipeline traps (-> cudaErrorLaunchFailure at the next sync) after
+// YT8M_WAIT_TIMEOUT_NS of wall-clock instead of hanging the GPU.
+#ifndef YT8M_WAIT_TIMEOUT_NS
+#define YT8M_WAIT_TIMEOUT_NS 4000000000ull
 #endif
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > YT8M_SPIN_LIMIT) { __trap(); }
+    if ((++spins & 0x3FFu) == 0 && global_timer_ns() - t0 > YT8M_WAIT_TIMEOUT_NS) { __trap(); }
   }
 }
 

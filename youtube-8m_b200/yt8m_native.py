@@ -1,0 +1,292 @@
+"""ctypes binding of libyt8m_b200.so (the C ABI declared in include/yt8m_b200.h).
+
+This is the ONLY route from the Python plugins to arithmetic: there is no CPU or PyTorch fallback.
+If the library is missing or fails to load, importing this module raises.  Every wrapper takes
+torch CUDA tensors (used purely as device-memory handles), passes raw pointers + the current CUDA
+stream, and raises ``Yt8mError`` with ``yt8m_last_error()`` on a non-zero status.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libyt8m_b200.so")
+
+c_void_p, c_int, c_ll, c_float, c_size_t = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_size_t
+
+
+class Yt8mError(RuntimeError):
+  pass
+
+
+def _load():
+  if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        "libyt8m_b200.so not found at %s -- build it with `python youtube-8m_b200/build_native.py` "
+        "(there is no fallback path)" % LIB_PATH)
+  return ctypes.CDLL(LIB_PATH)
+
+
+_lib = _load()
+
+_SIGS = {
+    "yt8m_version": (c_int, []),
+    "yt8m_last_error": (ctypes.c_char_p, []),
+    "yt8m_l2norm_rows_fwd": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "yt8m_linear_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "yt8m_linear_fwd": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_size_t, c_void_p]),
+    "yt8m_pack_transpose_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "yt8m_moe_packed_rows": (c_ll, [c_int, c_int]),
+    "yt8m_moe_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_void_p]),
+    "yt8m_moe_fwd": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll,
+                             c_void_p]),
+    "yt8m_group_max_rows": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p]),
+    "yt8m_lstm_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "yt8m_lstm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "yt8m_lstm_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "yt8m_attn_pool_fwd": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
+    "yt8m_netvlad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "yt8m_context_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
+    "yt8m_split_bf16": (c_int, [c_void_p, c_ll, c_int, c_ll, c_void_p, c_void_p, c_ll, c_void_p]),
+    "yt8m_xent_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p]),
+    "yt8m_topk_rows": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+}
+for _name, (_res, _args) in _SIGS.items():
+  _fn = getattr(_lib, _name)          # AttributeError here == header/library mismatch: fail loudly
+  _fn.restype = _res
+  _fn.argtypes = _args
+
+EXPORTS = tuple(_SIGS)
+
+ACT = {"none": 0, None: 0, "relu": 1, "relu6": 2, "sigmoid": 3, "tanh": 4}
+SRC_F32, SRC_BF16, SRC_U8 = 0, 1, 2
+
+
+def version():
+  return _lib.yt8m_version()
+
+
+def _check(rc, what):
+  if rc != 0:
+    raise Yt8mError("%s failed (%d): %s" % (what, rc, _lib.yt8m_last_error().decode()))
+
+
+def _p(t):
+  if t is None:
+    return None
+  if not t.is_cuda:
+    raise Yt8mError("yt8m_b200 needs CUDA tensors (got a %s tensor); there is no CPU path" % t.device)
+  return t.data_ptr()
+
+
+def _stream():
+  return torch.cuda.current_stream().cuda_stream
+
+
+def _bf16(shape, device):
+  return torch.empty(shape, dtype=torch.bfloat16, device=device)
+
+
+def _f32(shape, device):
+  return torch.empty(shape, dtype=torch.float32, device=device)
+
+
+def pad8(n):
+  return (n + 7) // 8 * 8
+
+
+# ------------------------------------------------------------------------------------------------
+# wrappers
+# ------------------------------------------------------------------------------------------------
+
+def l2norm_rows(x, normalize=True, num_frames=None, want_f32=False):
+  """x: [..., dim] fp32 / bf16 / uint8 (contiguous).  Returns bf16 (and fp32 if asked)."""
+  assert x.is_contiguous()
+  dim = x.shape[-1]
+  rows = x.numel() // dim
+  src = {torch.float32: SRC_F32, torch.bfloat16: SRC_BF16, torch.uint8: SRC_U8}[x.dtype]
+  out = _bf16(x.shape, x.device)
+  of = _f32(x.shape, x.device) if want_f32 else None
+  fpv = x.shape[-2] if (num_frames is not None and x.dim() >= 3) else 0
+  _check(_lib.yt8m_l2norm_rows_fwd(_p(x), src, rows, dim, int(bool(normalize)), _p(num_frames), fpv, _p(out), _p(of),
+                                   _stream()), "yt8m_l2norm_rows_fwd")
+  return (out, of) if want_f32 else out
+
+
+def split_bf16(x, out_hi=None, out_lo=None, want_lo=True):
+  """fp32 [rows, cols] -> bf16 hi, lo (row stride padded to 8 elements, pad columns zero).
+  out_hi/out_lo may be column-slices of wider (pre-zeroed) buffers, e.g. to build a concatenation."""
+  assert x.dim() == 2 and x.stride(1) == 1
+  rows, cols = x.shape
+  if out_hi is None:
+    out_hi = torch.zeros((rows, pad8(cols)), dtype=torch.bfloat16, device=x.device)[:, :cols]
+    out_lo = torch.zeros((rows, pad8(cols)), dtype=torch.bfloat16, device=x.device)[:, :cols] if want_lo else None
+  _check(_lib.yt8m_split_bf16(_p(x), rows, cols, x.stride(0), _p(out_hi), _p(out_lo), out_hi.stride(0), _stream()),
+         "yt8m_split_bf16")
+  return out_hi, out_lo
+
+
+def pack_transpose(w_kn):
+  """fp32 [K, N] (TF layout) -> bf16 [N, pad8(K)] K-contiguous."""
+  k, n = w_kn.shape
+  out = _bf16((n, pad8(k)), w_kn.device)
+  _check(_lib.yt8m_pack_transpose_bf16(_p(w_kn.contiguous()), k, n, _p(out), out.stride(0), _stream()), "yt8m_pack_transpose_bf16")
+  return out
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes, device):
+  key = (device.index, torch.cuda.current_stream().cuda_stream)
+  buf = _ws_cache.get(key)
+  if buf is None or buf.numel() < nbytes:
+    buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+    _ws_cache[key] = buf
+  return buf
+
+
+def linear(a_hi, w_packed, a_lo=None, n=None, k=None, scale=None, shift=None, act=None, out_f32=True, out_bf16=False,
+           out_lo=False):
+  """act((A . W^T) * scale + shift).  a_hi/a_lo: bf16 [M, lda]; w_packed: bf16 [N, ldw].
+  Returns dict with the requested outputs ('f32', 'hi', 'lo')."""
+  m = a_hi.shape[0]
+  n = n or w_packed.shape[0]
+  k = k or min(a_hi.shape[1], w_packed.shape[1])
+  dev = a_hi.device
+  ld_out = pad8(n)
+  of = _f32((m, ld_out), dev) if out_f32 else None
+  oh = _bf16((m, ld_out), dev) if out_bf16 else None
+  ol = _bf16((m, ld_out), dev) if (out_bf16 and out_lo) else None
+  if ld_out != n:
+    for t in (of, oh, ol):
+      if t is not None:
+        t.zero_()
+  ws_bytes = _lib.yt8m_linear_workspace_bytes(m, n, k)
+  ws = _workspace(ws_bytes, dev)
+  _check(_lib.yt8m_linear_fwd(_p(a_hi), _p(a_lo), a_hi.stride(0), _p(w_packed), w_packed.stride(0), m, n, k, _p(scale),
+                              _p(shift), ACT[act], _p(of), _p(oh), _p(ol), ld_out, _p(ws), ws.numel(), _stream()),
+         "yt8m_linear_fwd")
+  res = {}
+  if of is not None:
+    res["f32"] = of[:, :n]
+  if oh is not None:
+    res["hi"] = oh[:, :n]
+  if ol is not None:
+    res["lo"] = ol[:, :n]
+  return res
+
+
+def moe_packed_rows(vocab, num_mixtures):
+  return _lib.yt8m_moe_packed_rows(vocab, num_mixtures)
+
+
+def moe_pack(gate_w, expert_w, expert_b, vocab, num_mixtures):
+  """TF-layout fp32 gate [D, V(M+1)], expert [D, VM], bias [VM] -> (w_packed bf16 [rows, pad8(D)], bias_packed)."""
+  d = gate_w.shape[0]
+  rows = moe_packed_rows(vocab, num_mixtures)
+  if rows <= 0:
+    raise Yt8mError("moe_pack: unsupported vocab=%d mixtures=%d" % (vocab, num_mixtures))
+  wp = _bf16((rows, pad8(d)), gate_w.device)
+  bp = _f32((rows,), gate_w.device)
+  _check(_lib.yt8m_moe_pack_weights(_p(gate_w.contiguous()), _p(expert_w.contiguous()), _p(expert_b.contiguous()), d, vocab,
+                                    num_mixtures, _p(wp), wp.stride(0), _p(bp), _stream()), "yt8m_moe_pack_weights")
+  return wp, bp
+
+
+def moe_fwd(x_hi, w_packed, bias_packed, vocab, num_mixtures, x_lo=None, d=None):
+  b = x_hi.shape[0]
+  d = d or min(x_hi.shape[1], w_packed.shape[1])
+  out = _f32((b, vocab), x_hi.device)
+  _check(_lib.yt8m_moe_fwd(_p(x_hi), _p(x_lo), x_hi.stride(0), _p(w_packed), w_packed.stride(0), _p(bias_packed), b, d, vocab,
+                           num_mixtures, _p(out), vocab, _stream()), "yt8m_moe_fwd")
+  return out
+
+
+def group_max_rows(x, heads):
+  rows, cols = x.shape
+  groups = rows // heads
+  out = _f32((groups, cols), x.device)
+  _check(_lib.yt8m_group_max_rows(_p(x.contiguous()), groups, heads, cols, _p(out), _stream()), "yt8m_group_max_rows")
+  return out
+
+
+def lstm_pack(w_tf, b_tf, in_dim, hidden):
+  wp = _bf16((4 * hidden, in_dim + hidden), w_tf.device)
+  bp = _f32((4 * hidden,), w_tf.device)
+  _check(_lib.yt8m_lstm_pack_weights(_p(w_tf.contiguous()), _p(b_tf.contiguous()), in_dim, hidden, _p(wp), _p(bp), _stream()),
+         "yt8m_lstm_pack_weights")
+  return wp, bp
+
+
+def lstm_fwd(x, num_frames, w_packed, b_packed, hidden, forget_bias=1.0, want_seq=False, want_seq_bf16=False):
+  """x: bf16 [B, T, D]; w_packed/b_packed: per-layer lists.  Returns (state [B, L*2*H], out_seq, out_seq_bf16)."""
+  b, t, d = x.shape
+  layers = len(w_packed)
+  dev = x.device
+  state = _f32((b, layers * 2 * hidden), dev)
+  seq = _f32((b, t, hidden), dev) if want_seq else None
+  seq_bf = _bf16((b, t, hidden), dev) if want_seq_bf16 else None
+  ws_bytes = _lib.yt8m_lstm_workspace_bytes(b, t, d, hidden, layers)
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+  wp = (c_void_p * layers)(*[w.data_ptr() for w in w_packed])
+  bp = (c_void_p * layers)(*[v.data_ptr() for v in b_packed])
+  _check(_lib.yt8m_lstm_fwd(_p(x), _p(num_frames), b, t, d, hidden, layers, ctypes.cast(wp, c_void_p), ctypes.cast(bp, c_void_p),
+                            float(forget_bias), _p(state), _p(seq), _p(seq_bf), _p(ws), ws_bytes, _stream()), "yt8m_lstm_fwd")
+  return state, seq, seq_bf
+
+
+def attn_pool(logits, feats, num_frames, heads, mode, want_bf16=True):
+  """logits fp32 [B, T, >=A]; feats bf16 [B, T, F] -> fp32 [B, A, F] (+ bf16 hi/lo)."""
+  b, t, f = feats.shape
+  out = _f32((b, heads, f), feats.device)
+  oh = _bf16((b, heads, f), feats.device) if want_bf16 else None
+  ol = _bf16((b, heads, f), feats.device) if want_bf16 else None
+  _check(_lib.yt8m_attn_pool_fwd(_p(logits), logits.stride(1), _p(feats), _p(num_frames), b, t, heads, f, mode, _p(out), _p(oh),
+                                 _p(ol), _stream()), "yt8m_attn_pool_fwd")
+  return out, oh, ol
+
+
+def netvlad_fwd(x, num_frames, cw_packed, scale, shift, cw2, want_f32=False, want_lo=False):
+  """x bf16 [B, T, D]; cw_packed bf16 [K, D]; cw2 fp32 [D, K] -> bf16 hi [B, D*K] (+lo, +fp32)."""
+  b, t, d = x.shape
+  k = cw_packed.shape[0]
+  oh = _bf16((b, d * k), x.device)
+  ol = _bf16((b, d * k), x.device) if want_lo else None
+  of = _f32((b, d * k), x.device) if want_f32 else None
+  _check(_lib.yt8m_netvlad_fwd(_p(x), _p(num_frames), b, t, d, k, _p(cw_packed), _p(scale), _p(shift), _p(cw2), _p(of), _p(oh),
+                               _p(ol), d * k, _stream()), "yt8m_netvlad_fwd")
+  return oh, ol, of
+
+
+def context_gate(x, g, scale=None, shift=None, want_bf16=True):
+  rows, cols = x.shape
+  out = _f32((rows, cols), x.device)
+  oh = _bf16((rows, cols), x.device) if want_bf16 else None
+  ol = _bf16((rows, cols), x.device) if want_bf16 else None
+  _check(_lib.yt8m_context_gate_fwd(_p(x.contiguous()), _p(g.contiguous()), _p(scale), _p(shift), rows, cols, _p(out), _p(oh),
+                                    _p(ol), _stream()), "yt8m_context_gate_fwd")
+  return out, oh, ol
+
+
+def xent(pred, labels, want_grad=False, grad_scale=1.0):
+  b, v = pred.shape
+  loss = _f32((1,), pred.device)
+  dp = _f32((b, v), pred.device) if want_grad else None
+  _check(_lib.yt8m_xent_fwd_bwd(_p(pred.contiguous()), _p(labels.contiguous()), b, v, _p(loss), _p(dp), float(grad_scale),
+                                _stream()), "yt8m_xent_fwd_bwd")
+  return loss, dp
+
+
+def topk_rows(x, k):
+  rows, cols = x.shape
+  idx = torch.empty((rows, k), dtype=torch.int32, device=x.device)
+  val = _f32((rows, k), x.device)
+  _check(_lib.yt8m_topk_rows(_p(x.contiguous()), rows, cols, k, _p(idx), _p(val), _stream()), "yt8m_topk_rows")
+  return idx, val
