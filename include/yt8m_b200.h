@@ -136,6 +136,11 @@ int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, in
 int yt8m_context_gate_fwd(const float* x, const float* g, const float* scale, const float* shift, long long rows,
                           int cols, float* out_f32, yt8m_bf16* out_hi, yt8m_bf16* out_lo, yt8m_stream_t stream);
 
+/* y = x * scale[c] + shift[c] on a contiguous [rows, cols] fp32 / bf16 matrix -> fp32 and/or bf16 hi (+lo):
+ * inference-mode slim.batch_norm applied to a GEMM operand (wh/all_frame_models/dbof_model.py:64-70). */
+int yt8m_col_affine(const void* x, int src_dtype, long long rows, int cols, const float* scale, const float* shift,
+                    float* out_f32, yt8m_bf16* out_hi, yt8m_bf16* out_lo, yt8m_stream_t stream);
+
 /* fp32 [rows, cols] -> bf16 hi (+lo) with destination row stride ld_out and column offset already applied
  * by the caller (used to build concatenated operands, e.g. chain_moe_model.py:16) */
 int yt8m_split_bf16(const float* x, long long rows, int cols, long long ld_in, yt8m_bf16* out_hi,

@@ -9,6 +9,7 @@ Deliberately written as straight loops over sorted lists -- a second, independen
 the arithmetic the reference does with heaps -- so that it can check both the reference fixtures
 and the product's vectorised implementation (youtube-8m_b200/eval_util.py).
 """
+import heapq
 import random
 
 import numpy as np
@@ -34,14 +35,28 @@ def perr(predictions, actuals):
 
 def top_k_pairs(predictions, actuals, k=20):
   """wh/eval_util.py:123-165: the (prediction, label) pairs of the k best classes of every row,
-  and the total number of positives in ``actuals`` (not only among the top k)."""
+  flattened CLASS-major / video-minor exactly like top_k_by_class + flatten (the order matters only for
+  how the reference breaks ties), and the total number of positives in ``actuals``."""
   k = min(k, predictions.shape[1])
-  ps, ls = [], []
+  per_class_p = [[] for _ in range(predictions.shape[1])]
+  per_class_l = [[] for _ in range(predictions.shape[1])]
   for row in range(predictions.shape[0]):
     idx = np.argpartition(predictions[row], -k)[-k:]
-    ps.extend(predictions[row][idx].tolist())
-    ls.extend(actuals[row][idx].tolist())
-  return np.asarray(ps), np.asarray(ls), float(np.sum(actuals))
+    for j in idx:
+      per_class_p[j].append(predictions[row][j])
+      per_class_l[j].append(actuals[row][j])
+  ps = [x for c in per_class_p for x in c]
+  ls = [x for c in per_class_l for x in c]
+  return ps, ls, float(np.sum(actuals))
+
+
+def heap_order(ps, ls, heap=None):
+  """wh/average_precision_calculator.py:127-133: the calculator keeps (prediction, actual) in a heapq
+  list; peek_ap_at_n reads them back in heap-array order."""
+  heap = [] if heap is None else heap
+  for p, l in zip(ps, ls):
+    heapq.heappush(heap, (p, l))
+  return heap
 
 
 def ap_at_n(predictions, actuals, n=None, total_num_positives=None):
@@ -71,26 +86,27 @@ def gap(predictions, actuals, top_k=20):
   """wh/eval_util.py:102-120 (calculate_gap): AP over the pooled per-video top-k pairs with
   numpos = all positives in ``actuals``."""
   p, l, numpos = top_k_pairs(predictions, actuals, top_k)
-  return ap_at_n(p, l, n=None, total_num_positives=numpos)
+  heap = heap_order(p, l)
+  hp, hl = zip(*heap)
+  return ap_at_n(np.array(hp), np.array(hl), n=None, total_num_positives=numpos)
 
 
 class StreamingGap:
-  """wh/eval_util.py:167-254 (EvaluationMetrics) restricted to hit@1 / perr / gap: accumulate
-  mini-batches, report epoch averages.  GAP is order-sensitive only through ties."""
+  """wh/eval_util.py:167-254 (EvaluationMetrics) restricted to hit@1 / perr / loss / gap: accumulate
+  mini-batches into one heap, report epoch averages."""
 
   def __init__(self, top_k=20):
     self.top_k = top_k
     self.clear()
 
   def clear(self):
-    self._p, self._l, self._pos = [], [], 0.0
+    self._heap, self._pos = [], 0.0
     self.sum_hit, self.sum_perr, self.sum_loss, self.n = 0.0, 0.0, 0.0, 0
 
   def accumulate(self, predictions, labels, loss):
     b = labels.shape[0]
     p, l, pos = top_k_pairs(predictions, labels, self.top_k)
-    self._p.append(p)
-    self._l.append(l)
+    heap_order(p, l, self._heap)
     self._pos += pos
     self.sum_hit += hit_at_one(predictions, labels) * b
     self.sum_perr += perr(predictions, labels) * b
@@ -100,8 +116,7 @@ class StreamingGap:
   def get(self):
     if self.n <= 0:
       raise ValueError("total_sample must be positive.")
-    p = np.concatenate(self._p)
-    l = np.concatenate(self._l)
+    hp, hl = zip(*self._heap)
     return {"avg_hit_at_one": self.sum_hit / self.n, "avg_perr": self.sum_perr / self.n,
             "avg_loss": self.sum_loss / self.n,
-            "gap": ap_at_n(p, l, n=None, total_num_positives=self._pos)}
+            "gap": ap_at_n(np.array(hp), np.array(hl), n=None, total_num_positives=self._pos)}

@@ -1,0 +1,75 @@
+"""The metric path is PINNED: oracle/gap_oracle.py and the product's vectorised eval_util.py are checked
+against golden vectors produced by the reference's own eval_util.py / average_precision_calculator.py
+(oracle/make_golden.py, run in the build container)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import gap_oracle
+from oracle.make_golden import golden_case
+import eval_util
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "gap_golden.json")))
+CASES = {c["name"]: c for c in GOLD["cases"]}
+
+
+def _inputs(c):
+  return golden_case(c["seed"], c["batch"], c["classes"], c["labels_per_video"], c["quant"])
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_oracle_matches_reference_golden(name):
+  c = CASES[name]
+  p, y = _inputs(c)
+  assert gap_oracle.hit_at_one(p, y) == pytest.approx(c["hit_at_one"], abs=1e-12)
+  assert gap_oracle.perr(p, y) == pytest.approx(c["perr"], abs=1e-7)
+  # 1e-6: the fixture was generated under numpy 2 (NEP 50), where the reference's `1.0 / numpy.float32`
+  # and `ap += ...` stay in float32; the oracle accumulates in float64 like the 2017 numpy did.
+  assert gap_oracle.gap(p, y, c["top_k"]) == pytest.approx(c["gap"], abs=1e-6)        # incl. the tie order
+  assert gap_oracle.ap_at_n(p[0], y[0]) == pytest.approx(c["ap_row0"], abs=1e-6)
+  assert gap_oracle.ap_at_n(p[0], y[0], n=7) == pytest.approx(c["ap_at_7_row0"], abs=1e-6)
+  sg = gap_oracle.StreamingGap(c["top_k"])
+  h = c["batch"] // 2
+  sg.accumulate(p[:h], y[:h], np.full(h, 1.5))
+  sg.accumulate(p[h:], y[h:], np.full(c["batch"] - h, 2.5))
+  g = sg.get()
+  for k in ("avg_hit_at_one", "avg_perr", "avg_loss", "gap"):
+    assert g[k] == pytest.approx(c["stream"][k], abs=1e-6), k
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_product_eval_util_matches_reference_golden(name):
+  c = CASES[name]
+  p, y = _inputs(c)
+  assert eval_util.calculate_hit_at_one(p, y) == pytest.approx(c["hit_at_one"], abs=1e-12)
+  assert eval_util.calculate_precision_at_equal_recall_rate(p, y) == pytest.approx(c["perr"], abs=1e-7)
+  # With exact ties the reference's AP depends on its heap-array order; the vectorised implementation
+  # pools in video order, so tied cases agree only to the tie ambiguity.  Tie-free cases are exact.
+  tol = 2e-2 if c["quant"] else 1e-6
+  assert eval_util.calculate_gap(p, y, c["top_k"]) == pytest.approx(c["gap"], abs=tol)
+  em = eval_util.EvaluationMetrics(c["classes"], c["top_k"])
+  h = c["batch"] // 2
+  em.accumulate(p[:h], y[:h], np.full(h, 1.5))
+  em.accumulate(p[h:], y[h:], np.full(c["batch"] - h, 2.5))
+  g = em.get()
+  assert g["avg_hit_at_one"] == pytest.approx(c["stream"]["avg_hit_at_one"], abs=1e-7)
+  assert g["avg_perr"] == pytest.approx(c["stream"]["avg_perr"], abs=1e-7)
+  assert g["avg_loss"] == pytest.approx(c["stream"]["avg_loss"], abs=1e-7)
+  assert g["gap"] == pytest.approx(c["stream"]["gap"], abs=tol)
+  assert float(np.mean(g["aps"])) == pytest.approx(c["stream"]["map"], abs=tol)
+
+
+def test_gap_edge_cases():
+  y = np.zeros((3, 10), dtype=np.float32)
+  p = np.random.RandomState(0).random_sample((3, 10)).astype(np.float32)
+  assert eval_util.calculate_gap(p, y) == 0.0                      # no positives -> 0 (numpos == 0)
+  assert gap_oracle.gap(p, y) == 0.0
+  y[0, 3] = 1
+  p[0, 3] = 2.0                                                   # the single positive ranked first
+  assert eval_util.calculate_gap(p, y, top_k=5) == pytest.approx(1.0)
+  with pytest.raises(ValueError):
+    eval_util.top_k_by_class(p, y, 0)
+  with pytest.raises(ValueError):
+    eval_util.EvaluationMetrics(10, 20).get()

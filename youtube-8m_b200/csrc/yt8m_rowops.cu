@@ -218,6 +218,28 @@ __global__ void context_gate_kernel(const float* __restrict__ x, const float* __
   }
 }
 
+// y = x * scale[c] + shift[c] -> bf16 hi/lo (+fp32): exact application of an inference-mode batch-norm
+// to a GEMM operand (wh/all_frame_models/dbof_model.py:64-70 input_bn).
+template <typename TIn>
+__global__ void col_affine_kernel(const TIn* __restrict__ x, long long rows, int cols, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, float* __restrict__ out, __nv_bfloat16* __restrict__ out_hi,
+                                  __nv_bfloat16* __restrict__ out_lo) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = static_cast<int>(i % cols);
+    float v = static_cast<float>(x[i]);
+    if (scale) v *= scale[c];
+    if (shift) v += shift[c];
+    if (out) out[i] = v;
+    if (out_hi) {
+      __nv_bfloat16 h, l;
+      split_bf16(v, h, l);
+      out_hi[i] = h;
+      if (out_lo) out_lo[i] = l;
+    }
+  }
+}
+
 __global__ void split_bf16_kernel(const float* __restrict__ x, long long rows, int cols, long long ld_in,
                                   __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ld_out) {
   const long long total = rows * cols;
@@ -337,6 +359,22 @@ int yt8m_context_gate_fwd(const float* x, const float* g, const float* scale, co
                                                                       reinterpret_cast<__nv_bfloat16*>(out_hi),
                                                                       reinterpret_cast<__nv_bfloat16*>(out_lo));
   return check_launch("context_gate_kernel");
+}
+
+int yt8m_col_affine(const void* x, int src_dtype, long long rows, int cols, const float* scale, const float* shift,
+                    float* out_f32, yt8m_bf16* out_hi, yt8m_bf16* out_lo, yt8m_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  YT8M_REQUIRE(x && (out_f32 || out_hi), YT8M_E_BADPTR, "yt8m_col_affine: null pointer");
+  YT8M_REQUIRE(rows > 0 && cols > 0, YT8M_E_BADSHAPE, "yt8m_col_affine: bad shape");
+  const int blocks = grid_for(rows * cols, 256);
+  __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(out_hi);
+  __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(out_lo);
+  if (src_dtype == YT8M_SRC_F32)
+    col_affine_kernel<float><<<blocks, 256, 0, stream>>>(static_cast<const float*>(x), rows, cols, scale, shift, out_f32, oh, ol);
+  else if (src_dtype == YT8M_SRC_BF16)
+    col_affine_kernel<__nv_bfloat16><<<blocks, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), rows, cols, scale, shift, out_f32, oh, ol);
+  else { set_error("yt8m_col_affine: src_dtype %d unsupported", src_dtype); return YT8M_E_UNSUPPORTED; }
+  return check_launch("col_affine_kernel");
 }
 
 int yt8m_split_bf16(const float* x, long long rows, int cols, long long ld_in, yt8m_bf16* out_hi, yt8m_bf16* out_lo,

@@ -53,6 +53,7 @@ _SIGS = {
                                  c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "yt8m_context_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
+    "yt8m_col_affine": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "yt8m_split_bf16": (c_int, [c_void_p, c_ll, c_int, c_ll, c_void_p, c_void_p, c_ll, c_void_p]),
     "yt8m_xent_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p]),
     "yt8m_topk_rows": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p]),
@@ -273,6 +274,17 @@ def context_gate(x, g, scale=None, shift=None, want_bf16=True):
   _check(_lib.yt8m_context_gate_fwd(_p(x.contiguous()), _p(g.contiguous()), _p(scale), _p(shift), rows, cols, _p(out), _p(oh),
                                     _p(ol), _stream()), "yt8m_context_gate_fwd")
   return out, oh, ol
+
+
+def col_affine(x, scale, shift, want_f32=False):
+  """x [rows, cols] fp32/bf16 contiguous (cols % 8 == 0) -> (hi, lo[, f32]) of x * scale + shift."""
+  assert x.is_contiguous() and x.shape[1] % 8 == 0
+  rows, cols = x.shape
+  src = SRC_F32 if x.dtype == torch.float32 else SRC_BF16
+  hi, lo = _bf16((rows, cols), x.device), _bf16((rows, cols), x.device)
+  of = _f32((rows, cols), x.device) if want_f32 else None
+  _check(_lib.yt8m_col_affine(_p(x), src, rows, cols, _p(scale), _p(shift), _p(of), _p(hi), _p(lo), _stream()), "yt8m_col_affine")
+  return (hi, lo, of) if want_f32 else (hi, lo)
 
 
 def xent(pred, labels, want_grad=False, grad_scale=1.0):
