@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""Benchmark of the yt8m_b200 hot path (contract: see the task statement / DESIGN.md §Measurement).
+
+    python bench.py --gpus 1 --steps 20 --warmup 5
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...        # the CPU restatement of the reference path, host cores
+
+Workload = BASELINE.json configs[1]: NetVLAD K=64 over 300x1152 frame features -> hidden FC 73,728->1024
+(+BN, ReLU6) -> MoE-2 head over 4716 labels, bf16 operands / fp32 accumulate, batch 256 per GPU.
+One "step" = one forward pass of the plugin (NetVLADModel.create_model) over one batch of synthetic
+frame features.  The path shards by video: each rank processes its own batch, no data-path collective
+("weak" scaling).  `value` = videos/s with inputs resident in HBM; `e2e` = the same through the
+reference-facing plugin call chain (DefaultTransformer.transform + create_model) from pinned HOST uint8
+features with the predictions copied back to the host, every step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "youtube-8m_b200"))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+T, D, V = 300, 1152, 4716
+K_CLUSTERS, HIDDEN, MIXTURES = 64, 1024, 2
+WORKLOAD = "NetVLAD K=64 over 300x1152 frame feats + FC 73728->1024 + MoE-2 head (4716 labels), forward pass"
+
+
+def parse():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=20)
+  ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--batch", type=int, default=256, help="videos per GPU per step")
+  ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+  ap.add_argument("--cpu-sample", type=int, default=16, help="videos per CPU-baseline forward")
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks: sample nvidia-smi during the timed region
+# ------------------------------------------------------------------------------------------------
+
+class ClockSampler(object):
+  Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+       "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index):
+    self.index, self.rows, self.proc = index, [], None
+
+  def start(self):
+    try:
+      self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                    "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+      threading.Thread(target=self._read, daemon=True).start()
+    except Exception:
+      self.proc = None
+
+  def _read(self):
+    for line in self.proc.stdout:
+      self.rows.append([c.strip() for c in line.split(",")])
+
+  def stop(self):
+    if self.proc is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+    time.sleep(0.15)
+    self.proc.terminate()
+    sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+    mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+    return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+            "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU restatement (oracle) timing -- cpu_baseline leg and --impl reference
+# ------------------------------------------------------------------------------------------------
+
+def cpu_forward_fn(sample, seed=8):
+  """Returns (fn, n_videos): fn() runs the oracle forward of the same workload on `sample` videos."""
+  import synth
+  from oracle import model_oracle
+  torch.set_num_threads(os.cpu_count())
+  g = torch.Generator().manual_seed(9)
+  x, nf, _ = synth.model_input(sample, T, D, seed=seed)
+  import math
+  sd = {
+      "cluster_weights": synth.normal((D, K_CLUSTERS), g, 1 / math.sqrt(D)),
+      "cluster_weights2": torch.randn(D, K_CLUSTERS, generator=g) / math.sqrt(D),
+      "hidden1_weights": synth.normal((K_CLUSTERS * D, HIDDEN), g, 1 / math.sqrt(K_CLUSTERS)),
+      "gates/weights": synth.xavier((HIDDEN, V * (MIXTURES + 1)), g),
+      "experts/weights": synth.xavier((HIDDEN, V * MIXTURES), g),
+      "experts/biases": torch.zeros(V * MIXTURES),
+  }
+  for scope, c in (("cluster_bn", K_CLUSTERS), ("hidden1_bn", HIDDEN)):
+    sd[scope + "/gamma"], sd[scope + "/beta"] = torch.ones(c), torch.zeros(c)
+    sd[scope + "/moving_mean"], sd[scope + "/moving_variance"] = torch.zeros(c), torch.ones(c)
+  return (lambda: model_oracle.netvlad(sd, x, nf, V, MIXTURES)), sample
+
+
+def time_cpu(sample, min_seconds=10.0, max_reps=50):
+  fn, n = cpu_forward_fn(sample)
+  fn()                                   # warm-up (page in the 300 MB of fp32 weights)
+  reps, t0 = 0, time.perf_counter()
+  while reps < max_reps and (reps < 2 or time.perf_counter() - t0 < min_seconds):
+    fn()
+    reps += 1
+  dt = time.perf_counter() - t0
+  return {"value": n * reps / dt, "unit": "videos/s", "cores": os.cpu_count(), "kind": "port",
+          "sample": "%d forwards of %d videos (fp32 torch-CPU restatement of the reference ops, %.1f s)" % (reps, n, dt)}
+
+
+def run_reference(args, rank):
+  """--impl reference: the reference's own path is TF-1.0 / python2 and cannot run; the arm
+  times the oracle port (kind "port") on the host cores, rank 0 only."""
+  if rank != 0:
+    return
+  fn, n = cpu_forward_fn(args.cpu_sample)
+  for _ in range(max(1, min(args.warmup, 2))):
+    fn()
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    fn()
+  dt = time.perf_counter() - t0
+  val = n * args.steps / dt
+  line = {"impl": "reference", "metric": "videos/sec", "value": val, "unit": "videos/s", "n_gpus": args.gpus, "steps": args.steps,
+          "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": WORKLOAD, "batch_per_step": n, "frames": T, "feature_dim": D},
+          "cpu_baseline": {"value": val, "unit": "videos/s", "cores": os.cpu_count(), "kind": "port",
+                           "sample": "each step = one forward of %d videos" % n},
+          "e2e": {"value": val, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+          "gpu_launches": 0}
+  print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+
+def main():
+  args = parse()
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  if args.impl == "reference":
+    run_reference(args, rank)
+    return
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py: no CUDA device; the yt8m_b200 path has no CPU fallback")
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  import torch.distributed as dist
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+
+  import yt8m_native as nat
+  import yt8m_ops as ops
+  import frame_level_models
+  import feature_transform
+  import synth
+  from yt8m_flags import FLAGS
+
+  B = args.batch
+  FLAGS.parse([], known_only=True)
+  FLAGS.netvlad_cluster_size, FLAGS.netvlad_hidden_size, FLAGS.moe_num_mixtures = K_CLUSTERS, HIDDEN, MIXTURES
+  FLAGS.video_level_classifier_model = "MoeModel"
+  ops.get_store().reset(seed=9)
+  model = frame_level_models.NetVLADModel()
+  transformer = feature_transform.DefaultTransformer()
+
+  u8, nf = synth.frames_u8(B, T, D, seed=8 + rank)
+  u8_pinned, nf_pinned = u8.pin_memory(), nf.pin_memory()
+  u8_dev = torch.empty_like(u8, device=dev)
+  nf_dev = torch.empty_like(nf, device=dev)
+  pred_host = torch.empty((B, V), dtype=torch.float32).pin_memory()
+  u8_dev.copy_(u8_pinned)
+  nf_dev.copy_(nf_pinned)
+  x_dev, _ = transformer.transform(u8_dev, nf_dev)          # resident bf16, L2-normalised rows
+
+  def step_resident():
+    return model.create_model(x_dev, vocab_size=V, num_frames=nf_dev)["predictions"]
+
+  def step_e2e():
+    u8_dev.copy_(u8_pinned, non_blocking=True)
+    nf_dev.copy_(nf_pinned, non_blocking=True)
+    xi, _ = transformer.transform(u8_dev, nf_dev)
+    p = model.create_model(xi, vocab_size=V, num_frames=nf_dev)["predictions"]
+    pred_host.copy_(p, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return pred_host
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  def timed(fn, steps, warmup):
+    for _ in range(warmup):
+      fn()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+      fn()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / steps
+    if world > 1:
+      t = torch.tensor([ms], device=dev)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = float(t)
+    return ms
+
+  W = max(args.warmup, 3)
+  sampler = ClockSampler(local_rank)
+  if rank == 0:
+    sampler.start()
+  l0 = nat.launch_count()
+  nat.kernel_timer_begin("netvlad")
+  ms = timed(step_resident, args.steps, W)
+  kt = nat.kernel_timer_end()
+  launches = (nat.launch_count() - l0) // (args.steps + W)
+  ms_e2e = timed(step_e2e, args.steps, W)
+  clocks = sampler.stop() if rank == 0 else None
+
+  if rank != 0:
+    if world > 1:
+      dist.destroy_process_group()
+    return
+
+  peaks = {}
+  try:
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+  except Exception:
+    pass
+  hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+  # dominant kernel: netvlad_fused_kernel, HBM bound.  Algorithmic bytes / video: the frames once
+  # (300*1152*2) + the descriptor once (1152*64*2 hi + lo) -- SURVEY.md §8(d), DESIGN.md §Kernels.
+  alg_bytes = B * (T * D * 2 + D * K_CLUSTERS * 2 * 2)
+  k_ms = sum(kt) / len(kt) if kt else None
+  achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None
+  traffic = None
+  try:
+    traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("netvlad_fused_kernel_dram_bytes_per_launch")
+  except Exception:
+    pass
+  line = {
+      "metric": "videos/sec", "value": world * B / (ms * 1e-3), "unit": "videos/s", "n_gpus": world, "steps": args.steps,
+      "warmup": W, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+      "data": "synthetic",
+      "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B, "frames": T, "feature_dim": D,
+                 "clusters": K_CLUSTERS, "hidden": HIDDEN, "mixtures": MIXTURES, "vocab": V, "parallelism": "dp%d" % world,
+                 "l2": "inputs larger than L2 (frames 177 MB + FC weights 151 MB per step vs 126 MB L2), no explicit flush"},
+      "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "videos/s", "ms_per_step": ms_e2e,
+              "h2d_bytes_per_step": u8.numel() + nf.numel() * 4, "d2h_bytes_per_step": pred_host.numel() * 4},
+      "gpu_launches": int(launches),
+      "roofline": {"bound": "hbm", "kernel": "netvlad_fused_kernel<64>", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                   "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
+                   "kernel_ms": k_ms, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback"},
+      "clocks": clocks,
+  }
+  if world == 1 and not args.no_cpu_baseline:
+    line["cpu_baseline"] = time_cpu(args.cpu_sample)
+  print(json.dumps(line))
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

@@ -47,6 +47,8 @@ typedef uint16_t yt8m_bf16;
 /* library version (major*10000 + minor*100 + patch) */
 int yt8m_version(void);
 const char* yt8m_last_error(void);
+/* number of CUDA kernels this library has launched in this process (successful launches only) */
+long long yt8m_launch_count(void);
 
 /* ---- frame-row transforms ----------------------------------------------------------------------
  * wh/all_feature_transform/default_transformer.py:5-8  (tf.nn.l2_normalize over the feature dim) and,

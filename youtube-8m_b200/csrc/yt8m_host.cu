@@ -5,11 +5,13 @@
 #include <cudaTypedefs.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <atomic>
 #include <mutex>
 
 namespace yt8m {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -24,6 +26,7 @@ int check_launch(const char* what) {
     set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
     return YT8M_E_CUDA;
   }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return YT8M_OK;
 }
 
@@ -82,4 +85,5 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d
 extern "C" {
 int yt8m_version(void) { return 100; }  // 0.1.0
 const char* yt8m_last_error(void) { return yt8m::g_err; }
+long long yt8m_launch_count(void) { return yt8m::g_launches.load(std::memory_order_relaxed); }
 }

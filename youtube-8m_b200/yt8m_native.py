@@ -33,6 +33,7 @@ _lib = _load()
 _SIGS = {
     "yt8m_version": (c_int, []),
     "yt8m_last_error": (ctypes.c_char_p, []),
+    "yt8m_launch_count": (c_ll, []),
     "yt8m_l2norm_rows_fwd": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "yt8m_linear_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "yt8m_linear_fwd": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
@@ -71,6 +72,44 @@ SRC_F32, SRC_BF16, SRC_U8 = 0, 1, 2
 
 def version():
   return _lib.yt8m_version()
+
+
+def launch_count():
+  """CUDA kernels launched by the library so far (bench.py's gpu_launches)."""
+  return _lib.yt8m_launch_count()
+
+
+_KT = None   # kernel timer state: {"tag": str, "ev": [(start_event, end_event), ...]}
+
+
+def kernel_timer_begin(tag):
+  """bench.py: record a CUDA-event pair (on the launching stream) around every library call whose
+  name contains `tag`, so a kernel's duration is measured live inside the timed region."""
+  global _KT
+  _KT = {"tag": tag, "ev": []}
+
+
+def kernel_timer_end():
+  """Returns the per-call durations in ms (synchronises) and stops timing."""
+  global _KT
+  kt, _KT = _KT, None
+  if not kt:
+    return []
+  torch.cuda.synchronize()
+  return [a.elapsed_time(b) for a, b in kt["ev"]]
+
+
+def _call(name, *args):
+  fn = getattr(_lib, name)
+  if _KT is not None and _KT["tag"] in name:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    rc = fn(*args)
+    e1.record()
+    _KT["ev"].append((e0, e1))
+  else:
+    rc = fn(*args)
+  _check(rc, name)
 
 
 def _check(rc, what):
@@ -171,9 +210,8 @@ def linear(a_hi, w_packed, a_lo=None, n=None, k=None, scale=None, shift=None, ac
         t.zero_()
   ws_bytes = _lib.yt8m_linear_workspace_bytes(m, n, k)
   ws = _workspace(ws_bytes, dev)
-  _check(_lib.yt8m_linear_fwd(_p(a_hi), _p(a_lo), a_hi.stride(0), _p(w_packed), w_packed.stride(0), m, n, k, _p(scale),
-                              _p(shift), ACT[act], _p(of), _p(oh), _p(ol), ld_out, _p(ws), ws.numel(), _stream()),
-         "yt8m_linear_fwd")
+  _call("yt8m_linear_fwd", _p(a_hi), _p(a_lo), a_hi.stride(0), _p(w_packed), w_packed.stride(0), m, n, k, _p(scale),
+        _p(shift), ACT[act], _p(of), _p(oh), _p(ol), ld_out, _p(ws), ws.numel(), _stream())
   res = {}
   if of is not None:
     res["f32"] = of[:, :n]
@@ -205,8 +243,8 @@ def moe_fwd(x_hi, w_packed, bias_packed, vocab, num_mixtures, x_lo=None, d=None)
   b = x_hi.shape[0]
   d = d or min(x_hi.shape[1], w_packed.shape[1])
   out = _f32((b, vocab), x_hi.device)
-  _check(_lib.yt8m_moe_fwd(_p(x_hi), _p(x_lo), x_hi.stride(0), _p(w_packed), w_packed.stride(0), _p(bias_packed), b, d, vocab,
-                           num_mixtures, _p(out), vocab, _stream()), "yt8m_moe_fwd")
+  _call("yt8m_moe_fwd", _p(x_hi), _p(x_lo), x_hi.stride(0), _p(w_packed), w_packed.stride(0), _p(bias_packed), b, d, vocab,
+        num_mixtures, _p(out), vocab, _stream())
   return out
 
 
@@ -261,8 +299,8 @@ def netvlad_fwd(x, num_frames, cw_packed, scale, shift, cw2, want_f32=False, wan
   oh = _bf16((b, d * k), x.device)
   ol = _bf16((b, d * k), x.device) if want_lo else None
   of = _f32((b, d * k), x.device) if want_f32 else None
-  _check(_lib.yt8m_netvlad_fwd(_p(x), _p(num_frames), b, t, d, k, _p(cw_packed), _p(scale), _p(shift), _p(cw2), _p(of), _p(oh),
-                               _p(ol), d * k, _stream()), "yt8m_netvlad_fwd")
+  _call("yt8m_netvlad_fwd", _p(x), _p(num_frames), b, t, d, k, _p(cw_packed), _p(scale), _p(shift), _p(cw2), _p(of), _p(oh),
+        _p(ol), d * k, _stream())
   return oh, ol, of
 
 
