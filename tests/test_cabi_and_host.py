@@ -1,0 +1,97 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/yt8m_b200.h declares, the
+flag shim parses like the reference's flags, the plugin registries expose the reference class names, and
+the product path refuses to run without a GPU (no fallback)."""
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+  import build_native
+  so = build_native.build()
+  header = open(os.path.join(ROOT, "include", "yt8m_b200.h")).read()
+  declared = set(re.findall(r"\b(yt8m_[a-z0-9_]+)\s*\(", header))
+  out = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True).stdout
+  exported = set(re.findall(r" T (yt8m_[a-z0-9_]+)", out))
+  assert declared and not (declared - exported), sorted(declared - exported)
+  import yt8m_native
+  assert set(yt8m_native.EXPORTS) == declared, sorted(set(yt8m_native.EXPORTS) ^ declared)
+  assert yt8m_native.version() >= 100
+  assert yt8m_native.moe_packed_rows(4716, 2) == 128 * ((4716 + 24) // 25)
+  assert yt8m_native.moe_packed_rows(4716, 64) == -1
+
+
+def test_sass_contains_tcgen05_and_tma():
+  import build_native
+  sass = subprocess.run(["cuobjdump", "-sass", build_native.build()], capture_output=True, text=True).stdout
+  for needle in ("UTCHMMA", "UTMALDG", "LDTM"):
+    assert needle in sass, needle
+  assert "HMMA.16816" not in sass              # no legacy mma.sync path
+
+
+def test_no_cpu_fallback():
+  import yt8m_native
+  if torch.cuda.is_available():
+    pytest.skip("CPU-only check")
+  with pytest.raises(yt8m_native.Yt8mError):
+    yt8m_native.l2norm_rows(torch.zeros(2, 8))
+  import video_level_models
+  with pytest.raises(Exception):
+    video_level_models.LogisticModel().create_model(torch.zeros(2, 8), vocab_size=4)
+
+
+def test_flags_shim():
+  import yt8m_flags as flags
+  fv = flags.FlagValues()
+  fv._define("model", "LogisticModel", "", "string")
+  fv._define("batch_size", 1024, "", "integer")
+  fv._define("base_learning_rate", 0.01, "", "float")
+  fv._define("frame_features", False, "", "bool")
+  fv._define("start_new_model", False, "", "bool")
+  rest = fv.parse(["--model=LstmModel", "--batch_size", "128", "--frame_features", "--base_learning_rate=0.001",
+                   "--nostart_new_model", "positional"])
+  assert rest == ["positional"]
+  assert (fv.model, fv.batch_size, fv.frame_features, fv.base_learning_rate, fv.start_new_model) == ("LstmModel", 128, True, 0.001, False)
+  with pytest.raises(ValueError):
+    fv.parse(["--no_such_flag=1"])
+  assert fv.parse(["--no_such_flag=1"], known_only=True) == ["--no_such_flag=1"]
+  fv.parse(["--frame_features=false"])
+  assert fv.frame_features is False
+  with fv.override(batch_size=7):
+    assert fv.batch_size == 7
+  assert fv.batch_size == 128
+  with pytest.raises(ValueError):
+    fv._define("model", 3, "", "integer")
+
+
+def test_plugin_registries_and_flag_defaults():
+  import frame_level_models, video_level_models, models
+  from yt8m_flags import FLAGS
+  FLAGS.reset()
+  # defaults copied from wh/frame_level_models.py:20-83 and wh/video_level_models.py:19-46
+  assert FLAGS.moe_num_mixtures == 2 and FLAGS.lstm_cells == "1024" and FLAGS.lstm_layers == 2
+  assert FLAGS.lstm_attentions == 8 and FLAGS.video_level_classifier_model == "MoeModel"
+  assert FLAGS.dbof_cluster_size == 8192 and FLAGS.iterations == 30 and FLAGS.deep_chain_layers == 3
+  for mod, names in ((video_level_models, ["LogisticModel", "MoeModel", "ChainMoeModel", "DeepCombineChainModel", "MoeExtendModel"]),
+                     (frame_level_models, ["LstmModel", "LstmMemoryModel", "LstmAttentionMaxPoolingModel", "LstmMultiAttentionModel",
+                                           "DbofModel", "AttentionModel", "NetVLADModel", "GatedNetVLADModel", "FrameLevelLogisticModel"])):
+    for n in names:
+      assert issubclass(getattr(mod, n), models.BaseModel), n
+  with pytest.raises(NotImplementedError):
+    models.BaseModel().create_model(None)
+
+
+def test_sample_frames_host_logic():
+  import frame_level_models as flm
+  g = torch.Generator().manual_seed(0)
+  nf = torch.tensor([300, 5, 1])
+  idx = flm.sample_frames(nf, 30, True, generator=g)
+  assert idx.shape == (3, 30) and bool((idx < nf.unsqueeze(1)).all()) and bool((idx >= 0).all())
+  seq = flm.sample_frames(nf, 30, False, generator=g)
+  assert bool((seq[0, 1:] - seq[0, :-1] == 1).all())            # a contiguous run when the video is long enough
+  assert bool((seq[1] <= 4).all()) and int(seq[2].max()) == 0     # clamped to the last valid frame
