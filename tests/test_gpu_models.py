@@ -119,7 +119,7 @@ def test_lstm_model(env):
   b = 6
   x, nf, _ = synth.model_input(b, seed=10)
   with FLAGS.override(lstm_cells="1024", lstm_layers=2, moe_num_mixtures=4):
-    out, sd = build_and_run(ops, flm.LstmModel(), {"basic_lstm_cell": 3.0, "gates": 10.0, "experts": 10.0},
+    out, sd = build_and_run(ops, flm.LstmModel(), {"basic_lstm_cell": 1.0, "gates": 10.0, "experts": 10.0},
                             model_input=x.to(DEV).to(torch.bfloat16), vocab_size=V, num_frames=nf.to(DEV))
   check(out["predictions"], model_oracle.lstm_model(sd, x, nf, V, 4), synth.labels(b, V))
 

@@ -124,7 +124,7 @@ int pick_split_k(int M, int N, int K, int block_n) {
   const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + block_n - 1) / block_n);
   const int num_kb = (K + kBlockK - 1) / kBlockK;
   if (tiles >= kNumSms / 2 || num_kb < 16) return 1;
-  int s = std::min((kNumSms + tiles - 1) / tiles, num_kb / 8);
+  int s = std::min(kNumSms / tiles, num_kb / 8);        // never spill into a second wave
   return std::max(s, 1);
 }
 

@@ -24,14 +24,17 @@ using namespace yt8m;
 namespace {
 
 constexpr int kNvThreads = 192;
+constexpr int kNvSms = 148;
 constexpr int kNtMax = 3;                 // up to 384 frames
 constexpr int kSlotBytes = 128 * 64 * 2;  // one TMA box: 128 rows x 64 bf16
 
 template <int KC>
 struct NvCfg {
   static constexpr int kNBlk = (KC + 63) / 64;                 // 64-cluster blocks of an assignment tile
-  static constexpr int kGM = 256 / KC;                         // M-blocks (128 D rows) per TMEM group
-  static constexpr int kSlots = (KC <= 64) ? 8 : 4;            // X ring slots (even)
+  static constexpr int kGM = 128 / KC > 0 ? 128 / KC : 1;      // M-blocks (128 D rows) per TMEM group (128 cols)
+  static constexpr int kGroupCols = kGM * KC;                  // 128 (KC <= 128)
+  static constexpr int kVBase0 = 512 - 2 * kGroupCols;         // two accumulator groups at the top of TMEM
+  static constexpr int kSlots = (KC <= 64) ? 8 : 4;            // X ring slots (even), 16 KB each
   static constexpr int kCwStages = 3;
   static constexpr int kCwBytes = KC * 128;                    // KC rows x 64 bf16
   static constexpr int kATileBytes = kNBlk * kSlotBytes;       // 128 frames x KC (64-wide blocks)
@@ -42,6 +45,9 @@ struct NvCfg {
   static constexpr int kSmallBytes = 5 * KC * 4 + 512;         // scale, shift, asum, ssq, fscale + barriers
   static constexpr int kTotal = kOffSmall + kSmallBytes + 1024;
   static_assert(kTotal <= 227 * 1024, "NetVLAD shared-memory budget exceeded");
+  // S tiles (NT * KC columns from 0) may reach into the accumulator groups (KC = 128): then the next
+  // video's assignment GEMM has to wait for the previous video's epilogue.
+  static constexpr bool kSOverlapsV = (kNtMax * KC > kVBase0);
 };
 
 // 32 values per lane, 32 lanes -> lane L returns sum over lanes of v[L]   (31 shuffles)
@@ -63,10 +69,21 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+struct RingPos {
+  int slot;
+  uint32_t phase;
+  __device__ __forceinline__ void advance(int n) {
+    if (++slot == n) { slot = 0; phase ^= 1u; }
+  }
+};
+
+// PERSISTENT: CTA c handles videos c, c + gridDim.x, ...  The TMA producer and the MMA issuer run ahead
+// into the next video's assignment GEMM (HBM reads) while the 4 softmax/epilogue warps are still
+// subtracting residuals / rescaling the previous video, so the HBM stream never waits for the epilogue.
 template <int KC>
 __global__ void __launch_bounds__(kNvThreads, 1)
 netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_cw,
-                     const int* __restrict__ num_frames, int T, int D, const float* __restrict__ scale,
+                     const int* __restrict__ num_frames, int B, int T, int D, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ cw2, float* __restrict__ out_f32,
                      __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ld_out) {
   using C = NvCfg<KC>;
@@ -83,31 +100,28 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(fscale_s + KC);
   uint64_t* cw_full = bars;                       // [3]
   uint64_t* cw_empty = cw_full + 3;               // [3]
-  uint64_t* x_full0 = cw_empty + 3;               // [8]
-  uint64_t* x_empty0 = x_full0 + 8;               // [8]
-  uint64_t* x_full1 = x_empty0 + 8;               // [4]
-  uint64_t* x_empty1 = x_full1 + 4;               // [4]
-  uint64_t* s_full = x_empty1 + 4;                // [1]
-  uint64_t* a_ready = s_full + 1;                 // [1]
-  uint64_t* v_full = a_ready + 1;                 // [2]
-  uint64_t* v_empty = v_full + 2;                 // [2]
+  uint64_t* x_full = cw_empty + 3;                // [8]  one ring for both phases
+  uint64_t* x_empty = x_full + 8;                 // [8]
+  uint64_t* s_full = x_empty + 8;                 // [1]  assignment accumulators complete (per video)
+  uint64_t* a_ready = s_full + 1;                 // [1]  assignment tiles written (per video)
+  uint64_t* v_full = a_ready + 1;                 // [2]  accumulator group complete
+  uint64_t* v_empty = v_full + 2;                 // [2]  accumulator group drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + 2);
   float* total_s = reinterpret_cast<float*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x;
   const int NT = (T + 127) / 128;
   const int NKB = D / 64;
   const int NMB = D / 128;
   const int NG = (NMB + C::kGM - 1) / C::kGM;
-  constexpr int kPairs = C::kSlots / 2;
+  const bool odd_p0 = ((NKB * NT) & 1) != 0;      // keep phase-1 slot pairs even-aligned in the ring
+  const int n_iter = (B - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_cw);
     for (int i = 0; i < 3; ++i) { mbar_init(&cw_full[i], 1); mbar_init(&cw_empty[i], 1); }
-    for (int i = 0; i < 8; ++i) { mbar_init(&x_full0[i], 1); mbar_init(&x_empty0[i], 1); }
-    for (int i = 0; i < 4; ++i) { mbar_init(&x_full1[i], 1); mbar_init(&x_empty1[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&x_full[i], 1); mbar_init(&x_empty[i], 1); }
     mbar_init(s_full, 1);
     mbar_init(a_ready, 4);
     for (int i = 0; i < 2; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 4); }
@@ -117,8 +131,6 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   for (int k = threadIdx.x; k < KC; k += kNvThreads) {
     scale_s[k] = scale ? scale[k] : 1.0f;
     shift_s[k] = shift ? shift[k] : 0.0f;
-    asum_s[k] = 0.0f;
-    ssq_s[k] = 0.0f;
   }
   tc_fence_before();
   __syncthreads();
@@ -128,236 +140,283 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   if (warp == 0) {
     // =================================== TMA producer ===================================
     if (lane == 0) {
-      int slot = 0, cst = 0;
-      uint32_t ph = 0, cph = 0;
-      for (int kb = 0; kb < NKB; ++kb) {
-        mbar_wait(&cw_empty[cst], cph ^ 1u);
-        mbar_arrive_expect_tx(&cw_full[cst], C::kCwBytes);
-        tma_load_2d(cws + cst * C::kCwBytes, &tm_cw, &cw_full[cst], kb * 64, 0, kEvictLast);
-        for (int i = 0; i < NT; ++i) {
-          mbar_wait(&x_empty0[slot], ph ^ 1u);
-          mbar_arrive_expect_tx(&x_full0[slot], kSlotBytes);
-          tma_load_3d(xs + slot * kSlotBytes, &tm_x, &x_full0[slot], kb * 64, i * 128, b, kEvictNormal);
-          if (++slot == C::kSlots) { slot = 0; ph ^= 1u; }
-        }
-        if (++cst == C::kCwStages) { cst = 0; cph ^= 1u; }
-      }
-      // phase 1: every phase-0 MMA has completed once s_full flips -> the whole X ring is free again
-      mbar_wait(s_full, 0);
-      int pair = 0;
-      uint32_t pph = 0;
-      for (int g = 0; g < NG; ++g)
-        for (int i = 0; i < NT; ++i)
-          for (int ml = 0; ml < C::kGM; ++ml) {
-            const int m = g * C::kGM + ml;
-            if (m >= NMB) break;
-            mbar_wait(&x_empty1[pair], pph ^ 1u);
-            mbar_arrive_expect_tx(&x_full1[pair], 2 * kSlotBytes);
-            tma_load_3d(xs + (2 * pair) * kSlotBytes, &tm_x, &x_full1[pair], m * 128, i * 128, b, kEvictFirst);
-            tma_load_3d(xs + (2 * pair + 1) * kSlotBytes, &tm_x, &x_full1[pair], m * 128 + 64, i * 128, b, kEvictFirst);
-            if (++pair == kPairs) { pair = 0; pph ^= 1u; }
+      RingPos xr{0, 0}, cr{0, 0};
+      for (int it = 0; it < n_iter; ++it) {
+        const int b = blockIdx.x + it * gridDim.x;
+        // ---- phase 0: D streams through the ring; HBM reads
+        for (int kb = 0; kb < NKB; ++kb) {
+          mbar_wait(&cw_empty[cr.slot], cr.phase ^ 1u);
+          mbar_arrive_expect_tx(&cw_full[cr.slot], C::kCwBytes);
+          tma_load_2d(cws + cr.slot * C::kCwBytes, &tm_cw, &cw_full[cr.slot], kb * 64, 0, kEvictLast);
+          cr.advance(C::kCwStages);
+          for (int i = 0; i < NT; ++i) {
+            mbar_wait(&x_empty[xr.slot], xr.phase ^ 1u);
+            mbar_arrive_expect_tx(&x_full[xr.slot], kSlotBytes);
+            tma_load_3d(xs + xr.slot * kSlotBytes, &tm_x, &x_full[xr.slot], kb * 64, i * 128, b, kEvictNormal);
+            xr.advance(C::kSlots);
           }
+        }
+        if (odd_p0) {                                        // dummy hand-shake keeps slot pairs even-aligned
+          mbar_wait(&x_empty[xr.slot], xr.phase ^ 1u);
+          mbar_arrive(&x_full[xr.slot]);
+          xr.advance(C::kSlots);
+        }
+        // ---- phase 1: the same video again (L2 hits), 128 frames x 128 D per slot pair
+        for (int g = 0; g < NG; ++g)
+          for (int i = 0; i < NT; ++i)
+            for (int ml = 0; ml < C::kGM; ++ml) {
+              const int m = g * C::kGM + ml;
+              if (m >= NMB) break;
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                mbar_wait(&x_empty[xr.slot], xr.phase ^ 1u);
+                mbar_arrive_expect_tx(&x_full[xr.slot], kSlotBytes);
+                tma_load_3d(xs + xr.slot * kSlotBytes, &tm_x, &x_full[xr.slot], m * 128 + h * 64, i * 128, b, kEvictFirst);
+                xr.advance(C::kSlots);
+              }
+            }
+      }
     }
   } else if (warp == 1) {
     // =================================== MMA issuer =====================================
     constexpr uint32_t idesc0 = make_idesc_bf16(128, KC, 0, 0);     // S = X . Cw^T      (both K-major)
     constexpr uint32_t idesc1 = make_idesc_bf16(128, KC, 1, 1);     // V^T = X^T . a     (both MN-major)
-    int slot = 0, cst = 0;
-    uint32_t ph = 0, cph = 0;
-    for (int kb = 0; kb < NKB; ++kb) {
-      mbar_wait(&cw_full[cst], cph);
-      for (int i = 0; i < NT; ++i) {
-        mbar_wait(&x_full0[slot], ph);
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_addr = smem_u32(xs + slot * kSlotBytes);
-          const uint32_t b_addr = smem_u32(cws + cst * C::kCwBytes);
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_base + i * KC, make_sdesc_sw128(a_addr + k * 32, 16, 1024),
-                      make_sdesc_sw128(b_addr + k * 32, 16, 1024), idesc0, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&x_empty0[slot]);
-        }
-        __syncwarp();
-        if (++slot == C::kSlots) { slot = 0; ph ^= 1u; }
-      }
-      if (lane == 0) umma_commit(&cw_empty[cst]);
-      __syncwarp();
-      if (++cst == C::kCwStages) { cst = 0; cph ^= 1u; }
-    }
-    if (lane == 0) umma_commit(s_full);
-    __syncwarp();
-    // phase 1 (needs every assignment tile: the accumulator groups reuse the S columns)
-    mbar_wait(a_ready, 0);
-    tc_fence_after();
-    int pair = 0;
-    uint32_t pph = 0;
-    for (int g = 0; g < NG; ++g) {
-      const int buf = g & 1;
-      if (g >= 2) {
-        mbar_wait(&v_empty[buf], ((g >> 1) - 1) & 1);
+    RingPos xr{0, 0}, cr{0, 0};
+    int gidx = 0;                                                   // accumulator groups issued so far
+    for (int it = 0; it < n_iter; ++it) {
+      if (C::kSOverlapsV && gidx >= 1) {
+        // the S tiles reach into the accumulator groups: wait until the previous video's groups are drained
+        const int g1 = gidx - 1;
+        mbar_wait(&v_empty[g1 & 1], (g1 >> 1) & 1);
+        if (gidx >= 2) { const int g2 = gidx - 2; mbar_wait(&v_empty[g2 & 1], (g2 >> 1) & 1); }
         tc_fence_after();
       }
-      for (int i = 0; i < NT; ++i) {
-        const int valid = min(128, T - i * 128);
-        const int nsteps = (valid + 15) >> 4;
-        for (int ml = 0; ml < C::kGM; ++ml) {
-          const int m = g * C::kGM + ml;
-          if (m >= NMB) break;
-          mbar_wait(&x_full1[pair], pph);
+      for (int kb = 0; kb < NKB; ++kb) {
+        mbar_wait(&cw_full[cr.slot], cr.phase);
+        for (int i = 0; i < NT; ++i) {
+          mbar_wait(&x_full[xr.slot], xr.phase);
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t a_addr = smem_u32(xs + (2 * pair) * kSlotBytes);
-            const uint32_t b_addr = smem_u32(atile + i * C::kATileBytes);
-            for (int s = 0; s < nsteps; ++s)
-              umma_bf16(tmem_base + buf * 256 + ml * KC, make_sdesc_sw128(a_addr + s * 2048, kSlotBytes, 1024),
-                        make_sdesc_sw128(b_addr + s * 2048, kSlotBytes, 1024), idesc1, (i > 0 || s > 0) ? 1u : 0u);
-            umma_commit(&x_empty1[pair]);
+            const uint32_t a_addr = smem_u32(xs + xr.slot * kSlotBytes);
+            const uint32_t b_addr = smem_u32(cws + cr.slot * C::kCwBytes);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem_base + i * KC, make_sdesc_sw128(a_addr + k * 32, 16, 1024),
+                        make_sdesc_sw128(b_addr + k * 32, 16, 1024), idesc0, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_commit(&x_empty[xr.slot]);
           }
           __syncwarp();
-          if (++pair == kPairs) { pair = 0; pph ^= 1u; }
+          xr.advance(C::kSlots);
         }
+        if (lane == 0) umma_commit(&cw_empty[cr.slot]);
+        __syncwarp();
+        cr.advance(C::kCwStages);
       }
-      if (lane == 0) umma_commit(&v_full[buf]);
+      if (lane == 0) umma_commit(s_full);
       __syncwarp();
+      if (odd_p0) {
+        mbar_wait(&x_full[xr.slot], xr.phase);
+        if (lane == 0) umma_commit(&x_empty[xr.slot]);
+        __syncwarp();
+        xr.advance(C::kSlots);
+      }
+      // phase 1 needs every assignment tile of this video
+      mbar_wait(a_ready, it & 1);
+      tc_fence_after();
+      for (int g = 0; g < NG; ++g, ++gidx) {
+        const int buf = gidx & 1;
+        if (gidx >= 2) {
+          mbar_wait(&v_empty[buf], ((gidx >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        for (int i = 0; i < NT; ++i) {
+          const int valid = min(128, T - i * 128);
+          const int nsteps = (valid + 15) >> 4;
+          for (int ml = 0; ml < C::kGM; ++ml) {
+            const int m = g * C::kGM + ml;
+            if (m >= NMB) break;
+            const int s0 = xr.slot;                                  // even: the pair (s0, s0 + 1)
+            mbar_wait(&x_full[s0], xr.phase);
+            mbar_wait(&x_full[s0 + 1], xr.phase);
+            tc_fence_after();
+            if (lane == 0) {
+              const uint32_t a_addr = smem_u32(xs + s0 * kSlotBytes);
+              const uint32_t b_addr = smem_u32(atile + i * C::kATileBytes);
+              for (int s = 0; s < nsteps; ++s)
+                umma_bf16(tmem_base + C::kVBase0 + buf * C::kGroupCols + ml * KC,
+                          make_sdesc_sw128(a_addr + s * 2048, kSlotBytes, 1024),
+                          make_sdesc_sw128(b_addr + s * 2048, kSlotBytes, 1024), idesc1, (i > 0 || s > 0) ? 1u : 0u);
+              umma_commit(&x_empty[s0]);
+              umma_commit(&x_empty[s0 + 1]);
+            }
+            __syncwarp();
+            xr.advance(C::kSlots);
+            xr.advance(C::kSlots);
+          }
+        }
+        if (lane == 0) umma_commit(&v_full[buf]);
+        __syncwarp();
+      }
     }
   } else {
     // ============================ softmax + epilogue warps (128 threads) ============================
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;                       // 0..127
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int nf = min(max(num_frames[b], 0), T);
-    mbar_wait(s_full, 0);
-    tc_fence_after();
-    for (int i = 0; i < NT; ++i) {
-      float l[KC];
-#pragma unroll
-      for (int c = 0; c < KC; c += 32) tmem_ld32(taddr + i * KC + c, reinterpret_cast<uint32_t*>(l) + c);
-      tmem_ld_wait();
-      const bool valid = (i * 128 + row) < nf;
-      float mx = -INFINITY;
-#pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        l[k] = l[k] * scale_s[k] + shift_s[k];
-        mx = fmaxf(mx, l[k]);
-      }
-      float sum = 0.0f;
-#pragma unroll
-      for (int k = 0; k < KC; ++k) {
-        l[k] = __expf(l[k] - mx);
-        sum += l[k];
-      }
-      const float inv = valid ? 1.0f / sum : 0.0f;
-      uint8_t* at = atile + i * C::kATileBytes;
-#pragma unroll
-      for (int c8 = 0; c8 < KC / 8; ++c8) {
-        uint32_t w[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(l[c8 * 8 + 2 * j] * inv);
-          const __nv_bfloat16 h1 = __float2bfloat16_rn(l[c8 * 8 + 2 * j + 1] * inv);
-          l[c8 * 8 + 2 * j] = __bfloat162float(h0);         // a_sum uses the rounded assignment too
-          l[c8 * 8 + 2 * j + 1] = __bfloat162float(h1);
-          w[j] = pack_bf16x2(h0, h1);
-        }
-        const int nb = c8 >> 3;
-        *reinterpret_cast<uint4*>(at + nb * kSlotBytes + sw128_offset(row, c8 & 7)) = make_uint4(w[0], w[1], w[2], w[3]);
-      }
-#pragma unroll
-      for (int c = 0; c < KC; c += 32) {
-        const float tot = warp_transpose_reduce32(l + c, lane);
-        atomicAdd(&asum_s[c + lane], tot);
-      }
-    }
-    tc_fence_before();
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(a_ready);
-    named_bar_sync(1, 128);                               // a_sum complete
-
-    __nv_bfloat16* ohi = out_hi + static_cast<long long>(b) * ld_out;
-    __nv_bfloat16* olo = out_lo ? out_lo + static_cast<long long>(b) * ld_out : nullptr;
-    for (int g = 0; g < NG; ++g) {
-      const int buf = g & 1;
-      mbar_wait(&v_full[buf], (g >> 1) & 1);
+    int gidx = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      const int b = blockIdx.x + it * gridDim.x;
+      const int nf = min(max(num_frames[b], 0), T);
+      if (et < KC) { asum_s[et] = 0.0f; ssq_s[et] = 0.0f; }
+      if (et == 0) *total_s = 0.0f;
+      named_bar_sync(1, 128);
+      mbar_wait(s_full, it & 1);
       tc_fence_after();
-      for (int ml = 0; ml < C::kGM; ++ml) {
-        const int m = g * C::kGM + ml;
-        if (m >= NMB) break;
-        const int d = m * 128 + row;
-        const float* c2 = cw2 + static_cast<long long>(d) * KC;
-#pragma unroll 1
+      for (int i = 0; i < NT; ++i) {
+        float l[KC];
+#pragma unroll
+        for (int c = 0; c < KC; c += 32) tmem_ld32(taddr + i * KC + c, reinterpret_cast<uint32_t*>(l) + c);
+        tmem_ld_wait();
+        const bool valid = (i * 128 + row) < nf;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          l[k] = l[k] * scale_s[k] + shift_s[k];
+          mx = fmaxf(mx, l[k]);
+        }
+        float sum = 0.0f;
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+          l[k] = __expf(l[k] - mx);
+          sum += l[k];
+        }
+        const float inv = valid ? 1.0f / sum : 0.0f;
+        uint8_t* at = atile + i * C::kATileBytes;
+#pragma unroll
+        for (int c8 = 0; c8 < KC / 8; ++c8) {
+          uint32_t w[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(l[c8 * 8 + 2 * j] * inv);
+            const __nv_bfloat16 h1 = __float2bfloat16_rn(l[c8 * 8 + 2 * j + 1] * inv);
+            l[c8 * 8 + 2 * j] = __bfloat162float(h0);         // a_sum uses the rounded assignment too
+            l[c8 * 8 + 2 * j + 1] = __bfloat162float(h1);
+            w[j] = pack_bf16x2(h0, h1);
+          }
+          const int nb = c8 >> 3;
+          *reinterpret_cast<uint4*>(at + nb * kSlotBytes + sw128_offset(row, c8 & 7)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+#pragma unroll
         for (int c = 0; c < KC; c += 32) {
-          float v[32];
-          tmem_ld32(taddr + buf * 256 + ml * KC + c, reinterpret_cast<uint32_t*>(v));
-          tmem_ld_wait();
-          float sq[32];
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 cc = __ldg(reinterpret_cast<const float4*>(c2 + c + j));
-            v[j] -= asum_s[c + j] * cc.x;
-            v[j + 1] -= asum_s[c + j + 1] * cc.y;
-            v[j + 2] -= asum_s[c + j + 2] * cc.z;
-            v[j + 3] -= asum_s[c + j + 3] * cc.w;
-          }
-          // stash un-normalised (bf16 hi [+ lo]); the sum of squares uses the stashed precision
-#pragma unroll
-          for (int j8 = 0; j8 < 4; ++j8) {
-            uint4 hi, lo;
-            pack8_hi_lo(v + 8 * j8, hi, lo);
-            const long long o = static_cast<long long>(d) * KC + c + 8 * j8;
-            *reinterpret_cast<uint4*>(ohi + o) = hi;
-            if (olo) *reinterpret_cast<uint4*>(olo + o) = lo;
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) sq[j] = v[j] * v[j];
-          const float tot = warp_transpose_reduce32(sq, lane);
-          atomicAdd(&ssq_s[c + lane], tot);
+          const float tot = warp_transpose_reduce32(l + c, lane);
+          atomicAdd(&asum_s[c + lane], tot);
         }
       }
       tc_fence_before();
+      fence_proxy_async();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&v_empty[buf]);
-    }
-    // ------------------------------- rescale in place -------------------------------
-    __threadfence_block();
-    named_bar_sync(1, 128);
-    const int et = threadIdx.x - 64;                       // 0..127
-    if (et == 0) *total_s = 0.0f;
-    named_bar_sync(1, 128);
-    if (et < KC) {
-      const float ss = ssq_s[et];
-      const float rs = rsqrtf(fmaxf(ss, 1e-12f));
-      fscale_s[et] = rs;
-      atomicAdd(total_s, ss * rs * rs);
-    }
-    named_bar_sync(1, 128);
-    const float gs = rsqrtf(fmaxf(*total_s, 1e-12f));
-    const long long n = static_cast<long long>(D) * KC;
-    float* of = out_f32 ? out_f32 + static_cast<long long>(b) * ld_out : nullptr;
-    for (long long e = static_cast<long long>(et) * 8; e < n; e += 128 * 8) {
-      const int k0 = static_cast<int>(e % KC);
-      const uint4 h = __ldcg(reinterpret_cast<const uint4*>(ohi + e));
-      uint4 lw = make_uint4(0, 0, 0, 0);
-      if (olo) lw = __ldcg(reinterpret_cast<const uint4*>(olo + e));
-      const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-      const uint32_t lv[4] = {lw.x, lw.y, lw.z, lw.w};
-      float v[8];
+      if (lane == 0) mbar_arrive(a_ready);
+      named_bar_sync(1, 128);                               // a_sum complete
+
+      __nv_bfloat16* ohi = out_hi + static_cast<long long>(b) * ld_out;
+      __nv_bfloat16* olo = out_lo ? out_lo + static_cast<long long>(b) * ld_out : nullptr;
+      for (int g = 0; g < NG; ++g, ++gidx) {
+        const int buf = gidx & 1;
+        // residual centres for this thread's rows: issue the loads before waiting on the tensor cores
+        mbar_wait(&v_full[buf], (gidx >> 1) & 1);
+        tc_fence_after();
+        for (int ml = 0; ml < C::kGM; ++ml) {
+          const int m = g * C::kGM + ml;
+          if (m >= NMB) break;
+          const int d = m * 128 + row;
+          const float* c2 = cw2 + static_cast<long long>(d) * KC;
+#pragma unroll 1
+          for (int c = 0; c < KC; c += 32) {
+            float4 cc[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lv[j] << 16);
-        v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lv[j] & 0xFFFF0000u);
-      }
+            for (int j = 0; j < 8; ++j) cc[j] = __ldg(reinterpret_cast<const float4*>(c2 + c) + j);
+            float v[32];
+            tmem_ld32(taddr + C::kVBase0 + buf * C::kGroupCols + ml * KC + c, reinterpret_cast<uint32_t*>(v));
+            tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] *= fscale_s[k0 + j] * gs;
-      uint4 nh, nl;
-      pack8_hi_lo(v, nh, nl);
-      *reinterpret_cast<uint4*>(ohi + e) = nh;
-      if (olo) *reinterpret_cast<uint4*>(olo + e) = nl;
-      if (of) {
-        *reinterpret_cast<float4*>(of + e) = make_float4(v[0], v[1], v[2], v[3]);
-        *reinterpret_cast<float4*>(of + e + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] -= asum_s[c + 4 * j] * cc[j].x;
+              v[4 * j + 1] -= asum_s[c + 4 * j + 1] * cc[j].y;
+              v[4 * j + 2] -= asum_s[c + 4 * j + 2] * cc[j].z;
+              v[4 * j + 3] -= asum_s[c + 4 * j + 3] * cc[j].w;
+            }
+            // stash un-normalised (bf16 hi [+ lo])
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              uint4 hi, lo;
+              pack8_hi_lo(v + 8 * j8, hi, lo);
+              const long long o = static_cast<long long>(d) * KC + c + 8 * j8;
+              *reinterpret_cast<uint4*>(ohi + o) = hi;
+              if (olo) *reinterpret_cast<uint4*>(olo + o) = lo;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = v[j] * v[j];
+            const float tot = warp_transpose_reduce32(v, lane);
+            atomicAdd(&ssq_s[c + lane], tot);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&v_empty[buf]);
       }
+      // ------------------------------- rescale in place -------------------------------
+      __threadfence_block();
+      named_bar_sync(1, 128);
+      if (et < KC) {
+        const float ss = ssq_s[et];
+        const float rs = rsqrtf(fmaxf(ss, 1e-12f));
+        fscale_s[et] = rs;
+        atomicAdd(total_s, ss * rs * rs);
+      }
+      named_bar_sync(1, 128);
+      const float gs = rsqrtf(fmaxf(*total_s, 1e-12f));
+      const long long n = static_cast<long long>(D) * KC;
+      float* of = out_f32 ? out_f32 + static_cast<long long>(b) * ld_out : nullptr;
+      constexpr int kU = 4;                                 // independent 16-byte loads in flight per thread
+      for (long long e0 = static_cast<long long>(et) * 8; e0 < n; e0 += 128 * 8 * kU) {
+        uint4 h[kU], lw[kU];
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const long long e = e0 + static_cast<long long>(u) * 128 * 8;
+          h[u] = make_uint4(0, 0, 0, 0);
+          lw[u] = make_uint4(0, 0, 0, 0);
+          if (e < n) {
+            h[u] = __ldcg(reinterpret_cast<const uint4*>(ohi + e));
+            if (olo) lw[u] = __ldcg(reinterpret_cast<const uint4*>(olo + e));
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const long long e = e0 + static_cast<long long>(u) * 128 * 8;
+          if (e >= n) break;
+          const int k0 = static_cast<int>(e % KC);
+          const uint32_t hw[4] = {h[u].x, h[u].y, h[u].z, h[u].w};
+          const uint32_t lv[4] = {lw[u].x, lw[u].y, lw[u].z, lw[u].w};
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lv[j] << 16);
+            v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lv[j] & 0xFFFF0000u);
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] *= fscale_s[k0 + j] * gs;
+          uint4 nh, nl;
+          pack8_hi_lo(v, nh, nl);
+          *reinterpret_cast<uint4*>(ohi + e) = nh;
+          if (olo) *reinterpret_cast<uint4*>(olo + e) = nl;
+          if (of) {
+            *reinterpret_cast<float4*>(of + e) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(of + e + 4) = make_float4(v[4], v[5], v[6], v[7]);
+          }
+        }
+      }
+      named_bar_sync(1, 128);                               // fscale_s / total_s are reused by the next video
     }
     tc_fence_before();
   }
@@ -383,7 +442,8 @@ int launch_netvlad(const yt8m_bf16* x, const int* num_frames, int B, int T, int 
     YT8M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kTotal));
     attr_done = true;
   }
-  kern<<<B, kNvThreads, C::kTotal, stream>>>(tm_x, tm_cw, num_frames, T, D, scale, shift, cw2, out_f32,
+  const int grid = B < kNvSms ? B : kNvSms;               // persistent: one CTA per SM
+  kern<<<grid, kNvThreads, C::kTotal, stream>>>(tm_x, tm_cw, num_frames, B, T, D, scale, shift, cw2, out_f32,
                                              reinterpret_cast<__nv_bfloat16*>(out_hi),
                                              reinterpret_cast<__nv_bfloat16*>(out_lo), ld_out);
   return check_launch("netvlad_fused_kernel");
