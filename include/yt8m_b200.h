@@ -133,6 +133,10 @@ int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, in
                      float* out_f32, yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out,
                      yt8m_stream_t stream);
 
+/* debug only: device buffer (>= 128 u64, or NULL to disable) that receives globaltimer stamps of the
+ * NetVLAD kernel's phases for CTA 0 (tools/netvlad_timeline.py decodes them) */
+int yt8m_debug_set_timeline(unsigned long long* dev_buf);
+
 /* ---- elementwise glue -----------------------------------------------------------------------------
  * y = x * sigmoid(g * scale + shift)  (context gating; g = x . Wg from yt8m_linear_fwd) */
 int yt8m_context_gate_fwd(const float* x, const float* g, const float* scale, const float* shift, long long rows,

@@ -129,7 +129,7 @@ def test_lstm_memory_model(env):
   b = 4
   x, nf, _ = synth.model_input(b, frames=60, seed=11)
   with FLAGS.override(lstm_cells="256", lstm_layers=2, moe_num_mixtures=2):
-    out, sd = build_and_run(ops, flm.LstmMemoryModel(), {"basic_lstm_cell": 3.0, "gates": 10.0, "experts": 10.0},
+    out, sd = build_and_run(ops, flm.LstmMemoryModel(), {"basic_lstm_cell": 1.5, "gates": 10.0, "experts": 10.0},
                             model_input=x.to(DEV).to(torch.bfloat16), vocab_size=V, num_frames=nf.to(DEV))
   check(out["predictions"], model_oracle.lstm_memory_model(sd, x, nf, V, 2))
 
@@ -140,7 +140,7 @@ def test_lstm_attention_max_pooling_model(env):
   x, nf, _ = synth.model_input(b, frames=80, seed=12)
   with FLAGS.override(lstm_cells="256", lstm_layers=2, moe_num_mixtures=2, lstm_attentions=8):
     out, sd = build_and_run(ops, flm.LstmAttentionMaxPoolingModel(),
-                            {"basic_lstm_cell": 3.0, "attention-": 20.0, "gates": 10.0, "experts": 10.0},
+                            {"basic_lstm_cell": 1.5, "attention-": 20.0, "gates": 10.0, "experts": 10.0},
                             model_input=x.to(DEV).to(torch.bfloat16), vocab_size=V, num_frames=nf.to(DEV))
   check(out["predictions"], model_oracle.lstm_attention_max_pooling(sd, x, nf, V, 2, 8))
 
@@ -151,7 +151,7 @@ def test_lstm_multi_attention_model(env):
   x, nf, _ = synth.model_input(b, frames=80, seed=13)
   with FLAGS.override(lstm_cells="256", lstm_layers=2, moe_num_mixtures=2, attention_size=4):
     out, sd = build_and_run(ops, flm.LstmMultiAttentionModel(),
-                            {"basic_lstm_cell": 3.0, "fully_connected": 10.0, "gates": 10.0, "experts": 10.0},
+                            {"basic_lstm_cell": 1.5, "fully_connected": 10.0, "gates": 10.0, "experts": 10.0},
                             model_input=x.to(DEV).to(torch.bfloat16), vocab_size=V, num_frames=nf.to(DEV))
   check(out["predictions"], model_oracle.lstm_multi_attention(sd, x, nf, V, 2, 4))
 

@@ -25,6 +25,13 @@ namespace {
 
 constexpr int kNvThreads = 192;
 constexpr int kNvSms = 148;
+
+// debug-only phase timeline (globaltimer ns) of CTA 0: set with yt8m_debug_set_timeline()
+__device__ unsigned long long* g_nv_timeline = nullptr;
+#define NV_T(slot)                                                                         \
+  do {                                                                                     \
+    if (g_nv_timeline && blockIdx.x == 0 && it < 4) g_nv_timeline[it * 32 + (slot)] = global_timer_ns(); \
+  } while (0)
 constexpr int kNtMax = 3;                 // up to 384 frames
 constexpr int kSlotBytes = 128 * 64 * 2;  // one TMA box: 128 rows x 64 bf16
 
@@ -143,6 +150,7 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       RingPos xr{0, 0}, cr{0, 0};
       for (int it = 0; it < n_iter; ++it) {
         const int b = blockIdx.x + it * gridDim.x;
+        NV_T(0);
         // ---- phase 0: D streams through the ring; HBM reads
         for (int kb = 0; kb < NKB; ++kb) {
           mbar_wait(&cw_empty[cr.slot], cr.phase ^ 1u);
@@ -161,6 +169,7 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           mbar_arrive(&x_full[xr.slot]);
           xr.advance(C::kSlots);
         }
+        NV_T(1);
         // ---- phase 1: the same video again (L2 hits), 128 frames x 128 D per slot pair
         for (int g = 0; g < NG; ++g)
           for (int i = 0; i < NT; ++i)
@@ -175,6 +184,7 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
                 xr.advance(C::kSlots);
               }
             }
+        NV_T(2);
       }
     }
   } else if (warp == 1) {
@@ -191,12 +201,14 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         if (gidx >= 2) { const int g2 = gidx - 2; mbar_wait(&v_empty[g2 & 1], (g2 >> 1) & 1); }
         tc_fence_after();
       }
+      if (lane == 0) NV_T(8);
       for (int kb = 0; kb < NKB; ++kb) {
         mbar_wait(&cw_full[cr.slot], cr.phase);
         for (int i = 0; i < NT; ++i) {
           mbar_wait(&x_full[xr.slot], xr.phase);
           tc_fence_after();
           if (lane == 0) {
+            if (kb == 0 && i == 0) NV_T(9);
             const uint32_t a_addr = smem_u32(xs + xr.slot * kSlotBytes);
             const uint32_t b_addr = smem_u32(cws + cr.slot * C::kCwBytes);
 #pragma unroll
@@ -212,7 +224,7 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         __syncwarp();
         cr.advance(C::kCwStages);
       }
-      if (lane == 0) umma_commit(s_full);
+      if (lane == 0) { umma_commit(s_full); NV_T(10); }
       __syncwarp();
       if (odd_p0) {
         mbar_wait(&x_full[xr.slot], xr.phase);
@@ -223,6 +235,7 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       // phase 1 needs every assignment tile of this video
       mbar_wait(a_ready, it & 1);
       tc_fence_after();
+      if (lane == 0) NV_T(11);
       for (int g = 0; g < NG; ++g, ++gidx) {
         const int buf = gidx & 1;
         if (gidx >= 2) {
@@ -254,7 +267,7 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             xr.advance(C::kSlots);
           }
         }
-        if (lane == 0) umma_commit(&v_full[buf]);
+        if (lane == 0) { umma_commit(&v_full[buf]); if (g == NG - 1) NV_T(12); }
         __syncwarp();
       }
     }
@@ -271,8 +284,16 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       if (et < KC) { asum_s[et] = 0.0f; ssq_s[et] = 0.0f; }
       if (et == 0) *total_s = 0.0f;
       named_bar_sync(1, 128);
+      if (et == 0) NV_T(16);
       mbar_wait(s_full, it & 1);
       tc_fence_after();
+      if (et == 0) NV_T(17);
+      constexpr bool kRegAcc = (KC <= 64);                // running sums live in registers, reduced once per video
+      float acc[kRegAcc ? KC : 1];
+      if (kRegAcc) {
+#pragma unroll
+        for (int k = 0; k < (kRegAcc ? KC : 1); ++k) acc[k] = 0.0f;
+      }
       for (int i = 0; i < NT; ++i) {
         float l[KC];
 #pragma unroll
@@ -307,35 +328,56 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           const int nb = c8 >> 3;
           *reinterpret_cast<uint4*>(at + nb * kSlotBytes + sw128_offset(row, c8 & 7)) = make_uint4(w[0], w[1], w[2], w[3]);
         }
+        if (kRegAcc) {
 #pragma unroll
-        for (int c = 0; c < KC; c += 32) {
-          const float tot = warp_transpose_reduce32(l + c, lane);
-          atomicAdd(&asum_s[c + lane], tot);
+          for (int k = 0; k < (kRegAcc ? KC : 1); ++k) acc[k] += l[k];
+        } else {
+#pragma unroll
+          for (int c = 0; c < KC; c += 32) {
+            const float tot = warp_transpose_reduce32(l + c, lane);
+            atomicAdd(&asum_s[c + lane], tot);
+          }
         }
       }
       tc_fence_before();
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(a_ready);
+      if (kRegAcc) {
+#pragma unroll
+        for (int c = 0; c < (kRegAcc ? KC : 32); c += 32) {
+          const float tot = warp_transpose_reduce32(acc + c, lane);
+          atomicAdd(&asum_s[c + lane], tot);
+        }
+      }
       named_bar_sync(1, 128);                               // a_sum complete
+      if (et == 0) NV_T(18);
 
       __nv_bfloat16* ohi = out_hi + static_cast<long long>(b) * ld_out;
       __nv_bfloat16* olo = out_lo ? out_lo + static_cast<long long>(b) * ld_out : nullptr;
+      if (kRegAcc) {
+#pragma unroll
+        for (int k = 0; k < (kRegAcc ? KC : 1); ++k) acc[k] = 0.0f;          // now: running sum of squares
+      }
+      constexpr int kChunks = KC / 32;
+      float4 cc[8];                                            // residual centres of the NEXT chunk (prefetch)
+      {
+        const float* c2 = cw2 + static_cast<long long>(row) * KC;            // M-block 0, chunk 0
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cc[j] = __ldg(reinterpret_cast<const float4*>(c2) + j);
+      }
       for (int g = 0; g < NG; ++g, ++gidx) {
         const int buf = gidx & 1;
-        // residual centres for this thread's rows: issue the loads before waiting on the tensor cores
         mbar_wait(&v_full[buf], (gidx >> 1) & 1);
         tc_fence_after();
+        if (et == 0 && g < 6) NV_T(19 + g);
         for (int ml = 0; ml < C::kGM; ++ml) {
           const int m = g * C::kGM + ml;
           if (m >= NMB) break;
           const int d = m * 128 + row;
-          const float* c2 = cw2 + static_cast<long long>(d) * KC;
-#pragma unroll 1
-          for (int c = 0; c < KC; c += 32) {
-            float4 cc[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cc[j] = __ldg(reinterpret_cast<const float4*>(c2 + c) + j);
+          for (int ch = 0; ch < kChunks; ++ch) {
+            const int c = ch * 32;
             float v[32];
             tmem_ld32(taddr + C::kVBase0 + buf * C::kGroupCols + ml * KC + c, reinterpret_cast<uint32_t*>(v));
             tmem_ld_wait();
@@ -346,28 +388,51 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
               v[4 * j + 2] -= asum_s[c + 4 * j + 2] * cc[j].z;
               v[4 * j + 3] -= asum_s[c + 4 * j + 3] * cc[j].w;
             }
-            // stash un-normalised (bf16 hi [+ lo])
+            {  // prefetch the centres of the next chunk (next chunk of this row, or the next M-block's row)
+              const bool last_chunk = (ch == kChunks - 1);
+              const int nm = last_chunk ? m + 1 : m;
+              const int ncol = last_chunk ? 0 : c + 32;
+              if (nm < NMB) {
+                const float* c2n = cw2 + static_cast<long long>(nm * 128 + row) * KC + ncol;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) cc[j] = __ldg(reinterpret_cast<const float4*>(c2n) + j);
+              }
+            }
+            // stash un-normalised (bf16 hi [+ lo]); keep it in L2 until the rescale pass reads it back
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
               uint4 hi, lo;
               pack8_hi_lo(v + 8 * j8, hi, lo);
               const long long o = static_cast<long long>(d) * KC + c + 8 * j8;
-              *reinterpret_cast<uint4*>(ohi + o) = hi;
-              if (olo) *reinterpret_cast<uint4*>(olo + o) = lo;
+              st_global_hint(ohi + o, hi, kEvictLast);
+              if (olo) st_global_hint(olo + o, lo, kEvictLast);
             }
+            if (kRegAcc) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = v[j] * v[j];
-            const float tot = warp_transpose_reduce32(v, lane);
-            atomicAdd(&ssq_s[c + lane], tot);
+              for (int j = 0; j < 32; ++j) acc[(kRegAcc ? c : 0) + (kRegAcc ? j : 0)] += v[j] * v[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = v[j] * v[j];
+              const float tot = warp_transpose_reduce32(v, lane);
+              atomicAdd(&ssq_s[c + lane], tot);
+            }
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&v_empty[buf]);
       }
+      if (kRegAcc) {
+#pragma unroll
+        for (int c = 0; c < (kRegAcc ? KC : 32); c += 32) {
+          const float tot = warp_transpose_reduce32(acc + c, lane);
+          atomicAdd(&ssq_s[c + lane], tot);
+        }
+      }
       // ------------------------------- rescale in place -------------------------------
       __threadfence_block();
       named_bar_sync(1, 128);
+      if (et == 0) NV_T(26);
       if (et < KC) {
         const float ss = ssq_s[et];
         const float rs = rsqrtf(fmaxf(ss, 1e-12f));
@@ -378,7 +443,7 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       const float gs = rsqrtf(fmaxf(*total_s, 1e-12f));
       const long long n = static_cast<long long>(D) * KC;
       float* of = out_f32 ? out_f32 + static_cast<long long>(b) * ld_out : nullptr;
-      constexpr int kU = 4;                                 // independent 16-byte loads in flight per thread
+      constexpr int kU = 8;                                 // independent 16-byte loads in flight per thread (x2 with lo)
       for (long long e0 = static_cast<long long>(et) * 8; e0 < n; e0 += 128 * 8 * kU) {
         uint4 h[kU], lw[kU];
 #pragma unroll
@@ -387,8 +452,8 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           h[u] = make_uint4(0, 0, 0, 0);
           lw[u] = make_uint4(0, 0, 0, 0);
           if (e < n) {
-            h[u] = __ldcg(reinterpret_cast<const uint4*>(ohi + e));
-            if (olo) lw[u] = __ldcg(reinterpret_cast<const uint4*>(olo + e));
+            h[u] = ld_global_hint(ohi + e, kEvictFirst);
+            if (olo) lw[u] = ld_global_hint(olo + e, kEvictFirst);
           }
         }
 #pragma unroll
@@ -417,6 +482,7 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         }
       }
       named_bar_sync(1, 128);                               // fscale_s / total_s are reused by the next video
+      if (et == 0) NV_T(27);
     }
     tc_fence_before();
   }
@@ -450,6 +516,11 @@ int launch_netvlad(const yt8m_bf16* x, const int* num_frames, int B, int T, int 
 }
 
 }  // namespace
+
+extern "C" int yt8m_debug_set_timeline(unsigned long long* dev_buf) {
+  YT8M_CUDA(cudaMemcpyToSymbol(g_nv_timeline, &dev_buf, sizeof(dev_buf)));
+  return YT8M_OK;
+}
 
 extern "C" int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K,
                                 const yt8m_bf16* cw_packed, const float* scale, const float* shift, const float* cw2,

@@ -52,6 +52,7 @@ _SIGS = {
                                    c_void_p, c_void_p]),
     "yt8m_netvlad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "yt8m_debug_set_timeline": (c_int, [c_void_p]),
     "yt8m_context_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
     "yt8m_col_affine": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -302,6 +303,11 @@ def netvlad_fwd(x, num_frames, cw_packed, scale, shift, cw2, want_f32=False, wan
   _call("yt8m_netvlad_fwd", _p(x), _p(num_frames), b, t, d, k, _p(cw_packed), _p(scale), _p(shift), _p(cw2), _p(of), _p(oh),
         _p(ol), d * k, _stream())
   return oh, ol, of
+
+
+def debug_set_timeline(buf):
+  """buf: int64 CUDA tensor with >= 128 elements, or None to switch the stamps off."""
+  _check(_lib.yt8m_debug_set_timeline(_p(buf)), "yt8m_debug_set_timeline")
 
 
 def context_gate(x, g, scale=None, shift=None, want_bf16=True):
