@@ -58,7 +58,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   uint64_t* tmem_full_bar = empty_bar + S::kStages;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
   const int num_kb_total = (shape.K + kBlockK - 1) / kBlockK;
@@ -86,45 +86,41 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb_begin; kb < kb_end; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        uint8_t* st = tiles + stage * S::kStageBytes;
-        mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes);
-        tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal);
-        if (A_SPLIT == 2)
-          tma_load_2d(st + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal);
-        tma_load_2d(st + A_SPLIT * S::kABytes, &tm_b, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N,
-                    kEvictNormal);
-        if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
-      }
+    const bool issuer = (lane == 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      uint8_t* st = tiles + stage * S::kStageBytes;
+      mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes, issuer);
+      tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal, issuer);
+      if (A_SPLIT == 2)
+        tma_load_2d(st + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal, issuer);
+      tma_load_2d(st + A_SPLIT * S::kABytes, &tm_b, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N, kEvictNormal, issuer);
+      __syncwarp();
+      if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
     constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
+    const bool issuer = (lane == 0);
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a_addr = smem_u32(tiles + stage * S::kStageBytes);
-        const uint32_t b_addr = a_addr + A_SPLIT * S::kABytes;
+      const uint32_t a_addr = smem_u32(tiles + stage * S::kStageBytes);
+      const uint64_t adesc0 = make_sdesc_sw128(a_addr, 16, 1024);
+      const uint64_t adesc1 = make_sdesc_sw128(a_addr + S::kABytes, 16, 1024);
+      const uint64_t bdesc0 = make_sdesc_sw128(a_addr + A_SPLIT * S::kABytes, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          const uint64_t bdesc = make_sdesc_sw128(b_addr + k * (kUmmaK * 2), 16, 1024);
-          const uint64_t adesc = make_sdesc_sw128(a_addr + k * (kUmmaK * 2), 16, 1024);
-          umma_bf16(tmem_base, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          if (A_SPLIT == 2) {
-            const uint64_t adesc2 = make_sdesc_sw128(a_addr + S::kABytes + k * (kUmmaK * 2), 16, 1024);
-            umma_bf16(tmem_base, adesc2, bdesc, idesc, 1u);
-          }
-        }
-        umma_commit(&empty_bar[stage]);
-        if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+      for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+        const uint64_t bdesc = sdesc_advance(bdesc0, k * (kUmmaK * 2));
+        umma_bf16(tmem_base, sdesc_advance(adesc0, k * (kUmmaK * 2)), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u, issuer);
+        if (A_SPLIT == 2) umma_bf16(tmem_base, sdesc_advance(adesc1, k * (kUmmaK * 2)), bdesc, idesc, 1u, issuer);
       }
+      umma_commit(&empty_bar[stage], issuer);
+      if (kb == num_kb - 1) umma_commit(tmem_full_bar, issuer);
       __syncwarp();
       if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
     }

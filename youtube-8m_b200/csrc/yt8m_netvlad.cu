@@ -116,7 +116,8 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(v_empty + 2);
   float* total_s = reinterpret_cast<float*>(tmem_slot + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for ptxas
+  const int lane = threadIdx.x & 31;
   const int NT = (T + 127) / 128;
   const int NKB = D / 64;
   const int NMB = D / 128;
@@ -146,30 +147,32 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 
   if (warp == 0) {
     // =================================== TMA producer ===================================
-    if (lane == 0) {
+    {
+      const bool issuer = (lane == 0);
       RingPos xr{0, 0}, cr{0, 0};
       for (int it = 0; it < n_iter; ++it) {
         const int b = blockIdx.x + it * gridDim.x;
-        NV_T(0);
+        if (issuer) NV_T(0);
         // ---- phase 0: D streams through the ring; HBM reads
         for (int kb = 0; kb < NKB; ++kb) {
           mbar_wait(&cw_empty[cr.slot], cr.phase ^ 1u);
-          mbar_arrive_expect_tx(&cw_full[cr.slot], C::kCwBytes);
-          tma_load_2d(cws + cr.slot * C::kCwBytes, &tm_cw, &cw_full[cr.slot], kb * 64, 0, kEvictLast);
+          mbar_arrive_expect_tx(&cw_full[cr.slot], C::kCwBytes, issuer);
+          tma_load_2d(cws + cr.slot * C::kCwBytes, &tm_cw, &cw_full[cr.slot], kb * 64, 0, kEvictLast, issuer);
           cr.advance(C::kCwStages);
           for (int i = 0; i < NT; ++i) {
             mbar_wait(&x_empty[xr.slot], xr.phase ^ 1u);
-            mbar_arrive_expect_tx(&x_full[xr.slot], kSlotBytes);
-            tma_load_3d(xs + xr.slot * kSlotBytes, &tm_x, &x_full[xr.slot], kb * 64, i * 128, b, kEvictNormal);
+            mbar_arrive_expect_tx(&x_full[xr.slot], kSlotBytes, issuer);
+            tma_load_3d(xs + xr.slot * kSlotBytes, &tm_x, &x_full[xr.slot], kb * 64, i * 128, b, kEvictNormal, issuer);
             xr.advance(C::kSlots);
           }
+          __syncwarp();
         }
         if (odd_p0) {                                        // dummy hand-shake keeps slot pairs even-aligned
           mbar_wait(&x_empty[xr.slot], xr.phase ^ 1u);
-          mbar_arrive(&x_full[xr.slot]);
+          if (issuer) mbar_arrive(&x_full[xr.slot]);
           xr.advance(C::kSlots);
         }
-        NV_T(1);
+        if (issuer) NV_T(1);
         // ---- phase 1: the same video again (L2 hits), 128 frames x 128 D per slot pair
         for (int g = 0; g < NG; ++g)
           for (int i = 0; i < NT; ++i)
@@ -179,12 +182,13 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
                 mbar_wait(&x_empty[xr.slot], xr.phase ^ 1u);
-                mbar_arrive_expect_tx(&x_full[xr.slot], kSlotBytes);
-                tma_load_3d(xs + xr.slot * kSlotBytes, &tm_x, &x_full[xr.slot], m * 128 + h * 64, i * 128, b, kEvictFirst);
+                mbar_arrive_expect_tx(&x_full[xr.slot], kSlotBytes, issuer);
+                tma_load_3d(xs + xr.slot * kSlotBytes, &tm_x, &x_full[xr.slot], m * 128 + h * 64, i * 128, b, kEvictFirst, issuer);
                 xr.advance(C::kSlots);
               }
+              __syncwarp();
             }
-        NV_T(2);
+        if (issuer) NV_T(2);
       }
     }
   } else if (warp == 1) {
@@ -192,6 +196,7 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     constexpr uint32_t idesc0 = make_idesc_bf16(128, KC, 0, 0);     // S = X . Cw^T      (both K-major)
     constexpr uint32_t idesc1 = make_idesc_bf16(128, KC, 1, 1);     // V^T = X^T . a     (both MN-major)
     RingPos xr{0, 0}, cr{0, 0};
+    const bool issuer = (lane == 0);
     int gidx = 0;                                                   // accumulator groups issued so far
     for (int it = 0; it < n_iter; ++it) {
       if (C::kSOverlapsV && gidx >= 1) {
@@ -207,28 +212,29 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         for (int i = 0; i < NT; ++i) {
           mbar_wait(&x_full[xr.slot], xr.phase);
           tc_fence_after();
-          if (lane == 0) {
-            if (kb == 0 && i == 0) NV_T(9);
-            const uint32_t a_addr = smem_u32(xs + xr.slot * kSlotBytes);
-            const uint32_t b_addr = smem_u32(cws + cr.slot * C::kCwBytes);
+          if (lane == 0 && kb == 0 && i == 0) NV_T(9);
+          {
+            const uint64_t adesc0 = make_sdesc_sw128(smem_u32(xs + xr.slot * kSlotBytes), 16, 1024);
+            const uint64_t bdesc0 = make_sdesc_sw128(smem_u32(cws + cr.slot * C::kCwBytes), 16, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + i * KC, make_sdesc_sw128(a_addr + k * 32, 16, 1024),
-                        make_sdesc_sw128(b_addr + k * 32, 16, 1024), idesc0, (kb > 0 || k > 0) ? 1u : 0u);
-            umma_commit(&x_empty[xr.slot]);
+              umma_bf16(tmem_base + i * KC, sdesc_advance(adesc0, k * 32), sdesc_advance(bdesc0, k * 32), idesc0,
+                        (kb > 0 || k > 0) ? 1u : 0u, issuer);
+            umma_commit(&x_empty[xr.slot], issuer);
           }
           __syncwarp();
           xr.advance(C::kSlots);
         }
-        if (lane == 0) umma_commit(&cw_empty[cr.slot]);
+        umma_commit(&cw_empty[cr.slot], issuer);
         __syncwarp();
         cr.advance(C::kCwStages);
       }
-      if (lane == 0) { umma_commit(s_full); NV_T(10); }
+      umma_commit(s_full, issuer);
+      if (lane == 0) NV_T(10);
       __syncwarp();
       if (odd_p0) {
         mbar_wait(&x_full[xr.slot], xr.phase);
-        if (lane == 0) umma_commit(&x_empty[xr.slot]);
+        umma_commit(&x_empty[xr.slot], issuer);
         __syncwarp();
         xr.advance(C::kSlots);
       }
@@ -252,22 +258,23 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             mbar_wait(&x_full[s0], xr.phase);
             mbar_wait(&x_full[s0 + 1], xr.phase);
             tc_fence_after();
-            if (lane == 0) {
-              const uint32_t a_addr = smem_u32(xs + s0 * kSlotBytes);
-              const uint32_t b_addr = smem_u32(atile + i * C::kATileBytes);
+            {
+              const uint64_t adesc0 = make_sdesc_sw128(smem_u32(xs + s0 * kSlotBytes), kSlotBytes, 1024);
+              const uint64_t bdesc0 = make_sdesc_sw128(smem_u32(atile + i * C::kATileBytes), kSlotBytes, 1024);
+              const uint32_t dcol = tmem_base + C::kVBase0 + buf * C::kGroupCols + ml * KC;
               for (int s = 0; s < nsteps; ++s)
-                umma_bf16(tmem_base + C::kVBase0 + buf * C::kGroupCols + ml * KC,
-                          make_sdesc_sw128(a_addr + s * 2048, kSlotBytes, 1024),
-                          make_sdesc_sw128(b_addr + s * 2048, kSlotBytes, 1024), idesc1, (i > 0 || s > 0) ? 1u : 0u);
-              umma_commit(&x_empty[s0]);
-              umma_commit(&x_empty[s0 + 1]);
+                umma_bf16(dcol, sdesc_advance(adesc0, s * 2048), sdesc_advance(bdesc0, s * 2048), idesc1,
+                          (i > 0 || s > 0) ? 1u : 0u, issuer);
+              umma_commit(&x_empty[s0], issuer);
+              umma_commit(&x_empty[s0 + 1], issuer);
             }
             __syncwarp();
             xr.advance(C::kSlots);
             xr.advance(C::kSlots);
           }
         }
-        if (lane == 0) { umma_commit(&v_full[buf]); if (g == NG - 1) NV_T(12); }
+        umma_commit(&v_full[buf], issuer);
+        if (lane == 0 && g == NG - 1) NV_T(12);
         __syncwarp();
       }
     }
