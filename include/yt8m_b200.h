@@ -136,6 +136,8 @@ int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, in
 /* debug only: device buffer (>= 128 u64, or NULL to disable) that receives globaltimer stamps of the
  * NetVLAD kernel's phases for CTA 0 (tools/netvlad_timeline.py decodes them) */
 int yt8m_debug_set_timeline(unsigned long long* dev_buf);
+/* debug only: ablation switches of the NetVLAD kernel (results become wrong); 0 = normal operation */
+int yt8m_debug_set_flags(int flags);
 
 /* ---- elementwise glue -----------------------------------------------------------------------------
  * y = x * sigmoid(g * scale + shift)  (context gating; g = x . Wg from yt8m_linear_fwd) */

@@ -3,7 +3,8 @@
 //   D[M, N] = epilogue( A[M, K] . W[N, K]^T )        A, W bf16 (K contiguous), fp32 accumulate in TMEM
 //
 // One CTA computes one 128 x BLOCK_N output tile (optionally one K-split of it):
-//   warp 0      : TMA producer  (cp.async.bulk.tensor 2D, SWIZZLE_128B boxes of 64 K-elements)
+//   warps 0, 6  : TMA producers (A tiles / W tiles; one thread issues a TMA op every ~140 ns whatever the
+//                 box size -- measured, tools/micro/tma_ingest.cu -- so the two operands get a warp each)
 //   warp 1      : TMEM allocator + single-thread tcgen05.mma issuer (UMMA 128 x BLOCK_N x 16)
 //   warps 2..5  : epilogue -- tcgen05.ld the accumulator row owned by each thread, apply the fused
 //                 epilogue (bias/activation, MoE softmax x sigmoid, LSTM gates) and store.
@@ -18,7 +19,7 @@ namespace yt8m {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kUmmaK = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 224;     // warp 0: A producer, 1: MMA, 2-5: epilogue, 6: W producer
 
 struct GemmShape {
   int M, N, K;
@@ -72,7 +73,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     if (A_SPLIT == 2) tma_prefetch_desc(&tm_a_lo);
     tma_prefetch_desc(&tm_b);
     for (int s = 0; s < S::kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
+      mbar_init(&full_bar[s], 2);      // one arrive.expect_tx from each producer warp
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -85,17 +86,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp == 0) {
-    // ------------------------------- TMA producer -------------------------------
+    // ------------------------------- TMA producer: A (hi [+ lo]) -------------------------------
     const bool issuer = (lane == 0);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(&empty_bar[stage], phase ^ 1u);
       uint8_t* st = tiles + stage * S::kStageBytes;
-      mbar_arrive_expect_tx(&full_bar[stage], S::kStageBytes, issuer);
+      mbar_arrive_expect_tx(&full_bar[stage], A_SPLIT * S::kABytes, issuer);
       tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal, issuer);
       if (A_SPLIT == 2)
         tma_load_2d(st + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal, issuer);
+      __syncwarp();
+      if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
+    }
+  } else if (warp == 6) {
+    // ------------------------------- TMA producer: W -------------------------------------------
+    const bool issuer = (lane == 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = kb_begin; kb < kb_end; ++kb) {
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      uint8_t* st = tiles + stage * S::kStageBytes;
+      mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes, issuer);
       tma_load_2d(st + A_SPLIT * S::kABytes, &tm_b, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N, kEvictNormal, issuer);
       __syncwarp();
       if (++stage == S::kStages) { stage = 0; phase ^= 1u; }

@@ -80,6 +80,27 @@ int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d
   return YT8M_OK;
 }
 
+int make_tmap_bf16_nd(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box) {
+  auto enc = get_encode();
+  YT8M_REQUIRE(enc != nullptr, YT8M_E_CUDA, "cuTensorMapEncodeTiled unavailable (no CUDA driver?)");
+  YT8M_REQUIRE(rank >= 2 && rank <= 5, YT8M_E_BADSHAPE, "tensor map rank %d", rank);
+  YT8M_REQUIRE(aligned16(ptr), YT8M_E_BADPTR, "TMA operand %p is not 16-byte aligned", ptr);
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) {
+    YT8M_REQUIRE(strides_bytes[i] % 16 == 0, YT8M_E_BADSHAPE, "TMA stride %llu bytes is not a multiple of 16",
+                 (unsigned long long)strides_bytes[i]);
+    gstr[i] = strides_bytes[i];
+  }
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gdim, gstr, bx, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  YT8M_REQUIRE(r == CUDA_SUCCESS, YT8M_E_CUDA, "cuTensorMapEncodeTiled(rank %d) failed: %d", rank, (int)r);
+  return YT8M_OK;
+}
+
 }  // namespace yt8m
 
 extern "C" {

@@ -19,6 +19,10 @@ int make_tmap_bf16_2d(CUtensorMap* out, const void* ptr, uint64_t rows, uint64_t
 int make_tmap_bf16_3d(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t ld1_elems,
                       uint64_t ld2_elems, uint32_t box_d1, uint32_t box_d0 = 64);
 
+// generic bf16 tensor map, SWIZZLE_128B: dims/box innermost first, strides (bytes) for dims 1..rank-1
+int make_tmap_bf16_nd(CUtensorMap* out, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box);
+
 int check_launch(const char* what);
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

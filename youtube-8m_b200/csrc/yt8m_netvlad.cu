@@ -23,11 +23,12 @@ using namespace yt8m;
 
 namespace {
 
-constexpr int kNvThreads = 192;
+constexpr int kNvThreads = 224;            // warp 0: X producer, 1: MMA, 2-5: softmax/epilogue, 6: centre producer
 constexpr int kNvSms = 148;
 
 // debug-only phase timeline (globaltimer ns) of CTA 0: set with yt8m_debug_set_timeline()
 __device__ unsigned long long* g_nv_timeline = nullptr;
+__device__ int g_nv_flags = 0;     // debug ablations: 1 = no stash stores, 2 = no rescale pass, 4 = no cw2 loads, 8 = no phase-1 loads
 #define NV_T(slot)                                                                         \
   do {                                                                                     \
     if (g_nv_timeline && blockIdx.x == 0 && it < 4) g_nv_timeline[it * 32 + (slot)] = global_timer_ns(); \
@@ -41,12 +42,17 @@ struct NvCfg {
   static constexpr int kGM = 128 / KC > 0 ? 128 / KC : 1;      // M-blocks (128 D rows) per TMEM group (128 cols)
   static constexpr int kGroupCols = kGM * KC;                  // 128 (KC <= 128)
   static constexpr int kVBase0 = 512 - 2 * kGroupCols;         // two accumulator groups at the top of TMEM
-  static constexpr int kSlots = (KC <= 64) ? 8 : 4;            // X ring slots (even), 16 KB each
-  static constexpr int kCwStages = 3;
-  static constexpr int kCwBytes = KC * 128;                    // KC rows x 64 bf16
+  // X ring: every TMA op brings 128 frames x 128 features (two 64-wide SWIZZLE_128B sub-tiles, 32 KB) --
+  // a thread can only issue one TMA op per ~140 ns, so the ops have to be big (tools/micro/tma_ingest.cu)
+  static constexpr int kXSlotBytes = 2 * kSlotBytes;
+  static constexpr int kSlots = (KC <= 64) ? 4 : 2;
+  static constexpr int kCwKb = (KC <= 64) ? 2 : 1;             // k-blocks per centre stage
+  static constexpr int kCwPer = 2 / kCwKb;                     // centre stages per k-block pair
+  static constexpr int kCwStages = (KC <= 64) ? 2 : 3;
+  static constexpr int kCwBytes = kCwKb * KC * 128;            // kCwKb x (KC rows x 64 bf16)
   static constexpr int kATileBytes = kNBlk * kSlotBytes;       // 128 frames x KC (64-wide blocks)
   static constexpr int kOffX = 0;
-  static constexpr int kOffCw = kOffX + kSlots * kSlotBytes;
+  static constexpr int kOffCw = kOffX + kSlots * kXSlotBytes;
   static constexpr int kOffA = kOffCw + ((kCwStages * kCwBytes + 1023) / 1024) * 1024;
   static constexpr int kOffSmall = kOffA + kNtMax * kATileBytes;
   static constexpr int kSmallBytes = 5 * KC * 4 + 512;         // scale, shift, asum, ssq, fscale + barriers
@@ -122,7 +128,6 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   const int NKB = D / 64;
   const int NMB = D / 128;
   const int NG = (NMB + C::kGM - 1) / C::kGM;
-  const bool odd_p0 = ((NKB * NT) & 1) != 0;      // keep phase-1 slot pairs even-aligned in the ring
   const int n_iter = (B - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
 
   if (warp == 0 && lane == 0) {
@@ -146,51 +151,48 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // =================================== TMA producer ===================================
-    {
-      const bool issuer = (lane == 0);
-      RingPos xr{0, 0}, cr{0, 0};
-      for (int it = 0; it < n_iter; ++it) {
-        const int b = blockIdx.x + it * gridDim.x;
-        if (issuer) NV_T(0);
-        // ---- phase 0: D streams through the ring; HBM reads
-        for (int kb = 0; kb < NKB; ++kb) {
-          mbar_wait(&cw_empty[cr.slot], cr.phase ^ 1u);
-          mbar_arrive_expect_tx(&cw_full[cr.slot], C::kCwBytes, issuer);
-          tma_load_2d(cws + cr.slot * C::kCwBytes, &tm_cw, &cw_full[cr.slot], kb * 64, 0, kEvictLast, issuer);
-          cr.advance(C::kCwStages);
-          for (int i = 0; i < NT; ++i) {
-            mbar_wait(&x_empty[xr.slot], xr.phase ^ 1u);
-            mbar_arrive_expect_tx(&x_full[xr.slot], kSlotBytes, issuer);
-            tma_load_3d(xs + xr.slot * kSlotBytes, &tm_x, &x_full[xr.slot], kb * 64, i * 128, b, kEvictNormal, issuer);
-            xr.advance(C::kSlots);
-          }
-          __syncwarp();
-        }
-        if (odd_p0) {                                        // dummy hand-shake keeps slot pairs even-aligned
+    // =================================== X producer ===================================
+    const bool issuer = (lane == 0);
+    RingPos xr{0, 0};
+    for (int it = 0; it < n_iter; ++it) {
+      const int b = blockIdx.x + it * gridDim.x;
+      if (issuer) NV_T(0);
+      // ---- phase 0: two 64-wide k-blocks of 128 frames per op; HBM reads
+      for (int kbp = 0; kbp < NKB / 2; ++kbp)
+        for (int i = 0; i < NT; ++i) {
           mbar_wait(&x_empty[xr.slot], xr.phase ^ 1u);
-          if (issuer) mbar_arrive(&x_full[xr.slot]);
+          mbar_arrive_expect_tx(&x_full[xr.slot], C::kXSlotBytes, issuer);
+          tma_load_4d(xs + xr.slot * C::kXSlotBytes, &tm_x, &x_full[xr.slot], 0, i * 128, 2 * kbp, b, kEvictNormal, issuer);
+          __syncwarp();
           xr.advance(C::kSlots);
         }
-        if (issuer) NV_T(1);
-        // ---- phase 1: the same video again (L2 hits), 128 frames x 128 D per slot pair
-        for (int g = 0; g < NG; ++g)
-          for (int i = 0; i < NT; ++i)
-            for (int ml = 0; ml < C::kGM; ++ml) {
-              const int m = g * C::kGM + ml;
-              if (m >= NMB) break;
-#pragma unroll
-              for (int h = 0; h < 2; ++h) {
-                mbar_wait(&x_empty[xr.slot], xr.phase ^ 1u);
-                mbar_arrive_expect_tx(&x_full[xr.slot], kSlotBytes, issuer);
-                tma_load_3d(xs + xr.slot * kSlotBytes, &tm_x, &x_full[xr.slot], m * 128 + h * 64, i * 128, b, kEvictFirst, issuer);
-                xr.advance(C::kSlots);
-              }
-              __syncwarp();
-            }
-        if (issuer) NV_T(2);
-      }
+      if (issuer) NV_T(1);
+      // ---- phase 1: the same video again (L2 hits), 128 frames x one 128-row M-block of D per op
+      for (int g = 0; g < NG; ++g)
+        for (int i = 0; i < NT; ++i)
+          for (int ml = 0; ml < C::kGM; ++ml) {
+            const int m = g * C::kGM + ml;
+            if (m >= NMB) break;
+            mbar_wait(&x_empty[xr.slot], xr.phase ^ 1u);
+            mbar_arrive_expect_tx(&x_full[xr.slot], C::kXSlotBytes, issuer);
+            tma_load_4d(xs + xr.slot * C::kXSlotBytes, &tm_x, &x_full[xr.slot], 0, i * 128, 2 * m, b, kEvictFirst, issuer);
+            __syncwarp();
+            xr.advance(C::kSlots);
+          }
+      if (issuer) NV_T(2);
     }
+  } else if (warp == 6) {
+    // =================================== centre (Cw) producer ===================================
+    const bool issuer = (lane == 0);
+    RingPos cr{0, 0};
+    for (int it = 0; it < n_iter; ++it)
+      for (int kc = 0; kc < NKB / C::kCwKb; ++kc) {
+        mbar_wait(&cw_empty[cr.slot], cr.phase ^ 1u);
+        mbar_arrive_expect_tx(&cw_full[cr.slot], C::kCwBytes, issuer);
+        tma_load_3d(cws + cr.slot * C::kCwBytes, &tm_cw, &cw_full[cr.slot], 0, 0, kc * C::kCwKb, kEvictLast, issuer);
+        __syncwarp();
+        cr.advance(C::kCwStages);
+      }
   } else if (warp == 1) {
     // =================================== MMA issuer =====================================
     constexpr uint32_t idesc0 = make_idesc_bf16(128, KC, 0, 0);     // S = X . Cw^T      (both K-major)
@@ -207,37 +209,43 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         tc_fence_after();
       }
       if (lane == 0) NV_T(8);
-      for (int kb = 0; kb < NKB; ++kb) {
-        mbar_wait(&cw_full[cr.slot], cr.phase);
+      for (int kbp = 0; kbp < NKB / 2; ++kbp) {
+        // centre tiles of this k-block pair: one stage (two k-blocks) or two stages (one each)
+        uint32_t cw_addr[2];
+        int cw_slot[2];
+#pragma unroll
+        for (int j = 0; j < C::kCwPer; ++j) {
+          mbar_wait(&cw_full[cr.slot], cr.phase);
+          cw_slot[j] = cr.slot;
+          cw_addr[j] = smem_u32(cws + cr.slot * C::kCwBytes);
+          cr.advance(C::kCwStages);
+        }
+        if (C::kCwPer == 1) { cw_addr[1] = cw_addr[0] + KC * 128; cw_slot[1] = cw_slot[0]; }
         for (int i = 0; i < NT; ++i) {
           mbar_wait(&x_full[xr.slot], xr.phase);
           tc_fence_after();
-          if (lane == 0 && kb == 0 && i == 0) NV_T(9);
-          {
-            const uint64_t adesc0 = make_sdesc_sw128(smem_u32(xs + xr.slot * kSlotBytes), 16, 1024);
-            const uint64_t bdesc0 = make_sdesc_sw128(smem_u32(cws + cr.slot * C::kCwBytes), 16, 1024);
+          if (lane == 0 && kbp == 0 && i == 0) NV_T(9);
+          const uint32_t x_addr = smem_u32(xs + xr.slot * C::kXSlotBytes);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint64_t adesc0 = make_sdesc_sw128(x_addr + j * kSlotBytes, 16, 1024);
+            const uint64_t bdesc0 = make_sdesc_sw128(cw_addr[j], 16, 1024);
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(tmem_base + i * KC, sdesc_advance(adesc0, k * 32), sdesc_advance(bdesc0, k * 32), idesc0,
-                        (kb > 0 || k > 0) ? 1u : 0u, issuer);
-            umma_commit(&x_empty[xr.slot], issuer);
+                        (kbp > 0 || j > 0 || k > 0) ? 1u : 0u, issuer);
           }
+          umma_commit(&x_empty[xr.slot], issuer);
           __syncwarp();
           xr.advance(C::kSlots);
         }
-        umma_commit(&cw_empty[cr.slot], issuer);
+        umma_commit(&cw_empty[cw_slot[0]], issuer);
+        if (C::kCwPer == 2) umma_commit(&cw_empty[cw_slot[1]], issuer);
         __syncwarp();
-        cr.advance(C::kCwStages);
       }
       umma_commit(s_full, issuer);
       if (lane == 0) NV_T(10);
       __syncwarp();
-      if (odd_p0) {
-        mbar_wait(&x_full[xr.slot], xr.phase);
-        umma_commit(&x_empty[xr.slot], issuer);
-        __syncwarp();
-        xr.advance(C::kSlots);
-      }
       // phase 1 needs every assignment tile of this video
       mbar_wait(a_ready, it & 1);
       tc_fence_after();
@@ -254,22 +262,18 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           for (int ml = 0; ml < C::kGM; ++ml) {
             const int m = g * C::kGM + ml;
             if (m >= NMB) break;
-            const int s0 = xr.slot;                                  // even: the pair (s0, s0 + 1)
-            mbar_wait(&x_full[s0], xr.phase);
-            mbar_wait(&x_full[s0 + 1], xr.phase);
+            mbar_wait(&x_full[xr.slot], xr.phase);
             tc_fence_after();
             {
-              const uint64_t adesc0 = make_sdesc_sw128(smem_u32(xs + s0 * kSlotBytes), kSlotBytes, 1024);
+              const uint64_t adesc0 = make_sdesc_sw128(smem_u32(xs + xr.slot * C::kXSlotBytes), kSlotBytes, 1024);
               const uint64_t bdesc0 = make_sdesc_sw128(smem_u32(atile + i * C::kATileBytes), kSlotBytes, 1024);
               const uint32_t dcol = tmem_base + C::kVBase0 + buf * C::kGroupCols + ml * KC;
               for (int s = 0; s < nsteps; ++s)
                 umma_bf16(dcol, sdesc_advance(adesc0, s * 2048), sdesc_advance(bdesc0, s * 2048), idesc1,
                           (i > 0 || s > 0) ? 1u : 0u, issuer);
-              umma_commit(&x_empty[s0], issuer);
-              umma_commit(&x_empty[s0 + 1], issuer);
+              umma_commit(&x_empty[xr.slot], issuer);
             }
             __syncwarp();
-            xr.advance(C::kSlots);
             xr.advance(C::kSlots);
           }
         }
@@ -282,7 +286,8 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     // ============================ softmax + epilogue warps (128 threads) ============================
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;                       // 0..127
+    const int et = threadIdx.x - 64;                       // 0..127 (warps 2..5)
+    const int dbg_flags = g_nv_flags;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     int gidx = 0;
     for (int it = 0; it < n_iter; ++it) {
@@ -399,7 +404,7 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
               const bool last_chunk = (ch == kChunks - 1);
               const int nm = last_chunk ? m + 1 : m;
               const int ncol = last_chunk ? 0 : c + 32;
-              if (nm < NMB) {
+              if (nm < NMB && !(dbg_flags & 4)) {
                 const float* c2n = cw2 + static_cast<long long>(nm * 128 + row) * KC + ncol;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) cc[j] = __ldg(reinterpret_cast<const float4*>(c2n) + j);
@@ -411,8 +416,10 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
               uint4 hi, lo;
               pack8_hi_lo(v + 8 * j8, hi, lo);
               const long long o = static_cast<long long>(d) * KC + c + 8 * j8;
-              st_global_hint(ohi + o, hi, kEvictLast);
-              if (olo) st_global_hint(olo + o, lo, kEvictLast);
+              if (!(dbg_flags & 1)) {
+                st_global_hint(ohi + o, hi, kEvictLast);
+                if (olo) st_global_hint(olo + o, lo, kEvictLast);
+              }
             }
             if (kRegAcc) {
 #pragma unroll
@@ -451,7 +458,7 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
       const long long n = static_cast<long long>(D) * KC;
       float* of = out_f32 ? out_f32 + static_cast<long long>(b) * ld_out : nullptr;
       constexpr int kU = 8;                                 // independent 16-byte loads in flight per thread (x2 with lo)
-      for (long long e0 = static_cast<long long>(et) * 8; e0 < n; e0 += 128 * 8 * kU) {
+      for (long long e0 = static_cast<long long>(et) * 8; e0 < ((dbg_flags & 2) ? 0 : n); e0 += 128 * 8 * kU) {
         uint4 h[kU], lw[kU];
 #pragma unroll
         for (int u = 0; u < kU; ++u) {
@@ -507,8 +514,20 @@ int launch_netvlad(const yt8m_bf16* x, const int* num_frames, int B, int T, int 
   using C = NvCfg<KC>;
   CUtensorMap tm_x, tm_cw;
   int rc;
-  if ((rc = make_tmap_bf16_3d(&tm_x, x, D, T, B, D, static_cast<uint64_t>(T) * D, 128)) != YT8M_OK) return rc;
-  if ((rc = make_tmap_bf16_2d(&tm_cw, cw_packed, KC, D, D, KC)) != YT8M_OK) return rc;
+  // X viewed as [B][D/64][T][64]: one box = 128 frames x two 64-wide k-blocks (32 KB)
+  {
+    const uint64_t dims[4] = {64, static_cast<uint64_t>(T), static_cast<uint64_t>(D / 64), static_cast<uint64_t>(B)};
+    const uint64_t strides[3] = {static_cast<uint64_t>(D) * 2, 128, static_cast<uint64_t>(T) * D * 2};
+    const uint32_t box[4] = {64, 128, 2, 1};
+    if ((rc = make_tmap_bf16_nd(&tm_x, x, 4, dims, strides, box)) != YT8M_OK) return rc;
+  }
+  // Cw viewed as [D/64][KC][64]
+  {
+    const uint64_t dims[3] = {64, static_cast<uint64_t>(KC), static_cast<uint64_t>(D / 64)};
+    const uint64_t strides[2] = {static_cast<uint64_t>(D) * 2, 128};
+    const uint32_t box[3] = {64, static_cast<uint32_t>(KC), static_cast<uint32_t>(C::kCwKb)};
+    if ((rc = make_tmap_bf16_nd(&tm_cw, cw_packed, 3, dims, strides, box)) != YT8M_OK) return rc;
+  }
   auto kern = netvlad_fused_kernel<KC>;
   static bool attr_done = false;
   if (!attr_done) {
@@ -526,6 +545,10 @@ int launch_netvlad(const yt8m_bf16* x, const int* num_frames, int B, int T, int 
 
 extern "C" int yt8m_debug_set_timeline(unsigned long long* dev_buf) {
   YT8M_CUDA(cudaMemcpyToSymbol(g_nv_timeline, &dev_buf, sizeof(dev_buf)));
+  return YT8M_OK;
+}
+extern "C" int yt8m_debug_set_flags(int flags) {
+  YT8M_CUDA(cudaMemcpyToSymbol(g_nv_flags, &flags, sizeof(flags)));
   return YT8M_OK;
 }
 

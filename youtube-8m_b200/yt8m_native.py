@@ -53,6 +53,7 @@ _SIGS = {
     "yt8m_netvlad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "yt8m_debug_set_timeline": (c_int, [c_void_p]),
+    "yt8m_debug_set_flags": (c_int, [c_int]),
     "yt8m_context_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
     "yt8m_col_affine": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -308,6 +309,10 @@ def netvlad_fwd(x, num_frames, cw_packed, scale, shift, cw2, want_f32=False, wan
 def debug_set_timeline(buf):
   """buf: int64 CUDA tensor with >= 128 elements, or None to switch the stamps off."""
   _check(_lib.yt8m_debug_set_timeline(_p(buf)), "yt8m_debug_set_timeline")
+
+
+def debug_set_flags(flags):
+  _check(_lib.yt8m_debug_set_flags(int(flags)), "yt8m_debug_set_flags")
 
 
 def context_gate(x, g, scale=None, shift=None, want_bf16=True):
