@@ -24,15 +24,16 @@ ingest_kernel(const __grid_constant__ CUtensorMap tm, int slots, int iters, int 
   const unsigned long long t0 = global_timer_ns();
   if (warp < nprod) {
     // producer warp p handles slots p, p+nprod, ...
-    const bool issuer = lane == 0;
     uint32_t phase = 0;
     int slot = warp;
     const int row_tiles = rows_total / BOX_ROWS;
     for (int it = warp; it < iters; it += nprod) {
       mbar_wait(&empty[slot], phase ^ 1u);
-      mbar_arrive_expect_tx(&full[slot], kSlot, issuer);
       const int tile = (blockIdx.x * 977 + it) % row_tiles;
-      tma_load_2d(smem + slot * kSlot, &tm, &full[slot], 0, tile * BOX_ROWS, kEvictNormal, issuer);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&full[slot], kSlot);
+        tma_load_2d(smem + slot * kSlot, &tm, &full[slot], 0, tile * BOX_ROWS, kEvictNormal);
+      }
       __syncwarp();
       slot += nprod;
       if (slot >= slots) { slot -= slots; phase ^= 1u; }

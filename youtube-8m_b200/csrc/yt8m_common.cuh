@@ -82,10 +82,6 @@ __device__ __forceinline__ void fence_barrier_init() {
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-               : "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -130,48 +126,37 @@ constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
 constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
 
-// The TMA wrappers are executed CONVERGENTLY by the whole producer warp with warp-uniform operands;
-// `issue` (true in one lane) predicates the instruction (see umma_bf16 for why).
+// TMA loads: call inside `if (elect_one()) { ... }` (see umma_bf16).
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                            uint64_t policy, bool issue) {
+                                            uint64_t policy) {
   asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %6, 0;\n\t"
-      "@q cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;\n\t}\n"
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
-      "l"(policy), "r"(static_cast<uint32_t>(issue))
+      "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                            int c2, uint64_t policy, bool issue) {
+                                            int c2, uint64_t policy) {
   asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %7, 0;\n\t"
-      "@q cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4, %5}], [%2], %6;\n\t}\n"
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
-      "r"(c2), "l"(policy), "r"(static_cast<uint32_t>(issue))
+      "r"(c2), "l"(policy)
       : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
-                                            int c2, int c3, uint64_t policy, bool issue) {
+                                            int c2, int c3, uint64_t policy) {
   asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %8, 0;\n\t"
-      "@q cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;\n\t}\n"
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1),
-      "r"(c2), "r"(c3), "l"(policy), "r"(static_cast<uint32_t>(issue))
+      "r"(c2), "r"(c3), "l"(policy)
       : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes, bool issue) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %2, 0;\n\t"
-      "@q mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n\t}\n"
-      ::"r"(smem_u32(bar)), "r"(bytes), "r"(static_cast<uint32_t>(issue))
-      : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
 }
 
 // 16-byte global store / load with an explicit L2 eviction policy (same policy words as the TMA hints)
@@ -207,29 +192,23 @@ __device__ __forceinline__ void tc_fence_before() {
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32.
-// Executed CONVERGENTLY by the whole MMA warp with warp-uniform operands; `issue` (true in exactly one
-// lane) predicates the instruction itself.  Keeping the descriptor arithmetic outside any divergent
-// branch lets ptxas hold the descriptors in uniform registers -- inside an `if (lane == 0)` it wraps
-// every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall loop (~100 cycles per MMA).
+// D[tmem] (+)= A[smem] * B[smem], bf16 x bf16 -> fp32.  Call inside `if (elect_one()) { ... }`:
+// ptxas recognises the elect.sync-guarded single-lane region and keeps descriptors in uniform
+// registers with back-to-back UTCHMMA.  (Inside `if (lane == 0)`, or with a predicated instruction,
+// it wraps EVERY UTCHMMA in an ELECT / R2UR / BRA.U.ANY loop -- ~150 ns per MMA, measured.)
 __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate, bool issue) {
+                                          uint32_t accumulate) {
   asm volatile(
-      "{\n\t.reg .pred p, q;\n\t"
+      "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
-      "setp.ne.b32 q, %5, 0;\n\t"
-      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(issue))
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// arrive on an mbarrier when all previously issued tcgen05.mma of the issuing thread have completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar, bool issue) {
-  asm volatile(
-      "{\n\t.reg .pred q;\n\t"
-      "setp.ne.b32 q, %1, 0;\n\t"
-      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}\n"
-      ::"r"(smem_u32(bar)), "r"(static_cast<uint32_t>(issue))
-      : "memory");
+// arrive on an mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
 }
 // TMEM -> registers: 32 lanes x 32 consecutive fp32 columns (thread i of the warp gets lane base+i)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {

@@ -87,29 +87,30 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 
   if (warp == 0) {
     // ------------------------------- TMA producer: A (hi [+ lo]) -------------------------------
-    const bool issuer = (lane == 0);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(&empty_bar[stage], phase ^ 1u);
-      uint8_t* st = tiles + stage * S::kStageBytes;
-      mbar_arrive_expect_tx(&full_bar[stage], A_SPLIT * S::kABytes, issuer);
-      tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal, issuer);
-      if (A_SPLIT == 2)
-        tma_load_2d(st + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal, issuer);
+      if (elect_one()) {
+        uint8_t* st = tiles + stage * S::kStageBytes;
+        mbar_arrive_expect_tx(&full_bar[stage], A_SPLIT * S::kABytes);
+        tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal);
+        if (A_SPLIT == 2) tma_load_2d(st + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal);
+      }
       __syncwarp();
       if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 6) {
     // ------------------------------- TMA producer: W -------------------------------------------
-    const bool issuer = (lane == 0);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = kb_begin; kb < kb_end; ++kb) {
       mbar_wait(&empty_bar[stage], phase ^ 1u);
-      uint8_t* st = tiles + stage * S::kStageBytes;
-      mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes, issuer);
-      tma_load_2d(st + A_SPLIT * S::kABytes, &tm_b, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N, kEvictNormal, issuer);
+      if (elect_one()) {
+        uint8_t* st = tiles + stage * S::kStageBytes;
+        mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes);
+        tma_load_2d(st + A_SPLIT * S::kABytes, &tm_b, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N, kEvictNormal);
+      }
       __syncwarp();
       if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
     }
@@ -118,22 +119,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
     int stage = 0;
     uint32_t phase = 0;
-    const bool issuer = (lane == 0);
     for (int kb = 0; kb < num_kb; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      const uint32_t a_addr = smem_u32(tiles + stage * S::kStageBytes);
-      const uint64_t adesc0 = make_sdesc_sw128(a_addr, 16, 1024);
-      const uint64_t adesc1 = make_sdesc_sw128(a_addr + S::kABytes, 16, 1024);
-      const uint64_t bdesc0 = make_sdesc_sw128(a_addr + A_SPLIT * S::kABytes, 16, 1024);
+      if (elect_one()) {
+        const uint32_t a_addr = smem_u32(tiles + stage * S::kStageBytes);
+        const uint64_t adesc0 = make_sdesc_sw128(a_addr, 16, 1024);
+        const uint64_t adesc1 = make_sdesc_sw128(a_addr + S::kABytes, 16, 1024);
+        const uint64_t bdesc0 = make_sdesc_sw128(a_addr + A_SPLIT * S::kABytes, 16, 1024);
 #pragma unroll
-      for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-        const uint64_t bdesc = sdesc_advance(bdesc0, k * (kUmmaK * 2));
-        umma_bf16(tmem_base, sdesc_advance(adesc0, k * (kUmmaK * 2)), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u, issuer);
-        if (A_SPLIT == 2) umma_bf16(tmem_base, sdesc_advance(adesc1, k * (kUmmaK * 2)), bdesc, idesc, 1u, issuer);
+        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+          const uint64_t bdesc = sdesc_advance(bdesc0, k * (kUmmaK * 2));
+          umma_bf16(tmem_base, sdesc_advance(adesc0, k * (kUmmaK * 2)), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          if (A_SPLIT == 2) umma_bf16(tmem_base, sdesc_advance(adesc1, k * (kUmmaK * 2)), bdesc, idesc, 1u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (kb == num_kb - 1) umma_commit(tmem_full_bar);
       }
-      umma_commit(&empty_bar[stage], issuer);
-      if (kb == num_kb - 1) umma_commit(tmem_full_bar, issuer);
       __syncwarp();
       if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
     }

@@ -152,21 +152,22 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 
   if (warp == 0) {
     // =================================== X producer ===================================
-    const bool issuer = (lane == 0);
     RingPos xr{0, 0};
     for (int it = 0; it < n_iter; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
-      if (issuer) NV_T(0);
+      if (lane == 0) NV_T(0);
       // ---- phase 0: two 64-wide k-blocks of 128 frames per op; HBM reads
       for (int kbp = 0; kbp < NKB / 2; ++kbp)
         for (int i = 0; i < NT; ++i) {
           mbar_wait(&x_empty[xr.slot], xr.phase ^ 1u);
-          mbar_arrive_expect_tx(&x_full[xr.slot], C::kXSlotBytes, issuer);
-          tma_load_4d(xs + xr.slot * C::kXSlotBytes, &tm_x, &x_full[xr.slot], 0, i * 128, 2 * kbp, b, kEvictNormal, issuer);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&x_full[xr.slot], C::kXSlotBytes);
+            tma_load_4d(xs + xr.slot * C::kXSlotBytes, &tm_x, &x_full[xr.slot], 0, i * 128, 2 * kbp, b, kEvictNormal);
+          }
           __syncwarp();
           xr.advance(C::kSlots);
         }
-      if (issuer) NV_T(1);
+      if (lane == 0) NV_T(1);
       // ---- phase 1: the same video again (L2 hits), 128 frames x one 128-row M-block of D per op
       for (int g = 0; g < NG; ++g)
         for (int i = 0; i < NT; ++i)
@@ -174,22 +175,25 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             const int m = g * C::kGM + ml;
             if (m >= NMB) break;
             mbar_wait(&x_empty[xr.slot], xr.phase ^ 1u);
-            mbar_arrive_expect_tx(&x_full[xr.slot], C::kXSlotBytes, issuer);
-            tma_load_4d(xs + xr.slot * C::kXSlotBytes, &tm_x, &x_full[xr.slot], 0, i * 128, 2 * m, b, kEvictFirst, issuer);
+            if (elect_one()) {
+              mbar_arrive_expect_tx(&x_full[xr.slot], C::kXSlotBytes);
+              tma_load_4d(xs + xr.slot * C::kXSlotBytes, &tm_x, &x_full[xr.slot], 0, i * 128, 2 * m, b, kEvictFirst);
+            }
             __syncwarp();
             xr.advance(C::kSlots);
           }
-      if (issuer) NV_T(2);
+      if (lane == 0) NV_T(2);
     }
   } else if (warp == 6) {
     // =================================== centre (Cw) producer ===================================
-    const bool issuer = (lane == 0);
     RingPos cr{0, 0};
     for (int it = 0; it < n_iter; ++it)
       for (int kc = 0; kc < NKB / C::kCwKb; ++kc) {
         mbar_wait(&cw_empty[cr.slot], cr.phase ^ 1u);
-        mbar_arrive_expect_tx(&cw_full[cr.slot], C::kCwBytes, issuer);
-        tma_load_3d(cws + cr.slot * C::kCwBytes, &tm_cw, &cw_full[cr.slot], 0, 0, kc * C::kCwKb, kEvictLast, issuer);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&cw_full[cr.slot], C::kCwBytes);
+          tma_load_3d(cws + cr.slot * C::kCwBytes, &tm_cw, &cw_full[cr.slot], 0, 0, kc * C::kCwKb, kEvictLast);
+        }
         __syncwarp();
         cr.advance(C::kCwStages);
       }
@@ -198,7 +202,6 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
     constexpr uint32_t idesc0 = make_idesc_bf16(128, KC, 0, 0);     // S = X . Cw^T      (both K-major)
     constexpr uint32_t idesc1 = make_idesc_bf16(128, KC, 1, 1);     // V^T = X^T . a     (both MN-major)
     RingPos xr{0, 0}, cr{0, 0};
-    const bool issuer = (lane == 0);
     int gidx = 0;                                                   // accumulator groups issued so far
     for (int it = 0; it < n_iter; ++it) {
       if (C::kSOverlapsV && gidx >= 1) {
@@ -225,25 +228,29 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           mbar_wait(&x_full[xr.slot], xr.phase);
           tc_fence_after();
           if (lane == 0 && kbp == 0 && i == 0) NV_T(9);
-          const uint32_t x_addr = smem_u32(xs + xr.slot * C::kXSlotBytes);
+          if (elect_one()) {
+            const uint32_t x_addr = smem_u32(xs + xr.slot * C::kXSlotBytes);
 #pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint64_t adesc0 = make_sdesc_sw128(x_addr + j * kSlotBytes, 16, 1024);
-            const uint64_t bdesc0 = make_sdesc_sw128(cw_addr[j], 16, 1024);
+            for (int j = 0; j < 2; ++j) {
+              const uint64_t adesc0 = make_sdesc_sw128(x_addr + j * kSlotBytes, 16, 1024);
+              const uint64_t bdesc0 = make_sdesc_sw128(cw_addr[j], 16, 1024);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem_base + i * KC, sdesc_advance(adesc0, k * 32), sdesc_advance(bdesc0, k * 32), idesc0,
-                        (kbp > 0 || j > 0 || k > 0) ? 1u : 0u, issuer);
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem_base + i * KC, sdesc_advance(adesc0, k * 32), sdesc_advance(bdesc0, k * 32), idesc0,
+                          (kbp > 0 || j > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(&x_empty[xr.slot]);
           }
-          umma_commit(&x_empty[xr.slot], issuer);
           __syncwarp();
           xr.advance(C::kSlots);
         }
-        umma_commit(&cw_empty[cw_slot[0]], issuer);
-        if (C::kCwPer == 2) umma_commit(&cw_empty[cw_slot[1]], issuer);
+        if (elect_one()) {
+          umma_commit(&cw_empty[cw_slot[0]]);
+          if (C::kCwPer == 2) umma_commit(&cw_empty[cw_slot[1]]);
+        }
         __syncwarp();
       }
-      umma_commit(s_full, issuer);
+      if (elect_one()) umma_commit(s_full);
       if (lane == 0) NV_T(10);
       __syncwarp();
       // phase 1 needs every assignment tile of this video
@@ -264,20 +271,20 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
             if (m >= NMB) break;
             mbar_wait(&x_full[xr.slot], xr.phase);
             tc_fence_after();
-            {
+            if (elect_one()) {
               const uint64_t adesc0 = make_sdesc_sw128(smem_u32(xs + xr.slot * C::kXSlotBytes), kSlotBytes, 1024);
               const uint64_t bdesc0 = make_sdesc_sw128(smem_u32(atile + i * C::kATileBytes), kSlotBytes, 1024);
               const uint32_t dcol = tmem_base + C::kVBase0 + buf * C::kGroupCols + ml * KC;
               for (int s = 0; s < nsteps; ++s)
                 umma_bf16(dcol, sdesc_advance(adesc0, s * 2048), sdesc_advance(bdesc0, s * 2048), idesc1,
-                          (i > 0 || s > 0) ? 1u : 0u, issuer);
-              umma_commit(&x_empty[xr.slot], issuer);
+                          (i > 0 || s > 0) ? 1u : 0u);
+              umma_commit(&x_empty[xr.slot]);
             }
             __syncwarp();
             xr.advance(C::kSlots);
           }
         }
-        umma_commit(&v_full[buf], issuer);
+        if (elect_one()) umma_commit(&v_full[buf]);
         if (lane == 0 && g == NG - 1) NV_T(12);
         __syncwarp();
       }
