@@ -159,6 +159,37 @@ int yt8m_split_bf16(const float* x, long long rows, int cols, long long ld_in, y
 int yt8m_xent_fwd_bwd(const float* pred, const float* labels, int B, int V, float* loss_out, float* dpred,
                       float grad_scale, yt8m_stream_t stream);
 
+/* ---- training step (wh/train.py:440-466, wh/utils.py:164-174) ---------------------------------------
+ * Master weights / gradients / Adam moments are kept in the PACKED [out, in] layout of the forward kernels.
+ *
+ * yt8m_logistic_bwd_dz: dz = dp * p * (1 - p) as bf16 hi/lo (sigmoid backward, logistic_model.py:23-25).
+ * yt8m_wgrad: out[M, N] = A^T . B, A = a_hi (+ a_lo) stored [Kb, lda >= M], B stored [Kb, ldb >= N]: the
+ *   contraction runs over the batch rows of both stored matrices (MN-major tcgen05 operands, no transposes),
+ *   e.g. dW^T[V, D] = dZ^T . X.
+ * yt8m_colsum_bf16: out[n] = sum_rows (hi + lo)[r, n]   (bias gradients).
+ * yt8m_moe_bwd_dlogits: recomputes the MoE logits tile and writes dL/dlogits (packed column order, bf16
+ *   hi/lo) from dL/dp -- backward of wh/all_video_models/moe_model.py:54-64.  num_mixtures in {1, 2, 4}.
+ * yt8m_grad_reg_sumsq: grad += l2 * param; sums4 = {sum g^2 seg0, seg1, sum w^2 seg0, seg1}; for MoE packed
+ *   weights (moe_per = 2M+1, moe_nmix = M) segment 0 = gate rows, 1 = expert rows (two tensors in the
+ *   reference, hence two norms); moe_per = 0 -> one segment.
+ * yt8m_clip_adam_step: g *= clip / max(||g||_seg, clip)  (tf.clip_by_norm per tensor), then TF-1.0 Adam
+ *   (theta -= lr_t * m / (sqrt(v) + eps), lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller), and the
+ *   bf16 operand copy is refreshed in place.  only_segment >= 0 restricts the update (MoE bias rows). */
+int yt8m_logistic_bwd_dz(const float* dp, const float* p, int B, int V, yt8m_bf16* dz_hi, yt8m_bf16* dz_lo, long long ld,
+                         yt8m_stream_t stream);
+int yt8m_wgrad(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, const yt8m_bf16* b, long long ldb, int M, int N,
+               int Kb, float* out, long long ld_out, yt8m_stream_t stream);
+int yt8m_colsum_bf16(const yt8m_bf16* hi, const yt8m_bf16* lo, long long ld, int rows, int cols, float* out,
+                     yt8m_stream_t stream);
+int yt8m_moe_bwd_dlogits(const yt8m_bf16* x_hi, const yt8m_bf16* x_lo, long long ldx, const yt8m_bf16* w_packed, long long ldw,
+                         const float* bias_packed, const float* dp, long long ld_dp, int B, int D, int vocab, int num_mixtures,
+                         yt8m_bf16* dl_hi, yt8m_bf16* dl_lo, long long ld_dl, yt8m_stream_t stream);
+int yt8m_grad_reg_sumsq(float* grad, const float* param, long long rows, int row_len, float l2, int moe_per, int moe_nmix,
+                        float* sums4, yt8m_stream_t stream);
+int yt8m_clip_adam_step(float* param, const float* grad, float* m, float* v, long long rows, int row_len, const float* sums4,
+                        float clip, float lr_t, float beta1, float beta2, float eps, int moe_per, int moe_nmix, int only_segment,
+                        yt8m_bf16* param_bf16, yt8m_stream_t stream);
+
 /* top-k per row, descending (wh/inference.py:76-87 format_lines; wh/eval_util.py:164 top_k_triplets).
  * k <= 32.  idx_out: int32 [rows, k]; val_out: fp32 [rows, k]. */
 int yt8m_topk_rows(const float* x, long long rows, int cols, int k, int* idx_out, float* val_out,

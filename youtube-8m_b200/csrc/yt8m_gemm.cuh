@@ -26,10 +26,13 @@ struct GemmShape {
   int kb_per_split;                    // K-blocks handled by one blockIdx.z
 };
 
-template <int BLOCK_N, int A_SPLIT>
+// MN = false: operands stored [rows, K] with K contiguous (forward / dgrad): stage = 64 K-elements.
+// MN = true : operands stored [K, rows] with the OUTPUT index contiguous (wgrad: out = A^T . B, contraction over
+//             the batch rows): stage = 128 contraction rows, tiles are 64-column boxes of 128 rows.
+template <int BLOCK_N, int A_SPLIT, bool MN = false>
 struct GemmSmem {
-  static constexpr int kABytes = kBlockM * kBlockK * 2;               // 16 KB
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kABytes = MN ? 2 * 128 * 128 : kBlockM * kBlockK * 2;      // 16 KB (K-major) / 32 KB (MN)
+  static constexpr int kBBytes = MN ? (BLOCK_N / 64) * 128 * 128 : BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = A_SPLIT * kABytes + kBBytes;
   static constexpr int kBudget = 200 * 1024;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
@@ -46,11 +49,12 @@ __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n
 //                                       int n0 (global N index of tile col 0), uint32_t tmem_row_addr, bool row_valid); }
 // run() is called by every epilogue thread (uniformly per warp: tcgen05.ld is warp-collective).
 
-template <int BLOCK_N, int A_SPLIT, class Epi>
+template <int BLOCK_N, int A_SPLIT, class Epi, bool MN = false>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b, const GemmShape shape, const typename Epi::Params ep) {
-  using S = GemmSmem<BLOCK_N, A_SPLIT>;
+  using S = GemmSmem<BLOCK_N, A_SPLIT, MN>;
+  constexpr int kStageK = MN ? 128 : kBlockK;          // contraction elements per pipeline stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
@@ -62,7 +66,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
   const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
-  const int num_kb_total = (shape.K + kBlockK - 1) / kBlockK;
+  const int num_kb_total = (shape.K + kStageK - 1) / kStageK;
   const int kb_begin = split * shape.kb_per_split;
   const int kb_end = min(kb_begin + shape.kb_per_split, num_kb_total);
   const int num_kb = kb_end - kb_begin;
@@ -94,8 +98,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       if (elect_one()) {
         uint8_t* st = tiles + stage * S::kStageBytes;
         mbar_arrive_expect_tx(&full_bar[stage], A_SPLIT * S::kABytes);
-        tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal);
-        if (A_SPLIT == 2) tma_load_2d(st + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal);
+        if (MN) {
+          // two 64-column boxes of 128 contraction rows per operand half
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tma_load_2d(st + h * 16384, &tm_a_hi, &full_bar[stage], m_tile * kBlockM + h * 64, kb * 128, kEvictNormal);
+            if (A_SPLIT == 2)
+              tma_load_2d(st + S::kABytes + h * 16384, &tm_a_lo, &full_bar[stage], m_tile * kBlockM + h * 64, kb * 128, kEvictNormal);
+          }
+        } else {
+          tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal);
+          if (A_SPLIT == 2) tma_load_2d(st + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal);
+        }
       }
       __syncwarp();
       if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
@@ -109,14 +123,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       if (elect_one()) {
         uint8_t* st = tiles + stage * S::kStageBytes;
         mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes);
-        tma_load_2d(st + A_SPLIT * S::kABytes, &tm_b, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N, kEvictNormal);
+        if (MN) {
+#pragma unroll
+          for (int h = 0; h < BLOCK_N / 64; ++h)
+            tma_load_2d(st + A_SPLIT * S::kABytes + h * 16384, &tm_b, &full_bar[stage], n_tile * BLOCK_N + h * 64, kb * 128, kEvictNormal);
+        } else {
+          tma_load_2d(st + A_SPLIT * S::kABytes, &tm_b, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N, kEvictNormal);
+        }
       }
       __syncwarp();
       if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, MN ? 1 : 0, MN ? 1 : 0);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
@@ -124,14 +144,28 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a_addr = smem_u32(tiles + stage * S::kStageBytes);
-        const uint64_t adesc0 = make_sdesc_sw128(a_addr, 16, 1024);
-        const uint64_t adesc1 = make_sdesc_sw128(a_addr + S::kABytes, 16, 1024);
-        const uint64_t bdesc0 = make_sdesc_sw128(a_addr + A_SPLIT * S::kABytes, 16, 1024);
+        if (MN) {
+          // MN-major SWIZZLE_128B: 8-row groups 1024 B apart (SBO), 64-column blocks one box apart (LBO);
+          // one UMMA consumes 16 contraction rows = 2048 B
+          const uint64_t adesc0 = make_sdesc_sw128(a_addr, 16384, 1024);
+          const uint64_t adesc1 = make_sdesc_sw128(a_addr + S::kABytes, 16384, 1024);
+          const uint64_t bdesc0 = make_sdesc_sw128(a_addr + A_SPLIT * S::kABytes, 16384, 1024);
 #pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          const uint64_t bdesc = sdesc_advance(bdesc0, k * (kUmmaK * 2));
-          umma_bf16(tmem_base, sdesc_advance(adesc0, k * (kUmmaK * 2)), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          if (A_SPLIT == 2) umma_bf16(tmem_base, sdesc_advance(adesc1, k * (kUmmaK * 2)), bdesc, idesc, 1u);
+          for (int k = 0; k < 8; ++k) {
+            const uint64_t bdesc = sdesc_advance(bdesc0, k * 2048);
+            umma_bf16(tmem_base, sdesc_advance(adesc0, k * 2048), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (A_SPLIT == 2) umma_bf16(tmem_base, sdesc_advance(adesc1, k * 2048), bdesc, idesc, 1u);
+          }
+        } else {
+          const uint64_t adesc0 = make_sdesc_sw128(a_addr, 16, 1024);
+          const uint64_t adesc1 = make_sdesc_sw128(a_addr + S::kABytes, 16, 1024);
+          const uint64_t bdesc0 = make_sdesc_sw128(a_addr + A_SPLIT * S::kABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            const uint64_t bdesc = sdesc_advance(bdesc0, k * (kUmmaK * 2));
+            umma_bf16(tmem_base, sdesc_advance(adesc0, k * (kUmmaK * 2)), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (A_SPLIT == 2) umma_bf16(tmem_base, sdesc_advance(adesc1, k * (kUmmaK * 2)), bdesc, idesc, 1u);
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (kb == num_kb - 1) umma_commit(tmem_full_bar);

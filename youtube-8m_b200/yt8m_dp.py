@@ -1,0 +1,48 @@
+"""Data-parallel plumbing: one process per GPU, torch.distributed for the rendezvous and the collective.
+
+The path shards by video: forward / inference needs no collective at all; the training
+step has exactly one exchange -- an all-reduce(sum) of the flat fp32 gradient buffer (NCCL over
+NVLink/NVSwitch on the GPU box; gloo for the CPU tests of this host logic)."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def init_from_env(backend=None):
+  """Initialises torch.distributed from RANK / WORLD_SIZE / MASTER_* (torchrun).  Returns (rank, world, local_rank)."""
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  if world > 1 and not dist.is_initialized():
+    backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+    if backend == "nccl":
+      torch.cuda.set_device(local_rank)
+      dist.init_process_group(backend, device_id=torch.device("cuda", local_rank))
+    else:
+      dist.init_process_group(backend)
+  return rank, world, local_rank
+
+
+def world_size(group=None):
+  return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank(group=None):
+  return dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
+
+
+def all_reduce_sum_(flat, group=None):
+  """In-place sum over ranks of one flat buffer; a no-op for a single process."""
+  if world_size(group) > 1:
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+  return flat
+
+
+def shard_rows(n_rows, group=None):
+  """Contiguous row range [lo, hi) of the global batch owned by this rank (rank r owns rows
+  [r*B/W, (r+1)*B/W) -- SURVEY.md §8e)."""
+  w, r = world_size(group), rank(group)
+  per = (n_rows + w - 1) // w
+  lo = min(r * per, n_rows)
+  return lo, min(lo + per, n_rows)

@@ -59,6 +59,14 @@ _SIGS = {
     "yt8m_col_affine": (c_int, [c_void_p, c_int, c_ll, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "yt8m_split_bf16": (c_int, [c_void_p, c_ll, c_int, c_ll, c_void_p, c_void_p, c_ll, c_void_p]),
     "yt8m_xent_fwd_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p]),
+    "yt8m_logistic_bwd_dz": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_ll, c_void_p]),
+    "yt8m_wgrad": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_ll, c_void_p]),
+    "yt8m_colsum_bf16": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p]),
+    "yt8m_moe_bwd_dlogits": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_int, c_int,
+                                     c_void_p, c_void_p, c_ll, c_void_p]),
+    "yt8m_grad_reg_sumsq": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_float, c_int, c_int, c_void_p, c_void_p]),
+    "yt8m_clip_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_float, c_float, c_float,
+                                    c_float, c_float, c_int, c_int, c_int, c_void_p, c_void_p]),
     "yt8m_topk_rows": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 for _name, (_res, _args) in _SIGS.items():
@@ -351,3 +359,60 @@ def topk_rows(x, k):
   val = _f32((rows, k), x.device)
   _check(_lib.yt8m_topk_rows(_p(x.contiguous()), rows, cols, k, _p(idx), _p(val), _stream()), "yt8m_topk_rows")
   return idx, val
+
+
+# ------------------------------------------------------------------------------------------------
+# training-step wrappers
+# ------------------------------------------------------------------------------------------------
+
+def logistic_bwd_dz(dp, p):
+  b, v = p.shape
+  ld = pad8(v)
+  hi = torch.zeros((b, ld), dtype=torch.bfloat16, device=p.device)
+  lo = torch.zeros((b, ld), dtype=torch.bfloat16, device=p.device)
+  _check(_lib.yt8m_logistic_bwd_dz(_p(dp), _p(p), b, v, _p(hi), _p(lo), ld, _stream()), "yt8m_logistic_bwd_dz")
+  return hi, lo
+
+
+def wgrad(a_hi, a_lo, b, m, n, out=None):
+  """out[m, n] = A^T . B with A [Kb, >=m] (hi/lo) and B [Kb, >=n] stored batch-major."""
+  kb = a_hi.shape[0]
+  if out is None:
+    out = _f32((m, n), a_hi.device)
+  _check(_lib.yt8m_wgrad(_p(a_hi), _p(a_lo), a_hi.stride(0), _p(b), b.stride(0), m, n, kb, _p(out), out.stride(0), _stream()),
+         "yt8m_wgrad")
+  return out
+
+
+def colsum_bf16(hi, lo, cols, out=None):
+  if out is None:
+    out = _f32((cols,), hi.device)
+  _check(_lib.yt8m_colsum_bf16(_p(hi), _p(lo), hi.stride(0), hi.shape[0], cols, _p(out), _stream()), "yt8m_colsum_bf16")
+  return out
+
+
+def moe_bwd_dlogits(x_hi, x_lo, w_packed, bias_packed, dp, vocab, num_mixtures, d=None):
+  b = x_hi.shape[0]
+  d = d or min(x_hi.shape[1], w_packed.shape[1])
+  rows = w_packed.shape[0]
+  hi = _bf16((b, rows), x_hi.device)
+  lo = _bf16((b, rows), x_hi.device)
+  _check(_lib.yt8m_moe_bwd_dlogits(_p(x_hi), _p(x_lo), x_hi.stride(0), _p(w_packed), w_packed.stride(0), _p(bias_packed), _p(dp),
+                                   dp.stride(0), b, d, vocab, num_mixtures, _p(hi), _p(lo), rows, _stream()), "yt8m_moe_bwd_dlogits")
+  return hi, lo
+
+
+def grad_reg_sumsq(grad, param, l2, moe_per=0, moe_nmix=0):
+  rows, row_len = (param.shape[0], param.shape[1]) if param.dim() == 2 else (1, param.numel())
+  sums = _f32((4,), param.device)
+  _check(_lib.yt8m_grad_reg_sumsq(_p(grad), _p(param), rows, row_len, float(l2), moe_per, moe_nmix, _p(sums), _stream()),
+         "yt8m_grad_reg_sumsq")
+  return sums
+
+
+def clip_adam_step(param, grad, m, v, sums, clip, lr_t, beta1=0.9, beta2=0.999, eps=1e-8, moe_per=0, moe_nmix=0, only_segment=-1,
+                   param_bf16=None):
+  rows, row_len = (param.shape[0], param.shape[1]) if param.dim() == 2 else (1, param.numel())
+  _check(_lib.yt8m_clip_adam_step(_p(param), _p(grad), _p(m), _p(v), rows, row_len, _p(sums), float(clip), float(lr_t), float(beta1),
+                                  float(beta2), float(eps), moe_per, moe_nmix, only_segment, _p(param_bf16), _stream()),
+         "yt8m_clip_adam_step")
