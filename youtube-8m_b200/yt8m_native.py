@@ -370,7 +370,8 @@ def logistic_bwd_dz(dp, p):
   ld = pad8(v)
   hi = torch.zeros((b, ld), dtype=torch.bfloat16, device=p.device)
   lo = torch.zeros((b, ld), dtype=torch.bfloat16, device=p.device)
-  _check(_lib.yt8m_logistic_bwd_dz(_p(dp), _p(p), b, v, _p(hi), _p(lo), ld, _stream()), "yt8m_logistic_bwd_dz")
+  _check(_lib.yt8m_logistic_bwd_dz(_p(dp.contiguous()), _p(p.contiguous()), b, v, _p(hi), _p(lo), ld, _stream()),
+         "yt8m_logistic_bwd_dz")
   return hi, lo
 
 
