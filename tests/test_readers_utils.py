@@ -1,0 +1,94 @@
+"""CPU tests of the host-side data path: TFRecord framing (masked CRC-32C), Example / SequenceExample wire
+decoding, reader batching / padding / truncation semantics (wh/readers.py), checkpoint helpers and
+find_class_by_name's error behaviour (wh/train.py:212-215)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import readers
+import utils
+
+
+def test_crc32c_known_answers():
+  # RFC 3720 test vectors for CRC-32C (Castagnoli)
+  assert readers.crc32c(b"") == 0
+  assert readers.crc32c(bytes(32)) == 0x8A9136AA
+  assert readers.crc32c(bytes([0xFF] * 32)) == 0x62A8AB43
+  assert readers.crc32c(bytes(range(32))) == 0x46DD794E
+  assert readers.crc32c(b"123456789") == 0xE3069283
+
+
+def _video_records(n, classes=20):
+  return [readers.encode_example({"video_id": ("bytes", [b"vid%d" % i]), "labels": ("int64", [i % classes, (i + 5) % classes, classes + 3]),
+                                  "mean_rgb": ("float", np.arange(8, dtype=np.float32) + i),
+                                  "mean_audio": ("float", np.full(4, i, dtype=np.float32))}) for i in range(n)]
+
+
+def test_aggregated_reader_roundtrip(tmp_path):
+  p = str(tmp_path / "a.tfrecord")
+  readers.write_tfrecord(p, _video_records(5))
+  r = readers.YT8MAggregatedFeatureReader(num_classes=20, feature_names=["mean_rgb", "mean_audio"], feature_sizes=[8, 4])
+  batches = list(r.prepare_reader(str(tmp_path / "*.tfrecord"), batch_size=3, verify_crc=True))
+  assert [len(b[0]) for b in batches] == [3, 2]
+  ids, f, l, nf = batches[0]
+  assert ids == [b"vid0", b"vid1", b"vid2"] and f.shape == (3, 12) and f.dtype == torch.float32
+  assert f[2, :8].tolist() == list(np.arange(8) + 2.0) and f[2, 8:].tolist() == [2.0] * 4
+  assert l.shape == (3, 20) and l.sum(dim=1).tolist() == [2, 2, 2]        # labels >= num_classes are dropped
+  assert nf.tolist() == [1, 1, 1]
+  two_epochs = sum(len(b[0]) for b in r.prepare_reader(p, batch_size=4, num_epochs=2))
+  assert two_epochs == 10
+
+
+def test_frame_reader_pads_and_truncates(tmp_path):
+  recs = [readers.encode_sequence_example({"video_id": ("bytes", [b"v%d" % i]), "labels": ("int64", [1, 2])},
+                                          {"rgb": [("bytes", [bytes([j] * 6)]) for j in range(3 + 2 * i)],
+                                           "audio": [("bytes", [bytes([9] * 2)]) for j in range(3 + 2 * i)]}) for i in range(2)]
+  p = str(tmp_path / "f.tfrecord")
+  readers.write_tfrecord(p, recs)
+  r = readers.YT8MFrameFeatureReader(num_classes=20, feature_names=["rgb", "audio"], feature_sizes=[6, 2], max_frames=4)
+  (ids, f, l, nf), = list(r.prepare_reader(p, batch_size=8))
+  assert f.dtype == torch.uint8 and f.shape == (2, 4, 8)
+  assert nf.tolist() == [3, 4]                                              # 5 frames truncated to max_frames = 4
+  assert f[0, :, 0].tolist() == [0, 1, 2, 0] and f[0, :, 7].tolist() == [9, 9, 9, 0]   # zero padding past num_frames
+  assert f[1, :, 0].tolist() == [0, 1, 2, 3]
+  assert l[0].nonzero().flatten().tolist() == [1, 2]
+
+
+def test_corrupt_and_missing_files(tmp_path):
+  p = str(tmp_path / "a.tfrecord")
+  readers.write_tfrecord(p, _video_records(2))
+  data = bytearray(open(p, "rb").read())
+  data[20] ^= 0xFF
+  open(p, "wb").write(bytes(data))
+  with pytest.raises(IOError):
+    list(readers.tfrecord_iterator(p, verify=True))
+  open(p, "wb").write(bytes(data[:30]))
+  with pytest.raises(IOError):
+    list(readers.tfrecord_iterator(p))
+  r = readers.YT8MAggregatedFeatureReader(num_classes=20, feature_names=["mean_rgb"], feature_sizes=[8])
+  with pytest.raises(IOError):                                               # same failure as wh/train.py:193-195
+    list(r.prepare_reader(str(tmp_path / "nothing*.tfrecord")))
+  with pytest.raises(AssertionError):
+    readers.YT8MFrameFeatureReader(feature_names=["rgb", "audio"], feature_sizes=[1024])
+  with pytest.raises(NotImplementedError):
+    readers.BaseReader().prepare_reader(None)
+
+
+def test_utils(tmp_path):
+  import video_level_models, frame_level_models
+  assert utils.find_class_by_name("MoeModel", [frame_level_models, video_level_models]) is video_level_models.MoeModel
+  with pytest.raises(StopIteration):
+    utils.find_class_by_name("NoSuchModel", [frame_level_models, video_level_models])
+  assert utils.GetListOfFeatureNamesAndSizes("rgb, audio", "1024,128") == (["rgb", "audio"], [1024, 128])
+  q = utils.Dequantize(np.array([0.0, 255.0]))
+  assert np.allclose(q, [4 / 512 - 2, 4 + 4 / 512 - 2])
+  d = str(tmp_path / "ckpt")
+  for step in (10, 20, 30, 40):
+    utils.save_checkpoint(d, step, {"w": torch.ones(2) * step})
+  assert sorted(os.listdir(d)) == ["model.ckpt-20", "model.ckpt-30", "model.ckpt-40"]       # max_to_keep = 3
+  assert utils.latest_checkpoint(d).endswith("model.ckpt-40")
+  assert utils.load_checkpoint(utils.latest_checkpoint(d))["variables"]["w"].tolist() == [40.0, 40.0]
+  info = utils.FormatEpochInfo({"epoch_id": 7, "avg_hit_at_one": 0.5, "avg_perr": 0.25, "aps": [0.5, 1.0], "gap": 0.75, "avg_loss": 3.0})
+  assert info.startswith("epoch/eval number 7 | Avg_Hit@1: 0.500 | Avg_PERR: 0.250 | MAP: 0.750 | GAP: 0.750")

@@ -1,0 +1,318 @@
+"""YouTube-8M readers with the reference's classes (wh/readers.py:58-459): TFRecord files of
+tf.train.Example (video-level: ``mean_rgb`` / ``mean_audio`` float features) or tf.train.SequenceExample
+(frame-level: per-frame uint8-quantised ``rgb`` / ``audio`` byte strings), ``video_id`` + sparse ``labels``.
+
+The reference parses these inside TensorFlow queue runners; here the framing (length + masked CRC-32C) and
+the protobuf wire format are decoded on the host with no TensorFlow dependency, and batches are handed to
+the GPU still QUANTISED (uint8 [B, max_frames, D], zero padded -- wh/readers.py:21-56,186): de-quantisation
+(wh/utils.py:23-38) and the L2 normalisation are fused into one kernel behind DefaultTransformer.
+"""
+import glob
+import struct
+
+import numpy as np
+import torch
+
+# ------------------------------------------------------------------------------------------------
+# TFRecord framing
+# ------------------------------------------------------------------------------------------------
+_CRC_TABLE = None
+
+
+def _crc32c_table():
+  global _CRC_TABLE
+  if _CRC_TABLE is None:
+    t = []
+    for i in range(256):
+      c = i
+      for _ in range(8):
+        c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
+      t.append(c)
+    _CRC_TABLE = t
+  return _CRC_TABLE
+
+
+def crc32c(data):
+  t = _crc32c_table()
+  c = 0xFFFFFFFF
+  for b in data:
+    c = t[(c ^ b) & 0xFF] ^ (c >> 8)
+  return c ^ 0xFFFFFFFF
+
+
+def masked_crc32c(data):
+  c = crc32c(data)
+  return ((((c >> 15) | (c << 17)) & 0xFFFFFFFF) + 0xA282EAD8) & 0xFFFFFFFF
+
+
+def tfrecord_iterator(path, verify=False):
+  """Yields the serialized records of one TFRecord file."""
+  with open(path, "rb") as f:
+    while True:
+      head = f.read(12)
+      if not head:
+        return
+      if len(head) < 12:
+        raise IOError("truncated TFRecord header in %s" % path)
+      (length,), (len_crc,) = struct.unpack("<Q", head[:8]), struct.unpack("<I", head[8:])
+      if verify and masked_crc32c(head[:8]) != len_crc:
+        raise IOError("corrupt TFRecord length CRC in %s" % path)
+      data = f.read(length)
+      tail = f.read(4)
+      if len(data) < length or len(tail) < 4:
+        raise IOError("truncated TFRecord in %s" % path)
+      if verify and masked_crc32c(data) != struct.unpack("<I", tail)[0]:
+        raise IOError("corrupt TFRecord data CRC in %s" % path)
+      yield data
+
+
+def write_tfrecord(path, records):
+  with open(path, "wb") as f:
+    for data in records:
+      head = struct.pack("<Q", len(data))
+      f.write(head + struct.pack("<I", masked_crc32c(head)) + data + struct.pack("<I", masked_crc32c(data)))
+
+
+# ------------------------------------------------------------------------------------------------
+# protobuf wire format of tf.train.Example / SequenceExample (field numbers from example.proto / feature.proto)
+# ------------------------------------------------------------------------------------------------
+
+def _varint(buf, pos):
+  res, shift = 0, 0
+  while True:
+    b = buf[pos]
+    pos += 1
+    res |= (b & 0x7F) << shift
+    if not b & 0x80:
+      return res, pos
+    shift += 7
+
+
+def _fields(buf):
+  """Yields (field_number, wire_type, value) of one message; length-delimited values are memoryviews."""
+  pos, n = 0, len(buf)
+  while pos < n:
+    key, pos = _varint(buf, pos)
+    fnum, wt = key >> 3, key & 7
+    if wt == 0:
+      val, pos = _varint(buf, pos)
+    elif wt == 2:
+      ln, pos = _varint(buf, pos)
+      val = buf[pos:pos + ln]
+      pos += ln
+    elif wt == 5:
+      val = buf[pos:pos + 4]
+      pos += 4
+    elif wt == 1:
+      val = buf[pos:pos + 8]
+      pos += 8
+    else:
+      raise ValueError("unsupported protobuf wire type %d" % wt)
+    yield fnum, wt, val
+
+
+def _parse_feature(buf):
+  """Feature { bytes_list = 1; float_list = 2; int64_list = 3 } -> ("bytes"|"float"|"int64", values)."""
+  for fnum, _, val in _fields(buf):
+    if fnum == 1:
+      return "bytes", [bytes(v) for f, _, v in _fields(val) if f == 1]
+    if fnum == 2:
+      out = []
+      for f, wt, v in _fields(val):
+        if f == 1:
+          out.append(np.frombuffer(v, dtype="<f4"))          # packed (wt 2) or single fixed32 (wt 5)
+      return "float", np.concatenate(out) if out else np.zeros(0, np.float32)
+    if fnum == 3:
+      out = []
+      for f, wt, v in _fields(val):
+        if f != 1:
+          continue
+        if wt == 0:
+          out.append(v)
+        else:
+          p = 0
+          while p < len(v):
+            x, p = _varint(v, p)
+            out.append(x)
+      return "int64", np.asarray(out, dtype=np.int64)
+  return "none", []
+
+
+def _parse_features(buf):
+  """Features { map<string, Feature> feature = 1 }"""
+  out = {}
+  for fnum, _, entry in _fields(buf):
+    if fnum != 1:
+      continue
+    key, feat = None, None
+    for f, _, v in _fields(entry):
+      if f == 1:
+        key = bytes(v).decode("utf-8")
+      elif f == 2:
+        feat = _parse_feature(v)
+    out[key] = feat
+  return out
+
+
+def parse_example(data):
+  """tf.train.Example { Features features = 1 } -> {name: (kind, values)}"""
+  buf = memoryview(data)
+  for fnum, _, val in _fields(buf):
+    if fnum == 1:
+      return _parse_features(val)
+  return {}
+
+
+def parse_sequence_example(data):
+  """SequenceExample { Features context = 1; FeatureLists feature_lists = 2 } -> (context, {name: [Feature...]})"""
+  buf = memoryview(data)
+  context, lists = {}, {}
+  for fnum, _, val in _fields(buf):
+    if fnum == 1:
+      context = _parse_features(val)
+    elif fnum == 2:
+      for f, _, entry in _fields(val):                       # map<string, FeatureList>
+        if f != 1:
+          continue
+        key, feats = None, []
+        for g, _, v in _fields(entry):
+          if g == 1:
+            key = bytes(v).decode("utf-8")
+          elif g == 2:
+            feats = [_parse_feature(x) for h, _, x in _fields(v) if h == 1]
+        lists[key] = feats
+  return context, lists
+
+
+# ---- encoders (synthetic data / tests) ---------------------------------------------------------------
+
+def _enc_varint(x):
+  out = bytearray()
+  while True:
+    b = x & 0x7F
+    x >>= 7
+    out.append(b | (0x80 if x else 0))
+    if not x:
+      return bytes(out)
+
+
+def _ld(fnum, payload):
+  return _enc_varint((fnum << 3) | 2) + _enc_varint(len(payload)) + payload
+
+
+def _enc_feature(kind, values):
+  if kind == "bytes":
+    return _ld(1, b"".join(_ld(1, v) for v in values))
+  if kind == "float":
+    return _ld(2, _ld(1, np.asarray(values, dtype="<f4").tobytes()))
+  return _ld(3, _ld(1, b"".join(_enc_varint(int(v)) for v in values)))
+
+
+def _enc_features(feats):
+  return b"".join(_ld(1, _ld(1, k.encode()) + _ld(2, _enc_feature(kind, vals))) for k, (kind, vals) in feats.items())
+
+
+def encode_example(feats):
+  return _ld(1, _enc_features(feats))
+
+
+def encode_sequence_example(context, feature_lists):
+  fl = b"".join(_ld(1, _ld(1, k.encode()) + _ld(2, b"".join(_ld(1, _enc_feature(kind, vals)) for kind, vals in lst)))
+                for k, lst in feature_lists.items())
+  return _ld(1, _enc_features(context)) + _ld(2, fl)
+
+
+# ------------------------------------------------------------------------------------------------
+# readers
+# ------------------------------------------------------------------------------------------------
+
+class BaseReader(object):
+  """Inherit from this class when implementing new readers (wh/readers.py:58-63)."""
+
+  def prepare_reader(self, unused_filename_queue):
+    raise NotImplementedError()
+
+
+def _files(pattern):
+  files = sorted(glob.glob(pattern)) if isinstance(pattern, str) else list(pattern)
+  if not files:
+    # same failure mode as wh/train.py:193-195
+    raise IOError("Unable to find training files. data_pattern='" + str(pattern) + "'.")
+  return files
+
+
+class YT8MAggregatedFeatureReader(BaseReader):
+  """Video-level Examples (wh/readers.py:66-125)."""
+
+  def __init__(self, num_classes=4716, feature_sizes=(1024,), feature_names=("mean_inc3",)):
+    assert len(feature_names) == len(feature_sizes), \
+        "length of feature_names (={}) != length of feature_sizes (={})".format(len(feature_names), len(feature_sizes))
+    self.num_classes, self.feature_sizes, self.feature_names = num_classes, list(feature_sizes), list(feature_names)
+
+  def prepare_reader(self, data_pattern, batch_size=1024, num_epochs=1, verify_crc=False):
+    """Generator of (video_ids [B], features fp32 [B, sum(sizes)], labels bool [B, C], num_frames ones [B])."""
+    ids, feats, labels = [], [], []
+    for _ in range(num_epochs):
+      for path in _files(data_pattern):
+        for rec in tfrecord_iterator(path, verify_crc):
+          ex = parse_example(rec)
+          ids.append(ex["video_id"][1][0])
+          feats.append(np.concatenate([ex[n][1][:s] for n, s in zip(self.feature_names, self.feature_sizes)]))
+          lab = np.zeros(self.num_classes, dtype=bool)
+          lab[ex["labels"][1][ex["labels"][1] < self.num_classes]] = True
+          labels.append(lab)
+          if len(ids) == batch_size:
+            yield ids, torch.from_numpy(np.stack(feats)), torch.from_numpy(np.stack(labels)), torch.ones(len(ids), dtype=torch.int32)
+            ids, feats, labels = [], [], []
+    if ids:
+      yield ids, torch.from_numpy(np.stack(feats)), torch.from_numpy(np.stack(labels)), torch.ones(len(ids), dtype=torch.int32)
+
+
+class YT8MFrameFeatureReader(BaseReader):
+  """Frame-level SequenceExamples (wh/readers.py:128-259).  Batches keep the features uint8-quantised;
+  frames beyond max_frames are dropped and shorter videos are zero padded (resize_axis, :21-56)."""
+
+  def __init__(self, num_classes=4716, feature_sizes=(1024,), feature_names=("inc3",), max_frames=300):
+    assert len(feature_names) == len(feature_sizes), \
+        "length of feature_names (={}) != length of feature_sizes (={})".format(len(feature_names), len(feature_sizes))
+    self.num_classes, self.feature_sizes, self.feature_names = num_classes, list(feature_sizes), list(feature_names)
+    self.max_frames = max_frames
+
+  def get_video_matrix(self, frames, feature_size):
+    """decode_raw uint8 + pad / truncate to max_frames (wh/readers.py:159-186; de-quantisation happens on the GPU)."""
+    mat = np.frombuffer(b"".join(frames), dtype=np.uint8).reshape(-1, feature_size)
+    n = min(mat.shape[0], self.max_frames)
+    out = np.zeros((self.max_frames, feature_size), dtype=np.uint8)
+    out[:n] = mat[:n]
+    return out, n
+
+  def prepare_reader(self, data_pattern, batch_size=1024, num_epochs=1, verify_crc=False):
+    """Generator of (video_ids, features uint8 [B, max_frames, D], labels bool [B, C], num_frames int32 [B])."""
+    ids, mats, labels, nfs = [], [], [], []
+
+    def flush():
+      return ids, torch.from_numpy(np.stack(mats)), torch.from_numpy(np.stack(labels)), torch.tensor(nfs, dtype=torch.int32)
+
+    for _ in range(num_epochs):
+      for path in _files(data_pattern):
+        for rec in tfrecord_iterator(path, verify_crc):
+          ctx, lists = parse_sequence_example(rec)
+          parts, nf = [], -1
+          for name, size in zip(self.feature_names, self.feature_sizes):
+            m, n = self.get_video_matrix([f[1][0] for f in lists[name]], size)
+            if nf != -1 and n != nf:
+              raise ValueError("feature %s has %d frames, expected %d" % (name, n, nf))
+            nf = n
+            parts.append(m)
+          ids.append(ctx["video_id"][1][0])
+          mats.append(np.concatenate(parts, axis=1))
+          lab = np.zeros(self.num_classes, dtype=bool)
+          idx = ctx["labels"][1]
+          lab[idx[idx < self.num_classes]] = True
+          labels.append(lab)
+          nfs.append(nf)
+          if len(ids) == batch_size:
+            yield flush()
+            ids, mats, labels, nfs = [], [], [], []
+    if ids:
+      yield flush()

@@ -1,0 +1,176 @@
+"""Binary for training models on the YouTube-8M dataset -- the command line of wh/train.py (flags at
+:38-137, loop semantics at :504-622) on the B200 path.
+
+    python train.py --train_data_pattern='train*.tfrecord' --model=MoeModel --feature_names="mean_rgb,mean_audio" \
+        --feature_sizes="1024,128" --train_dir=/tmp/yt8m_model --start_new_model
+
+Multi-GPU: launch with torchrun (one process per GPU); every rank reads a disjoint slice of each batch and the
+step does ONE NCCL all-reduce of the flat gradient buffer (synchronous data parallel; the reference's
+asynchronous parameter-server mode is not reproduced -- SURVEY.md §5).
+"""
+import logging
+import os
+import shutil
+import sys
+import time
+
+import torch
+
+import eval_util
+import feature_transform  # noqa: F401 (registers flags)
+import frame_level_models
+import losses  # noqa: F401
+import readers
+import utils
+import video_level_models
+import yt8m_dp
+import yt8m_flags as flags
+
+FLAGS = flags.FLAGS
+
+if __name__ == "__main__":
+  flags.DEFINE_string("train_dir", "/tmp/yt8m_model/", "The directory to save the model files in.")
+  flags.DEFINE_string("train_data_pattern", "", "File glob for the training dataset (TFRecords of Example / SequenceExample).")
+  flags.DEFINE_string("feature_names", "mean_rgb", "Name of the feature to use for training.")
+  flags.DEFINE_string("feature_sizes", "1024", "Length of the feature vectors.")
+  flags.DEFINE_bool("frame_features", False, "If set, then --train_data_pattern must be frame-level features.")
+  flags.DEFINE_string("model", "LogisticModel", "Which architecture to use for the model.")
+  flags.DEFINE_bool("multitask", False, "Whether to consider support_predictions")
+  flags.DEFINE_bool("start_new_model", False, "If set, this will not resume from a checkpoint and will instead create a new model instance.")
+  flags.DEFINE_integer("batch_size", 1024, "How many examples to process per batch for training.")
+  flags.DEFINE_string("label_loss", "CrossEntropyLoss", "Which loss function to use for training the model.")
+  flags.DEFINE_float("regularization_penalty", 1, "How much weight to give to the regularization loss (the label loss has a weight of 1).")
+  flags.DEFINE_float("base_learning_rate", 0.01, "Which learning rate to start with.")
+  flags.DEFINE_float("learning_rate_decay", 0.95, "Learning rate decay factor to be applied every learning_rate_decay_examples.")
+  flags.DEFINE_float("learning_rate_decay_examples", 4000000, "Multiply current learning rate by learning_rate_decay every learning_rate_decay_examples.")
+  flags.DEFINE_integer("num_epochs", 5, "How many passes to make over the dataset before halting training.")
+  flags.DEFINE_integer("max_steps", None, "The maximum number of iterations of the training loop.")
+  flags.DEFINE_float("keep_checkpoint_every_n_hours", 1.0, "How many hours before saving a new checkpoint")
+  flags.DEFINE_integer("keep_checkpoint_interval", 15, "How many minutes to wait before saving a new checkpoint")
+  flags.DEFINE_integer("num_readers", 8, "How many threads to use for reading input files. (accepted, unused)")
+  flags.DEFINE_string("optimizer", "AdamOptimizer", "What optimizer class to use.")
+  flags.DEFINE_float("clip_gradient_norm", 1.0, "Norm to clip gradients to.")
+  flags.DEFINE_bool("log_device_placement", False, "Whether to write the device on which every op will run into the logs on startup.")
+  flags.DEFINE_integer("recall_at_n", 100, "N in recall@N.")
+  flags.DEFINE_bool("dropout", False, "Whether to consider dropout")
+  flags.DEFINE_float("keep_prob", 1.0, "probability to keep output (used in dropout, keep it unchanged in validationg and test)")
+  flags.DEFINE_float("noise_level", 0.0, "standard deviation of noise (added to hidden nodes)")
+
+
+def get_reader():
+  """wh/train.py:730-748."""
+  feature_names, feature_sizes = utils.GetListOfFeatureNamesAndSizes(FLAGS.feature_names, FLAGS.feature_sizes)
+  if FLAGS.frame_features:
+    return readers.YT8MFrameFeatureReader(feature_names=feature_names, feature_sizes=feature_sizes)
+  return readers.YT8MAggregatedFeatureReader(feature_names=feature_names, feature_sizes=feature_sizes)
+
+
+class Trainer(object):
+  """A Trainer to train a Tensorflow graph -- here: a HeadTrainer driving the CUDA training step
+  (wh/train.py:482-728 keeps the same responsibilities: resume, loop, log line, checkpoints)."""
+
+  def __init__(self, model_name, reader, train_dir, is_master=True):
+    self.model_name, self.reader, self.train_dir, self.is_master = model_name, reader, train_dir, is_master
+
+  def remove_training_directory(self, train_dir):
+    """wh/train.py:641-652."""
+    try:
+      logging.info("Removing existing train directory.")
+      shutil.rmtree(train_dir)
+    except OSError:
+      logging.error("Failed to delete directory " + train_dir + " when starting a new model. Please delete it manually and try again.")
+
+  def build_model(self, in_dim):
+    import yt8m_trainer
+    model_cls = utils.find_class_by_name(self.model_name, [frame_level_models, video_level_models])
+    if model_cls is video_level_models.LogisticModel:
+      kind = "logistic"
+    elif model_cls is video_level_models.MoeModel:
+      kind = "moe"
+    else:
+      raise NotImplementedError(
+          "train.py: the CUDA training step is built for the video-level heads LogisticModel and MoeModel this round; "
+          "%s runs forward-only (eval.py / inference.py)" % self.model_name)
+    if FLAGS.optimizer != "AdamOptimizer":
+      raise NotImplementedError("only --optimizer=AdamOptimizer (the reference default) is built")
+    if FLAGS.label_loss != "CrossEntropyLoss":
+      raise NotImplementedError("only --label_loss=CrossEntropyLoss (the reference default) is built")
+    return yt8m_trainer.HeadTrainer(kind, in_dim, self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures)
+
+  def run(self, start_new_model=False):
+    rank, world = yt8m_dp.rank(), yt8m_dp.world_size()
+    if self.is_master and start_new_model:
+      self.remove_training_directory(self.train_dir)
+    in_dim = sum(self.reader.feature_sizes)
+    trainer = self.build_model(in_dim)
+    transformer = utils.find_class_by_name(FLAGS.feature_transformer, [feature_transform])()
+    latest = None if start_new_model else utils.latest_checkpoint(self.train_dir)
+    if latest:
+      logging.info("Restoring from checkpoint %s", latest)
+      ck = utils.load_checkpoint(latest)
+      trainer.import_state({k: v.cuda() for k, v in ck["variables"].items()})
+      if ck.get("optimizer"):
+        trainer.adam_m.copy_(ck["optimizer"]["m"])
+        trainer.adam_v.copy_(ck["optimizer"]["v"])
+      trainer.global_step = ck["global_step"]
+    else:
+      import yt8m_ops as ops
+      logging.info("No checkpoint file found. Building a new model.")
+      ops.get_store().reset(seed=9)
+      model = utils.find_class_by_name(self.model_name, [frame_level_models, video_level_models])()
+      model.create_model(torch.zeros((2, in_dim), device="cuda"), vocab_size=self.reader.num_classes)   # creates the variables
+      trainer.import_state({k: v.value for k, v in ops.get_store().vars.items()})
+    logging.info("Entering training loop.")
+    steps, last_save = 0, time.time()
+    for video_ids, feats, labels, num_frames in self.reader.prepare_reader(FLAGS.train_data_pattern, FLAGS.batch_size, FLAGS.num_epochs):
+      steps += 1
+      t0 = time.time()
+      lo, hi = yt8m_dp.shard_rows(feats.shape[0])
+      x, _ = transformer.transform(feats[lo:hi].cuda(non_blocking=True), num_frames[lo:hi])
+      y = labels[lo:hi].cuda(non_blocking=True).float()
+      p = trainer.step(x, y, FLAGS.base_learning_rate, FLAGS.learning_rate_decay, FLAGS.learning_rate_decay_examples,
+                       FLAGS.clip_gradient_norm, FLAGS.regularization_penalty, global_batch=feats.shape[0])
+      if self.is_master:
+        pv, lv = p.cpu().numpy(), labels[lo:hi].numpy().astype("float32")
+        loss_val = float(trainer.last["label_loss_local"])
+        seconds = time.time() - t0
+        logging.info("training step " + str(trainer.global_step) + "| Hit@1: " + ("%.2f" % eval_util.calculate_hit_at_one(pv, lv)) +
+                     " PERR: " + ("%.2f" % eval_util.calculate_precision_at_equal_recall_rate(pv, lv)) + " GAP: " +
+                     ("%.2f" % eval_util.calculate_gap(pv, lv)) + " Recall@%d: " % FLAGS.recall_at_n + "N/A" + " Loss: " + str(loss_val) +
+                     " Examples/sec: %.1f" % (feats.shape[0] / max(seconds, 1e-9)))
+        if time.time() - last_save > FLAGS.keep_checkpoint_interval * 60:
+          self.save(trainer)
+          last_save = time.time()
+      if FLAGS.max_steps is not None and steps > FLAGS.max_steps:
+        logging.info("Done training -- max_steps limit reached.")
+        break
+    else:
+      logging.info("Done training -- epoch limit reached.")
+    if self.is_master:
+      self.save(trainer)
+    logging.info("Exited training loop.")
+    return trainer
+
+  def save(self, trainer):
+    path = utils.save_checkpoint(self.train_dir, trainer.global_step, trainer.export_state(),
+                                 {"m": trainer.adam_m.cpu(), "v": trainer.adam_v.cpu()},
+                                 {"model": self.model_name, "moe_num_mixtures": FLAGS.moe_num_mixtures,
+                                  "feature_names": FLAGS.feature_names, "feature_sizes": FLAGS.feature_sizes})
+    logging.info("Saved checkpoint %s", path)
+
+
+def main(unused_argv=None):
+  logging.basicConfig(level=logging.INFO, format="%(levelname)s:%(message)s")
+  rest = FLAGS.parse()
+  if rest:
+    logging.warning("ignoring positional arguments %s", rest)
+  if not torch.cuda.is_available():
+    raise SystemExit("train.py: no CUDA device; the yt8m_b200 path has no CPU fallback")
+  rank, world, local_rank = yt8m_dp.init_from_env()
+  torch.cuda.set_device(local_rank)
+  logging.info("rank %d / %d: torch %s", rank, world, torch.__version__)
+  Trainer(FLAGS.model, get_reader(), FLAGS.train_dir, is_master=(rank == 0)).run(start_new_model=FLAGS.start_new_model)
+
+
+if __name__ == "__main__":
+  main(sys.argv)
