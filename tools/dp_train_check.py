@@ -1,0 +1,53 @@
+"""torchrun --nproc-per-node N tools/dp_train_check.py : N-rank data-parallel training of the MoE head equals the
+single-process run on the concatenated batch; rank 0 prints the verdict."""
+import math, os, sys
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in ("youtube-8m_b200", "tests", ""):
+  sys.path.insert(0, os.path.join(ROOT, p))
+import synth, yt8m_dp, yt8m_trainer
+
+rank, world, local = yt8m_dp.init_from_env()
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+B, D, V, M = 256, 1024, 4716, 2
+g = torch.Generator().manual_seed(0)
+x = torch.randn(B, D, generator=g)
+x = synth.bf16r(x * torch.rsqrt((x * x).sum(1, keepdim=True)))
+y = synth.labels(B, V)
+gain = math.sqrt(D) / 4
+sd = {"gates/weights": synth.xavier((D, V * (M + 1)), g, gain), "experts/weights": synth.xavier((D, V * M), g, gain),
+      "experts/biases": torch.zeros(V * M)}
+
+def run(group_world):
+  t = yt8m_trainer.HeadTrainer("moe", D, V, mixtures=M, device=dev)
+  if group_world == 1:
+    t.world, t.group = 1, None
+    lo, hi = 0, B
+  else:
+    lo, hi = yt8m_dp.shard_rows(B)
+  t.import_state({k: v.to(dev) for k, v in sd.items()})
+  for _ in range(3):
+    if group_world == 1:
+      # single-process reference: bypass the collective
+      import yt8m_dp as dp
+      saved = dp.all_reduce_sum_
+      dp.all_reduce_sum_ = lambda flat, group=None: flat
+      t.step(x[lo:hi].to(dev).to(torch.bfloat16), y[lo:hi].to(dev), global_batch=B)
+      dp.all_reduce_sum_ = saved
+    else:
+      t.step(x[lo:hi].to(dev).to(torch.bfloat16), y[lo:hi].to(dev), global_batch=B)
+  torch.cuda.synchronize()
+  return t.param.clone()
+
+dp_param = run(world)
+single = run(1)
+diff = float((dp_param - single).abs().max())
+moved = float((single - single.new_zeros(1)).abs().max())
+all_same = torch.tensor([diff], device=dev)
+if world > 1:
+  torch.distributed.all_reduce(all_same, op=torch.distributed.ReduceOp.MAX)
+if rank == 0:
+  print("DP world=%d vs single process: max |dparam| = %.3e (lr-scale 1e-2)  -> %s" % (world, float(all_same), "OK" if float(all_same) < 2e-4 else "MISMATCH"))
+if world > 1:
+  torch.distributed.destroy_process_group()

@@ -34,7 +34,9 @@ t = buf.cpu().tolist()
 names = {0: "prod: p0 start", 1: "prod: p0 loads issued", 2: "prod: p1 loads issued", 8: "mma: iter start", 9: "mma: first x tile landed",
          10: "mma: s_full committed", 11: "mma: a_ready seen", 12: "mma: last group committed", 16: "epi: iter start",
          17: "epi: s_full seen", 18: "epi: softmax done", 19: "epi: group0 ready", 20: "epi: group1 ready", 21: "epi: group2 ready",
-         22: "epi: group3 ready", 23: "epi: group4 ready", 26: "epi: epilogue done", 27: "epi: rescale done"}
+         22: "epi: group3 ready", 23: "epi: group4 ready", 26: "epi: epilogue done", 3: "epi: group0 drained", 4: "epi: group1 drained", 5: "epi: group2 drained", 6: "epi: group3 drained",
+         7: "epi: group4 drained", 13: "mma: group0 issued", 14: "mma: group1 issued", 15: "mma: group2 issued", 25: "mma: group3 issued",
+         28: "mma: group4 issued", 27: "epi: rescale done"}
 t0 = min(v for v in t if v > 0)
 for it in range(4):
   ev = [(t[it * 32 + s] - t0, names[s]) for s in names if t[it * 32 + s] > 0]

@@ -285,6 +285,7 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           }
         }
         if (elect_one()) umma_commit(&v_full[buf]);
+        if (lane == 0 && g < 5) NV_T(g < 3 ? 13 + g : (g == 3 ? 25 : 28));
         if (lane == 0 && g == NG - 1) NV_T(12);
         __syncwarp();
       }
@@ -442,6 +443,7 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&v_empty[buf]);
+        if (et == 0 && g < 5) NV_T(3 + g);
       }
       if (kRegAcc) {
 #pragma unroll
