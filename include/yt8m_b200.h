@@ -127,11 +127,13 @@ int yt8m_attn_pool_fwd(const float* logits, long long ld_logits, const yt8m_bf16
 /* ---- NetVLAD (not in the reference; definition in oracle/yt8m_oracle.py:netvlad_pool) -----------
  * FUSED soft-assignment GEMM + masked softmax over K + residual aggregation GEMM + intra-norm +
  * final L2 norm.  x: bf16 [B, T, D]; cw_packed: bf16 [K, D]; scale/shift: [K] (folded BN or bias);
- * cw2: fp32 [D, K].  out: [B, D*K] (D-major, K-minor).  K in {16..128, multiple of 16}, D % 64 == 0. */
+ * cw2: fp32 [D, K]; cw2_hi / cw2_lo (nullable): its bf16 hi/lo split [D, K] -- with them, K = 64 and a dense
+ * output (ld_out = D*K) the residual runs on the tensor cores and the descriptor is written through TMA.
+ * out: [B, D*K] (D-major, K-minor).  K in {32, 64, 128}, D % 128 == 0, T <= 384. */
 int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K,
                      const yt8m_bf16* cw_packed, const float* scale, const float* shift, const float* cw2,
-                     float* out_f32, yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out,
-                     yt8m_stream_t stream);
+                     const yt8m_bf16* cw2_hi, const yt8m_bf16* cw2_lo, float* out_f32, yt8m_bf16* out_hi,
+                     yt8m_bf16* out_lo, long long ld_out, yt8m_stream_t stream);
 
 /* debug only: device buffer (>= 128 u64, or NULL to disable) that receives globaltimer stamps of the
  * NetVLAD kernel's phases for CTA 0 (tools/netvlad_timeline.py decodes them) */

@@ -325,7 +325,8 @@ class NetVLADModel(models.BaseModel):
       scale = None
       shift = st.get("cluster_biases", (cluster_size,), ops.random_normal(1 / math.sqrt(d)), round_bf16=False).value
     cwp = st.packed(cw, "kmajor", lambda: nat.pack_transpose(cw.value))
-    vlad_hi, vlad_lo, _ = nat.netvlad_fwd(x, nf, cwp, scale, shift, cw2.value, want_lo=True)
+    c2split = st.packed(cw2, "hi_lo", lambda: nat.split_bf16(cw2.value))     # residual centres as tensor-core operands
+    vlad_hi, vlad_lo, _ = nat.netvlad_fwd(x, nf, cwp, scale, shift, cw2.value, want_lo=True, cw2_split=c2split)
 
     hw = st.get("hidden1_weights", (cluster_size * d, hidden1_size), ops.random_normal(1 / math.sqrt(cluster_size)))
     hwp = st.packed(hw, "kmajor", lambda: nat.pack_transpose(hw.value))

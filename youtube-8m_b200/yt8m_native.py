@@ -51,7 +51,7 @@ _SIGS = {
     "yt8m_attn_pool_fwd": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     "yt8m_netvlad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "yt8m_debug_set_timeline": (c_int, [c_void_p]),
     "yt8m_debug_set_flags": (c_int, [c_int]),
     "yt8m_context_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
@@ -302,15 +302,19 @@ def attn_pool(logits, feats, num_frames, heads, mode, want_bf16=True):
   return out, oh, ol
 
 
-def netvlad_fwd(x, num_frames, cw_packed, scale, shift, cw2, want_f32=False, want_lo=False):
-  """x bf16 [B, T, D]; cw_packed bf16 [K, D]; cw2 fp32 [D, K] -> bf16 hi [B, D*K] (+lo, +fp32)."""
+def netvlad_fwd(x, num_frames, cw_packed, scale, shift, cw2, want_f32=False, want_lo=False, cw2_split=None):
+  """x bf16 [B, T, D]; cw_packed bf16 [K, D]; cw2 fp32 [D, K] (cw2_split = its (hi, lo) bf16 copies, made on
+  demand) -> bf16 hi [B, D*K] (+lo, +fp32)."""
   b, t, d = x.shape
   k = cw_packed.shape[0]
+  if cw2_split is None and k == 64:
+    cw2_split = split_bf16(cw2.contiguous())
+  c2h, c2l = cw2_split if cw2_split is not None else (None, None)
   oh = _bf16((b, d * k), x.device)
   ol = _bf16((b, d * k), x.device) if want_lo else None
   of = _f32((b, d * k), x.device) if want_f32 else None
-  _call("yt8m_netvlad_fwd", _p(x), _p(num_frames), b, t, d, k, _p(cw_packed), _p(scale), _p(shift), _p(cw2), _p(of), _p(oh),
-        _p(ol), d * k, _stream())
+  _call("yt8m_netvlad_fwd", _p(x), _p(num_frames), b, t, d, k, _p(cw_packed), _p(scale), _p(shift), _p(cw2), _p(c2h), _p(c2l),
+        _p(of), _p(oh), _p(ol), d * k, _stream())
   return oh, ol, of
 
 
