@@ -543,17 +543,24 @@ struct Nv3Cfg {
   static constexpr int kOffDiag = kOffA + kNtMax * kATileBytes;           // 176 KB
   static constexpr int kOffStage = kOffDiag + 2 * kDiagBytes;             // 192 KB
   static constexpr int kOffSmall = kOffStage + 2 * kSlotBytes;            // 224 KB
-  static constexpr int kSmallBytes = 5 * KC * 4 + 512;
+  static constexpr int kSmallBytes = 6 * KC * 4 + 512;         // scale, shift, asum, ssq, fscale[2] + barriers
   static constexpr int kTotal = kOffSmall + kSmallBytes + 1024;
   static_assert(kTotal <= 227 * 1024, "NetVLAD v3 shared-memory budget exceeded");
 };
 
-__global__ void __launch_bounds__(kNvThreads, 1)
+// Warpgroups: WG0 = warps 0-3 (X producer, MMA issuer, centre producer, idle), WG1 = warps 4-7 (softmax +
+// accumulator epilogue, one TMEM lane quadrant each), WG2 = warps 8-11 (final rescale of the PREVIOUS video, off
+// the critical path).  setmaxnreg hands WG1 the registers the other two do not need.
+constexpr int kNv3Threads = 384;
+
+__global__ void __launch_bounds__(kNv3Threads, 1)
 netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_cw,
                   const __grid_constant__ CUtensorMap tm_c2_hi, const __grid_constant__ CUtensorMap tm_c2_lo,
                   const __grid_constant__ CUtensorMap tm_out_hi, const __grid_constant__ CUtensorMap tm_out_lo,
                   const int* __restrict__ num_frames, int B, int T, int D, const float* __restrict__ scale,
-                  const float* __restrict__ shift, float* __restrict__ out_f32, int want_lo, long long ld_out) {
+                  const float* __restrict__ shift, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
+                  __nv_bfloat16* __restrict__ out_lo, long long ld_out) {
+  const int want_lo = out_lo != nullptr;
   using C = Nv3Cfg;
   constexpr int KC = C::KC;
   extern __shared__ uint8_t smem_raw[];
@@ -569,8 +576,8 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   float* shift_s = scale_s + KC;
   float* asum_s = shift_s + KC;
   float* ssq_s = asum_s + KC;
-  float* fscale_s = ssq_s + KC;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(fscale_s + KC);
+  float* fscale_s = ssq_s + KC;                   // [2][KC]: final per-cluster scale of video parity p (intra-norm x global norm)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(fscale_s + 2 * KC);
   uint64_t* cw_full = bars;                       // [2]
   uint64_t* cw_empty = cw_full + 2;               // [2]
   uint64_t* x_full = cw_empty + 2;                // [3]
@@ -579,8 +586,9 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   uint64_t* a_ready = s_full + 1;
   uint64_t* v_full = a_ready + 1;                 // [2]
   uint64_t* v_empty = v_full + 2;                 // [2]
-  uint64_t* stage_bar = v_empty + 2;              // rescale: stash tile landed in the staging buffer
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(stage_bar + 1);
+  uint64_t* resc_go = v_empty + 2;                // [2] WG1 -> WG2: stash of video parity p complete, fscale_s[p] valid
+  uint64_t* resc_done = resc_go + 2;              // [2] WG2 -> WG1: fscale_s[p] may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(resc_done + 2);
   float* total_s = reinterpret_cast<float*>(tmem_slot + 1);
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for ptxas
@@ -599,11 +607,11 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     mbar_init(s_full, 1);
     mbar_init(a_ready, 4);
     for (int i = 0; i < 2; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 4); }
-    mbar_init(stage_bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&resc_go[i], 1); mbar_init(&resc_done[i], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  for (int k = threadIdx.x; k < KC; k += kNvThreads) {
+  for (int k = threadIdx.x; k < KC; k += kNv3Threads) {
     scale_s[k] = scale ? scale[k] : 1.0f;
     shift_s[k] = shift ? shift[k] : 0.0f;
   }
@@ -612,6 +620,8 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+  setmaxnreg_dec<64>();
   if (warp == 0) {
     // =================================== X / cw2 producer ===================================
     RingPos xr{0, 0};
@@ -658,7 +668,7 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
       if (lane == 0) NV_T(2);
     }
-  } else if (warp == 6) {
+  } else if (warp == 2) {
     // =================================== assignment-centre (Cw) producer ===================================
     RingPos cr{0, 0};
     for (int it = 0; it < n_iter; ++it)
@@ -766,15 +776,16 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         __syncwarp();
       }
     }
-  } else {
-    // ============================ softmax + epilogue warps (128 threads) ============================
+  }
+  } else if (warp < 8) {
+    setmaxnreg_inc<232>();
+    // ============================ WG1: softmax + accumulator epilogue (128 threads) ============================
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;                       // 0..127 (warps 2..5)
-    const bool boss = (warp == 2);                          // warp whose elected lane owns the TMA store groups
+    const int et = threadIdx.x - 128;                      // 0..127 (warps 4..7)
+    const bool boss = (warp == 4);                          // warp whose elected lane owns the TMA store groups
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     int gidx = 0;
-    uint32_t stage_phase = 0;
     for (int it = 0; it < n_iter; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       const int nf = min(max(num_frames[b], 0), T);
@@ -900,67 +911,77 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const float tot = warp_transpose_reduce32(acc + c, lane);
         atomicAdd(&ssq_s[c + lane], tot);
       }
-      // ------------------------------- rescale (through the staging tile) -------------------------------
-      if (boss && elect_one()) bulk_wait_group0();           // every stash store is complete (visible to the loads below)
-      named_bar_sync(1, 128);
+      // ------------------------------- hand the video over to the rescale warpgroup -------------------------------
+      const int p = it & 1;
+      if (it >= 2) mbar_wait(&resc_done[p], ((it >> 1) - 1) & 1);     // WG2 finished with fscale_s[p] (video it-2)
+      named_bar_sync(1, 128);                                         // ssq_s complete
       if (et == 0) NV_T(26);
       if (et < KC) {
         const float ss = ssq_s[et];
         const float rs = rsqrtf(fmaxf(ss, 1e-12f));
-        fscale_s[et] = rs;
+        fscale_s[p * KC + et] = rs;
         atomicAdd(total_s, ss * rs * rs);
       }
       named_bar_sync(1, 128);
-      const float gs = rsqrtf(fmaxf(*total_s, 1e-12f));
-      float fs[KC];
-#pragma unroll
-      for (int k = 0; k < KC; ++k) fs[k] = fscale_s[k] * gs;
+      if (et < KC) fscale_s[p * KC + et] *= rsqrtf(fmaxf(*total_s, 1e-12f));
+      if (boss && elect_one()) bulk_wait_group0();                    // every stash store has been performed
+      __threadfence();
+      named_bar_sync(1, 128);
+      if (et == 0) { mbar_arrive(&resc_go[p]); NV_T(27); }
+    }
+    tc_fence_before();
+  } else {
+    setmaxnreg_dec<104>();
+    // ============================ WG2: final rescale of video it (coalesced, latency-tolerant) ============================
+    const int rt = threadIdx.x - 256;                      // 0..127
+    for (int it = 0; it < n_iter; ++it) {
+      const int b = blockIdx.x + it * gridDim.x;
+      const int p = it & 1;
+      mbar_wait(&resc_go[p], (it >> 1) & 1);
+      const float* fsp = fscale_s + p * KC;
+      __nv_bfloat16* ohi = out_hi + static_cast<long long>(b) * ld_out;
+      __nv_bfloat16* olo = out_lo ? out_lo + static_cast<long long>(b) * ld_out : nullptr;
       float* of = out_f32 ? out_f32 + static_cast<long long>(b) * ld_out : nullptr;
-      for (int m = 0; m < NMB; ++m) {
-        if (boss && elect_one()) {
-          bulk_wait_group_read0();                             // staging tile free
-          mbar_arrive_expect_tx(stage_bar, want_lo ? 2 * kSlotBytes : kSlotBytes);
-          tma_load_2d(stage_hi, &tm_out_hi, stage_bar, 0, b * D + m * 128, kEvictFirst);
-          if (want_lo) tma_load_2d(stage_lo, &tm_out_lo, stage_bar, 0, b * D + m * 128, kEvictFirst);
-        }
-        mbar_wait(stage_bar, stage_phase);
-        stage_phase ^= 1u;
+      const long long n = static_cast<long long>(D) * KC;
+      constexpr int kU = 4;
+      for (long long e0 = static_cast<long long>(rt) * 8; e0 < n; e0 += 128 * 8 * kU) {
+        uint4 h[kU], lw[kU];
 #pragma unroll
-        for (int c8 = 0; c8 < 8; ++c8) {
-          const uint4 h = *reinterpret_cast<const uint4*>(stage_hi + sw128_offset(row, c8));
-          uint4 lw = make_uint4(0, 0, 0, 0);
-          if (want_lo) lw = *reinterpret_cast<const uint4*>(stage_lo + sw128_offset(row, c8));
-          const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
-          const uint32_t lv[4] = {lw.x, lw.y, lw.z, lw.w};
+        for (int u = 0; u < kU; ++u) {
+          const long long e = e0 + static_cast<long long>(u) * 128 * 8;
+          h[u] = make_uint4(0, 0, 0, 0);
+          lw[u] = make_uint4(0, 0, 0, 0);
+          if (e < n) {
+            h[u] = ld_global_hint(ohi + e, kEvictFirst);
+            if (olo) lw[u] = ld_global_hint(olo + e, kEvictFirst);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < kU; ++u) {
+          const long long e = e0 + static_cast<long long>(u) * 128 * 8;
+          if (e >= n) break;
+          const int k0 = static_cast<int>(e % KC);
+          const uint32_t hw[4] = {h[u].x, h[u].y, h[u].z, h[u].w};
+          const uint32_t lv[4] = {lw[u].x, lw[u].y, lw[u].z, lw[u].w};
           float v[8];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            v[2 * j] = (__uint_as_float(hw[j] << 16) + __uint_as_float(lv[j] << 16)) * fs[c8 * 8 + 2 * j];
-            v[2 * j + 1] = (__uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lv[j] & 0xFFFF0000u)) * fs[c8 * 8 + 2 * j + 1];
+            v[2 * j] = (__uint_as_float(hw[j] << 16) + __uint_as_float(lv[j] << 16)) * fsp[k0 + 2 * j];
+            v[2 * j + 1] = (__uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lv[j] & 0xFFFF0000u)) * fsp[k0 + 2 * j + 1];
           }
           uint4 nh, nl;
           pack8_hi_lo(v, nh, nl);
-          *reinterpret_cast<uint4*>(stage_hi + sw128_offset(row, c8)) = nh;
-          if (want_lo) *reinterpret_cast<uint4*>(stage_lo + sw128_offset(row, c8)) = nl;
+          *reinterpret_cast<uint4*>(ohi + e) = nh;
+          if (olo) *reinterpret_cast<uint4*>(olo + e) = nl;
           if (of) {
-            float* o = of + static_cast<long long>(m * 128 + row) * KC + c8 * 8;
-            *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-            *reinterpret_cast<float4*>(o + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            *reinterpret_cast<float4*>(of + e) = make_float4(v[0], v[1], v[2], v[3]);
+            *reinterpret_cast<float4*>(of + e + 4) = make_float4(v[4], v[5], v[6], v[7]);
           }
         }
-        fence_proxy_async();
-        named_bar_sync(1, 128);
-        if (boss && elect_one()) {
-          tma_store_2d(&tm_out_hi, stage_hi, 0, b * D + m * 128);
-          if (want_lo) tma_store_2d(&tm_out_lo, stage_lo, 0, b * D + m * 128);
-          bulk_commit_group();
-        }
-        __syncwarp();
       }
-      if (et == 0) NV_T(27);
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbar_arrive(&resc_done[p]);
     }
-    if (boss && elect_one()) bulk_wait_group0();
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 1) {
@@ -997,8 +1018,9 @@ int launch_netvlad_v3(const yt8m_bf16* x, const int* num_frames, int B, int T, i
     attr_done = true;
   }
   const int grid = B < kNvSms ? B : kNvSms;
-  netvlad_v3_kernel<<<grid, kNvThreads, C::kTotal, stream>>>(tm_x, tm_cw, tm_c2_hi, tm_c2_lo, tm_out_hi, tm_out_lo, num_frames, B, T, D,
-                                                             scale, shift, out_f32, out_lo ? 1 : 0, ld_out);
+  netvlad_v3_kernel<<<grid, kNv3Threads, C::kTotal, stream>>>(tm_x, tm_cw, tm_c2_hi, tm_c2_lo, tm_out_hi, tm_out_lo, num_frames, B, T, D,
+                                                              scale, shift, out_f32, reinterpret_cast<__nv_bfloat16*>(out_hi),
+                                                              reinterpret_cast<__nv_bfloat16*>(out_lo), ld_out);
   return check_launch("netvlad_v3_kernel");
 }
 
