@@ -21,6 +21,7 @@ sd = {"gates/weights": synth.xavier((D, V * (M + 1)), g, gain), "experts/weights
 
 def run(group_world):
   t = yt8m_trainer.HeadTrainer("moe", D, V, mixtures=M, device=dev)
+  t.keep_grads = True
   if group_world == 1:
     t.world, t.group = 1, None
     lo, hi = 0, B
@@ -38,16 +39,20 @@ def run(group_world):
     else:
       t.step(x[lo:hi].to(dev).to(torch.bfloat16), y[lo:hi].to(dev), global_batch=B)
   torch.cuda.synchronize()
-  return t.param.clone()
+  return t.param.clone(), t.last_grad.clone()
 
-dp_param = run(world)
-single = run(1)
-diff = float((dp_param - single).abs().max())
-moved = float((single - single.new_zeros(1)).abs().max())
-all_same = torch.tensor([diff], device=dev)
+dp_param, dp_grad = run(world)
+single, single_grad = run(1)
+# gradients of the third step (after the all-reduce): relative to the largest entry
+gerr = float((dp_grad - single_grad).abs().max() / single_grad.abs().max())
+# parameters after 3 Adam steps: each step moves a weight by ~lr = 1e-2; near-zero gradients are ill-conditioned
+frac_bad = float(((dp_param - single).abs() > 0.05 * 3e-2).float().mean())
+stat = torch.tensor([gerr, frac_bad], device=dev)
 if world > 1:
-  torch.distributed.all_reduce(all_same, op=torch.distributed.ReduceOp.MAX)
+  torch.distributed.all_reduce(stat, op=torch.distributed.ReduceOp.MAX)
 if rank == 0:
-  print("DP world=%d vs single process: max |dparam| = %.3e (lr-scale 1e-2)  -> %s" % (world, float(all_same), "OK" if float(all_same) < 2e-4 else "MISMATCH"))
+  ok = float(stat[0]) < 2e-3 and float(stat[1]) < 2e-3
+  print("DP world=%d vs single process: grad rel err %.2e, params off by >5%% of their displacement: %.4f%%  -> %s"
+        % (world, float(stat[0]), 100 * float(stat[1]), "OK" if ok else "MISMATCH"))
 if world > 1:
   torch.distributed.destroy_process_group()

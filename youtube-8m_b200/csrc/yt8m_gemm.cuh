@@ -70,6 +70,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   const int kb_begin = split * shape.kb_per_split;
   const int kb_end = min(kb_begin + shape.kb_per_split, num_kb_total);
   const int num_kb = kb_end - kb_begin;
+  // CTAs that share an operand tile (same m_tile or same n_tile) start their K loop at different k-blocks, so they do
+  // not all request the same L2 lines at the same instant (no TMA multicast in this kernel)
+  const int kb_rot = num_kb > 0 ? static_cast<int>((n_tile * 5u + m_tile * 3u) % static_cast<unsigned>(num_kb)) : 0;
   constexpr uint32_t kTmemCols = tmem_cols_for(BLOCK_N);
 
   if (warp == 0 && lane == 0) {
@@ -93,7 +96,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     // ------------------------------- TMA producer: A (hi [+ lo]) -------------------------------
     int stage = 0;
     uint32_t phase = 0;
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
+    for (int kbi = 0; kbi < num_kb; ++kbi) {
+      const int kb = kb_begin + (kbi + kb_rot >= num_kb ? kbi + kb_rot - num_kb : kbi + kb_rot);
       mbar_wait(&empty_bar[stage], phase ^ 1u);
       if (elect_one()) {
         uint8_t* st = tiles + stage * S::kStageBytes;
@@ -118,7 +122,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     // ------------------------------- TMA producer: W -------------------------------------------
     int stage = 0;
     uint32_t phase = 0;
-    for (int kb = kb_begin; kb < kb_end; ++kb) {
+    for (int kbi = 0; kbi < num_kb; ++kbi) {
+      const int kb = kb_begin + (kbi + kb_rot >= num_kb ? kbi + kb_rot - num_kb : kbi + kb_rot);
       mbar_wait(&empty_bar[stage], phase ^ 1u);
       if (elect_one()) {
         uint8_t* st = tiles + stage * S::kStageBytes;
