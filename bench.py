@@ -122,7 +122,7 @@ def pick_threads(fn):
   return best
 
 
-def time_cpu(sample, min_seconds=10.0, max_reps=50):
+def time_cpu(sample, min_seconds=10.0, max_reps=100000):
   fn, n = cpu_forward_fn(sample)
   threads = pick_threads(fn)             # also the warm-up (pages in the 300 MB of fp32 weights)
   reps, t0 = 0, time.perf_counter()
