@@ -19,7 +19,6 @@ namespace yt8m {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 bf16 = 128 B = one SWIZZLE_128B row
 constexpr int kUmmaK = 16;
-constexpr int kGemmPf = 8;             // L2 prefetch distance in k-blocks (on top of the shared-memory ring)
 constexpr int kGemmThreads = 224;     // warp 0: A producer, 1: MMA, 2-5: epilogue, 6: W producer
 
 struct GemmShape {
@@ -114,12 +113,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
         } else {
           tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal);
           if (A_SPLIT == 2) tma_load_2d(st + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal);
-          if (kbi + kGemmPf < num_kb) {                      // L2 prefetch a few stages ahead (latency-bound ring)
-            const int r = kbi + kGemmPf + kb_rot;
-            const int pk = kb_begin + (r >= num_kb ? r - num_kb : r);
-            tma_prefetch_2d(&tm_a_hi, pk * kBlockK, m_tile * kBlockM);
-            if (A_SPLIT == 2) tma_prefetch_2d(&tm_a_lo, pk * kBlockK, m_tile * kBlockM);
-          }
         }
       }
       __syncwarp();
@@ -141,11 +134,6 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
             tma_load_2d(st + A_SPLIT * S::kABytes + h * 16384, &tm_b, &full_bar[stage], n_tile * BLOCK_N + h * 64, kb * 128, kEvictNormal);
         } else {
           tma_load_2d(st + A_SPLIT * S::kABytes, &tm_b, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N, kEvictNormal);
-          if (kbi + kGemmPf < num_kb) {
-            const int r = kbi + kGemmPf + kb_rot;
-            const int pk = kb_begin + (r >= num_kb ? r - num_kb : r);
-            tma_prefetch_2d(&tm_b, pk * kBlockK, n_tile * BLOCK_N);
-          }
         }
       }
       __syncwarp();

@@ -601,7 +601,6 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const int n_iter = (B - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) / static_cast<int>(gridDim.x);
   // the last frame tile is loaded with a 64-row box when it holds <= 64 frames (T = 300: 44): 17 % less X traffic
   const bool short_last = (T - (NT - 1) * 128) <= 64;
-  constexpr int kPf = 8;                          // L2 prefetch distance of the HBM phase, in ring ops
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_cw); tma_prefetch_desc(&tm_c2_hi); tma_prefetch_desc(&tm_c2_lo);
@@ -632,14 +631,6 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     for (int it = 0; it < n_iter; ++it) {
       const int b = blockIdx.x + it * gridDim.x;
       if (lane == 0) NV_T(0);
-      const int n_p0 = (NKB / 2) * NT;
-      if (it == 0 && elect_one()) {                                   // prime the L2 prefetch window of the first video
-        for (int j = 0; j < kPf && j < n_p0; ++j) {
-          const int pi = j % NT, pk = j / NT;
-          tma_prefetch_4d((short_last && pi == NT - 1) ? &tm_x64 : &tm_x, 0, pi * 128, 2 * pk, b);
-        }
-      }
-      __syncwarp();
       for (int kbp = 0; kbp < NKB / 2; ++kbp)
         for (int i = 0; i < NT; ++i) {
           mbar_wait(&x_empty[xr.slot], xr.phase ^ 1u);
@@ -647,13 +638,6 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
             const bool sh = short_last && i == NT - 1;
             mbar_arrive_expect_tx(&x_full[xr.slot], sh ? C::kXSlotBytes / 2 : C::kXSlotBytes);
             tma_load_4d(xs + xr.slot * C::kXSlotBytes, sh ? &tm_x64 : &tm_x, &x_full[xr.slot], 0, i * 128, 2 * kbp, b, kEvictNormal);
-            // L2 prefetch kPf ops ahead; past the end of this video it reaches into the next one
-            int j = kbp * NT + i + kPf, pb = b;
-            if (j >= n_p0) { j -= n_p0; pb = b + gridDim.x; }
-            if (pb < B && j < n_p0) {
-              const int pi = j % NT, pk = j / NT;
-              tma_prefetch_4d((short_last && pi == NT - 1) ? &tm_x64 : &tm_x, 0, pi * 128, 2 * pk, pb);
-            }
           }
           __syncwarp();
           xr.advance(C::kSlots);
