@@ -1,0 +1,115 @@
+"""GPU edge cases the reference's data can produce: single-video batches, one-frame / zero-frame videos, ragged
+num_frames, tiny dimensions, all-padding rows -- CUDA vs oracle."""
+import math
+
+import pytest
+import torch
+
+import synth
+from oracle import yt8m_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture(scope="module")
+def nat():
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  import yt8m_native
+  return yt8m_native
+
+
+def bf(x):
+  return x.to(torch.bfloat16).to(DEV)
+
+
+def rel(got, want):
+  return float((got.float().cpu() - want).abs().max() / want.abs().max().clamp_min(1e-30))
+
+
+def test_netvlad_zero_one_and_full_frames(nat):
+  g = torch.Generator().manual_seed(0)
+  b, t, d, k = 5, 300, 1152, 64
+  x, nf, _ = synth.model_input(b, t, d, seed=20)
+  nf = torch.tensor([0, 1, 44, 129, 300], dtype=torch.int32)
+  x = x * (torch.arange(t).unsqueeze(0) < nf.unsqueeze(1)).float().unsqueeze(2)     # reader pads with zeros
+  cw, cw2 = synth.normal((d, k), g, 4.0), synth.normal((d, k), g, 1 / math.sqrt(d))
+  want = O.netvlad_pool(x, nf, cw, torch.ones(k), torch.zeros(k), cw2)
+  hi, lo, f32 = nat.netvlad_fwd(bf(x), nf.to(DEV), nat.pack_transpose(cw.to(DEV)), None, None, cw2.to(DEV), want_f32=True, want_lo=True)
+  assert float(f32[0].abs().max()) == 0.0 and float(want[0].abs().max()) == 0.0           # no frames -> zero descriptor
+  assert bool(torch.isfinite(f32).all())
+  assert float((f32.cpu() - want).norm() / want.norm()) < 1e-3
+  for i in range(1, b):
+    assert abs(float(f32[i].norm()) - 1.0) < 1e-3
+
+
+def test_single_video_and_single_row(nat):
+  g = torch.Generator().manual_seed(1)
+  x, nf, _ = synth.model_input(1, 300, 1152, seed=21)
+  cw, cw2 = synth.normal((1152, 64), g, 4.0), synth.normal((1152, 64), g, 0.03)
+  want = O.netvlad_pool(x, nf, cw, torch.ones(64), torch.zeros(64), cw2)
+  _, _, f32 = nat.netvlad_fwd(bf(x), nf.to(DEV), nat.pack_transpose(cw.to(DEV)), None, None, cw2.to(DEV), want_f32=True)
+  assert float((f32.cpu() - want).norm() / want.norm()) < 1e-3
+  # MoE / linear with one row and tiny shapes
+  d, v, m = 8, 3, 2
+  gw, ew, eb = synth.xavier((d, v * 3), g, 2.0), synth.xavier((d, v * 2), g, 2.0), 0.1 * torch.randn(v * 2, generator=g)
+  xr = synth.bf16r(torch.randn(1, d, generator=g))
+  wp, bp = nat.moe_pack(gw.to(DEV), ew.to(DEV), eb.to(DEV), v, m)
+  assert rel(nat.moe_fwd(bf(xr), wp, bp, v, m), O.moe_model(xr, gw, ew, eb, v, m)) < 1e-5
+  w = synth.xavier((d, 1), g)
+  got = nat.linear(bf(xr), nat.pack_transpose(w.to(DEV)), n=1, k=d)["f32"]
+  assert rel(got, xr @ w) < 1e-5
+
+
+def test_lstm_ragged_including_zero_length(nat):
+  g = torch.Generator().manual_seed(2)
+  b, t, d, h = 6, 9, 64, 32
+  x = synth.bf16r(torch.randn(b, t, d, generator=g) * 0.5)
+  nf = torch.tensor([0, 1, 9, 5, 2, 9], dtype=torch.int32)
+  ws = [(synth.xavier((d + h, 4 * h), g, 2.0), 0.1 * torch.randn(4 * h, generator=g)), (synth.xavier((2 * h, 4 * h), g, 2.0), torch.zeros(4 * h))]
+  outs, states = O.dynamic_rnn_lstm(x, nf, ws)
+  packed = [nat.lstm_pack(w.to(DEV), bb.to(DEV), d if l == 0 else h, h) for l, (w, bb) in enumerate(ws)]
+  state, seq, _ = nat.lstm_fwd(bf(x), nf.to(DEV), [p[0] for p in packed], [p[1] for p in packed], h, want_seq=True)
+  assert rel(state, O.lstm_model_state(states)) < 1e-4
+  assert float(state[0].abs().max()) == 0.0                      # zero-length video keeps the zero state
+  assert rel(seq, outs) < 1e-4 and float(seq[0].abs().max()) == 0.0
+
+
+def test_attention_ragged_and_single_frame(nat):
+  g = torch.Generator().manual_seed(3)
+  b, t, a, f = 4, 300, 8, 1152
+  x, _, _ = synth.model_input(b, t, f, seed=22)
+  nf = torch.tensor([1, 2, 299, 300], dtype=torch.int32)
+  x = x * (torch.arange(t).unsqueeze(0) < nf.unsqueeze(1)).float().unsqueeze(2)
+  logits = torch.randn(b, t, a, generator=g)
+  mask = O.sequence_mask(nf, t).unsqueeze(2)
+  w = torch.softmax(logits, dim=1) * mask
+  w = w / w.sum(dim=1, keepdim=True)
+  want = torch.einsum("bta,btf->baf", w, x)
+  got, _, _ = nat.attn_pool(logits.to(DEV), bf(x), nf.to(DEV), a, 0)
+  assert rel(got, want) < 1e-5
+  assert torch.allclose(got[0, 3].cpu(), x[0, 0], atol=1e-6)      # one valid frame: the pool IS that frame
+  # non-zero-frame mask variant gives the same answer when padding rows are exactly zero
+  got2, _, _ = nat.attn_pool(logits.to(DEV), bf(x), None, a, 0)
+  assert rel(got2, want) < 1e-5
+
+
+def test_l2norm_all_padding_and_uint8_extremes(nat):
+  u8 = torch.zeros((2, 4, 64), dtype=torch.uint8)
+  u8[1] = 255
+  nf = torch.tensor([0, 4], dtype=torch.int32)
+  out, f32 = nat.l2norm_rows(u8.to(DEV), num_frames=nf.to(DEV), want_f32=True)
+  assert float(f32[0].abs().max()) == 0.0                        # padding rows stay zero, not Dequantize(0)
+  assert torch.allclose(f32[1].cpu(), torch.full((4, 64), 1 / 8.0), atol=1e-6)
+
+
+def test_topk_with_ties_and_k1(nat):
+  x = torch.zeros(3, 40)
+  x[0, 7] = x[0, 3] = 0.5
+  x[1, 39] = 1.0
+  idx, val = nat.topk_rows(x.to(DEV), 3)
+  assert idx[0].tolist()[:2] == [3, 7] and val[0].tolist()[:2] == [0.5, 0.5]      # ties: lower class index first
+  assert idx[1, 0].item() == 39 and idx[2].tolist() == [0, 1, 2]
+  idx1, _ = nat.topk_rows(x.to(DEV), 1)
+  assert idx1.flatten().tolist() == [3, 39, 0]
