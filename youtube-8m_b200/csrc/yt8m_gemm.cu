@@ -10,10 +10,10 @@ namespace {
 
 constexpr int kNumSms = 148;
 
-template <int BLOCK_N, int A_SPLIT, class Epi>
+template <int BLOCK_N, int A_SPLIT, class Epi, int MT = 1>
 int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, const yt8m_bf16* w, long long ldw, int M,
                 int N_rows_w, int N, int K, int split_k, const typename Epi::Params& ep, cudaStream_t stream) {
-  using S = GemmSmem<BLOCK_N, A_SPLIT>;
+  using S = GemmSmem<BLOCK_N, A_SPLIT, false, MT>;
   CUtensorMap tm_a_hi, tm_a_lo, tm_b;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tm_a_hi, a_hi, M, K, lda, kBlockM)) != YT8M_OK) return rc;
@@ -23,7 +23,7 @@ int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, con
     tm_a_lo = tm_a_hi;
   }
   if ((rc = make_tmap_bf16_2d(&tm_b, w, N_rows_w, K, ldw, BLOCK_N)) != YT8M_OK) return rc;
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_SPLIT, Epi>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_SPLIT, Epi, false, MT>;
   static bool attr_done = false;   // per template instantiation
   if (!attr_done) {
     YT8M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
@@ -34,7 +34,7 @@ int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, con
   shape.M = M; shape.N = N; shape.K = K;
   shape.kb_per_split = (num_kb + split_k - 1) / split_k;
   const int splits = (num_kb + shape.kb_per_split - 1) / shape.kb_per_split;
-  dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + kBlockM - 1) / kBlockM, splits);
+  dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + MT * kBlockM - 1) / (MT * kBlockM), splits);
   kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tm_a_hi, tm_a_lo, tm_b, shape, ep);
   return check_launch("gemm_tcgen05_kernel");
 }
@@ -120,8 +120,8 @@ __global__ void group_max_kernel(const float* __restrict__ in, long long groups,
   }
 }
 
-int pick_split_k(int M, int N, int K, int block_n) {
-  const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + block_n - 1) / block_n);
+int pick_split_k(int M, int N, int K, int block_n, int mt) {
+  const int tiles = ((M + mt * kBlockM - 1) / (mt * kBlockM)) * ((N + block_n - 1) / block_n);
   const int num_kb = (K + kBlockK - 1) / kBlockK;
   if (tiles >= kNumSms / 2 || num_kb < 16) return 1;
   int s = std::min(kNumSms / tiles, num_kb / 8);        // never spill into a second wave
@@ -149,7 +149,8 @@ int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda,
   YT8M_REQUIRE(out_f32 || out_hi, YT8M_E_BADPTR, "yt8m_linear_fwd: no output");
   YT8M_REQUIRE(ld_out >= N, YT8M_E_BADSHAPE, "yt8m_linear_fwd: ld_out < N");
   const int block_n = N <= 32 ? 32 : (N >= 512 && M > 128 ? 256 : 128);
-  int split_k = pick_split_k(M, N, K, block_n);
+  const int mt = M > kBlockM ? 2 : 1;                    // two accumulators per CTA share every W tile
+  int split_k = pick_split_k(M, N, K, block_n, mt);
   if (split_k > 1 && (!workspace || workspace_bytes < yt8m_linear_workspace_bytes(M, N, K))) split_k = 1;
 
   EpiLinear::Params ep;
@@ -162,9 +163,11 @@ int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda,
     ep.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo); ep.ld_out = ld_out;
   }
   int rc;
-#define YT8M_DISPATCH(BN)                                                                                       \
-  rc = a_lo ? launch_gemm<BN, 2, EpiLinear>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream)           \
-            : launch_gemm<BN, 1, EpiLinear>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream)
+#define YT8M_DISPATCH(BN)                                                                                              \
+  rc = mt == 2 ? (a_lo ? launch_gemm<BN, 2, EpiLinear, 2>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream)    \
+                       : launch_gemm<BN, 1, EpiLinear, 2>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream))   \
+               : (a_lo ? launch_gemm<BN, 2, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream)    \
+                       : launch_gemm<BN, 1, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream))
   if (block_n == 32) { YT8M_DISPATCH(32); }
   else if (block_n == 256) { YT8M_DISPATCH(256); }
   else { YT8M_DISPATCH(128); }
@@ -223,8 +226,11 @@ int yt8m_moe_fwd(const yt8m_bf16* x_hi, const yt8m_bf16* x_lo, long long ldx, co
   case NM: {                                                                                                \
     EpiMoe<NM>::Params ep;                                                                                  \
     ep.out = out; ep.ld_out = ld_out; ep.bias_packed = bias_packed; ep.vocab = vocab;                      \
-    return x_lo ? launch_gemm<128, 2, EpiMoe<NM>>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream) \
-                : launch_gemm<128, 1, EpiMoe<NM>>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream); \
+    if (B > 128)                                                                                            \
+      return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream) \
+                  : launch_gemm<128, 1, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream); \
+    return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 1>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream) \
+                : launch_gemm<128, 1, EpiMoe<NM>, 1>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream); \
   }
   switch (num_mixtures) {
     YT8M_MOE_CASE(1)

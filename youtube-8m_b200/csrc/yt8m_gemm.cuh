@@ -29,9 +29,12 @@ struct GemmShape {
 // MN = false: operands stored [rows, K] with K contiguous (forward / dgrad): stage = 64 K-elements.
 // MN = true : operands stored [K, rows] with the OUTPUT index contiguous (wgrad: out = A^T . B, contraction over
 //             the batch rows): stage = 128 contraction rows, tiles are 64-column boxes of 128 rows.
-template <int BLOCK_N, int A_SPLIT, bool MN = false>
+// MT = number of 128-row M tiles one CTA owns (1 or 2): with MT = 2 every W tile is used for 256 output rows, i.e.
+// 1.5x the tensor work per byte brought into shared memory -- the rings are bytes-in-flight / latency bound.
+template <int BLOCK_N, int A_SPLIT, bool MN = false, int MT = 1>
 struct GemmSmem {
-  static constexpr int kABytes = MN ? 2 * 128 * 128 : kBlockM * kBlockK * 2;      // 16 KB (K-major) / 32 KB (MN)
+  static constexpr int kATile = MN ? 2 * 128 * 128 : kBlockM * kBlockK * 2;       // one 128-row A tile: 16 KB (K-major) / 32 KB (MN)
+  static constexpr int kABytes = MT * kATile;                                      // all M tiles of one operand half (hi or lo)
   static constexpr int kBBytes = MN ? (BLOCK_N / 64) * 128 * 128 : BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = A_SPLIT * kABytes + kBBytes;
   static constexpr int kBudget = 200 * 1024;
@@ -49,11 +52,12 @@ __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n
 //                                       int n0 (global N index of tile col 0), uint32_t tmem_row_addr, bool row_valid); }
 // run() is called by every epilogue thread (uniformly per warp: tcgen05.ld is warp-collective).
 
-template <int BLOCK_N, int A_SPLIT, class Epi, bool MN = false>
+template <int BLOCK_N, int A_SPLIT, class Epi, bool MN = false, int MT = 1>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b, const GemmShape shape, const typename Epi::Params ep) {
-  using S = GemmSmem<BLOCK_N, A_SPLIT, MN>;
+  using S = GemmSmem<BLOCK_N, A_SPLIT, MN, MT>;
+  static_assert(MT * BLOCK_N <= 512, "accumulators exceed TMEM");
   constexpr int kStageK = MN ? 128 : kBlockK;          // contraction elements per pipeline stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -73,7 +77,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   // CTAs that share an operand tile (same m_tile or same n_tile) start their K loop at different k-blocks, so they do
   // not all request the same L2 lines at the same instant (no TMA multicast in this kernel)
   const int kb_rot = num_kb > 0 ? static_cast<int>((n_tile * 5u + m_tile * 3u) % static_cast<unsigned>(num_kb)) : 0;
-  constexpr uint32_t kTmemCols = tmem_cols_for(BLOCK_N);
+  constexpr uint32_t kTmemCols = tmem_cols_for(MT * BLOCK_N);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
@@ -102,17 +106,22 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       if (elect_one()) {
         uint8_t* st = tiles + stage * S::kStageBytes;
         mbar_arrive_expect_tx(&full_bar[stage], A_SPLIT * S::kABytes);
-        if (MN) {
-          // two 64-column boxes of 128 contraction rows per operand half
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            tma_load_2d(st + h * 16384, &tm_a_hi, &full_bar[stage], m_tile * kBlockM + h * 64, kb * 128, kEvictNormal);
-            if (A_SPLIT == 2)
-              tma_load_2d(st + S::kABytes + h * 16384, &tm_a_lo, &full_bar[stage], m_tile * kBlockM + h * 64, kb * 128, kEvictNormal);
+        for (int mt = 0; mt < MT; ++mt) {
+          const int row0 = (m_tile * MT + mt) * kBlockM;
+          uint8_t* at = st + mt * S::kATile;
+          if (MN) {
+            // two 64-column boxes of 128 contraction rows per operand half
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              tma_load_2d(at + h * 16384, &tm_a_hi, &full_bar[stage], row0 + h * 64, kb * 128, kEvictNormal);
+              if (A_SPLIT == 2)
+                tma_load_2d(at + S::kABytes + h * 16384, &tm_a_lo, &full_bar[stage], row0 + h * 64, kb * 128, kEvictNormal);
+            }
+          } else {
+            tma_load_2d(at, &tm_a_hi, &full_bar[stage], kb * kBlockK, row0, kEvictNormal);
+            if (A_SPLIT == 2) tma_load_2d(at + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, row0, kEvictNormal);
           }
-        } else {
-          tma_load_2d(st, &tm_a_hi, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal);
-          if (A_SPLIT == 2) tma_load_2d(st + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, m_tile * kBlockM, kEvictNormal);
         }
       }
       __syncwarp();
@@ -148,28 +157,34 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       if (elect_one()) {
-        const uint32_t a_addr = smem_u32(tiles + stage * S::kStageBytes);
-        if (MN) {
-          // MN-major SWIZZLE_128B: 8-row groups 1024 B apart (SBO), 64-column blocks one box apart (LBO);
-          // one UMMA consumes 16 contraction rows = 2048 B
-          const uint64_t adesc0 = make_sdesc_sw128(a_addr, 16384, 1024);
-          const uint64_t adesc1 = make_sdesc_sw128(a_addr + S::kABytes, 16384, 1024);
-          const uint64_t bdesc0 = make_sdesc_sw128(a_addr + A_SPLIT * S::kABytes, 16384, 1024);
+        const uint32_t s_addr = smem_u32(tiles + stage * S::kStageBytes);
+        const uint32_t b_addr = s_addr + A_SPLIT * S::kABytes;
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const uint64_t bdesc = sdesc_advance(bdesc0, k * 2048);
-            umma_bf16(tmem_base, sdesc_advance(adesc0, k * 2048), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            if (A_SPLIT == 2) umma_bf16(tmem_base, sdesc_advance(adesc1, k * 2048), bdesc, idesc, 1u);
-          }
-        } else {
-          const uint64_t adesc0 = make_sdesc_sw128(a_addr, 16, 1024);
-          const uint64_t adesc1 = make_sdesc_sw128(a_addr + S::kABytes, 16, 1024);
-          const uint64_t bdesc0 = make_sdesc_sw128(a_addr + A_SPLIT * S::kABytes, 16, 1024);
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t a_addr = s_addr + mt * S::kATile;
+          const uint32_t d_tmem = tmem_base + mt * BLOCK_N;
+          if (MN) {
+            // MN-major SWIZZLE_128B: 8-row groups 1024 B apart (SBO), 64-column blocks one box apart (LBO);
+            // one UMMA consumes 16 contraction rows = 2048 B
+            const uint64_t adesc0 = make_sdesc_sw128(a_addr, 16384, 1024);
+            const uint64_t adesc1 = make_sdesc_sw128(a_addr + S::kABytes, 16384, 1024);
+            const uint64_t bdesc0 = make_sdesc_sw128(b_addr, 16384, 1024);
 #pragma unroll
-          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            const uint64_t bdesc = sdesc_advance(bdesc0, k * (kUmmaK * 2));
-            umma_bf16(tmem_base, sdesc_advance(adesc0, k * (kUmmaK * 2)), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            if (A_SPLIT == 2) umma_bf16(tmem_base, sdesc_advance(adesc1, k * (kUmmaK * 2)), bdesc, idesc, 1u);
+            for (int k = 0; k < 8; ++k) {
+              const uint64_t bdesc = sdesc_advance(bdesc0, k * 2048);
+              umma_bf16(d_tmem, sdesc_advance(adesc0, k * 2048), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              if (A_SPLIT == 2) umma_bf16(d_tmem, sdesc_advance(adesc1, k * 2048), bdesc, idesc, 1u);
+            }
+          } else {
+            const uint64_t adesc0 = make_sdesc_sw128(a_addr, 16, 1024);
+            const uint64_t adesc1 = make_sdesc_sw128(a_addr + S::kABytes, 16, 1024);
+            const uint64_t bdesc0 = make_sdesc_sw128(b_addr, 16, 1024);
+#pragma unroll
+            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+              const uint64_t bdesc = sdesc_advance(bdesc0, k * (kUmmaK * 2));
+              umma_bf16(d_tmem, sdesc_advance(adesc0, k * (kUmmaK * 2)), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+              if (A_SPLIT == 2) umma_bf16(d_tmem, sdesc_advance(adesc1, k * (kUmmaK * 2)), bdesc, idesc, 1u);
+            }
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -182,13 +197,16 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     // ------------------------------- epilogue -----------------------------------
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
     const int row_in_tile = q * 32 + lane;
-    const int row = m_tile * kBlockM + row_in_tile;
     if (num_kb > 0) {
       mbar_wait(tmem_full_bar, 0);
       tc_fence_after();
     }
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    Epi::template run<BLOCK_N>(ep, shape, row, n_tile * BLOCK_N, taddr, row < shape.M, num_kb > 0, split);
+#pragma unroll 1
+    for (int mt = 0; mt < MT; ++mt) {
+      const int row = (m_tile * MT + mt) * kBlockM + row_in_tile;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mt * BLOCK_N;
+      Epi::template run<BLOCK_N>(ep, shape, row, n_tile * BLOCK_N, taddr, row < shape.M, num_kb > 0, split);
+    }
     tc_fence_before();
   }
   __syncthreads();
