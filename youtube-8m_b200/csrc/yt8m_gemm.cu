@@ -149,7 +149,11 @@ int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda,
   YT8M_REQUIRE(out_f32 || out_hi, YT8M_E_BADPTR, "yt8m_linear_fwd: no output");
   YT8M_REQUIRE(ld_out >= N, YT8M_E_BADSHAPE, "yt8m_linear_fwd: ld_out < N");
   const int block_n = N <= 32 ? 32 : (N >= 512 && M > 128 ? 256 : 128);
-  const int mt = M > kBlockM ? 2 : 1;                    // two accumulators per CTA share every W tile
+  // two accumulators per CTA share every W tile -- unless that would leave only two pipeline stages (hi/lo A with
+  // 256-wide tiles: measured slower, the ring is latency-bound) or the grid cannot fill the SMs anyway (then
+  // split-K takes over and pairing M tiles would only double the number of fp32 atomics per output element)
+  const long long tiles1 = static_cast<long long>((M + kBlockM - 1) / kBlockM) * ((N + block_n - 1) / block_n);
+  const int mt = (M > kBlockM && !(a_lo && block_n == 256) && tiles1 >= 2 * 148) ? 2 : 1;
   int split_k = pick_split_k(M, N, K, block_n, mt);
   if (split_k > 1 && (!workspace || workspace_bytes < yt8m_linear_workspace_bytes(M, N, K))) split_k = 1;
 
@@ -226,7 +230,7 @@ int yt8m_moe_fwd(const yt8m_bf16* x_hi, const yt8m_bf16* x_lo, long long ldx, co
   case NM: {                                                                                                \
     EpiMoe<NM>::Params ep;                                                                                  \
     ep.out = out; ep.ld_out = ld_out; ep.bias_packed = bias_packed; ep.vocab = vocab;                      \
-    if (B > 128)                                                                                            \
+    if (B > 128 && (D >= 2048 || B > 256))   /* two accumulators per CTA pay off once the K loop is long */    \
       return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream) \
                   : launch_gemm<128, 1, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream); \
     return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 1>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream) \
