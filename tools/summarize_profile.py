@@ -36,7 +36,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 idx = {h: i for i, h in enumerate(hdr)}
 summary = {}
 with open(os.path.join(out, tag + "_ncu_full.md"), "w") as f:
-  f.write("# ncu --set full summary (%s)\n\n`ncu --set full --clock-control none --import-source on -k regex:netvlad_fused|gemm_tcgen05|l2norm_rows` over one bench step.\n\n" % tag)
+  f.write("# ncu --set full summary (%s)\n\n`ncu --set full --clock-control none --import-source on -k regex:netvlad|gemm_tcgen05|l2norm_rows` over one bench step.\n\n" % tag)
   for r in rr[2:]:
     name = r[idx["Kernel Name"]].replace("void ", "")
     short = name.split("(")[0][:100]
