@@ -43,6 +43,8 @@ def parse():
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--cpu-sample", type=int, default=16, help="videos per CPU-baseline forward")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--operand-format", default="f16", choices=["f16", "bf16x2"],
+                  help="how the descriptor / hidden layer travel between kernels (see --netvlad_operand_format)")
   return ap.parse_args()
 
 
@@ -190,6 +192,7 @@ def main():
   FLAGS.parse([], known_only=True)
   FLAGS.netvlad_cluster_size, FLAGS.netvlad_hidden_size, FLAGS.moe_num_mixtures = K_CLUSTERS, HIDDEN, MIXTURES
   FLAGS.video_level_classifier_model = "MoeModel"
+  FLAGS.netvlad_operand_format = args.operand_format
   ops.get_store().reset(seed=9)
   model = frame_level_models.NetVLADModel()
   transformer = feature_transform.DefaultTransformer()
@@ -284,9 +287,11 @@ def main():
   except Exception:
     pass
   hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-  # dominant kernel: netvlad_fused_kernel, HBM bound.  Algorithmic bytes / video: the frames once
-  # (300*1152*2) + the descriptor once (1152*64*2 hi + lo) -- SURVEY.md §8(d), DESIGN.md §Kernels.
-  alg_bytes = B * (T * D * 2 + D * K_CLUSTERS * 2 * 2)
+  # dominant kernel: netvlad_v3_kernel, HBM bound.  Algorithmic bytes / video: the frames once
+  # (300*1152*2) + the descriptor once (1152*64*2: one fp16 tensor; x2 for a bf16 hi + lo pair) -- SURVEY.md §8(d),
+  # DESIGN.md §Kernels.
+  fmt = FLAGS.netvlad_operand_format
+  alg_bytes = B * (T * D * 2 + D * K_CLUSTERS * 2 * (1 if fmt == "f16" else 2))
   k_ms = sum(kt) / len(kt) if kt else None
   achieved = alg_bytes / (k_ms * 1e-3) / 1e9 if k_ms else None
   traffic = None
@@ -300,6 +305,8 @@ def main():
       "data": "synthetic",
       "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B, "frames": T, "feature_dim": D,
                  "clusters": K_CLUSTERS, "hidden": HIDDEN, "mixtures": MIXTURES, "vocab": V, "parallelism": "dp%d" % world,
+                 "operands": "frames bf16, weights bf16, descriptor + hidden layer %s, fp32 accumulate" %
+                             ("fp16 (11 significant bits)" if fmt == "f16" else "bf16 hi+lo pairs"),
                  "l2": "inputs larger than L2 (frames 177 MB + FC weights 151 MB per step vs 126 MB L2), no explicit flush"},
       "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "videos/s", "ms_per_step": ms_e2e,
               "h2d_bytes_per_step": u8.numel() + nf.numel() * 4, "d2h_bytes_per_step": pred_host.numel() * 4},

@@ -44,6 +44,13 @@ typedef uint16_t yt8m_bf16;
 #define YT8M_ACT_SIGMOID 3
 #define YT8M_ACT_TANH 4
 
+/* 16-bit operand formats of activations travelling between kernels.  Weights are always bf16.
+ *   YT8M_FMT_BF16: bf16, optionally as a hi + lo pair (lo = bf16(v - hi): ~16 significant bits, two MMAs per tile)
+ *   YT8M_FMT_F16 : IEEE fp16 in the same 2-byte storage (11 significant bits, ONE MMA per tile, no lo tensor) --
+ *                  for bounded activations (L2-normalised descriptors, ReLU6 outputs) */
+#define YT8M_FMT_BF16 0
+#define YT8M_FMT_F16 1
+
 /* library version (major*10000 + minor*100 + patch) */
 int yt8m_version(void);
 const char* yt8m_last_error(void);
@@ -74,8 +81,8 @@ int yt8m_l2norm_rows_fwd(const void* x, int src_dtype, long long rows, int dim, 
 size_t yt8m_linear_workspace_bytes(int M, int N, int K);
 int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, const yt8m_bf16* w,
                     long long ldw, int M, int N, int K, const float* col_scale, const float* col_shift,
-                    int act, float* out_f32, yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out,
-                    void* workspace, size_t workspace_bytes, yt8m_stream_t stream);
+                    int act, int a_fmt, int out_fmt, float* out_f32, yt8m_bf16* out_hi, yt8m_bf16* out_lo,
+                    long long ld_out, void* workspace, size_t workspace_bytes, yt8m_stream_t stream);
 
 /* fp32 [K, N] (TF layout) -> bf16 [N, ldw] (K contiguous, zero padded to ldw) */
 int yt8m_pack_transpose_bf16(const float* w_kn, int K, int N, yt8m_bf16* w_packed, long long ldw,
@@ -91,8 +98,8 @@ int yt8m_moe_pack_weights(const float* gate_w, const float* expert_w, const floa
                           int num_mixtures, yt8m_bf16* w_packed, long long ldw, float* bias_packed,
                           yt8m_stream_t stream);
 int yt8m_moe_fwd(const yt8m_bf16* x_hi, const yt8m_bf16* x_lo, long long ldx, const yt8m_bf16* w_packed,
-                 long long ldw, const float* bias_packed, int B, int D, int vocab, int num_mixtures, float* out,
-                 long long ld_out, yt8m_stream_t stream);
+                 long long ldw, const float* bias_packed, int B, int D, int vocab, int num_mixtures, int x_fmt,
+                 float* out, long long ld_out, yt8m_stream_t stream);
 
 /* max over groups of `heads` consecutive rows: out[b, :] = max_a in[b*heads + a, :]
  * (wh/all_frame_models/lstm_attention_max_pooling_model.py:65-66, zt/video_level_models.py:2327-2328) */
@@ -129,11 +136,12 @@ int yt8m_attn_pool_fwd(const float* logits, long long ld_logits, const yt8m_bf16
  * final L2 norm.  x: bf16 [B, T, D]; cw_packed: bf16 [K, D]; scale/shift: [K] (folded BN or bias);
  * cw2: fp32 [D, K]; cw2_hi / cw2_lo (nullable): its bf16 hi/lo split [D, K] -- with them, K = 64 and a dense
  * output (ld_out = D*K) the residual runs on the tensor cores and the descriptor is written through TMA.
- * out: [B, D*K] (D-major, K-minor).  K in {32, 64, 128}, D % 128 == 0, T <= 384. */
+ * out: [B, D*K] (D-major, K-minor).  K in {32, 64, 128}, D % 128 == 0, T <= 384.
+ * out_fmt = YT8M_FMT_F16: out_hi receives fp16 (out_lo must be NULL). */
 int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K,
                      const yt8m_bf16* cw_packed, const float* scale, const float* shift, const float* cw2,
                      const yt8m_bf16* cw2_hi, const yt8m_bf16* cw2_lo, float* out_f32, yt8m_bf16* out_hi,
-                     yt8m_bf16* out_lo, long long ld_out, yt8m_stream_t stream);
+                     yt8m_bf16* out_lo, long long ld_out, int out_fmt, yt8m_stream_t stream);
 
 /* debug only: device buffer (>= 128 u64, or NULL to disable) that receives globaltimer stamps of the
  * NetVLAD kernel's phases for CTA 0 (tools/netvlad_timeline.py decodes them) */

@@ -15,33 +15,33 @@ def err():
 
 
 def test_linear_argument_checks():
-  assert lib.yt8m_linear_fwd(None, None, 64, P, 64, 8, 8, 64, None, None, 0, P, None, None, 8, None, 0, None) == BADPTR
+  assert lib.yt8m_linear_fwd(None, None, 64, P, 64, 8, 8, 64, None, None, 0, 0, 0, P, None, None, 8, None, 0, None) == BADPTR
   assert "null" in err()
-  assert lib.yt8m_linear_fwd(P, None, 64, P, 64, 0, 8, 64, None, None, 0, P, None, None, 8, None, 0, None) == BADSHAPE
-  assert lib.yt8m_linear_fwd(P, None, 60, P, 64, 8, 8, 60, None, None, 0, P, None, None, 8, None, 0, None) == BADSHAPE   # lda % 8
+  assert lib.yt8m_linear_fwd(P, None, 64, P, 64, 0, 8, 64, None, None, 0, 0, 0, P, None, None, 8, None, 0, None) == BADSHAPE
+  assert lib.yt8m_linear_fwd(P, None, 60, P, 64, 8, 8, 60, None, None, 0, 0, 0, P, None, None, 8, None, 0, None) == BADSHAPE   # lda % 8
   assert "multiples of 8" in err()
-  assert lib.yt8m_linear_fwd(P, None, 64, P, 64, 8, 8, 64, None, None, 0, None, None, None, 8, None, 0, None) == BADPTR   # no output
-  assert lib.yt8m_linear_fwd(P, None, 64, P, 64, 8, 16, 64, None, None, 0, P, None, None, 8, None, 0, None) == BADSHAPE  # ld_out < N
+  assert lib.yt8m_linear_fwd(P, None, 64, P, 64, 8, 8, 64, None, None, 0, 0, 0, None, None, None, 8, None, 0, None) == BADPTR   # no output
+  assert lib.yt8m_linear_fwd(P, None, 64, P, 64, 8, 16, 64, None, None, 0, 0, 0, P, None, None, 8, None, 0, None) == BADSHAPE  # ld_out < N
 
 
 def test_moe_argument_checks():
   assert lib.yt8m_moe_packed_rows(4716, 2) == 128 * 189
   assert lib.yt8m_moe_packed_rows(0, 2) == -1 and lib.yt8m_moe_packed_rows(10, 0) == -1 and lib.yt8m_moe_packed_rows(10, 64) == -1
-  assert lib.yt8m_moe_fwd(P, None, 64, P, 64, P, 4, 64, 100, 5, P, 100, None) == UNSUPPORTED
+  assert lib.yt8m_moe_fwd(P, None, 64, P, 64, P, 4, 64, 100, 5, 0, P, 100, None) == UNSUPPORTED
   assert "num_mixtures=5" in err()
-  assert lib.yt8m_moe_fwd(P, None, 64, P, 64, P, 0, 64, 100, 2, P, 100, None) == BADSHAPE
-  assert lib.yt8m_moe_fwd(P, None, 64, P, 64, P, 4, 64, 100, 2, P, 50, None) == BADSHAPE      # ld_out < vocab
-  assert lib.yt8m_moe_fwd(None, None, 64, P, 64, P, 4, 64, 100, 2, P, 100, None) == BADPTR
+  assert lib.yt8m_moe_fwd(P, None, 64, P, 64, P, 0, 64, 100, 2, 0, P, 100, None) == BADSHAPE
+  assert lib.yt8m_moe_fwd(P, None, 64, P, 64, P, 4, 64, 100, 2, 0, P, 50, None) == BADSHAPE      # ld_out < vocab
+  assert lib.yt8m_moe_fwd(None, None, 64, P, 64, P, 4, 64, 100, 2, 0, P, 100, None) == BADPTR
   assert lib.yt8m_moe_pack_weights(P, P, P, 64, 100, 2, P, 60, P, None) == BADSHAPE             # ldw < D
   assert lib.yt8m_moe_bwd_dlogits(P, None, 64, P, 64, P, P, 100, 4, 64, 100, 8, P, P, 128 * 4, None) in (UNSUPPORTED, BADSHAPE)
 
 
 def test_netvlad_lstm_attention_argument_checks():
-  assert lib.yt8m_netvlad_fwd(P, P, 2, 300, 1152, 48, P, None, None, P, None, None, None, P, None, 1152 * 48, None) == UNSUPPORTED
+  assert lib.yt8m_netvlad_fwd(P, P, 2, 300, 1152, 48, P, None, None, P, None, None, None, P, None, 1152 * 48, 0, None) == UNSUPPORTED
   assert "K=48" in err()
-  assert lib.yt8m_netvlad_fwd(P, P, 2, 400, 1152, 64, P, None, None, P, None, None, None, P, None, 1152 * 64, None) == BADSHAPE   # T > 384
-  assert lib.yt8m_netvlad_fwd(P, P, 2, 300, 1100, 64, P, None, None, P, None, None, None, P, None, 1100 * 64, None) == BADSHAPE   # D % 128
-  assert lib.yt8m_netvlad_fwd(P, P, 2, 300, 1152, 64, P, None, None, P, None, None, None, None, None, 1152 * 64, None) == BADPTR  # stash
+  assert lib.yt8m_netvlad_fwd(P, P, 2, 400, 1152, 64, P, None, None, P, None, None, None, P, None, 1152 * 64, 0, None) == BADSHAPE   # T > 384
+  assert lib.yt8m_netvlad_fwd(P, P, 2, 300, 1100, 64, P, None, None, P, None, None, None, P, None, 1100 * 64, 0, None) == BADSHAPE   # D % 128
+  assert lib.yt8m_netvlad_fwd(P, P, 2, 300, 1152, 64, P, None, None, P, None, None, None, None, None, 1152 * 64, 0, None) == BADPTR  # stash
   assert lib.yt8m_lstm_workspace_bytes(4, 10, 64, 32, 0) == 0 and lib.yt8m_lstm_workspace_bytes(4, 10, 64, 32, 9) == 0
   assert lib.yt8m_lstm_workspace_bytes(64, 300, 1152, 1024, 2) > 64 * 300 * 4096 * 4
   assert lib.yt8m_lstm_pack_weights(P, P, 60, 32, P, P, None) == BADSHAPE                       # in_dim % 8

@@ -315,3 +315,59 @@ def test_context_gate(nat):
   out, hi, lo = nat.context_gate(x.to(DEV), gg.to(DEV), sc.to(DEV), sh.to(DEV))
   want = x * torch.sigmoid(gg * sc + sh)
   assert rel_err(out, want) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# fp16 activation operands (YT8M_FMT_F16): fp16 A x bf16 W on the tensor cores, one MMA per tile
+# ------------------------------------------------------------------------------------------------
+
+def test_linear_f16_operand_exact_and_rounded(nat):
+  g = gen(41)
+  m, n, k = 200, 384, 1024
+  a = torch.randn(m, k, generator=g)
+  a16 = a.to(torch.float16)                                  # what the kernel sees
+  w = synth.xavier((k, n), g)
+  wp = nat.pack_transpose(w.to(DEV))
+  res = nat.linear(a16.to(DEV), wp, n=n, k=k, out_f32=True, out_f16=True)
+  # fp16 x bf16 products are exact in the fp32 accumulator: against the fp16-rounded input only summation order differs
+  assert rel_err(res["f32"], a16.float() @ w) < 2e-5
+  # against the unrounded activation: 11 significant bits per element, averaged over k
+  assert rel_err(res["f32"], a @ w) < 5e-4
+  assert res["hi"].dtype == torch.float16
+  assert rel_err(res["hi"], res["f32"]) < 2 ** -10
+  # split-K path (few tiles, long K) writes fp16 from the finalize kernel
+  m2, n2, k2 = 64, 128, 8192
+  a2 = torch.randn(m2, k2, generator=g).to(torch.float16)
+  w2 = synth.xavier((k2, n2), g)
+  r2 = nat.linear(a2.to(DEV), nat.pack_transpose(w2.to(DEV)), n=n2, k=k2, act="relu6", out_f32=True, out_f16=True)
+  want2 = O.relu6(a2.float() @ w2)
+  assert rel_err(r2["f32"], want2) < 2e-5
+  assert rel_err(r2["hi"], want2) < 2 ** -10
+
+
+def test_moe_f16_operand(nat):
+  g = gen(42)
+  b, d, v, m = 130, 1024, 4716, 2
+  x = (torch.rand(b, d, generator=g) * 6.0).to(torch.float16)          # a ReLU6 activation
+  gw, ew, eb = _moe_weights(d, v, m, g, gain=0.3)
+  wp, bp = nat.moe_pack(gw.to(DEV), ew.to(DEV), eb.to(DEV), v, m)
+  got = nat.moe_fwd(x.to(DEV), wp, bp, v, m)
+  assert rel_err(got, O.moe_model(x.float(), gw, ew, eb, v, m)) < 2e-5
+
+
+@pytest.mark.parametrize("k", [64, 128])
+def test_netvlad_f16_output(nat, k):
+  g = gen(43 + k)
+  b, t, d = 7, 300, 1152
+  x, nf, _ = synth.model_input(b, t, d, seed=16)
+  cw, cw2 = synth.normal((d, k), g, 4.0), synth.normal((d, k), g, 1 / math.sqrt(d))
+  want = O.netvlad_pool(x, nf, cw, torch.ones(k), torch.zeros(k), cw2)
+  cwp = nat.pack_transpose(cw.to(DEV))
+  h16, lo, f32 = nat.netvlad_fwd(bf(x), nf.to(DEV), cwp, None, None, cw2.to(DEV), want_f32=True, out_f16=True)
+  assert h16.dtype == torch.float16 and lo is None
+  assert float((f32.cpu() - want).norm() / want.norm()) < 1.5e-3        # stash is fp16: one more 2^-11 rounding than hi+lo
+  assert rel_err(h16, f32) < 2 ** -10
+  # the fp16 descriptor as FC operand: 1e-3 of the output scale (north_star tolerance) with margin
+  w = synth.xavier((d * k, 256), g)
+  got = nat.linear(h16, nat.pack_transpose(w.to(DEV)), n=256, k=d * k)["f32"]
+  assert rel_err(got, want @ w) < 5e-4

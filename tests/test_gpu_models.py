@@ -100,14 +100,16 @@ def test_deep_combine_chain_model(env):
   check(out["support_predictions"], want_sup)
 
 
+@pytest.mark.parametrize("fmt", ["f16", "bf16x2"])
 @pytest.mark.parametrize("k,gating", [(64, False), (128, True)])
-def test_netvlad_model(env, k, gating):
+def test_netvlad_model(env, k, gating, fmt):
   flm, vlm, FLAGS, ops = env
   b = 6
   x, nf, _ = synth.model_input(b, seed=8)
   y = synth.labels(b, V)
   model = flm.GatedNetVLADModel() if gating else flm.NetVLADModel()
-  with FLAGS.override(netvlad_cluster_size=k, netvlad_hidden_size=1024, moe_num_mixtures=2 if not gating else 4):
+  with FLAGS.override(netvlad_cluster_size=k, netvlad_hidden_size=1024, moe_num_mixtures=2 if not gating else 4,
+                      netvlad_operand_format=fmt):
     out, sd = build_and_run(ops, model, {"cluster_weights": 30.0, "gates": 8.0, "experts": 8.0},
                             model_input=x.to(DEV).to(torch.bfloat16), vocab_size=V, num_frames=nf.to(DEV))
   want = model_oracle.netvlad(sd, x, nf, V, 2 if not gating else 4, gating=gating)

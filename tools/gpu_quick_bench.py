@@ -39,6 +39,10 @@ cw = (torch.randn(K, D, device=dev) / math.sqrt(D)).to(torch.bfloat16)
 cw2 = torch.randn(D, K, device=dev) / math.sqrt(D)
 ms = timeit(lambda: nat.netvlad_fwd(x, nf, cw, None, None, cw2))
 res["netvlad_k64_b256"] = {"ms": ms, "GBps_x": B * T * D * 2 / ms / 1e6, "videos_per_s": B / ms * 1e3}
+ms = timeit(lambda: nat.netvlad_fwd(x, nf, cw, None, None, cw2, want_lo=True))
+res["netvlad_k64_b256_hilo"] = {"ms": ms}
+ms = timeit(lambda: nat.netvlad_fwd(x, nf, cw, None, None, cw2, out_f16=True))
+res["netvlad_k64_b256_f16"] = {"ms": ms}
 
 u8 = torch.randint(0, 256, (B, T, D), dtype=torch.uint8, device=dev)
 ms = timeit(lambda: nat.l2norm_rows(u8, num_frames=nf))
@@ -48,6 +52,11 @@ vl = torch.randn(B, K * D, device=dev).to(torch.bfloat16)
 wfc = (torch.randn(1024, K * D, device=dev) * 0.01).to(torch.bfloat16)
 ms = timeit(lambda: nat.linear(vl, wfc, act="relu6", out_bf16=True))
 res["fc_73728x1024_b256"] = {"ms": ms, "TFLOPs": 2 * B * 1024 * K * D / ms / 1e9, "GBps_w": 1024 * K * D * 2 / ms / 1e6}
+ms = timeit(lambda: nat.linear(vl, wfc, a_lo=vl, act="relu6", out_bf16=True, out_lo=True))
+res["fc_73728x1024_b256_hilo"] = {"ms": ms}
+vl16 = vl.to(torch.float16)
+ms = timeit(lambda: nat.linear(vl16, wfc, act="relu6", out_f32=False, out_f16=True))
+res["fc_73728x1024_b256_f16"] = {"ms": ms}
 
 for (d_in, m) in [(1024, 2), (4096, 4)]:
   rows = nat.moe_packed_rows(V, m)
@@ -57,6 +66,9 @@ for (d_in, m) in [(1024, 2), (4096, 4)]:
     h = torch.randn(bb, d_in, device=dev).to(torch.bfloat16)
     ms = timeit(lambda: nat.moe_fwd(h, wp, bp, V, m))
     res["moe_d%d_m%d_b%d" % (d_in, m, bb)] = {"ms": ms, "TFLOPs": 2 * bb * rows * d_in / ms / 1e9}
+    if bb == 256:
+      ms = timeit(lambda: nat.moe_fwd(h, wp, bp, V, m, x_lo=h))
+      res["moe_d%d_m%d_b%d_hilo" % (d_in, m, bb)] = {"ms": ms}
 
 # big square GEMM through the same main loop (tensor-pipe ceiling of this kernel)
 a = torch.randn(8192, 8192, device=dev).to(torch.bfloat16)

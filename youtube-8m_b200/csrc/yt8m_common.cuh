@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 
@@ -56,6 +57,31 @@ __device__ __forceinline__ void pack8_hi_lo(const float* v, uint4& hi, uint4& lo
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// 8 fp32 -> 8 fp16 (round to nearest even), packed as one uint4; and back
+__device__ __forceinline__ uint4 pack8_f16(const float* v) {
+  uint32_t h[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const __half2 t = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+    h[j] = *reinterpret_cast<const uint32_t*>(&t);
+  }
+  return make_uint4(h[0], h[1], h[2], h[3]);
+}
+__device__ __forceinline__ void unpack8_f16(const uint4& q, float* v) {
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[j]));
+    v[2 * j] = f.x;
+    v[2 * j + 1] = f.y;
+  }
+}
+
+// fp32 x4 reduction into global memory (sm_90+), address 16-byte aligned
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

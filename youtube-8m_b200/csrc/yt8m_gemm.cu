@@ -12,7 +12,8 @@ constexpr int kNumSms = 148;
 
 template <int BLOCK_N, int A_SPLIT, class Epi, int MT = 1>
 int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, const yt8m_bf16* w, long long ldw, int M,
-                int N_rows_w, int N, int K, int split_k, const typename Epi::Params& ep, cudaStream_t stream) {
+                int N_rows_w, int N, int K, int split_k, const typename Epi::Params& ep, cudaStream_t stream,
+                int a_f16 = 0) {
   using S = GemmSmem<BLOCK_N, A_SPLIT, false, MT>;
   CUtensorMap tm_a_hi, tm_a_lo, tm_b;
   int rc;
@@ -31,7 +32,7 @@ int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, con
   }
   const int num_kb = (K + kBlockK - 1) / kBlockK;
   GemmShape shape;
-  shape.M = M; shape.N = N; shape.K = K;
+  shape.M = M; shape.N = N; shape.K = K; shape.a_f16 = a_f16;
   shape.kb_per_split = (num_kb + split_k - 1) / split_k;
   const int splits = (num_kb + shape.kb_per_split - 1) / shape.kb_per_split;
   dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + MT * kBlockM - 1) / (MT * kBlockM), splits);
@@ -42,7 +43,7 @@ int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, con
 // ----- split-K finalize: ws fp32 [M, N] -> affine + activation -> outputs -------------------------
 __global__ void linear_finalize_kernel(const float* __restrict__ ws, long long M, int N, const float* __restrict__ scale,
                                        const float* __restrict__ shift, int act, float* out_f32,
-                                       __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, long long ld_out) {
+                                       __nv_bfloat16* out_hi, __nv_bfloat16* out_lo, long long ld_out, int out_f16) {
   const long long total = M * N;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / N;
@@ -54,10 +55,14 @@ __global__ void linear_finalize_kernel(const float* __restrict__ ws, long long M
     const long long o = r * ld_out + c;
     if (out_f32) out_f32[o] = v;
     if (out_hi) {
-      __nv_bfloat16 h, l;
-      split_bf16(v, h, l);
-      out_hi[o] = h;
-      if (out_lo) out_lo[o] = l;
+      if (out_f16) {
+        reinterpret_cast<__half*>(out_hi)[o] = __float2half_rn(v);
+      } else {
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        out_hi[o] = h;
+        if (out_lo) out_lo[o] = l;
+      }
     }
   }
 }
@@ -138,9 +143,9 @@ size_t yt8m_linear_workspace_bytes(int M, int N, int K) {
 }
 
 int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, const yt8m_bf16* w, long long ldw, int M,
-                    int N, int K, const float* col_scale, const float* col_shift, int act, float* out_f32,
-                    yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out, void* workspace, size_t workspace_bytes,
-                    yt8m_stream_t stream_) {
+                    int N, int K, const float* col_scale, const float* col_shift, int act, int a_fmt, int out_fmt,
+                    float* out_f32, yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out, void* workspace,
+                    size_t workspace_bytes, yt8m_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   YT8M_REQUIRE(a_hi && w, YT8M_E_BADPTR, "yt8m_linear_fwd: null operand");
   YT8M_REQUIRE(M > 0 && N > 0 && K > 0, YT8M_E_BADSHAPE, "yt8m_linear_fwd: bad shape M=%d N=%d K=%d", M, N, K);
@@ -148,6 +153,11 @@ int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda,
                "yt8m_linear_fwd: lda=%lld ldw=%lld must be multiples of 8 and >= K=%d", lda, ldw, K);
   YT8M_REQUIRE(out_f32 || out_hi, YT8M_E_BADPTR, "yt8m_linear_fwd: no output");
   YT8M_REQUIRE(ld_out >= N, YT8M_E_BADSHAPE, "yt8m_linear_fwd: ld_out < N");
+  YT8M_REQUIRE((a_fmt == YT8M_FMT_BF16 || a_fmt == YT8M_FMT_F16) && (out_fmt == YT8M_FMT_BF16 || out_fmt == YT8M_FMT_F16),
+               YT8M_E_UNSUPPORTED, "yt8m_linear_fwd: operand format must be YT8M_FMT_BF16 or YT8M_FMT_F16");
+  YT8M_REQUIRE(!(a_fmt == YT8M_FMT_F16 && a_lo) && !(out_fmt == YT8M_FMT_F16 && out_lo), YT8M_E_UNSUPPORTED,
+               "yt8m_linear_fwd: an fp16 operand is a single tensor (no lo half)");
+  const int a_f16 = a_fmt == YT8M_FMT_F16;
   const int block_n = N <= 32 ? 32 : (N >= 512 && M > 128 ? 256 : 128);
   // two accumulators per CTA share every W tile -- unless that would leave only two pipeline stages (hi/lo A with
   // 256-wide tiles: measured slower, the ring is latency-bound) or the grid cannot fill the SMs anyway (then
@@ -159,6 +169,7 @@ int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda,
 
   EpiLinear::Params ep;
   ep.col_scale = col_scale; ep.col_shift = col_shift; ep.act = act; ep.split_k = split_k;
+  ep.out_f16 = out_fmt == YT8M_FMT_F16;
   if (split_k > 1) {
     YT8M_CUDA(cudaMemsetAsync(workspace, 0, static_cast<size_t>(M) * N * sizeof(float), stream));
     ep.out_f32 = static_cast<float*>(workspace); ep.out_hi = nullptr; ep.out_lo = nullptr; ep.ld_out = N;
@@ -168,10 +179,10 @@ int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda,
   }
   int rc;
 #define YT8M_DISPATCH(BN)                                                                                              \
-  rc = mt == 2 ? (a_lo ? launch_gemm<BN, 2, EpiLinear, 2>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream)    \
-                       : launch_gemm<BN, 1, EpiLinear, 2>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream))   \
-               : (a_lo ? launch_gemm<BN, 2, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream)    \
-                       : launch_gemm<BN, 1, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream))
+  rc = mt == 2 ? (a_lo ? launch_gemm<BN, 2, EpiLinear, 2>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream, a_f16)    \
+                       : launch_gemm<BN, 1, EpiLinear, 2>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream, a_f16))   \
+               : (a_lo ? launch_gemm<BN, 2, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream, a_f16)    \
+                       : launch_gemm<BN, 1, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream, a_f16))
   if (block_n == 32) { YT8M_DISPATCH(32); }
   else if (block_n == 256) { YT8M_DISPATCH(256); }
   else { YT8M_DISPATCH(128); }
@@ -182,7 +193,7 @@ int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda,
     const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, kNumSms * 8));
     linear_finalize_kernel<<<blocks, 256, 0, stream>>>(static_cast<const float*>(workspace), M, N, col_scale, col_shift,
                                                        act, out_f32, reinterpret_cast<__nv_bfloat16*>(out_hi),
-                                                       reinterpret_cast<__nv_bfloat16*>(out_lo), ld_out);
+                                                       reinterpret_cast<__nv_bfloat16*>(out_lo), ld_out, ep.out_f16);
     return check_launch("linear_finalize_kernel");
   }
   return YT8M_OK;
@@ -216,8 +227,8 @@ int yt8m_moe_pack_weights(const float* gate_w, const float* expert_w, const floa
 }
 
 int yt8m_moe_fwd(const yt8m_bf16* x_hi, const yt8m_bf16* x_lo, long long ldx, const yt8m_bf16* w_packed, long long ldw,
-                 const float* bias_packed, int B, int D, int vocab, int num_mixtures, float* out, long long ld_out,
-                 yt8m_stream_t stream_) {
+                 const float* bias_packed, int B, int D, int vocab, int num_mixtures, int x_fmt, float* out,
+                 long long ld_out, yt8m_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   YT8M_REQUIRE(x_hi && w_packed && bias_packed && out, YT8M_E_BADPTR, "yt8m_moe_fwd: null pointer");
   const long long rows = yt8m_moe_packed_rows(vocab, num_mixtures);
@@ -225,16 +236,19 @@ int yt8m_moe_fwd(const yt8m_bf16* x_hi, const yt8m_bf16* x_lo, long long ldx, co
                num_mixtures);
   YT8M_REQUIRE(ldx % 8 == 0 && ldw % 8 == 0 && ldx >= D && ldw >= D && ld_out >= vocab, YT8M_E_BADSHAPE,
                "yt8m_moe_fwd: strides must be multiples of 8 and >= D");
+  YT8M_REQUIRE(x_fmt == YT8M_FMT_BF16 || (x_fmt == YT8M_FMT_F16 && !x_lo), YT8M_E_UNSUPPORTED,
+               "yt8m_moe_fwd: x_fmt must be YT8M_FMT_BF16, or YT8M_FMT_F16 without a lo half");
+  const int x_f16 = x_fmt == YT8M_FMT_F16;
   const int n = static_cast<int>(rows);
 #define YT8M_MOE_CASE(NM)                                                                                   \
   case NM: {                                                                                                \
     EpiMoe<NM>::Params ep;                                                                                  \
     ep.out = out; ep.ld_out = ld_out; ep.bias_packed = bias_packed; ep.vocab = vocab;                      \
     if (B > 128 && (D >= 2048 || B > 256))   /* two accumulators per CTA pay off once the K loop is long */    \
-      return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream) \
-                  : launch_gemm<128, 1, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream); \
-    return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 1>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream) \
-                : launch_gemm<128, 1, EpiMoe<NM>, 1>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream); \
+      return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16) \
+                  : launch_gemm<128, 1, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16); \
+    return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 1>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16) \
+                : launch_gemm<128, 1, EpiMoe<NM>, 1>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16); \
   }
   switch (num_mixtures) {
     YT8M_MOE_CASE(1)
@@ -333,8 +347,8 @@ int yt8m_lstm_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D
   YT8M_CUDA(cudaMemsetAsync(ws.c[0][0], 0, ws.total - (reinterpret_cast<char*>(ws.c[0][0]) - static_cast<char*>(workspace)), stream));
 
   // hoisted input projection of layer 0: xw = x . Wx0^T + b0  (packed column order), one big GEMM
-  int rc = yt8m_linear_fwd(x, nullptr, D, w_packed[0], D + H, B * T, 4 * H, D, nullptr, b_packed[0], YT8M_ACT_NONE, ws.xw,
-                           nullptr, nullptr, 4 * H, nullptr, 0, stream_);
+  int rc = yt8m_linear_fwd(x, nullptr, D, w_packed[0], D + H, B * T, 4 * H, D, nullptr, b_packed[0], YT8M_ACT_NONE,
+                           YT8M_FMT_BF16, YT8M_FMT_BF16, ws.xw, nullptr, nullptr, 4 * H, nullptr, 0, stream_);
   if (rc != YT8M_OK) return rc;
 
   for (int t = 0; t < T; ++t) {

@@ -24,6 +24,7 @@ constexpr int kGemmThreads = 224;     // warp 0: A producer, 1: MMA, 2-5: epilog
 struct GemmShape {
   int M, N, K;
   int kb_per_split;                    // K-blocks handled by one blockIdx.z
+  int a_f16;                           // 1: the A operand holds IEEE fp16 (11 significant bits) instead of bf16; W stays bf16
 };
 
 // MN = false: operands stored [rows, K] with K contiguous (forward / dgrad): stage = 64 K-elements.
@@ -150,7 +151,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, MN ? 1 : 0, MN ? 1 : 0);
+    // a_format field (bits 7..9): 1 = bf16, 0 = fp16 -- the two operands of kind::f16 carry independent formats
+    const uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, MN ? 1 : 0, MN ? 1 : 0) ^ (shape.a_f16 ? (1u << 7) : 0u);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < num_kb; ++kb) {
@@ -243,6 +245,7 @@ struct EpiLinear {
     const float* col_shift;    // nullable (=> 0): bias / folded BN shift
     int act;
     int split_k;               // > 1: atomicAdd raw partials into out_f32, nothing else
+    int out_f16;               // 1: out_hi receives fp16 (one 11-bit operand for the next GEMM), out_lo unused
   };
   template <int BLOCK_N>
   static __device__ __forceinline__ void run(const Params& p, const GemmShape& s, int row, int n0, uint32_t taddr,
@@ -262,9 +265,17 @@ struct EpiLinear {
       if (col0 >= s.N) continue;
       const long long base = static_cast<long long>(row) * p.ld_out + col0;
       if (p.split_k > 1) {
+        if (col0 + 32 <= s.N && (p.ld_out & 3) == 0) {
+          // 16-byte vector reductions: a quarter of the L2 atomic operations of the scalar form
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j < s.N) atomicAdd(p.out_f32 + base + j, __uint_as_float(r[j]));
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(p.out_f32 + base + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                       __uint_as_float(r[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < s.N) atomicAdd(p.out_f32 + base + j, __uint_as_float(r[j]));
+        }
         continue;
       }
       float v[32];
@@ -297,18 +308,26 @@ struct EpiLinear {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 h, l;
-            pack8_hi_lo(v + 8 * j, h, l);
+            if (p.out_f16) {
+              h = pack8_f16(v + 8 * j);
+            } else {
+              pack8_hi_lo(v + 8 * j, h, l);
+              if (dl) dl[j] = l;
+            }
             dh[j] = h;
-            if (dl) dl[j] = l;
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j)
             if (col0 + j < s.N) {
-              __nv_bfloat16 h, l;
-              split_bf16(v[j], h, l);
-              p.out_hi[base + j] = h;
-              if (p.out_lo) p.out_lo[base + j] = l;
+              if (p.out_f16) {
+                reinterpret_cast<__half*>(p.out_hi)[base + j] = __float2half_rn(v[j]);
+              } else {
+                __nv_bfloat16 h, l;
+                split_bf16(v[j], h, l);
+                p.out_hi[base + j] = h;
+                if (p.out_lo) p.out_lo[base + j] = l;
+              }
             }
         }
       }

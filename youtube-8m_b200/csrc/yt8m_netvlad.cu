@@ -23,6 +23,26 @@ using namespace yt8m;
 
 namespace {
 
+// The stash / output of the descriptor is either bf16 hi (+ lo) or, with out_f16, one IEEE fp16 tensor.
+__device__ __forceinline__ void unpack8_stash(const uint4& h, const uint4& l, int f16, float* v) {
+  if (f16) {
+    unpack8_f16(h, v);
+  } else {
+    const uint32_t hw[4] = {h.x, h.y, h.z, h.w};
+    const uint32_t lv[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lv[j] << 16);
+      v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lv[j] & 0xFFFF0000u);
+    }
+  }
+}
+__device__ __forceinline__ void pack8_stash(const float* v, int f16, uint4& h, uint4& l) {
+  if (f16) { h = pack8_f16(v); l = make_uint4(0, 0, 0, 0); }
+  else pack8_hi_lo(v, h, l);
+}
+
+
 constexpr int kNvThreads = 224;            // warp 0: X producer, 1: MMA, 2-5: softmax/epilogue, 6: centre producer
 constexpr int kNvSms = 148;
 
@@ -98,7 +118,7 @@ __global__ void __launch_bounds__(kNvThreads, 1)
 netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_cw,
                      const int* __restrict__ num_frames, int B, int T, int D, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ cw2, float* __restrict__ out_f32,
-                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ld_out) {
+                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ld_out, int out_f16) {
   using C = NvCfg<KC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -422,7 +442,7 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
               uint4 hi, lo;
-              pack8_hi_lo(v + 8 * j8, hi, lo);
+              pack8_stash(v + 8 * j8, out_f16, hi, lo);
               const long long o = static_cast<long long>(d) * KC + c + 8 * j8;
               if (!(dbg_flags & 1)) {
                 st_global_hint(ohi + o, hi, kEvictLast);
@@ -484,18 +504,12 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
           const long long e = e0 + static_cast<long long>(u) * 128 * 8;
           if (e >= n) break;
           const int k0 = static_cast<int>(e % KC);
-          const uint32_t hw[4] = {h[u].x, h[u].y, h[u].z, h[u].w};
-          const uint32_t lv[4] = {lw[u].x, lw[u].y, lw[u].z, lw[u].w};
           float v[8];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            v[2 * j] = __uint_as_float(hw[j] << 16) + __uint_as_float(lv[j] << 16);
-            v[2 * j + 1] = __uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lv[j] & 0xFFFF0000u);
-          }
+          unpack8_stash(h[u], lw[u], out_f16, v);
 #pragma unroll
           for (int j = 0; j < 8; ++j) v[j] *= fscale_s[k0 + j] * gs;
           uint4 nh, nl;
-          pack8_hi_lo(v, nh, nl);
+          pack8_stash(v, out_f16, nh, nl);
           *reinterpret_cast<uint4*>(ohi + e) = nh;
           if (olo) *reinterpret_cast<uint4*>(olo + e) = nl;
           if (of) {
@@ -560,7 +574,7 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                   const __grid_constant__ CUtensorMap tm_out_hi, const __grid_constant__ CUtensorMap tm_out_lo,
                   const int* __restrict__ num_frames, int B, int T, int D, const float* __restrict__ scale,
                   const float* __restrict__ shift, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
-                  __nv_bfloat16* __restrict__ out_lo, long long ld_out) {
+                  __nv_bfloat16* __restrict__ out_lo, long long ld_out, int out_f16) {
   const int want_lo = out_lo != nullptr;
   using C = Nv3Cfg;
   constexpr int KC = C::KC;
@@ -895,7 +909,7 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
               uint4 hi, lo;
-              pack8_hi_lo(v + 8 * j8, hi, lo);
+              pack8_stash(v + 8 * j8, out_f16, hi, lo);
               *reinterpret_cast<uint4*>(stage_hi + sw128_offset(row, ch * 4 + j8)) = hi;
               if (want_lo) *reinterpret_cast<uint4*>(stage_lo + sw128_offset(row, ch * 4 + j8)) = lo;
             }
@@ -971,16 +985,12 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           const long long e = e0 + static_cast<long long>(u) * 128 * 8;
           if (e >= n) break;
           const int k0 = static_cast<int>(e % KC);
-          const uint32_t hw[4] = {h[u].x, h[u].y, h[u].z, h[u].w};
-          const uint32_t lv[4] = {lw[u].x, lw[u].y, lw[u].z, lw[u].w};
           float v[8];
+          unpack8_stash(h[u], lw[u], out_f16, v);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            v[2 * j] = (__uint_as_float(hw[j] << 16) + __uint_as_float(lv[j] << 16)) * fsp[k0 + 2 * j];
-            v[2 * j + 1] = (__uint_as_float(hw[j] & 0xFFFF0000u) + __uint_as_float(lv[j] & 0xFFFF0000u)) * fsp[k0 + 2 * j + 1];
-          }
+          for (int j = 0; j < 8; ++j) v[j] *= fsp[k0 + j];
           uint4 nh, nl;
-          pack8_hi_lo(v, nh, nl);
+          pack8_stash(v, out_f16, nh, nl);
           *reinterpret_cast<uint4*>(ohi + e) = nh;
           if (olo) *reinterpret_cast<uint4*>(olo + e) = nl;
           if (of) {
@@ -1002,7 +1012,7 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 
 int launch_netvlad_v3(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, const yt8m_bf16* cw_packed,
                       const float* scale, const float* shift, const yt8m_bf16* cw2_hi, const yt8m_bf16* cw2_lo, float* out_f32,
-                      yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out, cudaStream_t stream) {
+                      yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out, int out_f16, cudaStream_t stream) {
   using C = Nv3Cfg;
   CUtensorMap tm_x, tm_x64, tm_cw, tm_c2_hi, tm_c2_lo, tm_out_hi, tm_out_lo;
   int rc;
@@ -1032,14 +1042,14 @@ int launch_netvlad_v3(const yt8m_bf16* x, const int* num_frames, int B, int T, i
   const int grid = B < kNvSms ? B : kNvSms;
   netvlad_v3_kernel<<<grid, kNv3Threads, C::kTotal, stream>>>(tm_x, tm_x64, tm_cw, tm_c2_hi, tm_c2_lo, tm_out_hi, tm_out_lo, num_frames, B, T, D,
                                                               scale, shift, out_f32, reinterpret_cast<__nv_bfloat16*>(out_hi),
-                                                              reinterpret_cast<__nv_bfloat16*>(out_lo), ld_out);
+                                                              reinterpret_cast<__nv_bfloat16*>(out_lo), ld_out, out_f16);
   return check_launch("netvlad_v3_kernel");
 }
 
 template <int KC>
 int launch_netvlad(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, const yt8m_bf16* cw_packed,
                    const float* scale, const float* shift, const float* cw2, float* out_f32, yt8m_bf16* out_hi,
-                   yt8m_bf16* out_lo, long long ld_out, cudaStream_t stream) {
+                   yt8m_bf16* out_lo, long long ld_out, int out_f16, cudaStream_t stream) {
   using C = NvCfg<KC>;
   CUtensorMap tm_x, tm_cw;
   int rc;
@@ -1066,7 +1076,7 @@ int launch_netvlad(const yt8m_bf16* x, const int* num_frames, int B, int T, int 
   const int grid = B < kNvSms ? B : kNvSms;               // persistent: one CTA per SM
   kern<<<grid, kNvThreads, C::kTotal, stream>>>(tm_x, tm_cw, num_frames, B, T, D, scale, shift, cw2, out_f32,
                                              reinterpret_cast<__nv_bfloat16*>(out_hi),
-                                             reinterpret_cast<__nv_bfloat16*>(out_lo), ld_out);
+                                             reinterpret_cast<__nv_bfloat16*>(out_lo), ld_out, out_f16);
   return check_launch("netvlad_fused_kernel");
 }
 
@@ -1084,7 +1094,7 @@ extern "C" int yt8m_debug_set_flags(int flags) {
 extern "C" int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K,
                                 const yt8m_bf16* cw_packed, const float* scale, const float* shift, const float* cw2,
                                 const yt8m_bf16* cw2_hi, const yt8m_bf16* cw2_lo, float* out_f32, yt8m_bf16* out_hi,
-                                yt8m_bf16* out_lo, long long ld_out, yt8m_stream_t stream_) {
+                                yt8m_bf16* out_lo, long long ld_out, int out_fmt, yt8m_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   YT8M_REQUIRE(x && num_frames && cw_packed && cw2 && out_hi, YT8M_E_BADPTR,
                "yt8m_netvlad_fwd: null pointer (out_hi is required: it doubles as the stash)");
@@ -1093,13 +1103,16 @@ extern "C" int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B
   YT8M_REQUIRE(ld_out >= static_cast<long long>(D) * K && ld_out % 8 == 0, YT8M_E_BADSHAPE, "yt8m_netvlad_fwd: ld_out");
   YT8M_REQUIRE(aligned16(out_hi) && (!out_lo || aligned16(out_lo)) && (!out_f32 || aligned16(out_f32)) && aligned16(cw2),
                YT8M_E_BADPTR, "yt8m_netvlad_fwd: outputs / cw2 must be 16-byte aligned");
+  YT8M_REQUIRE(out_fmt == YT8M_FMT_BF16 || (out_fmt == YT8M_FMT_F16 && !out_lo), YT8M_E_UNSUPPORTED,
+               "yt8m_netvlad_fwd: out_fmt must be YT8M_FMT_BF16, or YT8M_FMT_F16 without a lo tensor");
+  const int out_f16 = out_fmt == YT8M_FMT_F16;
   // K = 64 with the bf16 hi/lo copy of cw2 and a dense output: the TMA-staged kernel
   if (K == 64 && cw2_hi && cw2_lo && ld_out == static_cast<long long>(D) * K)
-    return launch_netvlad_v3(x, num_frames, B, T, D, cw_packed, scale, shift, cw2_hi, cw2_lo, out_f32, out_hi, out_lo, ld_out, stream);
+    return launch_netvlad_v3(x, num_frames, B, T, D, cw_packed, scale, shift, cw2_hi, cw2_lo, out_f32, out_hi, out_lo, ld_out, out_f16, stream);
   switch (K) {
-    case 32: return launch_netvlad<32>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, stream);
-    case 64: return launch_netvlad<64>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, stream);
-    case 128: return launch_netvlad<128>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, stream);
+    case 32: return launch_netvlad<32>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, out_f16, stream);
+    case 64: return launch_netvlad<64>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, out_f16, stream);
+    case 128: return launch_netvlad<128>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, out_f16, stream);
     default:
       set_error("yt8m_netvlad_fwd: cluster count K=%d unsupported (32, 64, 128)", K);
       return YT8M_E_UNSUPPORTED;

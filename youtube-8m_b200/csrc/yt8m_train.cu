@@ -194,7 +194,7 @@ int launch_gemm_t(const CUtensorMap& tm_a_hi, const CUtensorMap& tm_a_lo, const 
   }
   constexpr int kStageK = MN ? 128 : kBlockK;
   GemmShape shape;
-  shape.M = M; shape.N = N; shape.K = K;
+  shape.M = M; shape.N = N; shape.K = K; shape.a_f16 = 0;
   shape.kb_per_split = (K + kStageK - 1) / kStageK;
   dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + kBlockM - 1) / kBlockM, 1);
   kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tm_a_hi, tm_a_lo, tm_b, shape, ep);

@@ -43,6 +43,9 @@ flags.DEFINE_integer("netvlad_cluster_size", 64, "Number of NetVLAD clusters.")
 flags.DEFINE_integer("netvlad_hidden_size", 1024, "Number of units in the NetVLAD hidden layer.")
 flags.DEFINE_bool("netvlad_add_batch_norm", True, "Batch-normalise the assignment logits and the hidden layer.")
 flags.DEFINE_bool("netvlad_relu", True, "ReLU6 after the NetVLAD hidden layer (as DBoF does).")
+flags.DEFINE_string("netvlad_operand_format", "f16",
+                    "How the descriptor and the hidden layer travel to the next GEMM: 'f16' = one IEEE fp16 tensor "
+                    "(11 significant bits, one MMA per weight tile), 'bf16x2' = bf16 hi + lo pair (~16 bits, two MMAs).")
 
 BN_EPS = 1e-3      # slim.batch_norm default epsilon
 
@@ -326,7 +329,10 @@ class NetVLADModel(models.BaseModel):
       shift = st.get("cluster_biases", (cluster_size,), ops.random_normal(1 / math.sqrt(d)), round_bf16=False).value
     cwp = st.packed(cw, "kmajor", lambda: nat.pack_transpose(cw.value))
     c2split = st.packed(cw2, "hi_lo", lambda: nat.split_bf16(cw2.value))     # residual centres as tensor-core operands
-    vlad_hi, vlad_lo, _ = nat.netvlad_fwd(x, nf, cwp, scale, shift, cw2.value, want_lo=True, cw2_split=c2split)
+    if FLAGS.netvlad_operand_format not in ("f16", "bf16x2"):
+      raise ValueError("--netvlad_operand_format must be 'f16' or 'bf16x2'")
+    f16 = FLAGS.netvlad_operand_format == "f16"
+    vlad_hi, vlad_lo, _ = nat.netvlad_fwd(x, nf, cwp, scale, shift, cw2.value, want_lo=not f16, cw2_split=c2split, out_f16=f16)
 
     hw = st.get("hidden1_weights", (cluster_size * d, hidden1_size), ops.random_normal(1 / math.sqrt(cluster_size)))
     hwp = st.packed(hw, "kmajor", lambda: nat.pack_transpose(hw.value))
@@ -336,8 +342,9 @@ class NetVLADModel(models.BaseModel):
       s_h = None
       t_h = st.get("hidden1_biases", (hidden1_size,), ops.random_normal(0.01), round_bf16=False).value
     hidden = nat.linear(vlad_hi, hwp, a_lo=vlad_lo, n=hidden1_size, k=cluster_size * d, scale=s_h, shift=t_h,
-                        act="relu6" if FLAGS.netvlad_relu else None, out_bf16=True, out_lo=True)
-    act = ops.Act(f32=hidden["f32"], hi=hidden["hi"], lo=hidden["lo"], cols=hidden1_size)
+                        act="relu6" if FLAGS.netvlad_relu else None, out_f32=self.gating or not f16, out_bf16=not f16,
+                        out_lo=not f16, out_f16=f16)
+    act = ops.Act(f32=hidden.get("f32"), hi=hidden["hi"], lo=hidden.get("lo"), cols=hidden1_size)
     if self.gating:
       gw = st.get("gating_weights", (hidden1_size, hidden1_size), ops.random_normal(1 / math.sqrt(hidden1_size)))
       gwp = st.packed(gw, "kmajor", lambda: nat.pack_transpose(gw.value))

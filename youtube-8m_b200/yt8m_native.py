@@ -37,12 +37,12 @@ _SIGS = {
     "yt8m_l2norm_rows_fwd": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "yt8m_linear_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "yt8m_linear_fwd": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
-                                c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_size_t, c_void_p]),
+                                c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_size_t, c_void_p]),
     "yt8m_pack_transpose_bf16": (c_int, [c_void_p, c_int, c_int, c_void_p, c_ll, c_void_p]),
     "yt8m_moe_packed_rows": (c_ll, [c_int, c_int]),
     "yt8m_moe_pack_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_ll, c_void_p, c_void_p]),
-    "yt8m_moe_fwd": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_ll,
-                             c_void_p]),
+    "yt8m_moe_fwd": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p,
+                             c_ll, c_void_p]),
     "yt8m_group_max_rows": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p]),
     "yt8m_lstm_pack_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "yt8m_lstm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
@@ -51,7 +51,7 @@ _SIGS = {
     "yt8m_attn_pool_fwd": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     "yt8m_netvlad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "yt8m_debug_set_timeline": (c_int, [c_void_p]),
     "yt8m_debug_set_flags": (c_int, [c_int]),
     "yt8m_context_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
@@ -202,18 +202,33 @@ def _workspace(nbytes, device):
   return buf
 
 
+FMT_BF16, FMT_F16 = 0, 1
+
+
+def _fmt(t):
+  """Operand format of a 16-bit activation tensor: the torch dtype says which (yt8m_b200.h: YT8M_FMT_*)."""
+  if t.dtype == torch.float16:
+    return FMT_F16
+  if t.dtype == torch.bfloat16:
+    return FMT_BF16
+  raise Yt8mError("activation operands must be torch.bfloat16 or torch.float16, got %s" % t.dtype)
+
+
 def linear(a_hi, w_packed, a_lo=None, n=None, k=None, scale=None, shift=None, act=None, out_f32=True, out_bf16=False,
-           out_lo=False):
-  """act((A . W^T) * scale + shift).  a_hi/a_lo: bf16 [M, lda]; w_packed: bf16 [N, ldw].
-  Returns dict with the requested outputs ('f32', 'hi', 'lo')."""
+           out_lo=False, out_f16=False):
+  """act((A . W^T) * scale + shift).  a_hi/a_lo: bf16 [M, lda] (or a_hi fp16 alone); w_packed: bf16 [N, ldw].
+  Returns dict with the requested outputs ('f32', 'hi', 'lo'); out_f16 makes 'hi' an fp16 tensor."""
   m = a_hi.shape[0]
   n = n or w_packed.shape[0]
   k = k or min(a_hi.shape[1], w_packed.shape[1])
   dev = a_hi.device
   ld_out = pad8(n)
   of = _f32((m, ld_out), dev) if out_f32 else None
-  oh = _bf16((m, ld_out), dev) if out_bf16 else None
-  ol = _bf16((m, ld_out), dev) if (out_bf16 and out_lo) else None
+  if out_f16:
+    oh, ol = torch.empty((m, ld_out), dtype=torch.float16, device=dev), None
+  else:
+    oh = _bf16((m, ld_out), dev) if out_bf16 else None
+    ol = _bf16((m, ld_out), dev) if (out_bf16 and out_lo) else None
   if ld_out != n:
     for t in (of, oh, ol):
       if t is not None:
@@ -221,7 +236,8 @@ def linear(a_hi, w_packed, a_lo=None, n=None, k=None, scale=None, shift=None, ac
   ws_bytes = _lib.yt8m_linear_workspace_bytes(m, n, k)
   ws = _workspace(ws_bytes, dev)
   _call("yt8m_linear_fwd", _p(a_hi), _p(a_lo), a_hi.stride(0), _p(w_packed), w_packed.stride(0), m, n, k, _p(scale),
-        _p(shift), ACT[act], _p(of), _p(oh), _p(ol), ld_out, _p(ws), ws.numel(), _stream())
+        _p(shift), ACT[act], _fmt(a_hi), FMT_F16 if out_f16 else FMT_BF16, _p(of), _p(oh), _p(ol), ld_out, _p(ws), ws.numel(),
+        _stream())
   res = {}
   if of is not None:
     res["f32"] = of[:, :n]
@@ -254,7 +270,7 @@ def moe_fwd(x_hi, w_packed, bias_packed, vocab, num_mixtures, x_lo=None, d=None)
   d = d or min(x_hi.shape[1], w_packed.shape[1])
   out = _f32((b, vocab), x_hi.device)
   _call("yt8m_moe_fwd", _p(x_hi), _p(x_lo), x_hi.stride(0), _p(w_packed), w_packed.stride(0), _p(bias_packed), b, d, vocab,
-        num_mixtures, _p(out), vocab, _stream())
+        num_mixtures, _fmt(x_hi), _p(out), vocab, _stream())
   return out
 
 
@@ -302,19 +318,22 @@ def attn_pool(logits, feats, num_frames, heads, mode, want_bf16=True):
   return out, oh, ol
 
 
-def netvlad_fwd(x, num_frames, cw_packed, scale, shift, cw2, want_f32=False, want_lo=False, cw2_split=None):
+def netvlad_fwd(x, num_frames, cw_packed, scale, shift, cw2, want_f32=False, want_lo=False, cw2_split=None, out_f16=False):
   """x bf16 [B, T, D]; cw_packed bf16 [K, D]; cw2 fp32 [D, K] (cw2_split = its (hi, lo) bf16 copies, made on
-  demand) -> bf16 hi [B, D*K] (+lo, +fp32)."""
+  demand) -> bf16 hi [B, D*K] (+lo, +fp32); out_f16: one fp16 tensor instead of hi (+lo)."""
   b, t, d = x.shape
   k = cw_packed.shape[0]
   if cw2_split is None and k == 64:
     cw2_split = split_bf16(cw2.contiguous())
   c2h, c2l = cw2_split if cw2_split is not None else (None, None)
-  oh = _bf16((b, d * k), x.device)
-  ol = _bf16((b, d * k), x.device) if want_lo else None
+  if out_f16:
+    oh, ol = torch.empty((b, d * k), dtype=torch.float16, device=x.device), None
+  else:
+    oh = _bf16((b, d * k), x.device)
+    ol = _bf16((b, d * k), x.device) if want_lo else None
   of = _f32((b, d * k), x.device) if want_f32 else None
   _call("yt8m_netvlad_fwd", _p(x), _p(num_frames), b, t, d, k, _p(cw_packed), _p(scale), _p(shift), _p(cw2), _p(c2h), _p(c2l),
-        _p(of), _p(oh), _p(ol), d * k, _stream())
+        _p(of), _p(oh), _p(ol), d * k, FMT_F16 if out_f16 else FMT_BF16, _stream())
   return oh, ol, of
 
 
