@@ -44,10 +44,13 @@ typedef uint16_t yt8m_bf16;
 #define YT8M_ACT_SIGMOID 3
 #define YT8M_ACT_TANH 4
 
-/* 16-bit operand formats of activations travelling between kernels.  Weights are always bf16.
- *   YT8M_FMT_BF16: bf16, optionally as a hi + lo pair (lo = bf16(v - hi): ~16 significant bits, two MMAs per tile)
- *   YT8M_FMT_F16 : IEEE fp16 in the same 2-byte storage (11 significant bits, ONE MMA per tile, no lo tensor) --
- *                  for bounded activations (L2-normalised descriptors, ReLU6 outputs) */
+/* 16-bit operand formats of a GEMM (activation AND weight operand: the tensor core takes one 16-bit format per
+ * instruction; fp16 x bf16 faults).
+ *   YT8M_FMT_BF16: bf16 weights; activation bf16, optionally as a hi + lo pair (lo = bf16(v - hi): ~16 significant
+ *                  bits, two MMAs per weight tile)
+ *   YT8M_FMT_F16 : IEEE fp16 in the same 2-byte storage, 11 significant bits, ONE MMA per tile, no lo tensor -- for
+ *                  bounded activations (L2-normalised descriptors, ReLU6 outputs).  The weight operand is then the
+ *                  fp16 conversion of the packed bf16 weights (exact for |w| >= 2^-17, < 2^-24 absolute below). */
 #define YT8M_FMT_BF16 0
 #define YT8M_FMT_F16 1
 

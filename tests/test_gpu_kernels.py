@@ -327,9 +327,12 @@ def test_linear_f16_operand_exact_and_rounded(nat):
   a = torch.randn(m, k, generator=g)
   a16 = a.to(torch.float16)                                  # what the kernel sees
   w = synth.xavier((k, n), g)
-  wp = nat.pack_transpose(w.to(DEV))
+  wp = nat.pack_transpose(w.to(DEV)).to(torch.float16)       # xavier weights: bf16 values are exact in fp16
+  assert torch.equal(wp[:, :k].float().cpu(), w.t().contiguous())
   res = nat.linear(a16.to(DEV), wp, n=n, k=k, out_f32=True, out_f16=True)
-  # fp16 x bf16 products are exact in the fp32 accumulator: against the fp16-rounded input only summation order differs
+  with pytest.raises(nat.Yt8mError):                         # one 16-bit format per MMA: fp16 x bf16 is refused
+    nat.linear(a16.to(DEV), nat.pack_transpose(w.to(DEV)), n=n, k=k)
+  # fp16 x fp16 products are exact in the fp32 accumulator: against the fp16-rounded input only summation order differs
   assert rel_err(res["f32"], a16.float() @ w) < 2e-5
   # against the unrounded activation: 11 significant bits per element, averaged over k
   assert rel_err(res["f32"], a @ w) < 5e-4
@@ -339,7 +342,7 @@ def test_linear_f16_operand_exact_and_rounded(nat):
   m2, n2, k2 = 64, 128, 8192
   a2 = torch.randn(m2, k2, generator=g).to(torch.float16)
   w2 = synth.xavier((k2, n2), g)
-  r2 = nat.linear(a2.to(DEV), nat.pack_transpose(w2.to(DEV)), n=n2, k=k2, act="relu6", out_f32=True, out_f16=True)
+  r2 = nat.linear(a2.to(DEV), nat.pack_transpose(w2.to(DEV)).to(torch.float16), n=n2, k=k2, act="relu6", out_f32=True, out_f16=True)
   want2 = O.relu6(a2.float() @ w2)
   assert rel_err(r2["f32"], want2) < 2e-5
   assert rel_err(r2["hi"], want2) < 2 ** -10
@@ -351,7 +354,7 @@ def test_moe_f16_operand(nat):
   x = (torch.rand(b, d, generator=g) * 6.0).to(torch.float16)          # a ReLU6 activation
   gw, ew, eb = _moe_weights(d, v, m, g, gain=0.3)
   wp, bp = nat.moe_pack(gw.to(DEV), ew.to(DEV), eb.to(DEV), v, m)
-  got = nat.moe_fwd(x.to(DEV), wp, bp, v, m)
+  got = nat.moe_fwd(x.to(DEV), wp.to(torch.float16), bp, v, m)
   assert rel_err(got, O.moe_model(x.float(), gw, ew, eb, v, m)) < 2e-5
 
 
@@ -369,5 +372,5 @@ def test_netvlad_f16_output(nat, k):
   assert rel_err(h16, f32) < 2 ** -10
   # the fp16 descriptor as FC operand: 1e-3 of the output scale (north_star tolerance) with margin
   w = synth.xavier((d * k, 256), g)
-  got = nat.linear(h16, nat.pack_transpose(w.to(DEV)), n=256, k=d * k)["f32"]
+  got = nat.linear(h16, nat.pack_transpose(w.to(DEV)).to(torch.float16), n=256, k=d * k)["f32"]
   assert rel_err(got, want @ w) < 5e-4

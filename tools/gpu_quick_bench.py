@@ -55,7 +55,8 @@ res["fc_73728x1024_b256"] = {"ms": ms, "TFLOPs": 2 * B * 1024 * K * D / ms / 1e9
 ms = timeit(lambda: nat.linear(vl, wfc, a_lo=vl, act="relu6", out_bf16=True, out_lo=True))
 res["fc_73728x1024_b256_hilo"] = {"ms": ms}
 vl16 = vl.to(torch.float16)
-ms = timeit(lambda: nat.linear(vl16, wfc, act="relu6", out_f32=False, out_f16=True))
+wfc16 = wfc.to(torch.float16)
+ms = timeit(lambda: nat.linear(vl16, wfc16, act="relu6", out_f32=False, out_f16=True))
 res["fc_73728x1024_b256_f16"] = {"ms": ms}
 
 for (d_in, m) in [(1024, 2), (4096, 4)]:

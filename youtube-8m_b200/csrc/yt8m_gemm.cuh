@@ -24,7 +24,8 @@ constexpr int kGemmThreads = 224;     // warp 0: A producer, 1: MMA, 2-5: epilog
 struct GemmShape {
   int M, N, K;
   int kb_per_split;                    // K-blocks handled by one blockIdx.z
-  int a_f16;                           // 1: the A operand holds IEEE fp16 (11 significant bits) instead of bf16; W stays bf16
+  int a_f16;                           // 1: A AND W hold IEEE fp16 (11 significant bits) instead of bf16 (fp16 x bf16 in one
+                                       //    instruction is an illegal-instruction fault on sm_100a -- measured, tools/f16_diag.py)
 };
 
 // MN = false: operands stored [rows, K] with K contiguous (forward / dgrad): stage = 64 K-elements.
@@ -151,8 +152,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
-    // a_format field (bits 7..9): 1 = bf16, 0 = fp16 -- the two operands of kind::f16 carry independent formats
-    const uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, MN ? 1 : 0, MN ? 1 : 0) ^ (shape.a_f16 ? (1u << 7) : 0u);
+    // a_format (bits 7..9) and b_format (bits 10..12): 1 = bf16, 0 = fp16; the hardware wants them equal
+    const uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, MN ? 1 : 0, MN ? 1 : 0) ^ (shape.a_f16 ? ((1u << 7) | (1u << 10)) : 0u);
     int stage = 0;
     uint32_t phase = 0;
     for (int kb = 0; kb < num_kb; ++kb) {

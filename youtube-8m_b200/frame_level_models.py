@@ -335,7 +335,10 @@ class NetVLADModel(models.BaseModel):
     vlad_hi, vlad_lo, _ = nat.netvlad_fwd(x, nf, cwp, scale, shift, cw2.value, want_lo=not f16, cw2_split=c2split, out_f16=f16)
 
     hw = st.get("hidden1_weights", (cluster_size * d, hidden1_size), ops.random_normal(1 / math.sqrt(cluster_size)))
-    hwp = st.packed(hw, "kmajor", lambda: nat.pack_transpose(hw.value))
+    if f16:   # the fp16 conversion of the packed weights (a dtype conversion: bf16 values >= 2^-17 are exact in fp16)
+      hwp = st.packed(hw, "kmajor_f16", lambda: nat.pack_transpose(hw.value).to(torch.float16))
+    else:
+      hwp = st.packed(hw, "kmajor", lambda: nat.pack_transpose(hw.value))
     if add_batch_norm:
       s_h, t_h = _bn_affine("hidden1_bn", hidden1_size, is_training)
     else:
@@ -347,7 +350,10 @@ class NetVLADModel(models.BaseModel):
     act = ops.Act(f32=hidden.get("f32"), hi=hidden["hi"], lo=hidden.get("lo"), cols=hidden1_size)
     if self.gating:
       gw = st.get("gating_weights", (hidden1_size, hidden1_size), ops.random_normal(1 / math.sqrt(hidden1_size)))
-      gwp = st.packed(gw, "kmajor", lambda: nat.pack_transpose(gw.value))
+      if f16:
+        gwp = st.packed(gw, "kmajor_f16", lambda: nat.pack_transpose(gw.value).to(torch.float16))
+      else:
+        gwp = st.packed(gw, "kmajor", lambda: nat.pack_transpose(gw.value))
       if add_batch_norm:
         s_g, t_g = _bn_affine("gating_bn", hidden1_size, is_training)
       else:

@@ -233,6 +233,8 @@ def linear(a_hi, w_packed, a_lo=None, n=None, k=None, scale=None, shift=None, ac
     for t in (of, oh, ol):
       if t is not None:
         t.zero_()
+  if w_packed.dtype != a_hi.dtype:
+    raise Yt8mError("linear: activation (%s) and weight (%s) operands must share one 16-bit format" % (a_hi.dtype, w_packed.dtype))
   ws_bytes = _lib.yt8m_linear_workspace_bytes(m, n, k)
   ws = _workspace(ws_bytes, dev)
   _call("yt8m_linear_fwd", _p(a_hi), _p(a_lo), a_hi.stride(0), _p(w_packed), w_packed.stride(0), m, n, k, _p(scale),
@@ -268,6 +270,8 @@ def moe_pack(gate_w, expert_w, expert_b, vocab, num_mixtures):
 def moe_fwd(x_hi, w_packed, bias_packed, vocab, num_mixtures, x_lo=None, d=None):
   b = x_hi.shape[0]
   d = d or min(x_hi.shape[1], w_packed.shape[1])
+  if w_packed.dtype != x_hi.dtype:
+    raise Yt8mError("moe_fwd: activation (%s) and weight (%s) operands must share one 16-bit format" % (x_hi.dtype, w_packed.dtype))
   out = _f32((b, vocab), x_hi.device)
   _call("yt8m_moe_fwd", _p(x_hi), _p(x_lo), x_hi.stride(0), _p(w_packed), w_packed.stride(0), _p(bias_packed), b, d, vocab,
         num_mixtures, _fmt(x_hi), _p(out), vocab, _stream())

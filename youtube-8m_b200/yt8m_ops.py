@@ -244,8 +244,11 @@ def fully_connected(x, num_outputs, scope, activation_fn="relu", use_bias=True, 
   st = get_store()
   w = st.get(scope + "/weights", (x.cols, num_outputs), weights_initializer, l2=l2_penalty)
   b = st.get(scope + "/biases", (num_outputs,), biases_initializer, round_bf16=False) if use_bias else None
-  wp = st.packed(w, "kmajor", lambda: nat.pack_transpose(w.value))
   hi, lo = x.operand()
+  if hi.dtype == torch.float16:      # fp16 activation (e.g. a NetVLAD hidden layer feeding a chain model): fp16 weight copy
+    wp = st.packed(w, "kmajor_f16", lambda: nat.pack_transpose(w.value).to(torch.float16))
+  else:
+    wp = st.packed(w, "kmajor", lambda: nat.pack_transpose(w.value))
   res = nat.linear(hi, wp, a_lo=lo, n=num_outputs, k=x.cols, scale=scale, shift=b.value if b is not None else None,
                    act=activation_fn, out_f32=True, out_bf16=want_bf16, out_lo=want_bf16)
   return Act(f32=res["f32"], hi=res.get("hi"), lo=res.get("lo"), cols=num_outputs)
@@ -266,8 +269,14 @@ def moe_head(x, vocab_size, num_mixtures, gates_scope, experts_scope, l2_penalty
   def build():
     return nat.moe_pack(gw.value, ew.value, eb.value, v, m)
 
-  wp, bp = st.packed(gw, "moe", build, version=(gw.version, ew.version, eb.version))
   hi, lo = x.operand()
+  if hi.dtype == torch.float16:      # fp16 activation: the weight operand must be fp16 too (one format per MMA)
+    def build16():
+      wp, bp = build()
+      return wp.to(torch.float16), bp
+    wp, bp = st.packed(gw, "moe_f16", build16, version=(gw.version, ew.version, eb.version))
+  else:
+    wp, bp = st.packed(gw, "moe", build, version=(gw.version, ew.version, eb.version))
   return nat.moe_fwd(hi, wp, bp, v, m, x_lo=lo, d=d)
 
 
