@@ -140,7 +140,9 @@ int yt8m_attn_pool_fwd(const float* logits, long long ld_logits, const yt8m_bf16
  * cw2: fp32 [D, K]; cw2_hi / cw2_lo (nullable): its bf16 hi/lo split [D, K] -- with them, K = 64 and a dense
  * output (ld_out = D*K) the residual runs on the tensor cores and the descriptor is written through TMA.
  * out: [B, D*K] (D-major, K-minor).  K in {32, 64, 128}, D % 128 == 0, T <= 384.
- * out_fmt = YT8M_FMT_F16: out_hi receives fp16 (out_lo must be NULL). */
+ * out_fmt = YT8M_FMT_F16: out_hi receives fp16 (out_lo must be NULL).
+ * out_hi (+ out_lo) double as the stash of the un-normalised descriptor, which the final rescale reads back: out_f32
+ * therefore carries the precision of the stash (bf16 hi alone: 8 bits; hi + lo: ~16 bits; fp16: 11 bits). */
 int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K,
                      const yt8m_bf16* cw_packed, const float* scale, const float* shift, const float* cw2,
                      const yt8m_bf16* cw2_hi, const yt8m_bf16* cw2_lo, float* out_f32, yt8m_bf16* out_hi,

@@ -51,15 +51,14 @@ def test_single_video_and_single_row(nat):
   want = O.netvlad_pool(x, nf, cw, torch.ones(64), torch.zeros(64), cw2)
   cwp = nat.pack_transpose(cw.to(DEV))
   _, _, f32 = nat.netvlad_fwd(bf(x), nf.to(DEV), cwp, None, None, cw2.to(DEV), want_f32=True)
-  # one video alone: the bf16 rounding of its assignments does not average out over a batch, so the L2 bound
-  # is the per-video one (the batch tests hold 1e-3 over many videos)
-  assert float((f32.cpu() - want).norm() / want.norm()) < 3e-3
-  # ... and a video's descriptor does not depend on what else is in the batch (to fp32 rounding: the column
-  # sums of squares are accumulated with shared-memory atomics, whose order is not fixed)
+  assert float((f32.cpu() - want).norm() / want.norm()) < 1e-3
+  # ... and a video's descriptor does not depend on what else is in the batch.  Not bit-exact: the cluster sums
+  # are accumulated with shared-memory atomics in no fixed order, and a 1e-7 wobble can flip the rounding of the
+  # lo half of the stash (2^-16 relative)
   x3, nf3, _ = synth.model_input(3, 300, 1152, seed=22)
   x3[1], nf3[1] = x[0], nf[0]
   _, _, f32b = nat.netvlad_fwd(bf(x3), nf3.to(DEV), cwp, None, None, cw2.to(DEV), want_f32=True)
-  assert float((f32b[1] - f32[0]).abs().max()) <= 1e-6 * float(f32[0].abs().max())
+  assert float((f32b[1] - f32[0]).abs().max()) <= 1e-4 * float(f32[0].abs().max())
   # MoE / linear with one row and tiny shapes
   d, v, m = 8, 3, 2
   gw, ew, eb = synth.xavier((d, v * 3), g, 2.0), synth.xavier((d, v * 2), g, 2.0), 0.1 * torch.randn(v * 2, generator=g)

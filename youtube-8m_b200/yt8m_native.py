@@ -334,11 +334,13 @@ def netvlad_fwd(x, num_frames, cw_packed, scale, shift, cw2, want_f32=False, wan
     oh, ol = torch.empty((b, d * k), dtype=torch.float16, device=x.device), None
   else:
     oh = _bf16((b, d * k), x.device)
-    ol = _bf16((b, d * k), x.device) if want_lo else None
+    # the fp32 output is the rescaled STASH (un-normalised descriptor parked in out_hi [+ out_lo]): ask for the lo
+    # half whenever fp32 is wanted, or it would only be bf16-accurate
+    ol = _bf16((b, d * k), x.device) if (want_lo or want_f32) else None
   of = _f32((b, d * k), x.device) if want_f32 else None
   _call("yt8m_netvlad_fwd", _p(x), _p(num_frames), b, t, d, k, _p(cw_packed), _p(scale), _p(shift), _p(cw2), _p(c2h), _p(c2l),
         _p(of), _p(oh), _p(ol), d * k, FMT_F16 if out_f16 else FMT_BF16, _stream())
-  return oh, ol, of
+  return oh, (ol if want_lo else None), of
 
 
 def debug_set_timeline(buf):
