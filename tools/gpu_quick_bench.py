@@ -58,6 +58,10 @@ vl16 = vl.to(torch.float16)
 wfc16 = wfc.to(torch.float16)
 ms = timeit(lambda: nat.linear(vl16, wfc16, act="relu6", out_f32=False, out_f16=True))
 res["fc_73728x1024_b256_f16"] = {"ms": ms}
+nat.debug_set_flags(256)            # experiment: pair the two M tiles in one CTA (W read once per CTA, twice the splits)
+ms = timeit(lambda: nat.linear(vl16, wfc16, act="relu6", out_f32=False, out_f16=True))
+res["fc_73728x1024_b256_f16_mt2"] = {"ms": ms}
+nat.debug_set_flags(0)
 
 for (d_in, m) in [(1024, 2), (4096, 4)]:
   rows = nat.moe_packed_rows(V, m)
@@ -70,6 +74,10 @@ for (d_in, m) in [(1024, 2), (4096, 4)]:
     if bb == 256:
       ms = timeit(lambda: nat.moe_fwd(h, wp, bp, V, m, x_lo=h))
       res["moe_d%d_m%d_b%d_hilo" % (d_in, m, bb)] = {"ms": ms}
+      nat.debug_set_flags(1024)       # A/B: one CTA per SM
+      ms = timeit(lambda: nat.moe_fwd(h, wp, bp, V, m))
+      res["moe_d%d_m%d_b%d_1cta" % (d_in, m, bb)] = {"ms": ms}
+      nat.debug_set_flags(0)
 
 # big square GEMM through the same main loop (tensor-pipe ceiling of this kernel)
 a = torch.randn(8192, 8192, device=dev).to(torch.bfloat16)

@@ -10,11 +10,11 @@ namespace {
 
 constexpr int kNumSms = 148;
 
-template <int BLOCK_N, int A_SPLIT, class Epi, int MT = 1>
+template <int BLOCK_N, int A_SPLIT, class Epi, int MT = 1, int CTAS = 1>
 int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, const yt8m_bf16* w, long long ldw, int M,
                 int N_rows_w, int N, int K, int split_k, const typename Epi::Params& ep, cudaStream_t stream,
                 int a_f16 = 0) {
-  using S = GemmSmem<BLOCK_N, A_SPLIT, false, MT>;
+  using S = GemmSmem<BLOCK_N, A_SPLIT, false, MT, CTAS>;
   CUtensorMap tm_a_hi, tm_a_lo, tm_b;
   int rc;
   if ((rc = make_tmap_bf16_2d(&tm_a_hi, a_hi, M, K, lda, kBlockM)) != YT8M_OK) return rc;
@@ -24,7 +24,7 @@ int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, con
     tm_a_lo = tm_a_hi;
   }
   if ((rc = make_tmap_bf16_2d(&tm_b, w, N_rows_w, K, ldw, BLOCK_N)) != YT8M_OK) return rc;
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_SPLIT, Epi, false, MT>;
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_SPLIT, Epi, false, MT, CTAS>;
   static bool attr_done = false;   // per template instantiation
   if (!attr_done) {
     YT8M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
@@ -163,7 +163,9 @@ int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda,
   // 256-wide tiles: measured slower, the ring is latency-bound) or the grid cannot fill the SMs anyway (then
   // split-K takes over and pairing M tiles would only double the number of fp32 atomics per output element)
   const long long tiles1 = static_cast<long long>((M + kBlockM - 1) / kBlockM) * ((N + block_n - 1) / block_n);
-  const int mt = (M > kBlockM && !(a_lo && block_n == 256) && tiles1 >= 2 * 148) ? 2 : 1;
+  int mt = (M > kBlockM && !(a_lo && block_n == 256) && tiles1 >= 2 * 148) ? 2 : 1;
+  if ((host_debug_flags() & 256) && M > kBlockM && !(a_lo && block_n == 256)) mt = 2;      // experiment: force pairing
+  if (host_debug_flags() & 512) mt = 1;
   int split_k = pick_split_k(M, N, K, block_n, mt);
   if (split_k > 1 && (!workspace || workspace_bytes < yt8m_linear_workspace_bytes(M, N, K))) split_k = 1;
 
@@ -247,6 +249,9 @@ int yt8m_moe_fwd(const yt8m_bf16* x_hi, const yt8m_bf16* x_lo, long long ldx, co
     if (B > 128 && (D >= 2048 || B > 256))   /* two accumulators per CTA pay off once the K loop is long */    \
       return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16) \
                   : launch_gemm<128, 1, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16); \
+    if (D <= 2048 && !(host_debug_flags() & 1024))   /* short K loop: two co-resident CTAs per SM overlap epilogue and loads */ \
+      return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 1, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16) \
+                  : launch_gemm<128, 1, EpiMoe<NM>, 1, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16); \
     return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 1>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16) \
                 : launch_gemm<128, 1, EpiMoe<NM>, 1>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16); \
   }

@@ -33,13 +33,15 @@ struct GemmShape {
 //             the batch rows): stage = 128 contraction rows, tiles are 64-column boxes of 128 rows.
 // MT = number of 128-row M tiles one CTA owns (1 or 2): with MT = 2 every W tile is used for 256 output rows, i.e.
 // 1.5x the tensor work per byte brought into shared memory -- the rings are bytes-in-flight / latency bound.
-template <int BLOCK_N, int A_SPLIT, bool MN = false, int MT = 1>
+// CTAS = CTAs meant to be co-resident on one SM (1 or 2): with 2, each gets half the shared-memory budget and the
+// epilogue of one overlaps the main loop of the other (short-K problems: the MoE head at small batch).
+template <int BLOCK_N, int A_SPLIT, bool MN = false, int MT = 1, int CTAS = 1>
 struct GemmSmem {
   static constexpr int kATile = MN ? 2 * 128 * 128 : kBlockM * kBlockK * 2;       // one 128-row A tile: 16 KB (K-major) / 32 KB (MN)
   static constexpr int kABytes = MT * kATile;                                      // all M tiles of one operand half (hi or lo)
   static constexpr int kBBytes = MN ? (BLOCK_N / 64) * 128 * 128 : BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = A_SPLIT * kABytes + kBBytes;
-  static constexpr int kBudget = 200 * 1024;
+  static constexpr int kBudget = CTAS == 2 ? 96 * 1024 : 200 * 1024;
   static constexpr int kStages = (kBudget / kStageBytes) > 8 ? 8 : (kBudget / kStageBytes);
   static constexpr int kBarrierBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kBarrierBytes + 1024;  // +1024 for alignment slack
@@ -54,12 +56,12 @@ __host__ __device__ constexpr int tmem_cols_for(int n) { return n <= 32 ? 32 : n
 //                                       int n0 (global N index of tile col 0), uint32_t tmem_row_addr, bool row_valid); }
 // run() is called by every epilogue thread (uniformly per warp: tcgen05.ld is warp-collective).
 
-template <int BLOCK_N, int A_SPLIT, class Epi, bool MN = false, int MT = 1>
-__global__ void __launch_bounds__(kGemmThreads, 1)
+template <int BLOCK_N, int A_SPLIT, class Epi, bool MN = false, int MT = 1, int CTAS = 1>
+__global__ void __launch_bounds__(kGemmThreads, CTAS)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b, const GemmShape shape, const typename Epi::Params ep) {
-  using S = GemmSmem<BLOCK_N, A_SPLIT, MN, MT>;
-  static_assert(MT * BLOCK_N <= 512, "accumulators exceed TMEM");
+  using S = GemmSmem<BLOCK_N, A_SPLIT, MN, MT, CTAS>;
+  static_assert(CTAS * MT * BLOCK_N <= 512, "accumulators exceed TMEM");
   constexpr int kStageK = MN ? 128 : kBlockK;          // contraction elements per pipeline stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));

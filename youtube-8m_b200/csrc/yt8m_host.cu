@@ -20,6 +20,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+int& host_debug_flags() {
+  static int flags = 0;
+  return flags;
+}
+
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

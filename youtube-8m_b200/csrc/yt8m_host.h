@@ -25,6 +25,9 @@ int make_tmap_bf16_nd(CUtensorMap* out, const void* ptr, int rank, const uint64_
 
 int check_launch(const char* what);
 
+// debug / experiment switches set through yt8m_debug_set_flags (host copy; 0 in normal operation)
+int& host_debug_flags();
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace yt8m

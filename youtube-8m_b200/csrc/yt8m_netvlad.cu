@@ -1087,6 +1087,7 @@ extern "C" int yt8m_debug_set_timeline(unsigned long long* dev_buf) {
   return YT8M_OK;
 }
 extern "C" int yt8m_debug_set_flags(int flags) {
+  host_debug_flags() = flags;
   YT8M_CUDA(cudaMemcpyToSymbol(g_nv_flags, &flags, sizeof(flags)));
   return YT8M_OK;
 }
