@@ -142,11 +142,12 @@ int yt8m_attn_pool_fwd(const float* logits, long long ld_logits, const yt8m_bf16
  * out: [B, D*K] (D-major, K-minor).  K in {32, 64, 128}, D % 128 == 0, T <= 384.
  * out_fmt = YT8M_FMT_F16: out_hi receives fp16 (out_lo must be NULL).
  * out_hi (+ out_lo) double as the stash of the un-normalised descriptor, which the final rescale reads back: out_f32
- * therefore carries the precision of the stash (bf16 hi alone: 8 bits; hi + lo: ~16 bits; fp16: 11 bits). */
+ * therefore carries the precision of the stash (bf16 hi alone: 8 bits; hi + lo: ~16 bits; fp16: 11 bits).
+ * stats (nullable): fp32 [B, 2K+1] = {a_sum[K], ||V[:,k]||^2 [K], ||U||_F^2} saved for yt8m_netvlad_bwd_norm. */
 int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K,
                      const yt8m_bf16* cw_packed, const float* scale, const float* shift, const float* cw2,
                      const yt8m_bf16* cw2_hi, const yt8m_bf16* cw2_lo, float* out_f32, yt8m_bf16* out_hi,
-                     yt8m_bf16* out_lo, long long ld_out, int out_fmt, yt8m_stream_t stream);
+                     yt8m_bf16* out_lo, long long ld_out, int out_fmt, float* stats, yt8m_stream_t stream);
 
 /* debug only: device buffer (>= 128 u64, or NULL to disable) that receives globaltimer stamps of the
  * NetVLAD kernel's phases for CTA 0 (tools/netvlad_timeline.py decodes them) */
@@ -204,6 +205,23 @@ int yt8m_grad_reg_sumsq(float* grad, const float* param, long long rows, int row
 int yt8m_clip_adam_step(float* param, const float* grad, float* m, float* v, long long rows, int row_len, const float* sums4,
                         float clip, float lr_t, float beta1, float beta2, float eps, int moe_per, int moe_nmix, int only_segment,
                         yt8m_bf16* param_bf16, yt8m_stream_t stream);
+
+/* ---- backward of the NetVLAD layer and of a dense layer's activation (frame-level training step) ----------
+ * Definition: oracle/yt8m_oracle.py:netvlad_pool (not in the reference).  All tensors fp32 unless noted.
+ * yt8m_netvlad_bwd_norm:   dy, y [B, D*K] (y = the forward's fp32 output), stats from the forward, cw2 [D, K] ->
+ *   dv [B, D*K] = dL/dV (V = un-normalised descriptor), dasum [B, K] = dL/da_sum, dcw2 [D, K] (nullable) = dL/dcw2.
+ * yt8m_netvlad_bwd_assign: x bf16 [B, T, D], z [B*T, K] = scale * (x . Cw) + shift (recomputed with
+ *   yt8m_linear_fwd), dv, dasum -> dzs bf16 hi/lo [B*T, K] = dL/d(x . Cw) (i.e. dz * scale; rows t >= num_frames
+ *   are zero), dshift [K] (nullable) = dL/dshift.  da_ws: scratch fp32 [B*T, K].  dL/dCw^T [K, D] then is
+ *   yt8m_wgrad(dzs, x).  K in {32, 64, 128}, D % 32 == 0.
+ * yt8m_act_bwd: d_pre = dy * act'(y) * col_scale  (y = post-activation output of yt8m_linear_fwd) as bf16 hi/lo. */
+int yt8m_netvlad_bwd_norm(const float* dy, const float* y, const float* stats, const float* cw2, int B, int D, int K,
+                          float* dv, float* dasum, float* dcw2, yt8m_stream_t stream);
+int yt8m_netvlad_bwd_assign(const yt8m_bf16* x, const int* num_frames, const float* z, const float* dv, const float* dasum,
+                            const float* scale, int B, int T, int D, int K, float* da_ws, yt8m_bf16* dzs_hi,
+                            yt8m_bf16* dzs_lo, float* dshift, yt8m_stream_t stream);
+int yt8m_act_bwd(const float* dy, const float* y, long long rows, int cols, int act, const float* col_scale,
+                 yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out, yt8m_stream_t stream);
 
 /* top-k per row, descending (wh/inference.py:76-87 format_lines; wh/eval_util.py:164 top_k_triplets).
  * k <= 32.  idx_out: int32 [rows, k]; val_out: fp32 [rows, k]. */

@@ -37,11 +37,11 @@ def test_moe_argument_checks():
 
 
 def test_netvlad_lstm_attention_argument_checks():
-  assert lib.yt8m_netvlad_fwd(P, P, 2, 300, 1152, 48, P, None, None, P, None, None, None, P, None, 1152 * 48, 0, None) == UNSUPPORTED
+  assert lib.yt8m_netvlad_fwd(P, P, 2, 300, 1152, 48, P, None, None, P, None, None, None, P, None, 1152 * 48, 0, None, None) == UNSUPPORTED
   assert "K=48" in err()
-  assert lib.yt8m_netvlad_fwd(P, P, 2, 400, 1152, 64, P, None, None, P, None, None, None, P, None, 1152 * 64, 0, None) == BADSHAPE   # T > 384
-  assert lib.yt8m_netvlad_fwd(P, P, 2, 300, 1100, 64, P, None, None, P, None, None, None, P, None, 1100 * 64, 0, None) == BADSHAPE   # D % 128
-  assert lib.yt8m_netvlad_fwd(P, P, 2, 300, 1152, 64, P, None, None, P, None, None, None, None, None, 1152 * 64, 0, None) == BADPTR  # stash
+  assert lib.yt8m_netvlad_fwd(P, P, 2, 400, 1152, 64, P, None, None, P, None, None, None, P, None, 1152 * 64, 0, None, None) == BADSHAPE   # T > 384
+  assert lib.yt8m_netvlad_fwd(P, P, 2, 300, 1100, 64, P, None, None, P, None, None, None, P, None, 1100 * 64, 0, None, None) == BADSHAPE   # D % 128
+  assert lib.yt8m_netvlad_fwd(P, P, 2, 300, 1152, 64, P, None, None, P, None, None, None, None, None, 1152 * 64, 0, None, None) == BADPTR  # stash
   assert lib.yt8m_lstm_workspace_bytes(4, 10, 64, 32, 0) == 0 and lib.yt8m_lstm_workspace_bytes(4, 10, 64, 32, 9) == 0
   assert lib.yt8m_lstm_workspace_bytes(64, 300, 1152, 1024, 2) > 64 * 300 * 4096 * 4
   assert lib.yt8m_lstm_pack_weights(P, P, 60, 32, P, P, None) == BADSHAPE                       # in_dim % 8

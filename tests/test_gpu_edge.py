@@ -87,7 +87,7 @@ def test_lstm_ragged_including_zero_length(nat):
 def test_attention_ragged_and_single_frame(nat):
   g = torch.Generator().manual_seed(3)
   b, t, a, f = 4, 300, 8, 1152
-  x, _, _ = synth.model_input(b, t, f, seed=22)
+  x, _, _ = synth.model_input(b, t, f, seed=22, min_frames=t)     # every frame present, then cut to nf below
   nf = torch.tensor([1, 2, 299, 300], dtype=torch.int32)
   x = x * (torch.arange(t).unsqueeze(0) < nf.unsqueeze(1)).float().unsqueeze(2)
   logits = torch.randn(b, t, a, generator=g)

@@ -107,3 +107,71 @@ def test_moe_untouched_rows(tr):
   assert float(t.w.cpu()[~used].abs().max()) == 0.0
   assert float(t.b.cpu()[gates].abs().max()) == 0.0
   assert float(t.b.cpu()[experts].abs().max()) > 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# backward of the NetVLAD layer (kernel level): every gradient against torch autograd over the oracle forward
+# ------------------------------------------------------------------------------------------------
+
+def _rel_l2(got, want):
+  got, want = got.detach().float().cpu(), want.detach().float().cpu()
+  return float((got - want).norm() / want.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("k,with_scale", [(64, False), (64, True), (128, False)])
+def test_netvlad_backward_kernels(k, with_scale):
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  import yt8m_native as nat
+  g = torch.Generator().manual_seed(70 + k)
+  b, t, d = 5, 300, 1152
+  x, nf, _ = synth.model_input(b, t, d, seed=33)
+  nf[0], nf[1] = t, 1
+  cw = synth.normal((d, k), g, 4.0).requires_grad_(True)
+  shift = (0.1 * torch.randn(k, generator=g)).requires_grad_(True)
+  scale = (1.0 + 0.1 * torch.randn(k, generator=g)) if with_scale else torch.ones(k)
+  cw2 = synth.normal((d, k), g, 1 / math.sqrt(d)).requires_grad_(True)
+  dy = torch.randn(b, d * k, generator=g) * 1e-3
+  y = O.netvlad_pool(x, nf, cw, scale, shift, cw2)
+  (y * dy).sum().backward()
+
+  xd = x.to(DEV).to(torch.bfloat16)
+  cwp = nat.pack_transpose(cw.detach().to(DEV))
+  sc = scale.to(DEV) if with_scale else None
+  _, _, y32, stats = nat.netvlad_fwd(xd, nf.to(DEV), cwp, sc, shift.detach().to(DEV), cw2.detach().to(DEV), want_f32=True,
+                                     want_lo=True, want_stats=True)
+  assert _rel_l2(y32, y) < 1e-3
+  dv, dasum, dcw2 = nat.netvlad_bwd_norm(dy.to(DEV), y32, stats, cw2.detach().to(DEV))
+  z = nat.linear(xd.reshape(b * t, d), cwp, n=k, k=d, scale=sc, shift=shift.detach().to(DEV))["f32"]
+  dz_hi, dz_lo, dshift = nat.netvlad_bwd_assign(xd, nf.to(DEV), z, dv, dasum, scale=sc)
+  dcw_t = nat.wgrad(dz_hi, dz_lo, xd.reshape(b * t, d), k, d)                 # [K, D] = dL/dCw^T
+  # gradients pass through bf16 assignments / bf16 hi-lo dz: 1e-2 of the gradient's norm
+  assert _rel_l2(dcw2, cw2.grad) < 1e-2
+  assert _rel_l2(dshift, shift.grad) < 1e-2
+  assert _rel_l2(dcw_t.t(), cw.grad) < 1e-2
+  # padded frames carry no gradient
+  rows = dz_hi.float().reshape(b, t, k)
+  assert float(rows[1, 1:].abs().max()) == 0.0
+
+
+def test_act_bwd_and_wgrad_split():
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  import yt8m_native as nat
+  g = torch.Generator().manual_seed(5)
+  rows, cols = 37, 200
+  pre = torch.randn(rows, cols, generator=g) * 4
+  dy = torch.randn(rows, cols, generator=g)
+  sc = 1.0 + 0.1 * torch.randn(cols, generator=g)
+  for act, fn, dfn in (("relu6", O.relu6, lambda yy: ((yy > 0) & (yy < 6)).float()), ("sigmoid", torch.sigmoid, lambda yy: yy * (1 - yy)),
+                       (None, lambda v: v, lambda yy: torch.ones_like(yy))):
+    yy = fn(pre)
+    hi, lo = nat.act_bwd(dy.to(DEV), yy.to(DEV), act=act, col_scale=sc.to(DEV))
+    want = dy * dfn(yy) * sc
+    assert float(((hi.float() + lo.float()).cpu() - want).abs().max()) < 1e-4 * float(want.abs().max())
+  # wgrad with a long contraction and few output tiles takes the split path (fp32 atomics): same numbers
+  kb, m, n = 4096, 64, 256
+  a = synth.bf16r(torch.randn(kb, m, generator=g))
+  bm = synth.bf16r(torch.randn(kb, n, generator=g))
+  got = nat.wgrad(a.to(DEV).to(torch.bfloat16), None, bm.to(DEV).to(torch.bfloat16), m, n)
+  assert float((got.cpu() - a.t() @ bm).abs().max()) < 1e-3 * float((a.t() @ bm).abs().max())

@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(kNvThreads, 1)
 netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_cw,
                      const int* __restrict__ num_frames, int B, int T, int D, const float* __restrict__ scale,
                      const float* __restrict__ shift, const float* __restrict__ cw2, float* __restrict__ out_f32,
-                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ld_out, int out_f16) {
+                     __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long ld_out, int out_f16,
+                     float* __restrict__ stats) {
   using C = NvCfg<KC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -481,9 +482,14 @@ netvlad_fused_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_cons
         const float rs = rsqrtf(fmaxf(ss, 1e-12f));
         fscale_s[et] = rs;
         atomicAdd(total_s, ss * rs * rs);
+        if (stats) {                                           // saved for the backward pass: a_sum, ||V_k||^2
+          stats[static_cast<long long>(b) * (2 * KC + 1) + et] = asum_s[et];
+          stats[static_cast<long long>(b) * (2 * KC + 1) + KC + et] = ss;
+        }
       }
       named_bar_sync(1, 128);
       const float gs = rsqrtf(fmaxf(*total_s, 1e-12f));
+      if (stats && et == 0) stats[static_cast<long long>(b) * (2 * KC + 1) + 2 * KC] = *total_s;
       const long long n = static_cast<long long>(D) * KC;
       float* of = out_f32 ? out_f32 + static_cast<long long>(b) * ld_out : nullptr;
       constexpr int kU = 8;                                 // independent 16-byte loads in flight per thread (x2 with lo)
@@ -574,7 +580,7 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
                   const __grid_constant__ CUtensorMap tm_out_hi, const __grid_constant__ CUtensorMap tm_out_lo,
                   const int* __restrict__ num_frames, int B, int T, int D, const float* __restrict__ scale,
                   const float* __restrict__ shift, float* __restrict__ out_f32, __nv_bfloat16* __restrict__ out_hi,
-                  __nv_bfloat16* __restrict__ out_lo, long long ld_out, int out_f16) {
+                  __nv_bfloat16* __restrict__ out_lo, long long ld_out, int out_f16, float* __restrict__ stats) {
   const int want_lo = out_lo != nullptr;
   using C = Nv3Cfg;
   constexpr int KC = C::KC;
@@ -945,9 +951,14 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         const float rs = rsqrtf(fmaxf(ss, 1e-12f));
         fscale_s[p * KC + et] = rs;
         atomicAdd(total_s, ss * rs * rs);
+        if (stats) {                                           // saved for the backward pass: a_sum, ||V_k||^2
+          stats[static_cast<long long>(b) * (2 * KC + 1) + et] = asum_s[et];
+          stats[static_cast<long long>(b) * (2 * KC + 1) + KC + et] = ss;
+        }
       }
       named_bar_sync(1, 128);
       if (et < KC) fscale_s[p * KC + et] *= rsqrtf(fmaxf(*total_s, 1e-12f));
+      if (stats && et == 0) stats[static_cast<long long>(b) * (2 * KC + 1) + 2 * KC] = *total_s;
       if (boss && elect_one()) bulk_wait_group0();                    // every stash store has been performed
       __threadfence();
       named_bar_sync(1, 128);
@@ -1012,7 +1023,7 @@ netvlad_v3_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
 
 int launch_netvlad_v3(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, const yt8m_bf16* cw_packed,
                       const float* scale, const float* shift, const yt8m_bf16* cw2_hi, const yt8m_bf16* cw2_lo, float* out_f32,
-                      yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out, int out_f16, cudaStream_t stream) {
+                      yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out, int out_f16, float* stats, cudaStream_t stream) {
   using C = Nv3Cfg;
   CUtensorMap tm_x, tm_x64, tm_cw, tm_c2_hi, tm_c2_lo, tm_out_hi, tm_out_lo;
   int rc;
@@ -1042,14 +1053,14 @@ int launch_netvlad_v3(const yt8m_bf16* x, const int* num_frames, int B, int T, i
   const int grid = B < kNvSms ? B : kNvSms;
   netvlad_v3_kernel<<<grid, kNv3Threads, C::kTotal, stream>>>(tm_x, tm_x64, tm_cw, tm_c2_hi, tm_c2_lo, tm_out_hi, tm_out_lo, num_frames, B, T, D,
                                                               scale, shift, out_f32, reinterpret_cast<__nv_bfloat16*>(out_hi),
-                                                              reinterpret_cast<__nv_bfloat16*>(out_lo), ld_out, out_f16);
+                                                              reinterpret_cast<__nv_bfloat16*>(out_lo), ld_out, out_f16, stats);
   return check_launch("netvlad_v3_kernel");
 }
 
 template <int KC>
 int launch_netvlad(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, const yt8m_bf16* cw_packed,
                    const float* scale, const float* shift, const float* cw2, float* out_f32, yt8m_bf16* out_hi,
-                   yt8m_bf16* out_lo, long long ld_out, int out_f16, cudaStream_t stream) {
+                   yt8m_bf16* out_lo, long long ld_out, int out_f16, float* stats, cudaStream_t stream) {
   using C = NvCfg<KC>;
   CUtensorMap tm_x, tm_cw;
   int rc;
@@ -1076,7 +1087,7 @@ int launch_netvlad(const yt8m_bf16* x, const int* num_frames, int B, int T, int 
   const int grid = B < kNvSms ? B : kNvSms;               // persistent: one CTA per SM
   kern<<<grid, kNvThreads, C::kTotal, stream>>>(tm_x, tm_cw, num_frames, B, T, D, scale, shift, cw2, out_f32,
                                              reinterpret_cast<__nv_bfloat16*>(out_hi),
-                                             reinterpret_cast<__nv_bfloat16*>(out_lo), ld_out, out_f16);
+                                             reinterpret_cast<__nv_bfloat16*>(out_lo), ld_out, out_f16, stats);
   return check_launch("netvlad_fused_kernel");
 }
 
@@ -1095,7 +1106,7 @@ extern "C" int yt8m_debug_set_flags(int flags) {
 extern "C" int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K,
                                 const yt8m_bf16* cw_packed, const float* scale, const float* shift, const float* cw2,
                                 const yt8m_bf16* cw2_hi, const yt8m_bf16* cw2_lo, float* out_f32, yt8m_bf16* out_hi,
-                                yt8m_bf16* out_lo, long long ld_out, int out_fmt, yt8m_stream_t stream_) {
+                                yt8m_bf16* out_lo, long long ld_out, int out_fmt, float* stats, yt8m_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   YT8M_REQUIRE(x && num_frames && cw_packed && cw2 && out_hi, YT8M_E_BADPTR,
                "yt8m_netvlad_fwd: null pointer (out_hi is required: it doubles as the stash)");
@@ -1109,11 +1120,11 @@ extern "C" int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B
   const int out_f16 = out_fmt == YT8M_FMT_F16;
   // K = 64 with the bf16 hi/lo copy of cw2 and a dense output: the TMA-staged kernel
   if (K == 64 && cw2_hi && cw2_lo && ld_out == static_cast<long long>(D) * K)
-    return launch_netvlad_v3(x, num_frames, B, T, D, cw_packed, scale, shift, cw2_hi, cw2_lo, out_f32, out_hi, out_lo, ld_out, out_f16, stream);
+    return launch_netvlad_v3(x, num_frames, B, T, D, cw_packed, scale, shift, cw2_hi, cw2_lo, out_f32, out_hi, out_lo, ld_out, out_f16, stats, stream);
   switch (K) {
-    case 32: return launch_netvlad<32>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, out_f16, stream);
-    case 64: return launch_netvlad<64>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, out_f16, stream);
-    case 128: return launch_netvlad<128>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, out_f16, stream);
+    case 32: return launch_netvlad<32>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, out_f16, stats, stream);
+    case 64: return launch_netvlad<64>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, out_f16, stats, stream);
+    case 128: return launch_netvlad<128>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_f32, out_hi, out_lo, ld_out, out_f16, stats, stream);
     default:
       set_error("yt8m_netvlad_fwd: cluster count K=%d unsupported (32, 64, 128)", K);
       return YT8M_E_UNSUPPORTED;

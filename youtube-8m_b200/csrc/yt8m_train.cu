@@ -184,7 +184,7 @@ struct EpiMoeBwd {
 namespace {
 template <int BLOCK_N, int A_SPLIT, class Epi, bool MN>
 int launch_gemm_t(const CUtensorMap& tm_a_hi, const CUtensorMap& tm_a_lo, const CUtensorMap& tm_b, int M, int N, int K,
-                  const typename Epi::Params& ep, cudaStream_t stream) {
+                  const typename Epi::Params& ep, cudaStream_t stream, int split_k = 1) {
   using S = GemmSmem<BLOCK_N, A_SPLIT, MN>;
   auto kern = gemm_tcgen05_kernel<BLOCK_N, A_SPLIT, Epi, MN>;
   static bool attr_done = false;
@@ -195,8 +195,10 @@ int launch_gemm_t(const CUtensorMap& tm_a_hi, const CUtensorMap& tm_a_lo, const 
   constexpr int kStageK = MN ? 128 : kBlockK;
   GemmShape shape;
   shape.M = M; shape.N = N; shape.K = K; shape.a_f16 = 0;
-  shape.kb_per_split = (K + kStageK - 1) / kStageK;
-  dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + kBlockM - 1) / kBlockM, 1);
+  const int num_kb = (K + kStageK - 1) / kStageK;
+  shape.kb_per_split = (num_kb + split_k - 1) / split_k;
+  const int splits = (num_kb + shape.kb_per_split - 1) / shape.kb_per_split;
+  dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + kBlockM - 1) / kBlockM, splits);
   kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tm_a_hi, tm_a_lo, tm_b, shape, ep);
   return check_launch("gemm_tcgen05_kernel");
 }
@@ -230,10 +232,17 @@ int yt8m_wgrad(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, cons
   if (a_lo) { if ((rc = make_tmap_bf16_2d(&tm_a_lo, a_lo, Kb, M, lda, 128)) != YT8M_OK) return rc; }
   else tm_a_lo = tm_a_hi;
   if ((rc = make_tmap_bf16_2d(&tm_b, b, Kb, N, ldb, 128)) != YT8M_OK) return rc;
+  // few output tiles but a long contraction (e.g. dCw^T[64, 1152] over B*T frame rows): split the contraction rows
+  // over CTAs and reduce with fp32 vector atomics into the zeroed output
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128), num_kb = (Kb + 127) / 128;
+  int split_k = 1;
+  if (tiles < 74 && num_kb >= 8) split_k = std::max(1, std::min(148 / tiles, num_kb / 2));
   EpiLinear::Params ep{};
-  ep.out_f32 = out; ep.ld_out = ld_out; ep.act = ACT_NONE; ep.split_k = 1;
-  return a_lo ? launch_gemm_t<128, 2, EpiLinear, true>(tm_a_hi, tm_a_lo, tm_b, M, N, Kb, ep, stream)
-              : launch_gemm_t<128, 1, EpiLinear, true>(tm_a_hi, tm_a_lo, tm_b, M, N, Kb, ep, stream);
+  ep.out_f32 = out; ep.ld_out = ld_out; ep.act = ACT_NONE; ep.split_k = split_k;
+  if (split_k > 1)
+    YT8M_CUDA(cudaMemset2DAsync(out, static_cast<size_t>(ld_out) * sizeof(float), 0, static_cast<size_t>(N) * sizeof(float), M, stream));
+  return a_lo ? launch_gemm_t<128, 2, EpiLinear, true>(tm_a_hi, tm_a_lo, tm_b, M, N, Kb, ep, stream, split_k)
+              : launch_gemm_t<128, 1, EpiLinear, true>(tm_a_hi, tm_a_lo, tm_b, M, N, Kb, ep, stream, split_k);
 }
 
 int yt8m_colsum_bf16(const yt8m_bf16* hi, const yt8m_bf16* lo, long long ld, int rows, int cols, float* out,

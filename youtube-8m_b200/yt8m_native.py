@@ -51,7 +51,12 @@ _SIGS = {
     "yt8m_attn_pool_fwd": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     "yt8m_netvlad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
-                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
+    "yt8m_netvlad_bwd_norm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p]),
+    "yt8m_netvlad_bwd_assign": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "yt8m_act_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "yt8m_debug_set_timeline": (c_int, [c_void_p]),
     "yt8m_debug_set_flags": (c_int, [c_int]),
     "yt8m_context_gate_fwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
@@ -322,9 +327,11 @@ def attn_pool(logits, feats, num_frames, heads, mode, want_bf16=True):
   return out, oh, ol
 
 
-def netvlad_fwd(x, num_frames, cw_packed, scale, shift, cw2, want_f32=False, want_lo=False, cw2_split=None, out_f16=False):
+def netvlad_fwd(x, num_frames, cw_packed, scale, shift, cw2, want_f32=False, want_lo=False, cw2_split=None, out_f16=False,
+                want_stats=False):
   """x bf16 [B, T, D]; cw_packed bf16 [K, D]; cw2 fp32 [D, K] (cw2_split = its (hi, lo) bf16 copies, made on
-  demand) -> bf16 hi [B, D*K] (+lo, +fp32); out_f16: one fp16 tensor instead of hi (+lo)."""
+  demand) -> bf16 hi [B, D*K] (+lo, +fp32); out_f16: one fp16 tensor instead of hi (+lo).  want_stats appends
+  the fp32 [B, 2K+1] tensor the backward needs."""
   b, t, d = x.shape
   k = cw_packed.shape[0]
   if cw2_split is None and k == 64:
@@ -338,9 +345,49 @@ def netvlad_fwd(x, num_frames, cw_packed, scale, shift, cw2, want_f32=False, wan
     # half whenever fp32 is wanted, or it would only be bf16-accurate
     ol = _bf16((b, d * k), x.device) if (want_lo or want_f32) else None
   of = _f32((b, d * k), x.device) if want_f32 else None
+  stats = _f32((b, 2 * k + 1), x.device) if want_stats else None
   _call("yt8m_netvlad_fwd", _p(x), _p(num_frames), b, t, d, k, _p(cw_packed), _p(scale), _p(shift), _p(cw2), _p(c2h), _p(c2l),
-        _p(of), _p(oh), _p(ol), d * k, FMT_F16 if out_f16 else FMT_BF16, _stream())
+        _p(of), _p(oh), _p(ol), d * k, FMT_F16 if out_f16 else FMT_BF16, _p(stats), _stream())
+  if want_stats:
+    return oh, (ol if want_lo else None), of, stats
   return oh, (ol if want_lo else None), of
+
+
+def netvlad_bwd_norm(dy, y, stats, cw2, want_dcw2=True):
+  """dy, y fp32 [B, D*K]; stats [B, 2K+1]; cw2 fp32 [D, K] -> (dv [B, D*K], dasum [B, K], dcw2 [D, K] or None)."""
+  d, k = cw2.shape
+  b = dy.shape[0]
+  dv = _f32((b, d * k), dy.device)
+  dasum = _f32((b, k), dy.device)
+  dcw2 = _f32((d, k), dy.device) if want_dcw2 else None
+  _check(_lib.yt8m_netvlad_bwd_norm(_p(dy.contiguous()), _p(y.contiguous()), _p(stats), _p(cw2.contiguous()), b, d, k, _p(dv),
+                                    _p(dasum), _p(dcw2), _stream()), "yt8m_netvlad_bwd_norm")
+  return dv, dasum, dcw2
+
+
+def netvlad_bwd_assign(x, num_frames, z, dv, dasum, scale=None, want_dshift=True):
+  """x bf16 [B, T, D]; z fp32 [B*T, K]; dv [B, D*K]; dasum [B, K] -> (dzs_hi, dzs_lo bf16 [B*T, K], dshift [K] or None)."""
+  b, t, d = x.shape
+  k = dasum.shape[1]
+  ws = _f32((b * t, k), x.device)
+  hi, lo = _bf16((b * t, k), x.device), _bf16((b * t, k), x.device)
+  dshift = _f32((k,), x.device) if want_dshift else None
+  _check(_lib.yt8m_netvlad_bwd_assign(_p(x), _p(num_frames), _p(z.contiguous()), _p(dv), _p(dasum), _p(scale), b, t, d, k, _p(ws),
+                                      _p(hi), _p(lo), _p(dshift), _stream()), "yt8m_netvlad_bwd_assign")
+  return hi, lo, dshift
+
+
+def act_bwd(dy, y, act=None, col_scale=None):
+  """d_pre = dy * act'(y) * col_scale as bf16 (hi, lo) [rows, pad8(cols)] views."""
+  rows, cols = dy.shape
+  ld = pad8(cols)
+  hi, lo = _bf16((rows, ld), dy.device), _bf16((rows, ld), dy.device)
+  if ld != cols:
+    hi.zero_()
+    lo.zero_()
+  _check(_lib.yt8m_act_bwd(_p(dy.contiguous()), _p(y.contiguous()), rows, cols, ACT[act], _p(col_scale), _p(hi), _p(lo), ld,
+                           _stream()), "yt8m_act_bwd")
+  return hi[:, :cols], lo[:, :cols]
 
 
 def debug_set_timeline(buf):
