@@ -175,3 +175,58 @@ def test_act_bwd_and_wgrad_split():
   bm = synth.bf16r(torch.randn(kb, n, generator=g))
   got = nat.wgrad(a.to(DEV).to(torch.bfloat16), None, bm.to(DEV).to(torch.bfloat16), m, n)
   assert float((got.cpu() - a.t() @ bm).abs().max()) < 1e-3 * float((a.t() @ bm).abs().max())
+
+
+# ------------------------------------------------------------------------------------------------
+# the whole frame-level training step: NetVLAD + hidden FC + MoE head (BASELINE config 2, reduced sizes)
+# ------------------------------------------------------------------------------------------------
+
+def _netvlad_forward(params, x, nf, vocab, mixtures):
+  k = params["cluster_weights"].shape[1]
+  v = O.netvlad_pool(x, nf, params["cluster_weights"], torch.ones(k), params["cluster_biases"], params["cluster_weights2"])
+  h = O.relu6(v @ params["hidden1_weights"] + params["hidden1_biases"])
+  return O.moe_model(h, params["gates/weights"], params["experts/weights"], params["experts/biases"], vocab, mixtures)
+
+
+def test_netvlad_train_step_parity(tr):
+  g = torch.Generator().manual_seed(90)
+  b, t, d, k, h, v, mix = 6, 300, 1152, 64, 256, 500, 2
+  x, nf, _ = synth.model_input(b, t, d, seed=34)
+  y = synth.labels(b, v, seed=34, per_video=3.4)
+  sd = {"cluster_weights": synth.normal((d, k), g, 4.0), "cluster_biases": 0.1 * torch.randn(k, generator=g),
+        "cluster_weights2": synth.normal((d, k), g, 1 / math.sqrt(d)),
+        "hidden1_weights": synth.normal((k * d, h), g, 30.0 / math.sqrt(k)), "hidden1_biases": 0.1 * torch.randn(h, generator=g),
+        "gates/weights": synth.xavier((h, v * (mix + 1)), g, 2.0), "experts/weights": synth.xavier((h, v * mix), g, 2.0),
+        "experts/biases": 0.1 * torch.randn(v * mix, generator=g)}
+  t_ = tr.NetVLADTrainer(d, clusters=k, hidden=h, vocab=v, mixtures=mix)
+  t_.import_state(sd)
+  t_.keep_grads = True
+  xd, nfd, yd = x.to(DEV).to(torch.bfloat16), nf.to(DEV), y.to(DEV)
+  p0 = t_.step(xd, nfd, yd)
+  grad0 = t_.grads_tf_layout(t_.last_grad)
+  loss0 = float(t_.last["label_loss_local"])
+  # oracle: autograd over the fp32 forward
+  params = {kk: w.clone().requires_grad_(True) for kk, w in sd.items()}
+  pw = _netvlad_forward(params, x, nf, v, mix)
+  lw = O.cross_entropy_loss(pw, y)
+  gw = dict(zip(params, torch.autograd.grad(lw, list(params.values()))))
+  assert float((p0.cpu() - pw.detach()).abs().max()) < 1e-3
+  assert abs(loss0 - float(lw)) / float(lw) < 1e-3
+  for kk in gw:
+    assert float(gw[kk].norm()) > 0, kk
+    err = _rel_l2(grad0[kk], gw[kk])
+    assert err < 2e-2, (kk, err)
+  # two more steps: every tensor moves, the bf16 operand copies follow the masters, nothing becomes non-finite
+  for _ in range(2):
+    t_.step(xd, nfd, yd)
+  torch.cuda.synchronize()
+  got = t_.export_state()
+  for kk in sd:
+    assert bool(torch.isfinite(got[kk]).all()), kk
+    assert float((got[kk] - sd[kk]).abs().max()) > 0, kk
+  assert torch.equal(t_.cw_bf16.float(), t_.p["cw"].to(torch.bfloat16).float())
+  assert torch.equal(t_.wfc_bf16.float(), t_.p["wfc"].to(torch.bfloat16).float())
+  # Adam's first step moves every weight by ~lr * sign(g): check the displacement of the first step's direction
+  moved = got["cluster_weights2"] - sd["cluster_weights2"]
+  agree = (torch.sign(moved) == -torch.sign(gw["cluster_weights2"])).float().mean()
+  assert float(agree) > 0.9

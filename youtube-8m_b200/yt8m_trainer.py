@@ -45,7 +45,14 @@ def _moe_row_index(vocab, mixtures):
 class HeadTrainer(object):
   """Trains one video-level head.  kind = "logistic" | "moe"."""
 
-  def __init__(self, kind, in_dim, vocab, mixtures=2, l2_penalty=1e-8, device=None, group=None):
+  @staticmethod
+  def flat_size(kind, in_dim, vocab, mixtures=2):
+    rows = int(nat.moe_packed_rows(vocab, mixtures)) if kind == "moe" else vocab
+    return rows * nat.pad8(in_dim) + rows
+
+  def __init__(self, kind, in_dim, vocab, mixtures=2, l2_penalty=1e-8, device=None, group=None, storage=None):
+    """storage: optional (param, grad, adam_m, adam_v) flat fp32 views of flat_size() elements inside a larger
+    buffer (a frame-level trainer keeps ONE flat gradient buffer for the single all-reduce)."""
     assert kind in ("logistic", "moe")
     self.kind, self.d, self.v, self.m = kind, in_dim, vocab, mixtures
     self.l2 = l2_penalty
@@ -61,10 +68,14 @@ class HeadTrainer(object):
       self.per, self.rows = 0, vocab
     n_w, n_b = self.rows * self.dpad, self.rows
     # one flat buffer per role so that the gradient all-reduce is a single collective
-    self.param = torch.zeros(n_w + n_b, dtype=torch.float32, device=self.dev)
-    self.grad = torch.zeros_like(self.param)
-    self.adam_m = torch.zeros_like(self.param)
-    self.adam_v = torch.zeros_like(self.param)
+    if storage is not None:
+      self.param, self.grad, self.adam_m, self.adam_v = storage
+      assert all(t.numel() == n_w + n_b and t.dtype == torch.float32 for t in storage)
+    else:
+      self.param = torch.zeros(n_w + n_b, dtype=torch.float32, device=self.dev)
+      self.grad = torch.zeros_like(self.param)
+      self.adam_m = torch.zeros_like(self.param)
+      self.adam_v = torch.zeros_like(self.param)
     self.w, self.b = self.param[:n_w].view(self.rows, self.dpad), self.param[n_w:]
     self.gw, self.gb = self.grad[:n_w].view(self.rows, self.dpad), self.grad[n_w:]
     self.mw, self.mb = self.adam_m[:n_w].view(self.rows, self.dpad), self.adam_m[n_w:]
@@ -115,13 +126,10 @@ class HeadTrainer(object):
       return nat.linear(hi, self.w_bf16, a_lo=lo, n=self.v, k=self.d, shift=self.b, act="sigmoid")["f32"], (hi, lo)
     return nat.moe_fwd(hi, self.w_bf16, self.b, self.v, self.m, x_lo=lo, d=self.d), (hi, lo)
 
-  def step(self, x, labels, base_lr=0.01, lr_decay=0.95, lr_decay_examples=4000000, clip_gradient_norm=1.0,
-           regularization_penalty=1.0, global_batch=None):
-    """One optimiser step on this rank's shard (x [B_local, D], labels [B_local, V]).  Returns predictions;
-    loss terms are left on the device in ``self.last`` (fetch with .item() only when logging)."""
-    b_local = x.shape[0]
-    global_batch = global_batch or b_local * self.world
-    p, (hi, lo) = self.forward(x)
+  def backward(self, p, hi, lo, labels, global_batch, want_dx=False):
+    """Loss + gradients of this rank's shard into self.gw / self.gb (NOT yet all-reduced).  Returns (loss, dx):
+    dx [B_local, D] fp32 = dLoss/dx when want_dx (the head sits on top of a trainable frame-level model)."""
+    b_local = p.shape[0]
     # d(mean over the GLOBAL batch)/dp: xent divides by the local batch, so rescale by B_local / B_global
     loss, dp = nat.xent(p, labels, want_grad=True, grad_scale=b_local / float(global_batch))
     if self.kind == "logistic":
@@ -130,17 +138,38 @@ class HeadTrainer(object):
       dz_hi, dz_lo = nat.moe_bwd_dlogits(hi, lo, self.w_bf16, self.b, dp, self.v, self.m, d=self.d)
     nat.wgrad(dz_hi, dz_lo, hi, self.rows, self.d, out=self.gw)          # dW^T[rows, D] = dZ^T . X  (lo of x is dropped)
     nat.colsum_bf16(dz_hi, dz_lo, self.rows, out=self.gb)
-    yt8m_dp.all_reduce_sum_(self.grad, self.group)                        # the ONE collective of the step
-    if self.keep_grads:
-      self.last_grad = self.grad.clone()                                  # tests: gradient parity before reg/clip
-    lr = exponential_decay(base_lr, self.global_step, global_batch, lr_decay_examples, lr_decay)
-    lr_t = adam_lr_t(lr, self.global_step + 1)
+    dx = None
+    if want_dx:
+      # dX[B, D] = dZ[B, rows] . W[rows, D]: the K-major operand is W^T [D, rows] -- a bf16 transpose of the master
+      # (same rounding as the forward's operand copy)
+      wt = nat.pack_transpose(self.w)
+      dx = nat.linear(dz_hi, wt, a_lo=dz_lo, n=self.d, k=self.rows)["f32"]
+    return loss, dx
+
+  def apply(self, lr_t, clip_gradient_norm=1.0, regularization_penalty=1.0):
+    """L2 regulariser gradient, per-tensor clip, TF-Adam on this head's tensors (self.grad already all-reduced)."""
     sums_w = nat.grad_reg_sumsq(self.gw, self.w, self.l2 * regularization_penalty, self.per, self.m)
     sums_b = nat.grad_reg_sumsq(self.gb.view(self.rows, 1), self.b.view(self.rows, 1), 0.0, self.per, self.m)
     nat.clip_adam_step(self.w, self.gw, self.mw, self.vw, sums_w, clip_gradient_norm, lr_t, moe_per=self.per, moe_nmix=self.m,
                        param_bf16=self.w_bf16)
     nat.clip_adam_step(self.b.view(self.rows, 1), self.gb.view(self.rows, 1), self.mb.view(self.rows, 1), self.vb.view(self.rows, 1),
                        sums_b, clip_gradient_norm, lr_t, moe_per=self.per, moe_nmix=self.m, only_segment=1 if self.kind == "moe" else -1)
+    return sums_w
+
+  def step(self, x, labels, base_lr=0.01, lr_decay=0.95, lr_decay_examples=4000000, clip_gradient_norm=1.0,
+           regularization_penalty=1.0, global_batch=None):
+    """One optimiser step on this rank's shard (x [B_local, D], labels [B_local, V]).  Returns predictions;
+    loss terms are left on the device in ``self.last`` (fetch with .item() only when logging)."""
+    b_local = x.shape[0]
+    global_batch = global_batch or b_local * self.world
+    p, (hi, lo) = self.forward(x)
+    loss, _ = self.backward(p, hi, lo, labels, global_batch)
+    yt8m_dp.all_reduce_sum_(self.grad, self.group)                        # the ONE collective of the step
+    if self.keep_grads:
+      self.last_grad = self.grad.clone()                                  # tests: gradient parity before reg/clip
+    lr = exponential_decay(base_lr, self.global_step, global_batch, lr_decay_examples, lr_decay)
+    lr_t = adam_lr_t(lr, self.global_step + 1)
+    sums_w = self.apply(lr_t, clip_gradient_norm, regularization_penalty)
     self.global_step += 1
     self.last = {"label_loss_local": loss, "sums_w": sums_w, "lr": lr}
     return p
@@ -159,3 +188,128 @@ class HeadTrainer(object):
     """sum over weight tensors of l2 * ||W||^2 / 2 (slim.l2_regularizer) at the start of the last step."""
     s = self.last["sums_w"]
     return self.l2 * float(s[2] + s[3]) / 2.0
+
+
+class NetVLADTrainer(object):
+  """The training step for NetVLADModel + MoeModel (BASELINE config 2) on the GPU through the C ABI: fused NetVLAD
+  forward, hidden FC, MoE head, CrossEntropyLoss, and the full backward -- MoE head (fused recompute epilogue +
+  MN-major wgrad + dgrad), hidden FC (activation backward, wgrad, dgrad), NetVLAD layer (normalisation / residual /
+  assignment-softmax backward kernels + the cluster-weight wgrad over all B*T frame rows) -- then per-tensor
+  clip_by_norm and TF-Adam (wh/train.py:440-466).  NetVLAD itself is not part of the reference (oracle/
+  yt8m_oracle.py:netvlad_pool); the bias variant (--netvlad_add_batch_norm=False) is the one trained here.
+
+  One flat fp32 buffer holds every gradient, so data parallelism is ONE all-reduce per step.
+  Layouts: cluster_weights^T [K, D], cluster_biases [K], cluster_weights2 [D, K], hidden1_weights^T [H, K*D],
+  hidden1_biases [H], then the packed MoE head.  import_state / export_state speak the model's TF names."""
+
+  def __init__(self, feature_dim, clusters=64, hidden=1024, vocab=4716, mixtures=2, relu=True, l2_penalty=1e-8, device=None,
+               group=None):
+    self.d, self.k, self.h, self.v, self.m, self.relu = feature_dim, clusters, hidden, vocab, mixtures, relu
+    self.dev = device or torch.device("cuda", torch.cuda.current_device())
+    self.group = group
+    self.world = yt8m_dp.world_size(group)
+    kd = clusters * feature_dim
+    self.kd = kd
+    sizes = [("cw", clusters * feature_dim), ("cb", clusters), ("c2", feature_dim * clusters), ("wfc", hidden * kd), ("bfc", hidden),
+             ("head", HeadTrainer.flat_size("moe", hidden, vocab, mixtures))]
+    total = sum(n for _, n in sizes)
+    self.param = torch.zeros(total, dtype=torch.float32, device=self.dev)
+    self.grad = torch.zeros_like(self.param)
+    self.adam_m = torch.zeros_like(self.param)
+    self.adam_v = torch.zeros_like(self.param)
+    self._off = {}
+    off = 0
+    for name, n in sizes:
+      self._off[name] = (off, off + n)
+      off += n
+    shapes = {"cw": (clusters, feature_dim), "cb": (clusters, 1), "c2": (feature_dim, clusters), "wfc": (hidden, kd), "bfc": (hidden, 1)}
+    self.p, self.g, self.am, self.av = {}, {}, {}, {}
+    for name, shp in shapes.items():
+      a, b = self._off[name]
+      self.p[name], self.g[name] = self.param[a:b].view(shp), self.grad[a:b].view(shp)
+      self.am[name], self.av[name] = self.adam_m[a:b].view(shp), self.adam_v[a:b].view(shp)
+    a, b = self._off["head"]
+    self.head = HeadTrainer("moe", hidden, vocab, mixtures, l2_penalty, self.dev, group,
+                            storage=(self.param[a:b], self.grad[a:b], self.adam_m[a:b], self.adam_v[a:b]))
+    self.cw_bf16 = torch.zeros((clusters, feature_dim), dtype=torch.bfloat16, device=self.dev)
+    self.wfc_bf16 = torch.zeros((hidden, kd), dtype=torch.bfloat16, device=self.dev)
+    self.global_step = 0
+    self.keep_grads = False
+    self.last = {}
+
+  # ---- TF names / layouts ----------------------------------------------------------------------------
+  def import_state(self, sd):
+    dev = self.dev
+    self.p["cw"].copy_(sd["cluster_weights"].t().to(dev))
+    self.p["cb"].copy_(sd["cluster_biases"].view(-1, 1).to(dev))
+    self.p["c2"].copy_(sd["cluster_weights2"].to(dev))
+    self.p["wfc"].copy_(sd["hidden1_weights"].t().to(dev))
+    self.p["bfc"].copy_(sd["hidden1_biases"].view(-1, 1).to(dev))
+    self.head.import_state({k: sd[k] for k in ("gates/weights", "experts/weights", "experts/biases")})
+    self.cw_bf16.copy_(self.p["cw"])
+    self.wfc_bf16.copy_(self.p["wfc"])
+
+  def _tf_layout(self, views, head_flat):
+    out = {"cluster_weights": views["cw"].t().contiguous().cpu(), "cluster_biases": views["cb"].reshape(-1).cpu().clone(),
+           "cluster_weights2": views["c2"].cpu().clone(), "hidden1_weights": views["wfc"].t().contiguous().cpu(),
+           "hidden1_biases": views["bfc"].reshape(-1).cpu().clone()}
+    out.update(self.head.grads_tf_layout(head_flat))
+    return out
+
+  def export_state(self):
+    a, b = self._off["head"]
+    return self._tf_layout(self.p, self.param[a:b])
+
+  def grads_tf_layout(self, flat):
+    views = {}
+    for name in ("cw", "cb", "c2", "wfc", "bfc"):
+      a, b = self._off[name]
+      views[name] = flat[a:b].view(self.p[name].shape)
+    a, b = self._off["head"]
+    return self._tf_layout(views, flat[a:b])
+
+  # ---- forward / step --------------------------------------------------------------------------------
+  def forward(self, x, num_frames):
+    """x bf16 [B, T, D] (L2-normalised frame rows), num_frames int32 [B] -> predictions + what the backward needs."""
+    c2 = self.p["c2"]
+    cb = self.p["cb"].view(-1)
+    vh, vl, y32, stats = nat.netvlad_fwd(x, num_frames, self.cw_bf16, None, cb, c2, want_f32=True, want_lo=True, want_stats=True)
+    hid = nat.linear(vh, self.wfc_bf16, a_lo=vl, n=self.h, k=self.kd, shift=self.p["bfc"].view(-1),
+                     act="relu6" if self.relu else None, out_f32=True, out_bf16=True, out_lo=True)
+    p = nat.moe_fwd(hid["hi"], self.head.w_bf16, self.head.b, self.v, self.m, x_lo=hid["lo"], d=self.h)
+    return p, {"vh": vh, "vl": vl, "y32": y32, "stats": stats, "hid": hid}
+
+  def step(self, x, num_frames, labels, base_lr=0.01, lr_decay=0.95, lr_decay_examples=4000000, clip_gradient_norm=1.0,
+           regularization_penalty=1.0, global_batch=None):
+    b, t, d = x.shape
+    global_batch = global_batch or b * self.world
+    p, sv = self.forward(x, num_frames)
+    hid = sv["hid"]
+    loss, dhid = self.head.backward(p, hid["hi"], hid["lo"], labels, global_batch, want_dx=True)
+    # hidden FC: h = act(vlad . Wfc + b)
+    dpre_hi, dpre_lo = nat.act_bwd(dhid, hid["f32"], act="relu6" if self.relu else None)
+    nat.wgrad(dpre_hi, dpre_lo, sv["vh"], self.h, self.kd, out=self.g["wfc"])          # dWfc^T [H, K*D]
+    nat.colsum_bf16(dpre_hi, dpre_lo, self.h, out=self.g["bfc"].view(-1))
+    wfc_tf = nat.pack_transpose(self.p["wfc"])                                          # bf16 [K*D, H]: the dgrad operand
+    dvlad = nat.linear(dpre_hi, wfc_tf, a_lo=dpre_lo, n=self.kd, k=self.h)["f32"]       # [B, K*D]
+    del wfc_tf
+    # NetVLAD layer
+    dv, dasum, dc2 = nat.netvlad_bwd_norm(dvlad, sv["y32"], sv["stats"], self.p["c2"])
+    self.g["c2"].copy_(dc2)
+    z = nat.linear(x.reshape(b * t, d), self.cw_bf16, n=self.k, k=d, shift=self.p["cb"].view(-1))["f32"]
+    dz_hi, dz_lo, dshift = nat.netvlad_bwd_assign(x, num_frames, z, dv, dasum)
+    self.g["cb"].view(-1).copy_(dshift)
+    nat.wgrad(dz_hi, dz_lo, x.reshape(b * t, d), self.k, d, out=self.g["cw"])           # dCw^T [K, D]
+    yt8m_dp.all_reduce_sum_(self.grad, self.group)                                      # the ONE collective of the step
+    if self.keep_grads:
+      self.last_grad = self.grad.clone()
+    lr = exponential_decay(base_lr, self.global_step, global_batch, lr_decay_examples, lr_decay)
+    lr_t = adam_lr_t(lr, self.global_step + 1)
+    for name, bf in (("cw", self.cw_bf16), ("cb", None), ("c2", None), ("wfc", self.wfc_bf16), ("bfc", None)):
+      sums = nat.grad_reg_sumsq(self.g[name], self.p[name], 0.0)
+      nat.clip_adam_step(self.p[name], self.g[name], self.am[name], self.av[name], sums, clip_gradient_norm, lr_t, param_bf16=bf)
+    self.head.apply(lr_t, clip_gradient_norm, regularization_penalty)
+    self.global_step += 1
+    self.head.global_step = self.global_step
+    self.last = {"label_loss_local": loss, "lr": lr}
+    return p
