@@ -83,18 +83,24 @@ class Trainer(object):
   def build_model(self, in_dim):
     import yt8m_trainer
     model_cls = utils.find_class_by_name(self.model_name, [frame_level_models, video_level_models])
+    if FLAGS.optimizer != "AdamOptimizer":
+      raise NotImplementedError("only --optimizer=AdamOptimizer (the reference default) is built")
+    if FLAGS.label_loss != "CrossEntropyLoss":
+      raise NotImplementedError("only --label_loss=CrossEntropyLoss (the reference default) is built")
+    if model_cls is frame_level_models.NetVLADModel:
+      if FLAGS.netvlad_add_batch_norm or FLAGS.video_level_classifier_model != "MoeModel":
+        raise NotImplementedError("train.py --model=NetVLADModel: the CUDA training step is built for "
+                                  "--netvlad_add_batch_norm=False with --video_level_classifier_model=MoeModel")
+      return yt8m_trainer.NetVLADTrainer(in_dim, clusters=FLAGS.netvlad_cluster_size, hidden=FLAGS.netvlad_hidden_size,
+                                         vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures, relu=FLAGS.netvlad_relu)
     if model_cls is video_level_models.LogisticModel:
       kind = "logistic"
     elif model_cls is video_level_models.MoeModel:
       kind = "moe"
     else:
       raise NotImplementedError(
-          "train.py: the CUDA training step is built for the video-level heads LogisticModel and MoeModel this round; "
+          "train.py: the CUDA training step is built for LogisticModel, MoeModel and NetVLADModel this round; "
           "%s runs forward-only (eval.py / inference.py)" % self.model_name)
-    if FLAGS.optimizer != "AdamOptimizer":
-      raise NotImplementedError("only --optimizer=AdamOptimizer (the reference default) is built")
-    if FLAGS.label_loss != "CrossEntropyLoss":
-      raise NotImplementedError("only --label_loss=CrossEntropyLoss (the reference default) is built")
     return yt8m_trainer.HeadTrainer(kind, in_dim, self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures)
 
   def run(self, start_new_model=False):
@@ -118,7 +124,11 @@ class Trainer(object):
       logging.info("No checkpoint file found. Building a new model.")
       ops.get_store().reset(seed=9)
       model = utils.find_class_by_name(self.model_name, [frame_level_models, video_level_models])()
-      model.create_model(torch.zeros((2, in_dim), device="cuda"), vocab_size=self.reader.num_classes)   # creates the variables
+      if FLAGS.frame_features:                                              # creates the variables
+        model.create_model(torch.zeros((2, self.reader.max_frames, in_dim), dtype=torch.bfloat16, device="cuda"),
+                           vocab_size=self.reader.num_classes, num_frames=torch.ones(2, dtype=torch.int32, device="cuda"))
+      else:
+        model.create_model(torch.zeros((2, in_dim), device="cuda"), vocab_size=self.reader.num_classes)
       trainer.import_state({k: v.value for k, v in ops.get_store().vars.items()})
     logging.info("Entering training loop.")
     steps, last_save = 0, time.time()
@@ -126,9 +136,10 @@ class Trainer(object):
       steps += 1
       t0 = time.time()
       lo, hi = yt8m_dp.shard_rows(feats.shape[0])
-      x, _ = transformer.transform(feats[lo:hi].cuda(non_blocking=True), num_frames[lo:hi])
+      x, nf = transformer.transform(feats[lo:hi].cuda(non_blocking=True), num_frames[lo:hi])
       y = labels[lo:hi].cuda(non_blocking=True).float()
-      p = trainer.step(x, y, FLAGS.base_learning_rate, FLAGS.learning_rate_decay, FLAGS.learning_rate_decay_examples,
+      frame_args = (nf.to("cuda", torch.int32),) if FLAGS.frame_features else ()
+      p = trainer.step(x, *frame_args, y, FLAGS.base_learning_rate, FLAGS.learning_rate_decay, FLAGS.learning_rate_decay_examples,
                        FLAGS.clip_gradient_norm, FLAGS.regularization_penalty, global_batch=feats.shape[0])
       if self.is_master:
         pv, lv = p.cpu().numpy(), labels[lo:hi].numpy().astype("float32")
