@@ -43,6 +43,7 @@ def parse():
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--cpu-sample", type=int, default=16, help="videos per CPU-baseline forward")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--train-steps", type=int, default=8, help="timed steps of the training-step side measurement (0 = skip)")
   ap.add_argument("--operand-format", default="f16", choices=["f16", "bf16x2"],
                   help="how the descriptor / hidden layer travel between kernels (see --netvlad_operand_format)")
   return ap.parse_args()
@@ -276,6 +277,28 @@ def main():
   ms_e2e = timed(step_e2e, args.steps, W)
   clocks = sampler.stop() if rank == 0 else None
 
+  # side measurement: the training step of the same workload (NetVLADTrainer: forward + full backward + per-tensor
+  # clip + Adam; under torchrun ONE NCCL all-reduce of the flat fp32 gradient per step), inputs resident
+  ms_train = None
+  if args.train_steps > 0:
+    import math
+    import yt8m_trainer
+    gw = torch.Generator(device=dev).manual_seed(9)
+
+    def rnd(shape, std):
+      return (torch.randn(shape, generator=gw, device=dev) * std).to(torch.bfloat16).float()
+
+    tr = yt8m_trainer.NetVLADTrainer(D, clusters=K_CLUSTERS, hidden=HIDDEN, vocab=V, mixtures=MIXTURES, device=dev)
+    tr.import_state({"cluster_weights": rnd((D, K_CLUSTERS), 1 / math.sqrt(D)), "cluster_biases": torch.zeros(K_CLUSTERS, device=dev),
+                     "cluster_weights2": rnd((D, K_CLUSTERS), 1 / math.sqrt(D)),
+                     "hidden1_weights": rnd((K_CLUSTERS * D, HIDDEN), 1 / math.sqrt(K_CLUSTERS)),
+                     "hidden1_biases": torch.zeros(HIDDEN, device=dev),
+                     "gates/weights": rnd((HIDDEN, V * (MIXTURES + 1)), 0.03), "experts/weights": rnd((HIDDEN, V * MIXTURES), 0.03),
+                     "experts/biases": torch.zeros(V * MIXTURES, device=dev)})
+    y_dev = synth.labels(B, V, seed=8 + rank).to(dev)
+    ms_train = timed(lambda: tr.step(x_dev, nf_dev, y_dev, global_batch=world * B), args.train_steps, 3)
+    del tr
+
   if rank != 0:
     if world > 1:
       dist.destroy_process_group()
@@ -311,6 +334,10 @@ def main():
       "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "videos/s", "ms_per_step": ms_e2e,
               "h2d_bytes_per_step": u8.numel() + nf.numel() * 4, "d2h_bytes_per_step": pred_host.numel() * 4},
       "gpu_launches": int(launches),
+      "train_step": None if ms_train is None else {
+          "value": world * B / (ms_train * 1e-3), "unit": "videos/s", "ms_per_step": ms_train, "steps": args.train_steps,
+          "what": "NetVLAD + FC + MoE-2 forward, full backward, per-tensor clip + Adam; resident inputs; "
+                  "one all-reduce of the flat fp32 gradient (%d M floats) per step when n_gpus > 1" % 100},
       "roofline": {"bound": "hbm", "kernel": "netvlad_v3_kernel (K=64)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                    "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
                    "kernel_ms": k_ms, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback"},

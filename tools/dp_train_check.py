@@ -54,5 +54,37 @@ if rank == 0:
   ok = float(stat[0]) < 2e-3 and float(stat[1]) < 2e-3
   print("DP world=%d vs single process: grad rel err %.2e, params off by >5%% of their displacement: %.4f%%  -> %s"
         % (world, float(stat[0]), 100 * float(stat[1]), "OK" if ok else "MISMATCH"))
+
+# ---- the frame-level step: NetVLAD + FC + MoE, gradient of the FIRST step (all-reduced) vs the single-process batch
+Bf, T, Df, K, H, Vf = 16, 300, 1152, 64, 256, 500
+xf, nff, _ = synth.model_input(Bf, T, Df, seed=5)
+yf = synth.labels(Bf, Vf, seed=5, per_video=3.4)
+sdf = {"cluster_weights": synth.normal((Df, K), g, 4.0), "cluster_biases": 0.1 * torch.randn(K, generator=g),
+       "cluster_weights2": synth.normal((Df, K), g, 1 / math.sqrt(Df)), "hidden1_weights": synth.normal((K * Df, H), g, 12.0 / math.sqrt(K)),
+       "hidden1_biases": 0.1 * torch.randn(H, generator=g), "gates/weights": synth.xavier((H, Vf * (M + 1)), g, 2.0),
+       "experts/weights": synth.xavier((H, Vf * M), g, 2.0), "experts/biases": 0.1 * torch.randn(Vf * M, generator=g)}
+
+def run_frames(group_world):
+  t = yt8m_trainer.NetVLADTrainer(Df, clusters=K, hidden=H, vocab=Vf, mixtures=M, device=dev)
+  t.keep_grads = True
+  t.import_state(sdf)
+  import yt8m_dp as dp
+  saved = dp.all_reduce_sum_
+  if group_world == 1:
+    dp.all_reduce_sum_ = lambda flat, group=None: flat
+    lo, hi = 0, Bf
+  else:
+    lo, hi = yt8m_dp.shard_rows(Bf)
+  t.step(xf[lo:hi].to(dev).to(torch.bfloat16), nff[lo:hi].to(dev), yf[lo:hi].to(dev), global_batch=Bf)
+  dp.all_reduce_sum_ = saved
+  torch.cuda.synchronize()
+  return t.last_grad.clone()
+
+gd, gs = run_frames(world), run_frames(1)
+ferr = torch.tensor([float((gd - gs).norm() / gs.norm())], device=dev)
+if world > 1:
+  torch.distributed.all_reduce(ferr, op=torch.distributed.ReduceOp.MAX)
+if rank == 0:
+  print("NetVLAD step, DP world=%d vs single process: flat gradient rel L2 err %.2e -> %s" % (world, float(ferr), "OK" if float(ferr) < 2e-3 else "MISMATCH"))
 if world > 1:
   torch.distributed.destroy_process_group()
