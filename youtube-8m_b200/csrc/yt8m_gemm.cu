@@ -27,7 +27,7 @@ int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, con
   auto kern = gemm_tcgen05_kernel<BLOCK_N, A_SPLIT, Epi, false, MT, CTAS>;
   static bool attr_done = false;   // per template instantiation
   if (!attr_done) {
-    YT8M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    YT8M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal + Epi::kSmemBytes));
     attr_done = true;
   }
   const int num_kb = (K + kBlockK - 1) / kBlockK;
@@ -36,7 +36,7 @@ int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, con
   shape.kb_per_split = (num_kb + split_k - 1) / split_k;
   const int splits = (num_kb + shape.kb_per_split - 1) / shape.kb_per_split;
   dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + MT * kBlockM - 1) / (MT * kBlockM), splits);
-  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tm_a_hi, tm_a_lo, tm_b, shape, ep);
+  kern<<<grid, kGemmThreads, S::kTotal + Epi::kSmemBytes, stream>>>(tm_a_hi, tm_a_lo, tm_b, shape, ep);
   return check_launch("gemm_tcgen05_kernel");
 }
 

@@ -70,6 +70,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   uint64_t* empty_bar = full_bar + S::kStages;
   uint64_t* tmem_full_bar = empty_bar + S::kStages;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint8_t* epi_smem = smem + S::kStages * S::kStageBytes + S::kBarrierBytes;     // Epi::kSmemBytes, a quarter per epilogue warp
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
@@ -210,7 +211,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     for (int mt = 0; mt < MT; ++mt) {
       const int row = (m_tile * MT + mt) * kBlockM + row_in_tile;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mt * BLOCK_N;
-      Epi::template run<BLOCK_N>(ep, shape, row, n_tile * BLOCK_N, taddr, row < shape.M, num_kb > 0, split);
+      Epi::template run<BLOCK_N>(ep, shape, row, n_tile * BLOCK_N, taddr, row < shape.M, num_kb > 0, split,
+                                 epi_smem + q * (Epi::kSmemBytes / 4));
     }
     tc_fence_before();
   }
@@ -239,6 +241,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 struct EpiLinear {
+  // each epilogue warp transposes its 32 x 32 chunk through shared memory (pitch 36 floats: conflict-free 16-byte
+  // accesses both ways) so that global stores / reductions are 128-byte row segments instead of 32 rows x 16 bytes
+  static constexpr int kPitch = 36;
+  static constexpr int kSmemBytes = 4 * 32 * kPitch * 4;
   struct Params {
     float* out_f32;            // nullable
     __nv_bfloat16* out_hi;     // nullable
@@ -252,7 +258,12 @@ struct EpiLinear {
   };
   template <int BLOCK_N>
   static __device__ __forceinline__ void run(const Params& p, const GemmShape& s, int row, int n0, uint32_t taddr,
-                                             bool row_valid, bool have_acc, int /*split*/) {
+                                             bool /*row_valid*/, bool have_acc, int /*split*/, uint8_t* smem) {
+    float* stage = reinterpret_cast<float*>(smem);
+    const int lane = threadIdx.x & 31;
+    const int row0 = row - lane;                      // first row of this warp's quadrant
+    const int sub_r = lane >> 3, c4 = (lane & 7) * 4; // store phase: 4 rows per pass, 8 lanes x 4 columns per row
+    const bool vec_ok = (p.ld_out & 3) == 0;
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N; c += 32) {
       uint32_t r[32];
@@ -263,75 +274,81 @@ struct EpiLinear {
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
-      if (!row_valid) continue;
       const int col0 = n0 + c;
-      if (col0 >= s.N) continue;
-      const long long base = static_cast<long long>(row) * p.ld_out + col0;
-      if (p.split_k > 1) {
-        if (col0 + 32 <= s.N && (p.ld_out & 3) == 0) {
-          // 16-byte vector reductions: a quarter of the L2 atomic operations of the scalar form
+      if (col0 >= s.N) continue;                      // warp-uniform
+      if (p.split_k <= 1) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            red_add_v4(p.out_f32 + base + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                       __uint_as_float(r[j + 3]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < s.N) atomicAdd(p.out_f32 + base + j, __uint_as_float(r[j]));
-        }
-        continue;
-      }
-      float v[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]);
-        const int col = col0 + j;
-        if (col < s.N) {
-          if (p.col_scale) x *= __ldg(p.col_scale + col);
-          if (p.col_shift) x += __ldg(p.col_shift + col);
-        }
-        v[j] = apply_act(x, p.act);
-      }
-      const bool full = (col0 + 32 <= s.N) && ((p.ld_out & 7) == 0);
-      if (p.out_f32) {
-        if (full) {
-          float4* dst = reinterpret_cast<float4*>(p.out_f32 + base);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < s.N) p.out_f32[base + j] = v[j];
-        }
-      }
-      if (p.out_hi) {
-        if (full) {
-          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + base);
-          uint4* dl = p.out_lo ? reinterpret_cast<uint4*>(p.out_lo + base) : nullptr;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 h, l;
-            if (p.out_f16) {
-              h = pack8_f16(v + 8 * j);
-            } else {
-              pack8_hi_lo(v + 8 * j, h, l);
-              if (dl) dl[j] = l;
-            }
-            dh[j] = h;
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r[j]);
+          const int col = col0 + j;
+          if (col < s.N) {
+            if (p.col_scale) x *= __ldg(p.col_scale + col);
+            if (p.col_shift) x += __ldg(p.col_shift + col);
           }
-        } else {
+          r[j] = __float_as_uint(apply_act(x, p.act));
+        }
+      }
+      __syncwarp();                                   // the previous chunk's readers are done with the staging tile
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < s.N) {
-              if (p.out_f16) {
-                reinterpret_cast<__half*>(p.out_hi)[base + j] = __float2half_rn(v[j]);
-              } else {
-                __nv_bfloat16 h, l;
-                split_bf16(v[j], h, l);
-                p.out_hi[base + j] = h;
-                if (p.out_lo) p.out_lo[base + j] = l;
-              }
+      for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<uint4*>(stage + lane * kPitch + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
+      __syncwarp();
+      const int col = col0 + c4;
+      const bool full = vec_ok && (col + 3 < s.N);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rr = it * 4 + sub_r;
+        const int grow = row0 + rr;
+        if (grow >= s.M || col >= s.N) continue;
+        const float4 v4 = *reinterpret_cast<const float4*>(stage + rr * kPitch + c4);
+        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+        const long long base = static_cast<long long>(grow) * p.ld_out + col;
+        if (p.split_k > 1) {
+          if (full) {
+            red_add_v4(p.out_f32 + base, v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (col + j < s.N) atomicAdd(p.out_f32 + base + j, v[j]);
+          }
+          continue;
+        }
+        if (p.out_f32) {
+          if (full) {
+            *reinterpret_cast<float4*>(p.out_f32 + base) = v4;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (col + j < s.N) p.out_f32[base + j] = v[j];
+          }
+        }
+        if (p.out_hi) {
+          if (p.out_f16) {
+            __half* oh = reinterpret_cast<__half*>(p.out_hi);
+            if (full) {
+              const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+              *reinterpret_cast<uint2*>(oh + base) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (col + j < s.N) oh[base + j] = __float2half_rn(v[j]);
             }
+          } else {
+            __nv_bfloat16 h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_bf16(v[j], h[j], l[j]);
+            if (full) {
+              *reinterpret_cast<uint2*>(p.out_hi + base) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+              if (p.out_lo) *reinterpret_cast<uint2*>(p.out_lo + base) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (col + j < s.N) {
+                  p.out_hi[base + j] = h[j];
+                  if (p.out_lo) p.out_lo[base + j] = l[j];
+                }
+            }
+          }
         }
       }
     }
@@ -349,6 +366,7 @@ struct EpiLinear {
 // ---------------------------------------------------------------------------------------------
 template <int NMIX>
 struct EpiMoe {
+  static constexpr int kSmemBytes = 0;
   static constexpr int kPer = 2 * NMIX + 1;
   static constexpr int kCpt = 128 / kPer;
   struct Params {
@@ -359,7 +377,7 @@ struct EpiMoe {
   };
   template <int BLOCK_N>
   static __device__ __forceinline__ void run(const Params& p, const GemmShape& /*s*/, int row, int n0, uint32_t taddr,
-                                             bool row_valid, bool /*have_acc*/, int /*split*/) {
+                                             bool row_valid, bool /*have_acc*/, int /*split*/, uint8_t* /*smem*/) {
     static_assert(BLOCK_N == 128, "MoE epilogue expects 128-column tiles");
     float acc[128];
 #pragma unroll
@@ -396,6 +414,7 @@ struct EpiMoe {
 //   dynamic_rnn(sequence_length): rows with t >= num_frames[b] keep (c, h) and emit 0.
 // ---------------------------------------------------------------------------------------------
 struct EpiLstm {
+  static constexpr int kSmemBytes = 0;
   struct Params {
     const float* xw;            // nullable: [B, 4H] slice for this t (row stride ld_xw), packed order
     long long ld_xw;
@@ -420,7 +439,7 @@ struct EpiLstm {
   };
   template <int BLOCK_N>
   static __device__ __forceinline__ void run(const Params& p, const GemmShape& /*s*/, int row, int n0, uint32_t taddr,
-                                             bool row_valid, bool /*have_acc*/, int /*split*/) {
+                                             bool row_valid, bool /*have_acc*/, int /*split*/, uint8_t* /*smem*/) {
     static_assert(BLOCK_N == 128, "LSTM epilogue expects 128-column tiles (32 units)");
     const int u0 = n0 / 4;
     const bool live = row_valid && (p.t < __ldg(p.num_frames + (row_valid ? row : 0)));

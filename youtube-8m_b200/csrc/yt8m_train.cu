@@ -59,31 +59,52 @@ __device__ __forceinline__ int row_segment(long long row, int per, int nmix) {
 
 // g += l2 * w (regulariser gradient, wh/train.py:440-442,459); per-segment sums of g^2 and w^2.
 // sums[0..1] = sum g^2 (segment 0 / 1), sums[2..3] = sum w^2.
+template <bool VEC>
 __global__ void grad_reg_sumsq_kernel(float* __restrict__ g, const float* __restrict__ w, long long rows, int row_len, float l2,
                                       int per, int nmix, float* __restrict__ sums) {
   float sg[2] = {0.0f, 0.0f}, sw[2] = {0.0f, 0.0f};
   const long long total = rows * row_len;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int seg = row_segment(i / row_len, per, nmix);
+  constexpr int kV = VEC ? 4 : 1;                   // VEC: row_len % 4 == 0 and 16-byte aligned pointers
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * kV; i < total; i += (long long)gridDim.x * blockDim.x * kV) {
+    const int seg = per > 0 ? row_segment(i / row_len, per, nmix) : 0;     // one tensor (per == 0): no division
     if (seg < 0) continue;
-    const float wv = w[i];
-    const float gv = g[i] + l2 * wv;
-    g[i] = gv;
-    sg[seg] += gv * gv;
-    sw[seg] += wv * wv;
+    float wv[kV], gv[kV];
+    if (VEC) {
+      const float4 w4 = *reinterpret_cast<const float4*>(w + i), g4 = *reinterpret_cast<const float4*>(g + i);
+      wv[0] = w4.x; wv[kV > 1 ? 1 : 0] = w4.y; wv[kV > 2 ? 2 : 0] = w4.z; wv[kV > 3 ? 3 : 0] = w4.w;
+      gv[0] = g4.x; gv[kV > 1 ? 1 : 0] = g4.y; gv[kV > 2 ? 2 : 0] = g4.z; gv[kV > 3 ? 3 : 0] = g4.w;
+    } else {
+      wv[0] = w[i];
+      gv[0] = g[i];
+    }
+#pragma unroll
+    for (int j = 0; j < kV; ++j) {
+      gv[j] += l2 * wv[j];
+      sg[seg] += gv[j] * gv[j];
+      sw[seg] += wv[j] * wv[j];
+    }
+    if (l2 != 0.0f) {
+      if (VEC) *reinterpret_cast<float4*>(g + i) = make_float4(gv[0], gv[kV > 1 ? 1 : 0], gv[kV > 2 ? 2 : 0], gv[kV > 3 ? 3 : 0]);
+      else g[i] = gv[0];
+    }
   }
+  __shared__ float red[4][8];
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const float a = warp_sum(sg[s]), b = warp_sum(sw[s]);
-    if ((threadIdx.x & 31) == 0) {
-      if (a != 0.0f) atomicAdd(&sums[s], a);
-      if (b != 0.0f) atomicAdd(&sums[2 + s], b);
-    }
+    if ((threadIdx.x & 31) == 0) { red[s][threadIdx.x >> 5] = a; red[2 + s][threadIdx.x >> 5] = b; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 4) {
+    float t = 0.0f;
+    for (int wq = 0; wq < (blockDim.x >> 5); ++wq) t += red[threadIdx.x][wq];
+    if (t != 0.0f) atomicAdd(&sums[threadIdx.x], t);
   }
 }
 
 // per-tensor clip_by_norm (g * c / max(||g||, c)) + TF-1.0 Adam (epsilon outside the sqrt, lr_t carries the bias
 // correction) + refresh of the bf16 operand copy.  only_seg >= 0 restricts the update to one segment.
+template <bool VEC>
 __global__ void clip_adam_kernel(float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                                  long long rows, int row_len, const float* __restrict__ sums, float clip, float lr_t, float beta1,
                                  float beta2, float eps, int per, int nmix, int only_seg, __nv_bfloat16* __restrict__ w_bf16) {
@@ -94,17 +115,39 @@ __global__ void clip_adam_kernel(float* __restrict__ w, const float* __restrict_
     scale[s] = clip > 0.0f ? clip / fmaxf(n, clip) : 1.0f;
   }
   const long long total = rows * row_len;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int seg = row_segment(i / row_len, per, nmix);
+  constexpr int kV = VEC ? 4 : 1;
+  for (long long i = (blockIdx.x * (long long)blockDim.x + threadIdx.x) * kV; i < total; i += (long long)gridDim.x * blockDim.x * kV) {
+    const int seg = per > 0 ? row_segment(i / row_len, per, nmix) : 0;
     if (seg < 0 || (only_seg >= 0 && seg != only_seg)) continue;
-    const float gv = g[i] * scale[seg];
-    const float mv = beta1 * m[i] + (1.0f - beta1) * gv;
-    const float vv = beta2 * v[i] + (1.0f - beta2) * gv * gv;
-    const float wv = w[i] - lr_t * mv / (sqrtf(vv) + eps);
-    m[i] = mv;
-    v[i] = vv;
-    w[i] = wv;
-    if (w_bf16) w_bf16[i] = __float2bfloat16_rn(wv);
+    float wv[4], gv[4], mv[4], vv[4];
+    if (VEC) {
+      const float4 a = *reinterpret_cast<const float4*>(w + i), b = *reinterpret_cast<const float4*>(g + i);
+      const float4 c = *reinterpret_cast<const float4*>(m + i), d = *reinterpret_cast<const float4*>(v + i);
+      wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w;
+      gv[0] = b.x; gv[1] = b.y; gv[2] = b.z; gv[3] = b.w;
+      mv[0] = c.x; mv[1] = c.y; mv[2] = c.z; mv[3] = c.w;
+      vv[0] = d.x; vv[1] = d.y; vv[2] = d.z; vv[3] = d.w;
+    } else {
+      wv[0] = w[i]; gv[0] = g[i]; mv[0] = m[i]; vv[0] = v[i];
+    }
+#pragma unroll
+    for (int j = 0; j < kV; ++j) {
+      const float gs = gv[j] * scale[seg];
+      mv[j] = beta1 * mv[j] + (1.0f - beta1) * gs;
+      vv[j] = beta2 * vv[j] + (1.0f - beta2) * gs * gs;
+      wv[j] -= lr_t * mv[j] / (sqrtf(vv[j]) + eps);
+    }
+    if (VEC) {
+      *reinterpret_cast<float4*>(m + i) = make_float4(mv[0], mv[1], mv[2], mv[3]);
+      *reinterpret_cast<float4*>(v + i) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+      *reinterpret_cast<float4*>(w + i) = make_float4(wv[0], wv[1], wv[2], wv[3]);
+      if (w_bf16)
+        *reinterpret_cast<uint2*>(w_bf16 + i) = make_uint2(pack_bf16x2(__float2bfloat16_rn(wv[0]), __float2bfloat16_rn(wv[1])),
+                                                            pack_bf16x2(__float2bfloat16_rn(wv[2]), __float2bfloat16_rn(wv[3])));
+    } else {
+      m[i] = mv[0]; v[i] = vv[0]; w[i] = wv[0];
+      if (w_bf16) w_bf16[i] = __float2bfloat16_rn(wv[0]);
+    }
   }
 }
 
@@ -119,6 +162,7 @@ namespace yt8m {
 // ---------------------------------------------------------------------------------------------
 template <int NMIX>
 struct EpiMoeBwd {
+  static constexpr int kSmemBytes = 0;
   static constexpr int kPer = 2 * NMIX + 1;
   static constexpr int kCpt = 128 / kPer;
   struct Params {
@@ -132,7 +176,7 @@ struct EpiMoeBwd {
   };
   template <int BLOCK_N>
   static __device__ __forceinline__ void run(const Params& p, const GemmShape& /*s*/, int row, int n0, uint32_t taddr,
-                                             bool row_valid, bool /*have_acc*/, int /*split*/) {
+                                             bool row_valid, bool /*have_acc*/, int /*split*/, uint8_t* /*smem*/) {
     static_assert(BLOCK_N == 128, "MoE epilogue expects 128-column tiles");
     float acc[128];
 #pragma unroll
@@ -189,7 +233,7 @@ int launch_gemm_t(const CUtensorMap& tm_a_hi, const CUtensorMap& tm_a_lo, const 
   auto kern = gemm_tcgen05_kernel<BLOCK_N, A_SPLIT, Epi, MN>;
   static bool attr_done = false;
   if (!attr_done) {
-    YT8M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal));
+    YT8M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal + Epi::kSmemBytes));
     attr_done = true;
   }
   constexpr int kStageK = MN ? 128 : kBlockK;
@@ -199,7 +243,7 @@ int launch_gemm_t(const CUtensorMap& tm_a_hi, const CUtensorMap& tm_a_lo, const 
   shape.kb_per_split = (num_kb + split_k - 1) / split_k;
   const int splits = (num_kb + shape.kb_per_split - 1) / shape.kb_per_split;
   dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + kBlockM - 1) / kBlockM, splits);
-  kern<<<grid, kGemmThreads, S::kTotal, stream>>>(tm_a_hi, tm_a_lo, tm_b, shape, ep);
+  kern<<<grid, kGemmThreads, S::kTotal + Epi::kSmemBytes, stream>>>(tm_a_hi, tm_a_lo, tm_b, shape, ep);
   return check_launch("gemm_tcgen05_kernel");
 }
 }  // namespace
@@ -296,7 +340,9 @@ int yt8m_grad_reg_sumsq(float* grad, const float* param, long long rows, int row
   YT8M_REQUIRE(grad && param && sums4, YT8M_E_BADPTR, "yt8m_grad_reg_sumsq: null pointer");
   YT8M_REQUIRE(rows > 0 && row_len > 0, YT8M_E_BADSHAPE, "yt8m_grad_reg_sumsq: bad shape");
   YT8M_CUDA(cudaMemsetAsync(sums4, 0, 4 * sizeof(float), stream));
-  grad_reg_sumsq_kernel<<<grid_for(rows * row_len, 1024), 256, 0, stream>>>(grad, param, rows, row_len, l2, moe_per, moe_nmix, sums4);
+  const bool vec = row_len % 4 == 0 && aligned16(grad) && aligned16(param);
+  if (vec) grad_reg_sumsq_kernel<true><<<grid_for(rows * row_len / 4, 2048), 256, 0, stream>>>(grad, param, rows, row_len, l2, moe_per, moe_nmix, sums4);
+  else grad_reg_sumsq_kernel<false><<<grid_for(rows * row_len, 2048), 256, 0, stream>>>(grad, param, rows, row_len, l2, moe_per, moe_nmix, sums4);
   return check_launch("grad_reg_sumsq_kernel");
 }
 
@@ -306,9 +352,15 @@ int yt8m_clip_adam_step(float* param, const float* grad, float* m, float* v, lon
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   YT8M_REQUIRE(param && grad && m && v && sums4, YT8M_E_BADPTR, "yt8m_clip_adam_step: null pointer");
   YT8M_REQUIRE(rows > 0 && row_len > 0, YT8M_E_BADSHAPE, "yt8m_clip_adam_step: bad shape");
-  clip_adam_kernel<<<grid_for(rows * row_len, 1024), 256, 0, stream>>>(param, grad, m, v, rows, row_len, sums4, clip, lr_t, beta1,
-                                                                      beta2, eps, moe_per, moe_nmix, only_segment,
-                                                                      reinterpret_cast<__nv_bfloat16*>(param_bf16));
+  __nv_bfloat16* pb = reinterpret_cast<__nv_bfloat16*>(param_bf16);
+  const bool vec = row_len % 4 == 0 && aligned16(param) && aligned16(grad) && aligned16(m) && aligned16(v) &&
+                   (!pb || (reinterpret_cast<uintptr_t>(pb) & 7u) == 0);
+  if (vec)
+    clip_adam_kernel<true><<<grid_for(rows * row_len / 4, 2048), 256, 0, stream>>>(param, grad, m, v, rows, row_len, sums4, clip, lr_t, beta1,
+                                                                                   beta2, eps, moe_per, moe_nmix, only_segment, pb);
+  else
+    clip_adam_kernel<false><<<grid_for(rows * row_len, 2048), 256, 0, stream>>>(param, grad, m, v, rows, row_len, sums4, clip, lr_t, beta1,
+                                                                                beta2, eps, moe_per, moe_nmix, only_segment, pb);
   return check_launch("clip_adam_kernel");
 }
 
