@@ -35,7 +35,8 @@ int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, con
   shape.M = M; shape.N = N; shape.K = K; shape.a_f16 = a_f16;
   shape.kb_per_split = (num_kb + split_k - 1) / split_k;
   const int splits = (num_kb + shape.kb_per_split - 1) / shape.kb_per_split;
-  dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + MT * kBlockM - 1) / (MT * kBlockM), splits);
+  const long long tiles = static_cast<long long>((N + BLOCK_N - 1) / BLOCK_N) * ((M + MT * kBlockM - 1) / (MT * kBlockM)) * splits;
+  const int grid = static_cast<int>(std::min<long long>(tiles, kNumSms * CTAS));       // persistent CTAs walk the tiles
   kern<<<grid, kGemmThreads, S::kTotal + Epi::kSmemBytes, stream>>>(tm_a_hi, tm_a_lo, tm_b, shape, ep);
   return check_launch("gemm_tcgen05_kernel");
 }

@@ -61,28 +61,47 @@ __global__ void __launch_bounds__(kGemmThreads, CTAS)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                     const __grid_constant__ CUtensorMap tm_b, const GemmShape shape, const typename Epi::Params ep) {
   using S = GemmSmem<BLOCK_N, A_SPLIT, MN, MT, CTAS>;
-  static_assert(CTAS * MT * BLOCK_N <= 512, "accumulators exceed TMEM");
+  // PERSISTENT: the grid is min(#tiles, SMs x CTAS) and every CTA walks tiles blockIdx.x, +gridDim.x, ...  The
+  // accumulator is double-buffered in TMEM when it fits (2 x MT x BLOCK_N columns), so the epilogue of tile i
+  // overlaps the loads and MMAs of tile i+1, and the smem ring never drains between tiles.
+  constexpr int kAccCols = MT * BLOCK_N;
+  constexpr int kAccBufs = (CTAS * 2 * kAccCols <= 512) ? 2 : 1;
+  static_assert(CTAS * kAccBufs * kAccCols <= 512, "accumulators exceed TMEM");
+  constexpr uint32_t kTmemCols = tmem_cols_for(kAccBufs * kAccCols);
   constexpr int kStageK = MN ? 128 : kBlockK;          // contraction elements per pipeline stage
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles = smem;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
   uint64_t* empty_bar = full_bar + S::kStages;
-  uint64_t* tmem_full_bar = empty_bar + S::kStages;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + S::kStages;    // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
   uint8_t* epi_smem = smem + S::kStages * S::kStageBytes + S::kBarrierBytes;     // Epi::kSmemBytes, a quarter per epilogue warp
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
-  const int n_tile = blockIdx.x, m_tile = blockIdx.y, split = blockIdx.z;
   const int num_kb_total = (shape.K + kStageK - 1) / kStageK;
-  const int kb_begin = split * shape.kb_per_split;
-  const int kb_end = min(kb_begin + shape.kb_per_split, num_kb_total);
-  const int num_kb = kb_end - kb_begin;
-  // CTAs that share an operand tile (same m_tile or same n_tile) start their K loop at different k-blocks, so they do
-  // not all request the same L2 lines at the same instant (no TMA multicast in this kernel)
-  const int kb_rot = num_kb > 0 ? static_cast<int>((n_tile * 5u + m_tile * 3u) % static_cast<unsigned>(num_kb)) : 0;
-  constexpr uint32_t kTmemCols = tmem_cols_for(MT * BLOCK_N);
+  const int n_tiles = (shape.N + BLOCK_N - 1) / BLOCK_N;
+  const int m_tiles = (shape.M + MT * kBlockM - 1) / (MT * kBlockM);
+  const int splits = (num_kb_total + shape.kb_per_split - 1) / shape.kb_per_split;
+  const int total_tiles = n_tiles * m_tiles * splits;
+
+  // tile id -> (n_tile fastest, then m_tile, then K split): CTAs running side by side share the A rows
+  struct Tile { int n_tile, m_tile, split, kb_begin, num_kb, kb_rot; };
+  auto decode = [&](int t) {
+    Tile r;
+    r.n_tile = t % n_tiles;
+    const int rest = t / n_tiles;
+    r.m_tile = rest % m_tiles;
+    r.split = rest / m_tiles;
+    r.kb_begin = r.split * shape.kb_per_split;
+    r.num_kb = min(r.kb_begin + shape.kb_per_split, num_kb_total) - r.kb_begin;     // >= 1 by construction of `splits`
+    // CTAs that share an operand tile start their K loop at different k-blocks, so they do not all request the same
+    // L2 lines at the same instant (no TMA multicast in this kernel)
+    r.kb_rot = static_cast<int>((r.n_tile * 5u + r.m_tile * 3u) % static_cast<unsigned>(r.num_kb));
+    return r;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_a_hi);
@@ -92,7 +111,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       mbar_init(&full_bar[s], 2);      // one arrive.expect_tx from each producer warp
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 4);                // one arrive per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_base_slot, kTmemCols);
@@ -105,117 +127,137 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     // ------------------------------- TMA producer: A (hi [+ lo]) -------------------------------
     int stage = 0;
     uint32_t phase = 0;
-    for (int kbi = 0; kbi < num_kb; ++kbi) {
-      const int kb = kb_begin + (kbi + kb_rot >= num_kb ? kbi + kb_rot - num_kb : kbi + kb_rot);
-      mbar_wait(&empty_bar[stage], phase ^ 1u);
-      if (elect_one()) {
-        uint8_t* st = tiles + stage * S::kStageBytes;
-        mbar_arrive_expect_tx(&full_bar[stage], A_SPLIT * S::kABytes);
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const Tile tl = decode(t);
+      for (int kbi = 0; kbi < tl.num_kb; ++kbi) {
+        const int kb = tl.kb_begin + (kbi + tl.kb_rot >= tl.num_kb ? kbi + tl.kb_rot - tl.num_kb : kbi + tl.kb_rot);
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (elect_one()) {
+          uint8_t* st = tiles + stage * S::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], A_SPLIT * S::kABytes);
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const int row0 = (m_tile * MT + mt) * kBlockM;
-          uint8_t* at = st + mt * S::kATile;
-          if (MN) {
-            // two 64-column boxes of 128 contraction rows per operand half
+          for (int mt = 0; mt < MT; ++mt) {
+            const int row0 = (tl.m_tile * MT + mt) * kBlockM;
+            uint8_t* at = st + mt * S::kATile;
+            if (MN) {
+              // two 64-column boxes of 128 contraction rows per operand half
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              tma_load_2d(at + h * 16384, &tm_a_hi, &full_bar[stage], row0 + h * 64, kb * 128, kEvictNormal);
-              if (A_SPLIT == 2)
-                tma_load_2d(at + S::kABytes + h * 16384, &tm_a_lo, &full_bar[stage], row0 + h * 64, kb * 128, kEvictNormal);
+              for (int h = 0; h < 2; ++h) {
+                tma_load_2d(at + h * 16384, &tm_a_hi, &full_bar[stage], row0 + h * 64, kb * 128, kEvictNormal);
+                if (A_SPLIT == 2)
+                  tma_load_2d(at + S::kABytes + h * 16384, &tm_a_lo, &full_bar[stage], row0 + h * 64, kb * 128, kEvictNormal);
+              }
+            } else {
+              tma_load_2d(at, &tm_a_hi, &full_bar[stage], kb * kBlockK, row0, kEvictNormal);
+              if (A_SPLIT == 2) tma_load_2d(at + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, row0, kEvictNormal);
             }
-          } else {
-            tma_load_2d(at, &tm_a_hi, &full_bar[stage], kb * kBlockK, row0, kEvictNormal);
-            if (A_SPLIT == 2) tma_load_2d(at + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, row0, kEvictNormal);
           }
         }
+        __syncwarp();
+        if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
       }
-      __syncwarp();
-      if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 6) {
     // ------------------------------- TMA producer: W -------------------------------------------
     int stage = 0;
     uint32_t phase = 0;
-    for (int kbi = 0; kbi < num_kb; ++kbi) {
-      const int kb = kb_begin + (kbi + kb_rot >= num_kb ? kbi + kb_rot - num_kb : kbi + kb_rot);
-      mbar_wait(&empty_bar[stage], phase ^ 1u);
-      if (elect_one()) {
-        uint8_t* st = tiles + stage * S::kStageBytes;
-        mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes);
-        if (MN) {
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const Tile tl = decode(t);
+      for (int kbi = 0; kbi < tl.num_kb; ++kbi) {
+        const int kb = tl.kb_begin + (kbi + tl.kb_rot >= tl.num_kb ? kbi + tl.kb_rot - tl.num_kb : kbi + tl.kb_rot);
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (elect_one()) {
+          uint8_t* st = tiles + stage * S::kStageBytes;
+          mbar_arrive_expect_tx(&full_bar[stage], S::kBBytes);
+          if (MN) {
 #pragma unroll
-          for (int h = 0; h < BLOCK_N / 64; ++h)
-            tma_load_2d(st + A_SPLIT * S::kABytes + h * 16384, &tm_b, &full_bar[stage], n_tile * BLOCK_N + h * 64, kb * 128, kEvictNormal);
-        } else {
-          tma_load_2d(st + A_SPLIT * S::kABytes, &tm_b, &full_bar[stage], kb * kBlockK, n_tile * BLOCK_N, kEvictNormal);
+            for (int h = 0; h < BLOCK_N / 64; ++h)
+              tma_load_2d(st + A_SPLIT * S::kABytes + h * 16384, &tm_b, &full_bar[stage], tl.n_tile * BLOCK_N + h * 64, kb * 128, kEvictNormal);
+          } else {
+            tma_load_2d(st + A_SPLIT * S::kABytes, &tm_b, &full_bar[stage], kb * kBlockK, tl.n_tile * BLOCK_N, kEvictNormal);
+          }
         }
+        __syncwarp();
+        if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
       }
-      __syncwarp();
-      if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
     }
   } else if (warp == 1) {
     // ------------------------------- MMA issuer ---------------------------------
     // a_format (bits 7..9) and b_format (bits 10..12): 1 = bf16, 0 = fp16; the hardware wants them equal
     const uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, MN ? 1 : 0, MN ? 1 : 0) ^ (shape.a_f16 ? ((1u << 7) | (1u << 10)) : 0u);
-    int stage = 0;
+    int stage = 0, it = 0;
     uint32_t phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      mbar_wait(&full_bar[stage], phase);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t s_addr = smem_u32(tiles + stage * S::kStageBytes);
-        const uint32_t b_addr = s_addr + A_SPLIT * S::kABytes;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const Tile tl = decode(t);
+      const int buf = it % kAccBufs, use = it / kAccBufs;
+      if (use > 0) {                                   // the epilogue has drained this accumulator buffer
+        mbar_wait(&tmem_empty_bar[buf], (use - 1) & 1);
+        tc_fence_after();
+      }
+      for (int kb = 0; kb < tl.num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t s_addr = smem_u32(tiles + stage * S::kStageBytes);
+          const uint32_t b_addr = s_addr + A_SPLIT * S::kABytes;
 #pragma unroll
-        for (int mt = 0; mt < MT; ++mt) {
-          const uint32_t a_addr = s_addr + mt * S::kATile;
-          const uint32_t d_tmem = tmem_base + mt * BLOCK_N;
-          if (MN) {
-            // MN-major SWIZZLE_128B: 8-row groups 1024 B apart (SBO), 64-column blocks one box apart (LBO);
-            // one UMMA consumes 16 contraction rows = 2048 B
-            const uint64_t adesc0 = make_sdesc_sw128(a_addr, 16384, 1024);
-            const uint64_t adesc1 = make_sdesc_sw128(a_addr + S::kABytes, 16384, 1024);
-            const uint64_t bdesc0 = make_sdesc_sw128(b_addr, 16384, 1024);
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t a_addr = s_addr + mt * S::kATile;
+            const uint32_t d_tmem = tmem_base + buf * kAccCols + mt * BLOCK_N;
+            if (MN) {
+              // MN-major SWIZZLE_128B: 8-row groups 1024 B apart (SBO), 64-column blocks one box apart (LBO);
+              // one UMMA consumes 16 contraction rows = 2048 B
+              const uint64_t adesc0 = make_sdesc_sw128(a_addr, 16384, 1024);
+              const uint64_t adesc1 = make_sdesc_sw128(a_addr + S::kABytes, 16384, 1024);
+              const uint64_t bdesc0 = make_sdesc_sw128(b_addr, 16384, 1024);
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const uint64_t bdesc = sdesc_advance(bdesc0, k * 2048);
-              umma_bf16(d_tmem, sdesc_advance(adesc0, k * 2048), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              if (A_SPLIT == 2) umma_bf16(d_tmem, sdesc_advance(adesc1, k * 2048), bdesc, idesc, 1u);
-            }
-          } else {
-            const uint64_t adesc0 = make_sdesc_sw128(a_addr, 16, 1024);
-            const uint64_t adesc1 = make_sdesc_sw128(a_addr + S::kABytes, 16, 1024);
-            const uint64_t bdesc0 = make_sdesc_sw128(b_addr, 16, 1024);
+              for (int k = 0; k < 8; ++k) {
+                const uint64_t bdesc = sdesc_advance(bdesc0, k * 2048);
+                umma_bf16(d_tmem, sdesc_advance(adesc0, k * 2048), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                if (A_SPLIT == 2) umma_bf16(d_tmem, sdesc_advance(adesc1, k * 2048), bdesc, idesc, 1u);
+              }
+            } else {
+              const uint64_t adesc0 = make_sdesc_sw128(a_addr, 16, 1024);
+              const uint64_t adesc1 = make_sdesc_sw128(a_addr + S::kABytes, 16, 1024);
+              const uint64_t bdesc0 = make_sdesc_sw128(b_addr, 16, 1024);
 #pragma unroll
-            for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-              const uint64_t bdesc = sdesc_advance(bdesc0, k * (kUmmaK * 2));
-              umma_bf16(d_tmem, sdesc_advance(adesc0, k * (kUmmaK * 2)), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-              if (A_SPLIT == 2) umma_bf16(d_tmem, sdesc_advance(adesc1, k * (kUmmaK * 2)), bdesc, idesc, 1u);
+              for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+                const uint64_t bdesc = sdesc_advance(bdesc0, k * (kUmmaK * 2));
+                umma_bf16(d_tmem, sdesc_advance(adesc0, k * (kUmmaK * 2)), bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                if (A_SPLIT == 2) umma_bf16(d_tmem, sdesc_advance(adesc1, k * (kUmmaK * 2)), bdesc, idesc, 1u);
+              }
             }
           }
+          umma_commit(&empty_bar[stage]);
+          if (kb == tl.num_kb - 1) umma_commit(&tmem_full_bar[buf]);
         }
-        umma_commit(&empty_bar[stage]);
-        if (kb == num_kb - 1) umma_commit(tmem_full_bar);
+        __syncwarp();
+        if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
       }
-      __syncwarp();
-      if (++stage == S::kStages) { stage = 0; phase ^= 1u; }
     }
   } else {
     // ------------------------------- epilogue -----------------------------------
     const int q = warp & 3;                          // TMEM lane quadrant this warp may access
     const int row_in_tile = q * 32 + lane;
-    if (num_kb > 0) {
-      mbar_wait(tmem_full_bar, 0);
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const Tile tl = decode(t);
+      const int buf = it % kAccBufs, use = it / kAccBufs;
+      mbar_wait(&tmem_full_bar[buf], use & 1);
       tc_fence_after();
-    }
 #pragma unroll 1
-    for (int mt = 0; mt < MT; ++mt) {
-      const int row = (m_tile * MT + mt) * kBlockM + row_in_tile;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + mt * BLOCK_N;
-      Epi::template run<BLOCK_N>(ep, shape, row, n_tile * BLOCK_N, taddr, row < shape.M, num_kb > 0, split,
-                                 epi_smem + q * (Epi::kSmemBytes / 4));
+      for (int mt = 0; mt < MT; ++mt) {
+        const int row = (tl.m_tile * MT + mt) * kBlockM + row_in_tile;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * kAccCols + mt * BLOCK_N;
+        Epi::template run<BLOCK_N>(ep, shape, row, tl.n_tile * BLOCK_N, taddr, row < shape.M, true, tl.split,
+                                   epi_smem + q * (Epi::kSmemBytes / 4));
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
-    tc_fence_before();
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
@@ -241,10 +283,9 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 struct EpiLinear {
-  // each epilogue warp transposes its 32 x 32 chunk through shared memory (pitch 36 floats: conflict-free 16-byte
-  // accesses both ways) so that global stores / reductions are 128-byte row segments instead of 32 rows x 16 bytes
-  static constexpr int kPitch = 36;
-  static constexpr int kSmemBytes = 4 * 32 * kPitch * 4;
+  // (a per-warp transpose through shared memory for 128-byte row stores was measured SLOWER: 8192^3 GEMM 1082 -> 894
+  //  TFLOP/s, wgrad +14% -- the strided 16-byte stores are not what bounds these epilogues)
+  static constexpr int kSmemBytes = 0;
   struct Params {
     float* out_f32;            // nullable
     __nv_bfloat16* out_hi;     // nullable
@@ -258,12 +299,7 @@ struct EpiLinear {
   };
   template <int BLOCK_N>
   static __device__ __forceinline__ void run(const Params& p, const GemmShape& s, int row, int n0, uint32_t taddr,
-                                             bool /*row_valid*/, bool have_acc, int /*split*/, uint8_t* smem) {
-    float* stage = reinterpret_cast<float*>(smem);
-    const int lane = threadIdx.x & 31;
-    const int row0 = row - lane;                      // first row of this warp's quadrant
-    const int sub_r = lane >> 3, c4 = (lane & 7) * 4; // store phase: 4 rows per pass, 8 lanes x 4 columns per row
-    const bool vec_ok = (p.ld_out & 3) == 0;
+                                             bool row_valid, bool have_acc, int /*split*/, uint8_t* /*smem*/) {
 #pragma unroll 1
     for (int c = 0; c < BLOCK_N; c += 32) {
       uint32_t r[32];
@@ -274,81 +310,75 @@ struct EpiLinear {
 #pragma unroll
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
+      if (!row_valid) continue;
       const int col0 = n0 + c;
-      if (col0 >= s.N) continue;                      // warp-uniform
-      if (p.split_k <= 1) {
+      if (col0 >= s.N) continue;
+      const long long base = static_cast<long long>(row) * p.ld_out + col0;
+      if (p.split_k > 1) {
+        if (col0 + 32 <= s.N && (p.ld_out & 3) == 0) {
+          // 16-byte vector reductions: a quarter of the L2 atomic operations of the scalar form
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]);
-          const int col = col0 + j;
-          if (col < s.N) {
-            if (p.col_scale) x *= __ldg(p.col_scale + col);
-            if (p.col_shift) x += __ldg(p.col_shift + col);
-          }
-          r[j] = __float_as_uint(apply_act(x, p.act));
+          for (int j = 0; j < 32; j += 4)
+            red_add_v4(p.out_f32 + base + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
+                       __uint_as_float(r[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < s.N) atomicAdd(p.out_f32 + base + j, __uint_as_float(r[j]));
+        }
+        continue;
+      }
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = __uint_as_float(r[j]);
+        const int col = col0 + j;
+        if (col < s.N) {
+          if (p.col_scale) x *= __ldg(p.col_scale + col);
+          if (p.col_shift) x += __ldg(p.col_shift + col);
+        }
+        v[j] = apply_act(x, p.act);
+      }
+      const bool full = (col0 + 32 <= s.N) && ((p.ld_out & 7) == 0);
+      if (p.out_f32) {
+        if (full) {
+          float4* dst = reinterpret_cast<float4*>(p.out_f32 + base);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < s.N) p.out_f32[base + j] = v[j];
         }
       }
-      __syncwarp();                                   // the previous chunk's readers are done with the staging tile
+      if (p.out_hi) {
+        if (full) {
+          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + base);
+          uint4* dl = p.out_lo ? reinterpret_cast<uint4*>(p.out_lo + base) : nullptr;
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
-        *reinterpret_cast<uint4*>(stage + lane * kPitch + 4 * q) = make_uint4(r[4 * q], r[4 * q + 1], r[4 * q + 2], r[4 * q + 3]);
-      __syncwarp();
-      const int col = col0 + c4;
-      const bool full = vec_ok && (col + 3 < s.N);
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int rr = it * 4 + sub_r;
-        const int grow = row0 + rr;
-        if (grow >= s.M || col >= s.N) continue;
-        const float4 v4 = *reinterpret_cast<const float4*>(stage + rr * kPitch + c4);
-        const float v[4] = {v4.x, v4.y, v4.z, v4.w};
-        const long long base = static_cast<long long>(grow) * p.ld_out + col;
-        if (p.split_k > 1) {
-          if (full) {
-            red_add_v4(p.out_f32 + base, v[0], v[1], v[2], v[3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (col + j < s.N) atomicAdd(p.out_f32 + base + j, v[j]);
-          }
-          continue;
-        }
-        if (p.out_f32) {
-          if (full) {
-            *reinterpret_cast<float4*>(p.out_f32 + base) = v4;
-          } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (col + j < s.N) p.out_f32[base + j] = v[j];
-          }
-        }
-        if (p.out_hi) {
-          if (p.out_f16) {
-            __half* oh = reinterpret_cast<__half*>(p.out_hi);
-            if (full) {
-              const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
-              *reinterpret_cast<uint2*>(oh + base) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+          for (int j = 0; j < 4; ++j) {
+            uint4 h, l;
+            if (p.out_f16) {
+              h = pack8_f16(v + 8 * j);
             } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (col + j < s.N) oh[base + j] = __float2half_rn(v[j]);
+              pack8_hi_lo(v + 8 * j, h, l);
+              if (dl) dl[j] = l;
             }
-          } else {
-            __nv_bfloat16 h[4], l[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) split_bf16(v[j], h[j], l[j]);
-            if (full) {
-              *reinterpret_cast<uint2*>(p.out_hi + base) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-              if (p.out_lo) *reinterpret_cast<uint2*>(p.out_lo + base) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (col + j < s.N) {
-                  p.out_hi[base + j] = h[j];
-                  if (p.out_lo) p.out_lo[base + j] = l[j];
-                }
-            }
+            dh[j] = h;
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < s.N) {
+              if (p.out_f16) {
+                reinterpret_cast<__half*>(p.out_hi)[base + j] = __float2half_rn(v[j]);
+              } else {
+                __nv_bfloat16 h, l;
+                split_bf16(v[j], h, l);
+                p.out_hi[base + j] = h;
+                if (p.out_lo) p.out_lo[base + j] = l;
+              }
+            }
         }
       }
     }

@@ -242,7 +242,8 @@ int launch_gemm_t(const CUtensorMap& tm_a_hi, const CUtensorMap& tm_a_lo, const 
   const int num_kb = (K + kStageK - 1) / kStageK;
   shape.kb_per_split = (num_kb + split_k - 1) / split_k;
   const int splits = (num_kb + shape.kb_per_split - 1) / shape.kb_per_split;
-  dim3 grid((N + BLOCK_N - 1) / BLOCK_N, (M + kBlockM - 1) / kBlockM, splits);
+  const long long tiles = static_cast<long long>((N + BLOCK_N - 1) / BLOCK_N) * ((M + kBlockM - 1) / kBlockM) * splits;
+  const int grid = static_cast<int>(std::min<long long>(tiles, 148));                  // persistent CTAs walk the tiles
   kern<<<grid, kGemmThreads, S::kTotal + Epi::kSmemBytes, stream>>>(tm_a_hi, tm_a_lo, tm_b, shape, ep);
   return check_launch("gemm_tcgen05_kernel");
 }
