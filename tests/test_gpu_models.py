@@ -196,3 +196,30 @@ def test_plugin_surface(env):
     with FLAGS.override(dbof_pooling_method="attention"):
       x, nf, _ = synth.model_input(2, frames=40, seed=1)
       flm.DbofModel().create_model(x.to(DEV).to(torch.bfloat16), vocab_size=V, num_frames=nf.to(DEV))
+
+
+def test_captured_step_replay_matches_eager(env):
+  """ops.CapturedStep: the CUDA-graph replay of create_model() gives the eager result bit for bit, sees inputs
+  refilled in place, and carries a live event pair around the NetVLAD kernel."""
+  flm, vlm, FLAGS, ops = env
+  b = 5
+  x, nf, _ = synth.model_input(b, seed=21)
+  x2, nf2, _ = synth.model_input(b, seed=22)
+  xd, nfd = x.to(DEV).to(torch.bfloat16), nf.to(DEV)
+  model = flm.NetVLADModel()
+  with FLAGS.override(netvlad_cluster_size=64, netvlad_hidden_size=1024, moe_num_mixtures=2):
+    ops.get_store().reset(seed=9)
+    fn = lambda: model.create_model(model_input=xd, vocab_size=V, num_frames=nfd)["predictions"]
+    eager1 = fn().clone()
+    step = ops.CapturedStep(fn, time_tag="netvlad")
+    got1 = step().clone()
+    xd.copy_(x2.to(DEV).to(torch.bfloat16))
+    nfd.copy_(nf2.to(DEV))
+    got2 = step().clone()
+    eager2 = fn().clone()
+    torch.cuda.synchronize()
+  assert torch.equal(got1, eager1)
+  assert torch.equal(got2, eager2)
+  assert not torch.equal(got1, got2)
+  ms = step.kernel_ms()
+  assert len(ms) == 1 and 0.0 < ms[0] < 50.0

@@ -12,11 +12,11 @@ tail -5 gpurun_out/bench.err
 if [ "$1" != "noprof" ]; then
 echo "=== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv \
-  python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/launches_run.log 2>&1
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline --train-steps 0 > gpurun_out/launches_run.log 2>&1
 tail -3 gpurun_out/launches_run.log
 echo "=== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"netvlad_fused|gemm_tcgen05" -s 4 -c 4 -f -o gpurun_out/prof \
-  python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/prof_run.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"netvlad|gemm_tcgen05|l2norm_rows" -s 5 -c 4 -f -o gpurun_out/prof \
+  python bench.py --steps 1 --warmup 3 --no-cpu-baseline --train-steps 0 > gpurun_out/prof_run.log 2>&1
 tail -3 gpurun_out/prof_run.log
 ls -la gpurun_out/
 fi

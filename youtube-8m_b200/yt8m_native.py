@@ -104,20 +104,30 @@ def kernel_timer_begin(tag):
   _KT = {"tag": tag, "ev": []}
 
 
-def kernel_timer_end():
-  """Returns the per-call durations in ms (synchronises) and stops timing."""
+def kernel_timer_end(read=True):
+  """Stops timing.  read=True: returns the per-call durations in ms (synchronises); read=False: returns the
+  event pairs (captured steps: read them with kernel_timer_read() after the replays)."""
   global _KT
   kt, _KT = _KT, None
   if not kt:
     return []
+  if not read:
+    return kt["ev"]
+  return kernel_timer_read(kt["ev"])
+
+
+def kernel_timer_read(pairs):
   torch.cuda.synchronize()
-  return [a.elapsed_time(b) for a, b in kt["ev"]]
+  return [a.elapsed_time(b) for a, b in pairs]
 
 
 def _call(name, *args):
   fn = getattr(_lib, name)
   if _KT is not None and _KT["tag"] in name:
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # inside a stream capture the pair becomes event-record NODES of the graph (external events): every replay
+    # re-records them, so elapsed_time() after a replay is that replay's kernel duration
+    ext = torch.cuda.is_current_stream_capturing()
+    e0, e1 = torch.cuda.Event(enable_timing=True, external=ext), torch.cuda.Event(enable_timing=True, external=ext)
     e0.record()
     rc = fn(*args)
     e1.record()
@@ -199,6 +209,9 @@ _ws_cache = {}
 
 
 def _workspace(nbytes, device):
+  if torch.cuda.is_current_stream_capturing():
+    # a captured step owns its workspace (graph-private pool); never share it with eager calls
+    return torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
   key = (device.index, torch.cuda.current_stream().cuda_stream)
   buf = _ws_cache.get(key)
   if buf is None or buf.numel() < nbytes:

@@ -303,3 +303,38 @@ def frames_operand(model_input):
   if x.dtype == torch.bfloat16:
     return x.contiguous()
   return nat.l2norm_rows(x.float().contiguous(), normalize=False)
+
+
+class CapturedStep(object):
+  """CUDA-graph replay of one fixed-shape plugin call (`fn()` -> tensor or dict of tensors): the launch-bound
+  host side of a step (Python, ctypes, tensor-map encoding, output allocation) is paid once at capture.
+  `fn` must read its inputs from fixed device buffers (refill them in place between replays) and launch only on
+  the current stream.  `time_tag`: library calls whose name contains it get a CUDA-event pair captured around
+  them (see yt8m_native.kernel_timer_begin); `kernel_ms()` returns those durations for the LAST replay."""
+
+  def __init__(self, fn, warmup=2, time_tag=None):
+    dev_stream = torch.cuda.Stream()
+    dev_stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(dev_stream):
+      for _ in range(max(warmup, 1)):     # lazy weight packing, function attributes, workspaces: all before capture
+        fn()
+    torch.cuda.current_stream().wait_stream(dev_stream)
+    torch.cuda.synchronize()
+    self.graph = torch.cuda.CUDAGraph()
+    self._pairs = []
+    if time_tag:
+      nat.kernel_timer_begin(time_tag)
+    try:
+      with torch.cuda.graph(self.graph, stream=dev_stream):
+        self.output = fn()
+    finally:
+      if time_tag:
+        self._pairs = nat.kernel_timer_end(read=False)
+
+  def __call__(self):
+    self.graph.replay()
+    return self.output
+
+  def kernel_ms(self):
+    return nat.kernel_timer_read(self._pairs)
+
