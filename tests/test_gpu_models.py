@@ -221,6 +221,6 @@ def test_captured_step_replay_matches_eager(env):
     torch.cuda.synchronize()
   assert torch.allclose(got1, eager1, rtol=2e-5, atol=1e-7)
   assert torch.allclose(got2, eager2, rtol=2e-5, atol=1e-7)
-  assert not torch.allclose(got1, got2, rtol=1e-3, atol=1e-6)
+  assert float((got1 - got2).abs().max()) > 1e-5          # the refilled inputs were seen
   ms = step.kernel_ms()
   assert len(ms) == 1 and 0.0 < ms[0] < 50.0

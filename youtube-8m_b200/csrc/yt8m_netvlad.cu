@@ -21,6 +21,12 @@
 
 using namespace yt8m;
 
+namespace yt8m {
+int launch_netvlad_v4(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, const yt8m_bf16* cw_packed,
+                      const float* scale, const float* shift, const float* cw2, yt8m_bf16* out, int out_f16, float* stats,
+                      cudaStream_t stream);
+}
+
 namespace {
 
 // The stash / output of the descriptor is either bf16 hi (+ lo) or, with out_f16, one IEEE fp16 tensor.
@@ -1093,7 +1099,14 @@ int launch_netvlad(const yt8m_bf16* x, const int* num_frames, int B, int T, int 
 
 }  // namespace
 
+namespace yt8m {
+unsigned long long*& host_debug_timeline() {
+  static unsigned long long* p = nullptr;
+  return p;
+}
+}
 extern "C" int yt8m_debug_set_timeline(unsigned long long* dev_buf) {
+  yt8m::host_debug_timeline() = dev_buf;        // the v4 kernel takes it as an argument
   YT8M_CUDA(cudaMemcpyToSymbol(g_nv_timeline, &dev_buf, sizeof(dev_buf)));
   return YT8M_OK;
 }
@@ -1118,6 +1131,10 @@ extern "C" int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B
   YT8M_REQUIRE(out_fmt == YT8M_FMT_BF16 || (out_fmt == YT8M_FMT_F16 && !out_lo), YT8M_E_UNSUPPORTED,
                "yt8m_netvlad_fwd: out_fmt must be YT8M_FMT_BF16, or YT8M_FMT_F16 without a lo tensor");
   const int out_f16 = out_fmt == YT8M_FMT_F16;
+  // K = 64, a single 16-bit output tensor, at least three 32-frame tiles: the one-pass cluster kernel (yt8m_netvlad_v4.cu)
+  if (K == 64 && !out_lo && !out_f32 && ld_out == static_cast<long long>(D) * K && D / 128 <= 9 && T > 64 &&
+      !(host_debug_flags() & 4096))
+    return launch_netvlad_v4(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_hi, out_f16, stats, stream);
   // K = 64 with the bf16 hi/lo copy of cw2 and a dense output: the TMA-staged kernel
   if (K == 64 && cw2_hi && cw2_lo && ld_out == static_cast<long long>(D) * K)
     return launch_netvlad_v3(x, num_frames, B, T, D, cw_packed, scale, shift, cw2_hi, cw2_lo, out_f32, out_hi, out_lo, ld_out, out_f16, stats, stream);
