@@ -175,7 +175,9 @@ def _lstm_weights(in_dim, h, layers, g, gain=1.0):
   return out
 
 
-@pytest.mark.parametrize("b,t,d,h,layers", [(4, 12, 64, 32, 1), (9, 20, 128, 64, 2), (130, 7, 1152, 128, 2)])
+@pytest.mark.parametrize("b,t,d,h,layers", [(4, 12, 64, 32, 1), (9, 20, 128, 64, 2), (130, 7, 1152, 128, 2),
+                                                 # H % 256 == 0: the persistent recurrence (yt8m_lstm_rec.cu), 64 videos per launch
+                                                 (3, 5, 64, 256, 1), (70, 9, 128, 256, 2), (64, 12, 1152, 1024, 2)])
 def test_lstm(nat, b, t, d, h, layers):
   g = gen(b * 3 + t)
   x = synth.bf16r(torch.randn(b, t, d, generator=g) * 0.5)

@@ -294,6 +294,10 @@ int yt8m_lstm_pack_weights(const float* w_tf, const float* b_tf, int in_dim, int
 namespace {
 struct LstmWs {
   float* xw;                     // [B*T, 4H]
+  // persistent-recurrence path (yt8m_lstm_rec.cu): output sequences of two consecutive layers, barrier counters
+  __nv_bfloat16* seq_hi[2];      // [B, T, H]
+  __nv_bfloat16* seq_lo[2];
+  unsigned int* counters;        // [L][ceil(B / chunk)]
   float* c[8][2];
   float* h[8][2];
   __nv_bfloat16* a_hi[8][2];     // layer 0: [B, H]; layer l>0: [B, 2H] = [h_{l-1} | h_l]
@@ -309,6 +313,14 @@ LstmWs carve_lstm_ws(void* base, int B, int T, int H, int L) {
     return p;
   };
   w.xw = static_cast<float*>(take(static_cast<size_t>(B) * T * 4 * H * sizeof(float)));
+  if (lstm_rec_supported(H)) {
+    for (int p = 0; p < 2; ++p) {
+      w.seq_hi[p] = static_cast<__nv_bfloat16*>(take(static_cast<size_t>(B) * T * H * 2));
+      w.seq_lo[p] = static_cast<__nv_bfloat16*>(take(static_cast<size_t>(B) * T * H * 2));
+    }
+    const int chunk = lstm_rec_batch_chunk();
+    w.counters = static_cast<unsigned int*>(take(sizeof(unsigned int) * L * ((B + chunk - 1) / chunk)));
+  }
   for (int l = 0; l < L; ++l)
     for (int p = 0; p < 2; ++p) {
       w.c[l][p] = static_cast<float*>(take(static_cast<size_t>(B) * H * sizeof(float)));
@@ -349,6 +361,34 @@ int yt8m_lstm_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D
   YT8M_REQUIRE(workspace_bytes >= yt8m_lstm_workspace_bytes(B, T, D, H, L), YT8M_E_BADSHAPE,
                "yt8m_lstm_fwd: workspace too small");
   LstmWs ws = carve_lstm_ws(workspace, B, T, H, L);
+  if (!(host_debug_flags() & 8192) && lstm_rec_available(H)) {
+    // one persistent launch per layer (and per 64 videos); the input projection of EVERY layer is one big GEMM
+    const int chunk = lstm_rec_batch_chunk();
+    const int n_chunks = (B + chunk - 1) / chunk;
+    for (int l = 0; l < L; ++l) {
+      const bool top = (l == L - 1);
+      int rc;
+      if (l == 0)
+        rc = yt8m_linear_fwd(x, nullptr, D, w_packed[0], D + H, B * T, 4 * H, D, nullptr, b_packed[0], YT8M_ACT_NONE,
+                             YT8M_FMT_BF16, YT8M_FMT_BF16, ws.xw, nullptr, nullptr, 4 * H, nullptr, 0, stream_);
+      else
+        rc = yt8m_linear_fwd(reinterpret_cast<const yt8m_bf16*>(ws.seq_hi[(l - 1) & 1]),
+                             reinterpret_cast<const yt8m_bf16*>(ws.seq_lo[(l - 1) & 1]), H, w_packed[l], 2 * H, B * T, 4 * H, H,
+                             nullptr, b_packed[l], YT8M_ACT_NONE, YT8M_FMT_BF16, YT8M_FMT_BF16, ws.xw, nullptr, nullptr, 4 * H,
+                             nullptr, 0, stream_);
+      if (rc != YT8M_OK) return rc;
+      yt8m_bf16* hi = reinterpret_cast<yt8m_bf16*>(ws.seq_hi[l & 1]);
+      if (top && out_seq_bf) hi = out_seq_bf;               // the bf16 output sequence IS the hi half of h_seq
+      const yt8m_bf16* w_rec = w_packed[l] + (l == 0 ? D : H);
+      const long long ldw = (l == 0) ? (D + H) : 2 * H;
+      rc = launch_lstm_rec(ws.xw, num_frames, B, T, H, w_rec, ldw, forget_bias, hi, reinterpret_cast<yt8m_bf16*>(ws.seq_lo[l & 1]),
+                           top ? out_seq : nullptr, state_out + static_cast<long long>(l) * 2 * H,
+                           state_out + static_cast<long long>(l) * 2 * H + H, static_cast<long long>(L) * 2 * H,
+                           ws.counters + l * n_chunks, stream);
+      if (rc != YT8M_OK) return rc;
+    }
+    return YT8M_OK;
+  }
   // zero initial state (c, h fp32 and the bf16 operand buffers), both ping-pong halves
   YT8M_CUDA(cudaMemsetAsync(ws.c[0][0], 0, ws.total - (reinterpret_cast<char*>(ws.c[0][0]) - static_cast<char*>(workspace)), stream));
 

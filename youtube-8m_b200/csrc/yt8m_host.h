@@ -28,6 +28,14 @@ int check_launch(const char* what);
 // debug / experiment switches set through yt8m_debug_set_flags (host copy; 0 in normal operation)
 int& host_debug_flags();
 
+// persistent LSTM recurrence (yt8m_lstm_rec.cu): one launch per layer and per lstm_rec_batch_chunk() videos
+bool lstm_rec_supported(int H);                 // shape rule only (used to size the workspace)
+bool lstm_rec_available(int H);                 // + the launch's clusters can be co-resident on this GPU
+int lstm_rec_batch_chunk();
+int launch_lstm_rec(const float* xw, const int* num_frames, int B, int T, int H, const yt8m_bf16* w_rec, long long ldw,
+                    float forget_bias, yt8m_bf16* h_hi, yt8m_bf16* h_lo, float* out_seq, float* c_out, float* h_out,
+                    long long ld_state, unsigned int* counters, cudaStream_t stream);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace yt8m
