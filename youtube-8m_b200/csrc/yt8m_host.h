@@ -28,6 +28,9 @@ int check_launch(const char* what);
 // debug / experiment switches set through yt8m_debug_set_flags (host copy; 0 in normal operation)
 int& host_debug_flags();
 
+// device buffer registered through yt8m_debug_set_timeline (nullptr in normal operation)
+unsigned long long*& host_debug_timeline();
+
 // persistent LSTM recurrence (yt8m_lstm_rec.cu): one launch per layer and per lstm_rec_batch_chunk() videos
 bool lstm_rec_supported(int H);                 // shape rule only (used to size the workspace)
 bool lstm_rec_available(int H);                 // + the launch's clusters can be co-resident on this GPU

@@ -60,6 +60,7 @@ struct LstmRecParams {
   float* h_out;
   long long ld_state;
   unsigned int* counter;      // zeroed before the launch
+  unsigned long long* timeline;   // debug only (yt8m_debug_set_timeline): 16 stamps per step of CTA 0, steps 8..15
   int Bc, T, H;
   float forget_bias;
 };
@@ -69,11 +70,24 @@ __device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int* p) {
   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// release at gpu scope: the CTA's earlier global stores (ordered before this thread by bar.sync) are visible to whoever
+// acquires the new counter value
+__device__ __forceinline__ void red_release_gpu_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 // orders generic-proxy global accesses with async-proxy (TMA) global accesses
 __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+
+// debug-only step timeline (globaltimer ns) of CTA 0, steps 8..15, 16 stamps per step:
+// 0 tma: grid barrier passed   1 mma: h tiles landed   2 epi: accumulator complete   3 epi: partials pushed
+// 4 epi: peers' partials landed   5 epi: h_t stored   6 epi: arrived on the grid barrier
+#define LR_T(t, slot)                                                                                             \
+  do {                                                                                                            \
+    if (p.timeline && blockIdx.x == 0 && (t) >= 8 && (t) < 16) p.timeline[((t) - 8) * 16 + (slot)] = global_timer_ns(); \
+  } while (0)
 
 __global__ void __cluster_dims__(kKS, 1, 1) __launch_bounds__(kThreads, 1)
 lstm_rec_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_hhi,
@@ -133,6 +147,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
       }
       fence_proxy_async_global();
       __syncwarp();
+      if (lane == 0) LR_T(t, 0);
       if (elect_one()) {
         mbar_arrive_expect_tx(h_full, 2 * nkb * kHTileBytes);
         tma_load_4d(hhi, &tm_hhi, h_full, 0, 0, static_cast<int>(rank) * nkb, t - 1, kEvictNormal);
@@ -147,6 +162,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
     for (int t = 1; t < T; ++t) {
       mbar_wait(h_full, (t - 1) & 1);
       tc_fence_after();
+      if (lane == 0) LR_T(t, 1);
       if (elect_one()) {
         const uint32_t w_addr = smem_u32(ws), hi_addr = smem_u32(hhi), lo_addr = smem_u32(hlo);
         for (int kb = 0; kb < nkb; ++kb) {
@@ -213,6 +229,7 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
         if (ew == 0 && lane == 0) mbar_arrive_expect_tx(recv_full, kRecvBytes);
         mbar_wait(acc_full, (t - 1) & 1);
         tc_fence_after();
+        if (ew == 0 && lane == 0) LR_T(t, 2);
         float v[kNB];
         tmem_ld32(taddr, reinterpret_cast<uint32_t*>(v));
         tmem_ld32(taddr + 32, reinterpret_cast<uint32_t*>(v + 32));
@@ -224,7 +241,9 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
           for (int j = 0; j < 4; ++j)
             st_async_v4(rbase[d] + j * 2048, rbar[d], v[16 * d + 4 * j], v[16 * d + 4 * j + 1], v[16 * d + 4 * j + 2],
                         v[16 * d + 4 * j + 3]);
+        if (ew == 0 && lane == 0) LR_T(t, 3);
         mbar_wait(recv_full, (t - 1) & 1);
+        if (ew == 0 && lane == 0) LR_T(t, 4);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const uint32_t off = (static_cast<uint32_t>(g) ^ swz) << 4;
@@ -250,12 +269,13 @@ lstm_rec_kernel(const __grid_constant__ CUtensorMap tm_w, const __grid_constant_
         p.h_lo[o] = __bfloat16_as_ushort(lo);
         if (p.out_seq) p.out_seq[o] = ho;
       }
+      if (ew == 0 && lane == 0) LR_T(t, 5);
       if (t + 1 < T) {
         fence_proxy_async_global();
         named_bar_sync(1, 128);                  // every thread's h_t stores (and recv reads) are done
         if (ew == 0 && lane == 0) {
-          __threadfence();
-          atomicAdd(p.counter, 1u);
+          red_release_gpu_add(p.counter, 1u);
+          LR_T(t, 6);
         }
       }
     }
@@ -352,6 +372,7 @@ int yt8m::launch_lstm_rec(const float* xw, const int* num_frames, int B, int T, 
     p.h_out = h_out + static_cast<long long>(b0) * ld_state;
     p.ld_state = ld_state;
     p.counter = counters + ch;
+    p.timeline = ch == 0 ? host_debug_timeline() : nullptr;
     p.Bc = Bc; p.T = T; p.H = H;
     p.forget_bias = forget_bias;
 

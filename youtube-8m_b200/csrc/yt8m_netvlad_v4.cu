@@ -35,7 +35,6 @@
 using namespace yt8m;
 
 namespace yt8m {
-unsigned long long*& host_debug_timeline();
 int launch_netvlad_v4(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, const yt8m_bf16* cw_packed,
                       const float* scale, const float* shift, const float* cw2, yt8m_bf16* out, int out_f16, float* stats,
                       cudaStream_t stream);
