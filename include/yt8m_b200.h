@@ -122,6 +122,26 @@ int yt8m_lstm_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D
                   float* state_out, float* out_seq, yt8m_bf16* out_seq_bf, void* workspace,
                   size_t workspace_bytes, yt8m_stream_t stream);
 
+/* Training: yt8m_lstm_fwd_train is yt8m_lstm_fwd that RETAINS every layer's output sequence in caller buffers
+ * seq_hi[l] / seq_lo[l] (bf16 hi/lo, [B, T, H], zero for t >= num_frames[b]); it needs the persistent recurrence
+ * (H in {256, 512, 768, 1024}).  yt8m_lstm_bwd is back-propagation through time of the same stack (the tf.gradients
+ * of wh/train.py:440-442 through wh/all_frame_models/lstm_model.py:30-47):
+ *   wt_packed[l]: bf16 [in_l + H, 4H] = the transpose of w_packed[l] (yt8m_pack_transpose_bf16 of the fp32 master);
+ *   dstate (nullable): dL/d state_out [B, L*2*H];  dout_seq (nullable): dL/d out_seq [B, T, H] of the top layer;
+ *   dw[l]: fp32 [4H, in_l + H], db[l]: fp32 [4H] -- gradients in the packed layout of the forward weights.
+ * Gate pre-activations are recomputed from the retained sequences with one GEMM per layer; the reverse recurrence
+ * runs one cell-backward kernel and one tensor-core GEMM (dh_{t-1} = dG_t . Wh) per step. */
+int yt8m_lstm_fwd_train(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int H, int L,
+                        const yt8m_bf16* const* w_packed, const float* const* b_packed, float forget_bias,
+                        float* state_out, float* out_seq, yt8m_bf16* const* seq_hi, yt8m_bf16* const* seq_lo,
+                        void* workspace, size_t workspace_bytes, yt8m_stream_t stream);
+size_t yt8m_lstm_bwd_workspace_bytes(int B, int T, int D, int H, int L);
+int yt8m_lstm_bwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int H, int L,
+                  const yt8m_bf16* const* w_packed, const float* const* b_packed, const yt8m_bf16* const* wt_packed,
+                  float forget_bias, const yt8m_bf16* const* seq_hi, const yt8m_bf16* const* seq_lo, const float* dstate,
+                  const float* dout_seq, float* const* dw, float* const* db, void* workspace, size_t workspace_bytes,
+                  yt8m_stream_t stream);
+
 /* ---- attention pooling over frames --------------------------------------------------------------
  * out[b, a, :] = sum_t w[b, t, a] * feats[b, t, :]
  *   mode 0 (softmax over T, masked, renormalised):
@@ -132,6 +152,13 @@ int yt8m_lstm_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D
  * feats: bf16 [B, T, F]. out: fp32 [B, A, F] (+ optional bf16 hi/lo copies as MoE operands). */
 int yt8m_attn_pool_fwd(const float* logits, long long ld_logits, const yt8m_bf16* feats, const int* num_frames,
                        int B, int T, int A, int F, int mode, float* out, yt8m_bf16* out_hi, yt8m_bf16* out_lo,
+                       yt8m_stream_t stream);
+
+/* backward of yt8m_attn_pool_fwd (same logits / feats / mask / mode): dout fp32 [B, A, F] ->
+ * dlogits fp32 [B, T, ld_dl >= A] (zero for masked frames) and, when dfeats != NULL, dfeats fp32 [B, T, F]
+ * (needed when feats are LSTM outputs: lstm_attention_max_pooling_model.py:63). */
+int yt8m_attn_pool_bwd(const float* logits, long long ld_logits, const yt8m_bf16* feats, const int* num_frames, int B,
+                       int T, int A, int F, int mode, const float* dout, float* dlogits, long long ld_dl, float* dfeats,
                        yt8m_stream_t stream);
 
 /* ---- NetVLAD (not in the reference; definition in oracle/yt8m_oracle.py:netvlad_pool) -----------
@@ -159,6 +186,12 @@ int yt8m_debug_set_flags(int flags);
  * y = x * sigmoid(g * scale + shift)  (context gating; g = x . Wg from yt8m_linear_fwd) */
 int yt8m_context_gate_fwd(const float* x, const float* g, const float* scale, const float* shift, long long rows,
                           int cols, float* out_f32, yt8m_bf16* out_hi, yt8m_bf16* out_lo, yt8m_stream_t stream);
+
+/* backward of yt8m_context_gate_fwd: dx = dy * sigmoid(z) (the direct path; nullable), dg = dy * x * sigmoid'(z) * scale
+ * as fp32 (nullable) and/or bf16 hi/lo with row stride ld_dg (operands of the gate layer's dgrad / wgrad GEMMs). */
+int yt8m_context_gate_bwd(const float* dy, const float* x, const float* g, const float* scale, const float* shift,
+                          long long rows, int cols, float* dx, float* dg, yt8m_bf16* dg_hi, yt8m_bf16* dg_lo, long long ld_dg,
+                          yt8m_stream_t stream);
 
 /* y = x * scale[c] + shift[c] on a contiguous [rows, cols] fp32 / bf16 matrix -> fp32 and/or bf16 hi (+lo):
  * inference-mode slim.batch_norm applied to a GEMM operand (wh/all_frame_models/dbof_model.py:64-70). */

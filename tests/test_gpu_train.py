@@ -230,3 +230,158 @@ def test_netvlad_train_step_parity(tr):
   moved = got["cluster_weights2"] - sd["cluster_weights2"]
   agree = (torch.sign(moved) == -torch.sign(gw["cluster_weights2"])).float().mean()
   assert float(agree) > 0.9
+
+
+# ------------------------------------------------------------------------------------------------
+# backward of the sequence poolers: LSTM (BPTT), attention pooling, context gating
+# ------------------------------------------------------------------------------------------------
+
+def _lstm_layers(d, h, layers, g, gain=2.0):
+  ws = []
+  for l in range(layers):
+    in_dim = d if l == 0 else h
+    ws.append((synth.xavier((in_dim + h, 4 * h), g, gain), synth.bf16r(0.1 * torch.randn(4 * h, generator=g))))
+  return ws
+
+
+@pytest.mark.parametrize("b,t,d,h,layers", [(5, 9, 64, 256, 2), (3, 17, 128, 256, 1), (66, 6, 64, 256, 2)])
+def test_lstm_bwd_parity(b, t, d, h, layers):
+  """yt8m_lstm_fwd_train + yt8m_lstm_bwd against autograd through the oracle's dynamic_rnn_lstm, with cotangents on
+  BOTH the final state and the top-layer output sequence; includes rows frozen early and a one-frame video."""
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  import yt8m_native as nat
+  import yt8m_trainer as tr
+  g = torch.Generator().manual_seed(17 + b)
+  x = synth.bf16r(torch.randn(b, t, d, generator=g) * 0.5)
+  nf = torch.randint(1, t + 1, (b,), generator=g, dtype=torch.int32)
+  nf[0], nf[1] = t, 1
+  x = x * (torch.arange(t).unsqueeze(0) < nf.unsqueeze(1)).float().unsqueeze(2)
+  ws = _lstm_layers(d, h, layers, g)
+  r_state = torch.randn(b, layers * 2 * h, generator=g)
+  r_seq = torch.randn(b, t, h, generator=g) * 0.3
+  # oracle
+  params = [(w.clone().requires_grad_(True), bb.clone().requires_grad_(True)) for w, bb in ws]
+  outs, states = O.dynamic_rnn_lstm(x, nf, params)
+  st = O.lstm_model_state(states)
+  loss = (st * r_state).sum() + (outs * r_seq).sum()
+  flat = [v for pr in params for v in pr]
+  grads = torch.autograd.grad(loss, flat)
+  # CUDA
+  xd, nfd = x.to(DEV).to(torch.bfloat16), nf.to(DEV)
+  packed = [nat.lstm_pack(w.to(DEV), bb.to(DEV), d if l == 0 else h, h) for l, (w, bb) in enumerate(ws)]
+  wp, bp = [p[0] for p in packed], [p[1] for p in packed]
+  state, seq, seq_hi, seq_lo = nat.lstm_fwd_train(xd, nfd, wp, bp, h, want_seq=True)
+  assert float((state.cpu() - st.detach()).abs().max()) < 1e-4
+  assert float((seq.cpu() - outs.detach()).abs().max()) < 1e-4
+  assert float(((seq_hi[-1].float() + seq_lo[-1].float()).cpu() - outs.detach()).abs().max()) < 1e-4
+  wt = [nat.pack_transpose(tr._lstm_tf_to_packed(w.to(DEV), h)) for w, _ in ws]
+  dw, db = nat.lstm_bwd(xd, nfd, wp, bp, wt, h, seq_hi, seq_lo, dstate=r_state.to(DEV), dout_seq=r_seq.to(DEV))
+  torch.cuda.synchronize()
+  for l in range(layers):
+    gw, gb = grads[2 * l], grads[2 * l + 1]
+    got_w = tr._lstm_packed_to_tf(dw[l], h).cpu()
+    got_b = db[l].view(h, 4).t().reshape(-1).cpu()
+    assert float(gw.norm()) > 0
+    # tolerance: the recurrent operand of the weight-gradient GEMM is the bf16 hi half of h (2^-9 relative per element)
+    assert _rel_l2(got_w, gw) < 5e-3, (l, _rel_l2(got_w, gw))
+    assert _rel_l2(got_b, gb) < 2e-3, (l, _rel_l2(got_b, gb))
+
+
+@pytest.mark.parametrize("mode,use_nf", [(0, True), (1, True), (0, False)])
+def test_attn_pool_bwd_parity(mode, use_nf):
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  import yt8m_native as nat
+  g = torch.Generator().manual_seed(23 + mode)
+  b, t, a, f = 4, 37, 8, 136
+  nf = torch.tensor([37, 5, 20, 1], dtype=torch.int32)
+  mask = (torch.arange(t).unsqueeze(0) < nf.unsqueeze(1)).float()
+  feats = synth.bf16r(torch.randn(b, t, f, generator=g)) * mask.unsqueeze(2)
+  logits = torch.randn(b, t, a, generator=g) * 2
+  dout = torch.randn(b, a, f, generator=g)
+  lg = logits.clone().requires_grad_(True)
+  ft = feats.clone().requires_grad_(True)
+  if mode == 0:
+    m = mask if use_nf else (ft.detach().abs().sum(dim=2) > 0).float()
+    w = torch.softmax(lg, dim=1) * m.unsqueeze(2)
+    w = w / w.sum(dim=1, keepdim=True)
+  else:
+    w = torch.sigmoid(lg) * mask.unsqueeze(2)
+    w = w / (w.sum(dim=1, keepdim=True) + 1e-8)
+  out = torch.einsum("bta,btf->baf", w, ft)
+  gl, gf = torch.autograd.grad((out * dout).sum(), [lg, ft])
+  dl, df = nat.attn_pool_bwd(logits.to(DEV), feats.to(DEV).to(torch.bfloat16), nf.to(DEV) if use_nf else None, a, mode, dout.to(DEV),
+                             want_dfeats=True)
+  fwd = nat.attn_pool(logits.to(DEV), feats.to(DEV).to(torch.bfloat16), nf.to(DEV) if use_nf else None, a, mode)[0]
+  assert float((fwd.cpu() - out.detach()).abs().max()) < 1e-4
+  assert float((dl.cpu() - gl).abs().max()) < 1e-4 * max(1.0, float(gl.abs().max()))
+  assert float((df.cpu() - gf).abs().max()) < 1e-4 * max(1.0, float(gf.abs().max()))
+  # padded frames carry no gradient
+  assert float(dl.cpu()[1, 5:].abs().max()) == 0.0
+
+
+def test_context_gate_bwd_parity():
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  import yt8m_native as nat
+  g = torch.Generator().manual_seed(29)
+  rows, cols = 19, 100
+  x = torch.randn(rows, cols, generator=g).requires_grad_(True)
+  gg = torch.randn(rows, cols, generator=g).requires_grad_(True)
+  sc = 1.0 + 0.1 * torch.randn(cols, generator=g)
+  sh = 0.1 * torch.randn(cols, generator=g)
+  dy = torch.randn(rows, cols, generator=g)
+  y = x * torch.sigmoid(gg * sc + sh)
+  # the direct path only: dL/dx through the gate input g is the caller's dgrad GEMM
+  gx, gg_ = torch.autograd.grad((y * dy).sum(), [x, gg])
+  dx, dg, dgh, dgl = nat.context_gate_bwd(dy.to(DEV), x.detach().to(DEV), gg.detach().to(DEV), sc.to(DEV), sh.to(DEV))
+  assert float((dx.cpu() - gx).abs().max()) < 1e-5
+  assert float((dg.cpu() - gg_).abs().max()) < 1e-5
+  assert float(((dgh.float() + dgl.float()).cpu() - gg_).abs().max()) < 1e-4 * float(gg_.abs().max())
+
+
+@pytest.mark.parametrize("memory", [False, True])
+def test_lstm_train_step_parity(tr, memory):
+  """LstmModel / LstmMemoryModel + MoE head: predictions, loss and every gradient of one step against autograd over the
+  oracle (BASELINE config 3 at reduced sizes), then two more steps move every tensor."""
+  g = torch.Generator().manual_seed(91)
+  b, t, d, h, layers, v, mix = 6, 24, 128, 256, 2, 300, 2
+  x, nf, _ = synth.model_input(b, t, d, seed=35, min_frames=3)
+  y = synth.labels(b, v, seed=35, per_video=3.4)
+  ws = _lstm_layers(d, h, layers, g)
+  head_in = layers * h if memory else layers * 2 * h
+  sd = {"gates/weights": synth.xavier((head_in, v * (mix + 1)), g, 2.0), "experts/weights": synth.xavier((head_in, v * mix), g, 2.0),
+        "experts/biases": 0.1 * torch.randn(v * mix, generator=g)}
+  for l, (w, bb) in enumerate(ws):
+    sd[tr.LstmTrainer.SCOPE % l + "/weights"] = w
+    sd[tr.LstmTrainer.SCOPE % l + "/biases"] = bb
+  t_ = tr.LstmTrainer(d, hidden=h, layers=layers, vocab=v, mixtures=mix, memory=memory)
+  t_.import_state(sd)
+  t_.keep_grads = True
+  xd, nfd, yd = x.to(DEV).to(torch.bfloat16), nf.to(DEV), y.to(DEV)
+  p0 = t_.step(xd, nfd, yd)
+  grad0 = t_.grads_tf_layout(t_.last_grad)
+  loss0 = float(t_.last["label_loss_local"])
+  params = {kk: w.clone().requires_grad_(True) for kk, w in sd.items()}
+  lw_ = [(params[tr.LstmTrainer.SCOPE % l + "/weights"], params[tr.LstmTrainer.SCOPE % l + "/biases"]) for l in range(layers)]
+  _, states = O.dynamic_rnn_lstm(x, nf, lw_)
+  feat = O.lstm_memory_model_state(states) if memory else O.lstm_model_state(states)
+  pw = O.moe_model(feat, params["gates/weights"], params["experts/weights"], params["experts/biases"], v, mix)
+  lw = O.cross_entropy_loss(pw, y)
+  gw = dict(zip(params, torch.autograd.grad(lw, list(params.values()))))
+  assert float((p0.cpu() - pw.detach()).abs().max()) < 1e-3
+  assert abs(loss0 - float(lw)) / float(lw) < 1e-3
+  for kk in gw:
+    assert float(gw[kk].norm()) > 0, kk
+    err = _rel_l2(grad0[kk], gw[kk])
+    assert err < 2e-2, (kk, err)
+  for _ in range(2):
+    t_.step(xd, nfd, yd)
+  torch.cuda.synchronize()
+  got = t_.export_state()
+  for kk in sd:
+    assert bool(torch.isfinite(got[kk]).all()), kk
+    assert float((got[kk] - sd[kk]).abs().max()) > 0, kk
+  for l in range(layers):
+    assert torch.equal(t_.w_bf16[l].float(), t_.p["w%d" % l].to(torch.bfloat16).float())

@@ -351,9 +351,11 @@ size_t yt8m_lstm_workspace_bytes(int B, int T, int D, int H, int L) {
   return carve_lstm_ws(nullptr, B, T, H, L).total;
 }
 
-int yt8m_lstm_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int H, int L,
-                  const yt8m_bf16* const* w_packed, const float* const* b_packed, float forget_bias, float* state_out,
-                  float* out_seq, yt8m_bf16* out_seq_bf, void* workspace, size_t workspace_bytes, yt8m_stream_t stream_) {
+// seq_hi_all / seq_lo_all (nullable): per-layer [B, T, H] buffers that RETAIN every layer's output sequence (training)
+static int lstm_fwd_impl(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int H, int L,
+                         const yt8m_bf16* const* w_packed, const float* const* b_packed, float forget_bias, float* state_out,
+                         float* out_seq, yt8m_bf16* out_seq_bf, yt8m_bf16* const* seq_hi_all, yt8m_bf16* const* seq_lo_all,
+                         void* workspace, size_t workspace_bytes, yt8m_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   YT8M_REQUIRE(x && num_frames && w_packed && b_packed && state_out && workspace, YT8M_E_BADPTR, "yt8m_lstm_fwd: null pointer");
   YT8M_REQUIRE(B > 0 && T > 0 && D % 8 == 0 && H % 32 == 0 && L >= 1 && L <= 8, YT8M_E_BADSHAPE,
@@ -372,16 +374,17 @@ int yt8m_lstm_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D
         rc = yt8m_linear_fwd(x, nullptr, D, w_packed[0], D + H, B * T, 4 * H, D, nullptr, b_packed[0], YT8M_ACT_NONE,
                              YT8M_FMT_BF16, YT8M_FMT_BF16, ws.xw, nullptr, nullptr, 4 * H, nullptr, 0, stream_);
       else
-        rc = yt8m_linear_fwd(reinterpret_cast<const yt8m_bf16*>(ws.seq_hi[(l - 1) & 1]),
-                             reinterpret_cast<const yt8m_bf16*>(ws.seq_lo[(l - 1) & 1]), H, w_packed[l], 2 * H, B * T, 4 * H, H,
-                             nullptr, b_packed[l], YT8M_ACT_NONE, YT8M_FMT_BF16, YT8M_FMT_BF16, ws.xw, nullptr, nullptr, 4 * H,
-                             nullptr, 0, stream_);
+        rc = yt8m_linear_fwd(seq_hi_all ? seq_hi_all[l - 1] : reinterpret_cast<const yt8m_bf16*>(ws.seq_hi[(l - 1) & 1]),
+                             seq_lo_all ? seq_lo_all[l - 1] : reinterpret_cast<const yt8m_bf16*>(ws.seq_lo[(l - 1) & 1]), H,
+                             w_packed[l], 2 * H, B * T, 4 * H, H, nullptr, b_packed[l], YT8M_ACT_NONE, YT8M_FMT_BF16,
+                             YT8M_FMT_BF16, ws.xw, nullptr, nullptr, 4 * H, nullptr, 0, stream_);
       if (rc != YT8M_OK) return rc;
-      yt8m_bf16* hi = reinterpret_cast<yt8m_bf16*>(ws.seq_hi[l & 1]);
-      if (top && out_seq_bf) hi = out_seq_bf;               // the bf16 output sequence IS the hi half of h_seq
+      yt8m_bf16* hi = seq_hi_all ? seq_hi_all[l] : reinterpret_cast<yt8m_bf16*>(ws.seq_hi[l & 1]);
+      yt8m_bf16* lo = seq_lo_all ? seq_lo_all[l] : reinterpret_cast<yt8m_bf16*>(ws.seq_lo[l & 1]);
+      if (top && out_seq_bf && !seq_hi_all) hi = out_seq_bf;   // the bf16 output sequence IS the hi half of h_seq
       const yt8m_bf16* w_rec = w_packed[l] + (l == 0 ? D : H);
       const long long ldw = (l == 0) ? (D + H) : 2 * H;
-      rc = launch_lstm_rec(ws.xw, num_frames, B, T, H, w_rec, ldw, forget_bias, hi, reinterpret_cast<yt8m_bf16*>(ws.seq_lo[l & 1]),
+      rc = launch_lstm_rec(ws.xw, num_frames, B, T, H, w_rec, ldw, forget_bias, hi, lo,
                            top ? out_seq : nullptr, state_out + static_cast<long long>(l) * 2 * H,
                            state_out + static_cast<long long>(l) * 2 * H + H, static_cast<long long>(L) * 2 * H,
                            ws.counters + l * n_chunks, stream);
@@ -389,6 +392,8 @@ int yt8m_lstm_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D
     }
     return YT8M_OK;
   }
+  YT8M_REQUIRE(!seq_hi_all, YT8M_E_UNSUPPORTED,
+               "yt8m_lstm_fwd_train: needs the persistent recurrence (H in {256, 512, 768, 1024} and an idle GPU), H=%d", H);
   // zero initial state (c, h fp32 and the bf16 operand buffers), both ping-pong halves
   YT8M_CUDA(cudaMemsetAsync(ws.c[0][0], 0, ws.total - (reinterpret_cast<char*>(ws.c[0][0]) - static_cast<char*>(workspace)), stream));
 
@@ -438,6 +443,25 @@ int yt8m_lstm_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, kNumSms * 4));
   lstm_gather_state_kernel<<<blocks, 256, 0, stream>>>(sp, B, H, L, state_out);
   return check_launch("lstm_gather_state_kernel");
+}
+
+int yt8m_lstm_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int H, int L,
+                  const yt8m_bf16* const* w_packed, const float* const* b_packed, float forget_bias, float* state_out,
+                  float* out_seq, yt8m_bf16* out_seq_bf, void* workspace, size_t workspace_bytes, yt8m_stream_t stream_) {
+  return lstm_fwd_impl(x, num_frames, B, T, D, H, L, w_packed, b_packed, forget_bias, state_out, out_seq, out_seq_bf, nullptr,
+                       nullptr, workspace, workspace_bytes, stream_);
+}
+
+int yt8m_lstm_fwd_train(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int H, int L,
+                        const yt8m_bf16* const* w_packed, const float* const* b_packed, float forget_bias, float* state_out,
+                        float* out_seq, yt8m_bf16* const* seq_hi, yt8m_bf16* const* seq_lo, void* workspace,
+                        size_t workspace_bytes, yt8m_stream_t stream_) {
+  YT8M_REQUIRE(seq_hi && seq_lo, YT8M_E_BADPTR, "yt8m_lstm_fwd_train: null sequence buffers");
+  for (int l = 0; l < L && l < 8; ++l)
+    YT8M_REQUIRE(seq_hi[l] && seq_lo[l] && aligned16(seq_hi[l]) && aligned16(seq_lo[l]), YT8M_E_BADPTR,
+                 "yt8m_lstm_fwd_train: sequence buffer of layer %d is null or not 16-byte aligned", l);
+  return lstm_fwd_impl(x, num_frames, B, T, D, H, L, w_packed, b_packed, forget_bias, state_out, out_seq, nullptr, seq_hi, seq_lo,
+                       workspace, workspace_bytes, stream_);
 }
 
 }  // extern "C"

@@ -48,6 +48,15 @@ _SIGS = {
     "yt8m_lstm_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "yt8m_lstm_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p,
                               c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "yt8m_lstm_fwd_train": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_void_p,
+                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "yt8m_lstm_bwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "yt8m_lstm_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_float,
+                              c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "yt8m_attn_pool_bwd": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_ll,
+                                   c_void_p, c_void_p]),
+    "yt8m_context_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_ll, c_void_p]),
     "yt8m_attn_pool_fwd": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     "yt8m_netvlad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -327,6 +336,74 @@ def lstm_fwd(x, num_frames, w_packed, b_packed, hidden, forget_bias=1.0, want_se
   _check(_lib.yt8m_lstm_fwd(_p(x), _p(num_frames), b, t, d, hidden, layers, ctypes.cast(wp, c_void_p), ctypes.cast(bp, c_void_p),
                             float(forget_bias), _p(state), _p(seq), _p(seq_bf), _p(ws), ws_bytes, _stream()), "yt8m_lstm_fwd")
   return state, seq, seq_bf
+
+
+def _ptr_array(tensors):
+  arr = (c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+  return arr, ctypes.cast(arr, c_void_p)
+
+
+def lstm_fwd_train(x, num_frames, w_packed, b_packed, hidden, forget_bias=1.0, want_seq=False):
+  """Training forward: as lstm_fwd, additionally returning every layer's output sequence as bf16 (hi, lo) lists
+  (what lstm_bwd needs).  Returns (state [B, L*2*H], out_seq or None, seq_hi[L], seq_lo[L])."""
+  b, t, d = x.shape
+  layers = len(w_packed)
+  dev = x.device
+  state = _f32((b, layers * 2 * hidden), dev)
+  seq = _f32((b, t, hidden), dev) if want_seq else None
+  seq_hi = [_bf16((b, t, hidden), dev) for _ in range(layers)]
+  seq_lo = [_bf16((b, t, hidden), dev) for _ in range(layers)]
+  ws_bytes = _lib.yt8m_lstm_workspace_bytes(b, t, d, hidden, layers)
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+  k1, wp = _ptr_array(w_packed)
+  k2, bp = _ptr_array(b_packed)
+  k3, sh = _ptr_array(seq_hi)
+  k4, sl = _ptr_array(seq_lo)
+  _call("yt8m_lstm_fwd_train", _p(x), _p(num_frames), b, t, d, hidden, layers, wp, bp, float(forget_bias), _p(state), _p(seq), sh, sl,
+        _p(ws), ws_bytes, _stream())
+  return state, seq, seq_hi, seq_lo
+
+
+def lstm_bwd(x, num_frames, w_packed, b_packed, wt_packed, hidden, seq_hi, seq_lo, dstate=None, dout_seq=None, dw=None, db=None,
+             forget_bias=1.0):
+  """Back-propagation through time.  wt_packed[l] = bf16 transpose [in_l + H, 4H] of w_packed[l]; dstate fp32
+  [B, L*2*H] and/or dout_seq fp32 [B, T, H].  Returns (dw[L] fp32 [4H, in_l + H], db[L] fp32 [4H]) in the packed layout."""
+  b, t, d = x.shape
+  layers = len(w_packed)
+  dev = x.device
+  if dw is None:
+    dw = [_f32((4 * hidden, (d if l == 0 else hidden) + hidden), dev) for l in range(layers)]
+  if db is None:
+    db = [_f32((4 * hidden,), dev) for _ in range(layers)]
+  ws_bytes = _lib.yt8m_lstm_bwd_workspace_bytes(b, t, d, hidden, layers)
+  ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+  keep = [_ptr_array(v) for v in (w_packed, b_packed, wt_packed, seq_hi, seq_lo, dw, db)]
+  wp, bp, wtp, sh, sl, dwp, dbp = [k[1] for k in keep]
+  _call("yt8m_lstm_bwd", _p(x), _p(num_frames), b, t, d, hidden, layers, wp, bp, wtp, float(forget_bias), sh, sl, _p(dstate),
+        _p(dout_seq), dwp, dbp, _p(ws), ws_bytes, _stream())
+  return dw, db
+
+
+def attn_pool_bwd(logits, feats, num_frames, heads, mode, dout, want_dfeats=False):
+  """Backward of attn_pool: dout fp32 [B, A, F] -> (dlogits fp32 [B, T, A], dfeats fp32 [B, T, F] or None)."""
+  b, t, f = feats.shape
+  dl = _f32((b, t, heads), feats.device)
+  df = _f32((b, t, f), feats.device) if want_dfeats else None
+  _call("yt8m_attn_pool_bwd", _p(logits), logits.stride(1), _p(feats), _p(num_frames), b, t, heads, f, mode, _p(dout.contiguous()),
+        _p(dl), heads, _p(df), _stream())
+  return dl, df
+
+
+def context_gate_bwd(dy, x, g, scale=None, shift=None, want_bf16=True):
+  """Backward of context_gate: returns (dx_direct fp32, dg fp32, dg_hi, dg_lo)."""
+  rows, cols = x.shape
+  dx, dg = _f32((rows, cols), x.device), _f32((rows, cols), x.device)
+  ld = pad8(cols)
+  gh = torch.zeros((rows, ld), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+  gl = torch.zeros((rows, ld), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+  _call("yt8m_context_gate_bwd", _p(dy.contiguous()), _p(x.contiguous()), _p(g.contiguous()), _p(scale), _p(shift), rows, cols, _p(dx),
+        _p(dg), _p(gh), _p(gl), ld, _stream())
+  return dx, dg, (gh[:, :cols] if want_bf16 else None), (gl[:, :cols] if want_bf16 else None)
 
 
 def attn_pool(logits, feats, num_frames, heads, mode, want_bf16=True):

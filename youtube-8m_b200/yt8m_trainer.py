@@ -313,3 +313,135 @@ class NetVLADTrainer(object):
     self.head.global_step = self.global_step
     self.last = {"label_loss_local": loss, "lr": lr}
     return p
+
+
+def _lstm_tf_to_packed(w_tf, hidden):
+  """TF BasicLSTMCell kernel [in+H, 4H] (columns g*H + u, gates i, j, f, o) -> packed [4H, in+H] (rows 4u + g)."""
+  k = w_tf.shape[0]
+  return w_tf.t().reshape(4, hidden, k).permute(1, 0, 2).reshape(4 * hidden, k).contiguous()
+
+
+def _lstm_packed_to_tf(w_packed, hidden):
+  k = w_packed.shape[1]
+  return w_packed.reshape(hidden, 4, k).permute(1, 0, 2).reshape(4 * hidden, k).t().contiguous()
+
+
+class LstmTrainer(object):
+  """The training step for LstmModel / LstmMemoryModel + MoeModel (BASELINE config 3) on the GPU through the C ABI:
+  persistent-recurrence forward that retains every layer's output sequence (yt8m_lstm_fwd_train), MoE head,
+  CrossEntropyLoss, MoE backward, back-propagation through time (yt8m_lstm_bwd), per-tensor clip_by_norm and TF-Adam
+  (wh/train.py:440-466 over wh/all_frame_models/lstm_model.py:30-57 / lstm_memory_model.py:47-73).
+
+  memory=False: classifier input = the non-tuple state [c0, h0, c1, h1, ...] (lstm_model.py:52);
+  memory=True : classifier input = concat of the layers' c states (lstm_memory_model.py:61).
+  One flat fp32 buffer holds every gradient: data parallelism is ONE all-reduce per step.
+  Layouts: per layer the packed kernel [4H, in+H] (rows 4u+g) and bias [4H]; then the packed MoE head.
+  import_state / export_state speak the reference's TF variable names and layouts."""
+
+  SCOPE = "RNN/multi_rnn_cell/cell_%d/basic_lstm_cell"
+
+  def __init__(self, feature_dim, hidden=1024, layers=2, vocab=4716, mixtures=2, memory=False, l2_penalty=1e-8, device=None,
+               group=None):
+    self.d, self.h, self.l, self.v, self.m, self.memory = feature_dim, hidden, layers, vocab, mixtures, memory
+    self.dev = device or torch.device("cuda", torch.cuda.current_device())
+    self.group = group
+    self.world = yt8m_dp.world_size(group)
+    self.head_in = layers * hidden if memory else layers * 2 * hidden
+    sizes = []
+    for l in range(layers):
+      k = (feature_dim if l == 0 else hidden) + hidden
+      sizes += [("w%d" % l, 4 * hidden * k), ("b%d" % l, 4 * hidden)]
+    sizes.append(("head", HeadTrainer.flat_size("moe", self.head_in, vocab, mixtures)))
+    total = sum(n for _, n in sizes)
+    self.param = torch.zeros(total, dtype=torch.float32, device=self.dev)
+    self.grad = torch.zeros_like(self.param)
+    self.adam_m = torch.zeros_like(self.param)
+    self.adam_v = torch.zeros_like(self.param)
+    self._off, off = {}, 0
+    for name, n in sizes:
+      self._off[name] = (off, off + n)
+      off += n
+    self.p, self.g, self.am, self.av = {}, {}, {}, {}
+    for l in range(layers):
+      k = (feature_dim if l == 0 else hidden) + hidden
+      for name, shp in (("w%d" % l, (4 * hidden, k)), ("b%d" % l, (4 * hidden, 1))):
+        a, b = self._off[name]
+        self.p[name], self.g[name] = self.param[a:b].view(shp), self.grad[a:b].view(shp)
+        self.am[name], self.av[name] = self.adam_m[a:b].view(shp), self.adam_v[a:b].view(shp)
+    a, b = self._off["head"]
+    self.head = HeadTrainer("moe", self.head_in, vocab, mixtures, l2_penalty, self.dev, group,
+                            storage=(self.param[a:b], self.grad[a:b], self.adam_m[a:b], self.adam_v[a:b]))
+    self.w_bf16 = [torch.zeros(self.p["w%d" % l].shape, dtype=torch.bfloat16, device=self.dev) for l in range(layers)]
+    if memory:
+      # columns of the full state [c0, h0, c1, h1, ...] that feed the classifier
+      self.state_cols = torch.cat([torch.arange(l * 2 * hidden, l * 2 * hidden + hidden) for l in range(layers)]).to(self.dev)
+    self.global_step = 0
+    self.keep_grads = False
+    self.last = {}
+
+  # ---- TF names / layouts ----------------------------------------------------------------------------
+  def import_state(self, sd):
+    for l in range(self.l):
+      scope = self.SCOPE % l
+      self.p["w%d" % l].copy_(_lstm_tf_to_packed(sd[scope + "/weights"].to(self.dev), self.h))
+      b = sd[scope + "/biases"].to(self.dev)
+      self.p["b%d" % l].copy_(b.reshape(4, self.h).t().reshape(-1, 1))
+      self.w_bf16[l].copy_(self.p["w%d" % l])
+    self.head.import_state({k: sd[k] for k in ("gates/weights", "experts/weights", "experts/biases")})
+
+  def _tf_layout(self, flat):
+    out = {}
+    for l in range(self.l):
+      scope = self.SCOPE % l
+      a, b = self._off["w%d" % l]
+      out[scope + "/weights"] = _lstm_packed_to_tf(flat[a:b].view(self.p["w%d" % l].shape), self.h).cpu()
+      a, b = self._off["b%d" % l]
+      out[scope + "/biases"] = flat[a:b].view(self.h, 4).t().reshape(-1).cpu().clone()
+    a, b = self._off["head"]
+    out.update(self.head.grads_tf_layout(flat[a:b]))
+    return out
+
+  def export_state(self):
+    return self._tf_layout(self.param)
+
+  def grads_tf_layout(self, flat):
+    return self._tf_layout(flat)
+
+  # ---- forward / step --------------------------------------------------------------------------------
+  def forward(self, x, num_frames):
+    """x bf16 [B, T, D] (L2-normalised frame rows), num_frames int32 [B] -> predictions + what the backward needs."""
+    bs = [self.p["b%d" % l].view(-1) for l in range(self.l)]
+    state, _, seq_hi, seq_lo = nat.lstm_fwd_train(x, num_frames, self.w_bf16, bs, self.h)
+    feat = state.index_select(1, self.state_cols) if self.memory else state
+    p, (hi, lo) = self.head.forward(feat)
+    return p, {"seq_hi": seq_hi, "seq_lo": seq_lo, "hi": hi, "lo": lo, "bs": bs}
+
+  def step(self, x, num_frames, labels, base_lr=0.01, lr_decay=0.95, lr_decay_examples=4000000, clip_gradient_norm=1.0,
+           regularization_penalty=1.0, global_batch=None):
+    b = x.shape[0]
+    global_batch = global_batch or b * self.world
+    p, sv = self.forward(x, num_frames)
+    loss, dfeat = self.head.backward(p, sv["hi"], sv["lo"], labels, global_batch, want_dx=True)
+    if self.memory:
+      dstate = torch.zeros((b, self.l * 2 * self.h), dtype=torch.float32, device=self.dev)
+      dstate.index_copy_(1, self.state_cols, dfeat[:, :self.head_in].contiguous())
+    else:
+      dstate = dfeat[:, :self.head_in].contiguous()
+    wt = [nat.pack_transpose(self.p["w%d" % l]) for l in range(self.l)]          # bf16 [in+H, 4H]: the dgrad operands
+    nat.lstm_bwd(x, num_frames, self.w_bf16, sv["bs"], wt, self.h, sv["seq_hi"], sv["seq_lo"], dstate=dstate,
+                 dw=[self.g["w%d" % l] for l in range(self.l)], db=[self.g["b%d" % l].view(-1) for l in range(self.l)])
+    del wt
+    yt8m_dp.all_reduce_sum_(self.grad, self.group)                                # the ONE collective of the step
+    if self.keep_grads:
+      self.last_grad = self.grad.clone()
+    lr = exponential_decay(base_lr, self.global_step, global_batch, lr_decay_examples, lr_decay)
+    lr_t = adam_lr_t(lr, self.global_step + 1)
+    for l in range(self.l):
+      for name, bf in (("w%d" % l, self.w_bf16[l]), ("b%d" % l, None)):
+        sums = nat.grad_reg_sumsq(self.g[name], self.p[name], 0.0)               # BasicLSTMCell carries no regulariser
+        nat.clip_adam_step(self.p[name], self.g[name], self.am[name], self.av[name], sums, clip_gradient_norm, lr_t, param_bf16=bf)
+    self.head.apply(lr_t, clip_gradient_norm, regularization_penalty)
+    self.global_step += 1
+    self.head.global_step = self.global_step
+    self.last = {"label_loss_local": loss, "lr": lr}
+    return p
