@@ -129,3 +129,38 @@ def test_train_frame_level_netvlad(tmp_path):
   assert os.path.exists(os.path.join(train_dir, "model.ckpt-20"))
   ev = _run("eval.py", "--eval_data_pattern=" + data, "--run_once", "--batch_size=16", *common)
   assert "epoch/eval number 20 | Avg_Hit@1:" in ev
+
+
+def test_train_frame_level_lstm(tmp_path):
+  """train.py --frame_features --model=LstmModel: persistent-recurrence forward + back-propagation through time + MoE
+  backward learn a synthetic task from uint8 frame TFRecords; eval.py reads the checkpoint back (BASELINE config 3 at
+  reduced width)."""
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  sys.path.insert(0, PKG)
+  import readers
+  rs = np.random.RandomState(3)
+  recs = []
+  for i in range(32):
+    n = int(rs.randint(20, 120))
+    lab = int(rs.randint(0, 8))
+    base = rs.randint(96, 160, (n, 1152))
+    base[:, lab * 16:(lab + 1) * 16] += 90
+    fr = np.clip(base, 0, 255).astype(np.uint8)
+    recs.append(readers.encode_sequence_example(
+        {"video_id": ("bytes", [b"t%d" % i]), "labels": ("int64", [lab])},
+        {"rgb": [("bytes", [fr[j, :1024].tobytes()]) for j in range(n)], "audio": [("bytes", [fr[j, 1024:].tobytes()]) for j in range(n)]}))
+  data = str(tmp_path / "frames.tfrecord")
+  readers.write_tfrecord(data, recs)
+  train_dir = str(tmp_path / "m")
+  common = ["--frame_features", "--feature_names=rgb,audio", "--feature_sizes=1024,128", "--model=LstmModel", "--lstm_cells=256",
+            "--lstm_layers=2", "--moe_num_mixtures=2", "--train_dir=" + train_dir]
+  log = _run("train.py", "--train_data_pattern=" + data, "--start_new_model", "--batch_size=16", "--num_epochs=10",
+             "--base_learning_rate=0.002", *common)
+  assert "training step 20|" in log and "Exited training loop." in log
+  first = float(log.split("training step 1|")[1].split("Loss: ")[1].split()[0])
+  last = float(log.split("training step 20|")[1].split("Loss: ")[1].split()[0])
+  assert last < 0.7 * first, (first, last)
+  assert os.path.exists(os.path.join(train_dir, "model.ckpt-20"))
+  ev = _run("eval.py", "--eval_data_pattern=" + data, "--run_once", "--batch_size=16", *common)
+  assert "epoch/eval number 20 | Avg_Hit@1:" in ev

@@ -95,6 +95,23 @@ b0 = torch.zeros(4 * H, device=dev)
 ms = timeit(lambda: nat.lstm_fwd(xl, nfl, [w0, w1], [b0, b0], H), iters=3, warm=1)
 res["lstm_l2_h1024_b64"] = {"ms": ms, "videos_per_s": Bl / ms * 1e3}
 
+# LSTM config 3 training step at B=64 and B=128: persistent forward + BPTT + MoE-4 head on the 4096-d state + Adam
+import yt8m_trainer  # noqa: E402
+for Bt in (64, 128):
+  trn = yt8m_trainer.LstmTrainer(D, hidden=H, layers=2, vocab=V, mixtures=4)
+  trn.param.normal_(0.0, 0.02)
+  for l in range(2):
+    trn.w_bf16[l].copy_(trn.p["w%d" % l])
+  trn.head.w_bf16.copy_(trn.head.w)
+  xt = (torch.randn(Bt, T, D, device=dev) * 0.03).to(torch.bfloat16)
+  nft = torch.randint(30, T + 1, (Bt,), dtype=torch.int32, device=dev)
+  yt = (torch.rand(Bt, V, device=dev) < 3.4 / V).float()
+  ms = timeit(lambda: trn.step(xt, nft, yt), iters=3, warm=1)
+  res["lstm_train_step_b%d" % Bt] = {"ms": ms, "videos_per_s": Bt / ms * 1e3}
+  ms = timeit(lambda: trn.forward(xt, nft), iters=3, warm=1)
+  res["lstm_train_fwd_b%d" % Bt] = {"ms": ms}
+  del trn
+
 for k, v in res.items():
   print(k, json.dumps(v))
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -93,13 +93,20 @@ class Trainer(object):
                                   "--netvlad_add_batch_norm=False with --video_level_classifier_model=MoeModel")
       return yt8m_trainer.NetVLADTrainer(in_dim, clusters=FLAGS.netvlad_cluster_size, hidden=FLAGS.netvlad_hidden_size,
                                          vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures, relu=FLAGS.netvlad_relu)
+    if model_cls in (frame_level_models.LstmModel, frame_level_models.LstmMemoryModel):
+      if FLAGS.video_level_classifier_model != "MoeModel":
+        raise NotImplementedError("train.py --model=%s: the CUDA training step is built for "
+                                  "--video_level_classifier_model=MoeModel" % self.model_name)
+      return yt8m_trainer.LstmTrainer(in_dim, hidden=int(FLAGS.lstm_cells), layers=FLAGS.lstm_layers, vocab=self.reader.num_classes,
+                                      mixtures=FLAGS.moe_num_mixtures, memory=model_cls is frame_level_models.LstmMemoryModel)
     if model_cls is video_level_models.LogisticModel:
       kind = "logistic"
     elif model_cls is video_level_models.MoeModel:
       kind = "moe"
     else:
       raise NotImplementedError(
-          "train.py: the CUDA training step is built for LogisticModel, MoeModel and NetVLADModel this round; "
+          "train.py: the CUDA training step is built for LogisticModel, MoeModel, NetVLADModel, LstmModel and "
+          "LstmMemoryModel this round; "
           "%s runs forward-only (eval.py / inference.py)" % self.model_name)
     return yt8m_trainer.HeadTrainer(kind, in_dim, self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures)
 
