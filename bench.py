@@ -212,10 +212,16 @@ def main():
     return model.create_model(x_dev, vocab_size=V, num_frames=nf_dev)["predictions"]
 
   # end-to-end: every step copies ITS batch host->device and its predictions device->host inside the timed region.
+  # The host batch is what readers.YT8MFrameFeatureReader(packed=True) yields: a readers.PackedFrames holding only the
+  # REAL frames of every video (uint8, as stored in the TFRecords) -- the zero padding up to 300 frames is produced
+  # on the GPU by the ingest kernel (yt8m_frames_unpack_u8: de-quantise + L2-normalise + pad), so it never crosses PCIe.
   # Like the reference's queue-runner input pipeline (wh/train.py:199-209) the next batch's upload is prefetched: a
   # copy stream fills the other of two device buffers while the compute stream works on the current one.
+  import readers
+  packed_host = readers.PackedFrames.from_padded(u8, nf).pin_memory()
   copy_stream = torch.cuda.Stream()
-  bufs = [(torch.empty_like(u8, device=dev), torch.empty_like(nf, device=dev)) for _ in range(2)]
+  bufs = [readers.PackedFrames(torch.empty_like(packed_host.data, device=dev), torch.empty_like(packed_host.num_frames, device=dev), T,
+                               torch.empty_like(packed_host.offsets, device=dev)) for _ in range(2)]
   ready = [torch.cuda.Event(), torch.cuda.Event()]
   consumed = [torch.cuda.Event(), torch.cuda.Event()]
   state = {"i": 0, "primed": False}
@@ -223,8 +229,9 @@ def main():
   def upload(slot):
     with torch.cuda.stream(copy_stream):
       copy_stream.wait_event(consumed[slot])                 # the compute stream is done reading this buffer
-      bufs[slot][0].copy_(u8_pinned, non_blocking=True)
-      bufs[slot][1].copy_(nf_pinned, non_blocking=True)
+      bufs[slot].data.copy_(packed_host.data, non_blocking=True)
+      bufs[slot].num_frames.copy_(packed_host.num_frames, non_blocking=True)
+      bufs[slot].offsets.copy_(packed_host.offsets, non_blocking=True)
       ready[slot].record(copy_stream)
 
   def step_e2e():
@@ -236,8 +243,8 @@ def main():
       state["primed"] = True
     upload(cur ^ 1)                                          # prefetch the next step's batch
     torch.cuda.current_stream().wait_event(ready[cur])
-    xi, _ = transformer.transform(bufs[cur][0], bufs[cur][1])
-    p = model.create_model(xi, vocab_size=V, num_frames=bufs[cur][1])["predictions"]
+    xi, _ = transformer.transform(bufs[cur], bufs[cur].num_frames)
+    p = model.create_model(xi, vocab_size=V, num_frames=bufs[cur].num_frames)["predictions"]
     consumed[cur].record(torch.cuda.current_stream())
     pred_host.copy_(p, non_blocking=True)
     torch.cuda.current_stream().synchronize()                # the caller holds this step's predictions on the host
@@ -323,7 +330,7 @@ def main():
   except Exception:
     pass
   hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-  # dominant kernel: netvlad_v3_kernel, HBM bound.  Algorithmic bytes / video: the frames once
+  # dominant kernel: netvlad_v4_kernel, HBM bound.  Algorithmic bytes / video: the frames once
   # (300*1152*2) + the descriptor once (1152*64*2: one fp16 tensor; x2 for a bf16 hi + lo pair) -- SURVEY.md §8(d),
   # DESIGN.md §Kernels.
   fmt = FLAGS.netvlad_operand_format
@@ -346,13 +353,15 @@ def main():
                              ("fp16 (11 significant bits)" if fmt == "f16" else "bf16 hi+lo pairs"),
                  "l2": "inputs larger than L2 (frames 177 MB + FC weights 151 MB per step vs 126 MB L2), no explicit flush"},
       "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "videos/s", "ms_per_step": ms_e2e,
-              "h2d_bytes_per_step": u8.numel() + nf.numel() * 4, "d2h_bytes_per_step": pred_host.numel() * 4},
+              "h2d_bytes_per_step": packed_host.nbytes(), "d2h_bytes_per_step": pred_host.numel() * 4,
+              "host_batch": "readers.PackedFrames: uint8 real frames only (%d of %d frame rows; num_frames ~ U{30..300}), padded on "
+                            "the GPU" % (packed_host.data.shape[0], B * T)},
       "gpu_launches": int(launches),
       "train_step": None if ms_train is None else {
           "value": world * B / (ms_train * 1e-3), "unit": "videos/s", "ms_per_step": ms_train, "steps": args.train_steps,
           "what": "NetVLAD + FC + MoE-2 forward, full backward, per-tensor clip + Adam; resident inputs; "
                   "one all-reduce of the flat fp32 gradient (%d M floats) per step when n_gpus > 1" % 100},
-      "roofline": {"bound": "hbm", "kernel": "netvlad_v3_kernel (K=64)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+      "roofline": {"bound": "hbm", "kernel": "netvlad_v4_kernel (K=64)", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                    "frac": (achieved / hbm_peak) if achieved else None, "traffic": traffic,
                    "kernel_ms": k_ms, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback"},
       "clocks": clocks,

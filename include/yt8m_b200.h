@@ -74,6 +74,13 @@ int yt8m_l2norm_rows_fwd(const void* x, int src_dtype, long long rows, int dim, 
                          const int* num_frames, int frames_per_video, yt8m_bf16* out_bf16, float* out_f32,
                          yt8m_stream_t stream);
 
+/* RAGGED ingest of a frame-level batch (wh/readers.py:159-186 resize_axis + Dequantize + default_transformer.py:5-8):
+ * `packed` holds only the real frames, uint8 [sum_b num_frames[b], dim], video b starting at row row_offsets[b]
+ * (the zero padding of the reference's reader never crosses PCIe); the output is the padded, de-quantised,
+ * L2-normalised [B, T, dim] the poolers consume (rows t >= num_frames[b] are zeros).  num_frames[b] <= T. */
+int yt8m_frames_unpack_u8(const uint8_t* packed, const long long* row_offsets, const int* num_frames, int B, int T,
+                          int dim, int normalize, yt8m_bf16* out_bf16, float* out_f32, yt8m_stream_t stream);
+
 /* ---- dense layer (slim.fully_connected / tf.matmul + bias / folded batch-norm + activation) ----
  * out[M, N] = act((A[M, K] . W[N, K]^T) * col_scale[N] + col_shift[N]);  A = a_hi (+ a_lo).
  * Replaces e.g. wh/all_video_models/logistic_model.py:23-25, wh/all_frame_models/dbof_model.py:76-115,

@@ -121,3 +121,47 @@ def test_topk_with_ties_and_k1(nat):
   assert idx[1, 0].item() == 39 and idx[2].tolist() == [0, 1, 2]
   idx1, _ = nat.topk_rows(x.to(DEV), 1)
   assert idx1.flatten().tolist() == [3, 39, 0]
+
+
+def test_ragged_ingest_equals_padded_ingest(nat):
+  """yt8m_frames_unpack_u8 on a readers.PackedFrames == yt8m_l2norm_rows_fwd on the reader's padded uint8 batch, bit for bit
+  (de-quantise + L2-normalise + zero padding); includes a zero-frame and a full-length video."""
+  import readers
+  import feature_transform
+  g = torch.Generator().manual_seed(12)
+  b, t, d = 7, 40, 1152
+  u8 = torch.randint(0, 256, (b, t, d), generator=g, dtype=torch.uint8)
+  nf = torch.tensor([40, 0, 1, 17, 39, 8, 40], dtype=torch.int32)
+  u8 = u8 * (torch.arange(t).unsqueeze(0) < nf.unsqueeze(1)).unsqueeze(2).to(torch.uint8)      # the reader pads with zeros
+  want = nat.l2norm_rows(u8.to(DEV), num_frames=nf.to(DEV))
+  packed = readers.PackedFrames.from_padded(u8, nf)
+  assert packed.data.shape[0] == int(nf.sum())
+  got, _ = feature_transform.DefaultTransformer().transform(packed.pin_memory(), nf)
+  assert got.shape == want.shape and torch.equal(got.view(torch.int16), want.view(torch.int16))
+  assert float(got[1].float().abs().max()) == 0.0
+  # oracle: Dequantize + l2_normalize of the real frames
+  x = O.l2_normalize(O.dequantize(u8.float()))
+  x = x * (torch.arange(t).unsqueeze(0) < nf.unsqueeze(1)).unsqueeze(2)
+  assert float((got.float().cpu() - x).abs().max()) < 2 ** -8
+
+
+@pytest.mark.parametrize("b,t,d", [(200, 96, 128), (1100, 96, 128), (90, 300, 256)])
+def test_netvlad_one_pass_kernel_short_and_empty_videos(nat, b, t, d):
+  """The one-pass cluster kernel (yt8m_netvlad_v4.cu: fp16 output, K = 64) streams only ceil(num_frames / 32) tiles per
+  video and hands videos to the clusters longest first (B <= 1024) or round-robin (B > 1024).  Many one- and two-tile
+  videos, empty videos and full-length ones in one batch, several videos per cluster: every descriptor vs the oracle."""
+  g = torch.Generator().manual_seed(b)
+  k = 64
+  x = synth.bf16r(torch.randn(b, t, d, generator=g))
+  x = x * torch.rsqrt((x * x).sum(dim=2, keepdim=True))
+  nf = torch.randint(0, t + 1, (b,), generator=g, dtype=torch.int32)
+  nf[:6] = torch.tensor([0, 1, t, 32, 33, 0], dtype=torch.int32)
+  x = synth.bf16r(x * (torch.arange(t).unsqueeze(0) < nf.unsqueeze(1)).float().unsqueeze(2))
+  cw, cw2 = synth.normal((d, k), g, 4.0), synth.normal((d, k), g, 1 / math.sqrt(d))
+  want = O.netvlad_pool(x, nf, cw, torch.ones(k), torch.zeros(k), cw2)
+  out = nat.netvlad_fwd(bf(x), nf.to(DEV), nat.pack_transpose(cw.to(DEV)), None, None, cw2.to(DEV), out_f16=True)[0]
+  got = out.view(torch.float16).float().cpu() if out.dtype != torch.float16 else out.float().cpu()
+  assert bool(torch.isfinite(got).all())
+  assert float(got[0].abs().max()) == 0.0 and float(got[5].abs().max()) == 0.0          # no frames -> zero descriptor
+  err = (got - want).norm(dim=1) / want.norm(dim=1).clamp_min(1e-6)
+  assert float(err.max()) < 4e-3, (int(err.argmax()), float(err.max()), int(nf[int(err.argmax())]))

@@ -92,3 +92,31 @@ def test_utils(tmp_path):
   assert utils.load_checkpoint(utils.latest_checkpoint(d))["variables"]["w"].tolist() == [40.0, 40.0]
   info = utils.FormatEpochInfo({"epoch_id": 7, "avg_hit_at_one": 0.5, "avg_perr": 0.25, "aps": [0.5, 1.0], "gap": 0.75, "avg_loss": 3.0})
   assert info.startswith("epoch/eval number 7 | Avg_Hit@1: 0.500 | Avg_PERR: 0.250 | MAP: 0.750 | GAP: 0.750")
+
+
+def test_packed_frames_equal_the_padded_batch(tmp_path):
+  """packed=True yields readers.PackedFrames: the same batch without the zero padding (only real frames cross PCIe)."""
+  rs = np.random.RandomState(4)
+  recs, lens = [], [3, 9, 1, 6, 12]                                   # 12 > max_frames: truncated like the padded reader
+  for i, n in enumerate(lens):
+    fr = rs.randint(0, 256, (n, 16)).astype(np.uint8)
+    recs.append(readers.encode_sequence_example(
+        {"video_id": ("bytes", [b"p%d" % i]), "labels": ("int64", [i])},
+        {"rgb": [("bytes", [fr[j, :8].tobytes()]) for j in range(n)], "audio": [("bytes", [fr[j, 8:].tobytes()]) for j in range(n)]}))
+  p = str(tmp_path / "f.tfrecord")
+  readers.write_tfrecord(p, recs)
+  r = readers.YT8MFrameFeatureReader(num_classes=10, feature_names=["rgb", "audio"], feature_sizes=[8, 8], max_frames=10)
+  (ids_a, padded, lab_a, nf_a), = list(r.prepare_reader(p, batch_size=8))
+  (ids_b, packed, lab_b, nf_b), = list(r.prepare_reader(p, batch_size=8, packed=True))
+  assert isinstance(packed, readers.PackedFrames) and ids_a == ids_b and torch.equal(lab_a, lab_b) and torch.equal(nf_a, nf_b)
+  assert nf_b.tolist() == [3, 9, 1, 6, 10]
+  assert packed.shape == tuple(padded.shape) and packed.data.shape == (29, 16) and packed.offsets.tolist() == [0, 3, 12, 13, 19]
+  assert torch.equal(packed.to_padded(), padded)
+  assert packed.nbytes() == 29 * 16 + 5 * 4 + 5 * 8
+  # slicing by video = data-parallel sharding
+  sh = packed[1:4]
+  assert sh.shape == (3, 10, 16) and sh.offsets.tolist() == [0, 9, 10] and torch.equal(sh.to_padded(), padded[1:4])
+  assert packed[2:2].shape[0] == 0
+  # synthetic batches: dropping the padding and restoring it is the identity
+  again = readers.PackedFrames.from_padded(padded, nf_a)
+  assert torch.equal(again.data, packed.data) and torch.equal(again.offsets, packed.offsets)

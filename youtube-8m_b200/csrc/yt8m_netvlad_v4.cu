@@ -62,7 +62,7 @@ constexpr int kOffStage = kOffPeer + 2 * kPeerBytes;          // 204 KB
 constexpr int kOffSmall = kOffStage + kStageBytes;            // 220 KB
 constexpr int kSmallFloats = 2 * KC /*scale, shift*/ + 2 * KC /*asum[2]*/ + KC /*ssq*/ + 2 * KC /*ssq_peer[2]*/ + KC /*fscale*/ +
                              KC /*contrib*/ + 4 * KC /*ssq per epilogue warp*/ + 4 * KC /*asum per softmax warp*/;
-constexpr int kSmallBytes = kSmallFloats * 4 + 512;
+constexpr int kSmallBytes = kSmallFloats * 4 + 512;   // + barriers, TMEM slot, schedule (1 + 2 * kMaxIter ints)
 constexpr int kSmemTotal = kOffSmall + kSmallBytes;
 static_assert(kSmemTotal <= 227 * 1024, "NetVLAD v4 shared-memory budget exceeded");
 
@@ -70,6 +70,8 @@ constexpr int kSCol = 0;                     // TMEM: S^T double buffer, 2 x 32 
 constexpr int kVCol = 64;                    // TMEM: V^T, kMaxMb x 64 columns
 constexpr int kThreads = 512;
 constexpr int kSms = 148;
+constexpr int kMaxSchedB = 1024;             // batches up to this size get the longest-first schedule (O(B^2 / 512) per CTA)
+constexpr int kMaxIter = 16;                 // >= ceil(kMaxSchedB / 74) videos per cluster
 
 // debug-only phase timeline (globaltimer ns) of cluster 0 / CTA rank 0, first 3 videos, 128 stamps per video:
 // [0,10) mma: tile landed   [10,20) reader: S ready   [20,30) softmax: logits ready   [30,40) mma: assignment ready
@@ -138,11 +140,14 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   uint64_t* sum_ready = peer_free + 2;           // [2]  readers -> softmax (4)
   uint64_t* a_ready = sum_ready + 2;             // [2]  softmax -> MMA (4)
   uint64_t* a_free = a_ready + 2;                // [2]  MMA -> softmax
-  uint64_t* asum_ready = a_free + 2;             // [1]  softmax -> epilogue, per video (4)
-  uint64_t* v_full = asum_ready + 1;             // [1]  MMA -> epilogue, per video
+  uint64_t* asum_ready = a_free + 2;             // [2]  softmax -> epilogue, by video parity (4): with one- and two-tile videos the
+                                                 //      softmax warps finish video it+1 before the epilogue has looked at video it
+  uint64_t* v_full = asum_ready + 2;             // [1]  MMA -> epilogue, per video
   uint64_t* v_free = v_full + 1;                 // [5]  epilogue -> MMA, per accumulator block and video (4)
   uint64_t* ssq_full = v_free + kMaxMb;          // [1]  the peer's 64 partial sums have landed (st.async bytes); [2] by video parity
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ssq_full + 2);
+  uint64_t* asum_free = ssq_full + 2;            // [2]  epilogue -> softmax, by video parity: a_sum of video it-2 has been consumed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(asum_free + 2);
+  int* sched = reinterpret_cast<int*>(tmem_slot + 2);   // [0] = videos of this cluster, [1 + w] = video of wave w, [1 + kMaxIter + w] = its tiles
 
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);   // warp-uniform for ptxas
   const int lane = threadIdx.x & 31;
@@ -150,12 +155,40 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
   const uint32_t peer = rank ^ 1u;
   const int n_clusters = static_cast<int>(gridDim.x) >> 1;
   const int cid = static_cast<int>(blockIdx.x) >> 1;
-  const int n_iter = (B - cid + n_clusters - 1) / n_clusters;
   const int NT = (T + kFT - 1) / kFT;
+  // PADDED FRAMES ARE NOT READ: a video is streamed for ceil(num_frames / 32) tiles only (at least one, which also
+  // zero-initialises the accumulators of an empty video).  Videos are handed to the clusters longest first in
+  // serpentine order (wave w: cluster c takes rank w*C + c, or w*C + C-1-c when w is odd), so the per-cluster sums of
+  // tiles stay within one video of each other; every CTA derives the same schedule from num_frames on its own.
+  auto tiles_of = [&](int nfv) { return min(max((min(nfv, T) + kFT - 1) / kFT, 1), NT); };
+  const bool use_list = B <= kMaxSchedB;
+  if (use_list) {
+    if (threadIdx.x == 0) sched[0] = 0;
+    __syncthreads();
+    for (int b = threadIdx.x; b < B; b += kThreads) {
+      const int ntb = tiles_of(__ldg(num_frames + b));
+      int r = 0;
+      for (int j = 0; j < B; ++j) {
+        const int ntj = tiles_of(__ldg(num_frames + j));
+        r += (ntj > ntb || (ntj == ntb && j < b)) ? 1 : 0;
+      }
+      const int w = r / n_clusters, pos = r - w * n_clusters;
+      if (((w & 1) ? n_clusters - 1 - pos : pos) == cid) {
+        sched[1 + w] = b;
+        sched[1 + kMaxIter + w] = ntb;
+        atomicMax(&sched[0], w + 1);
+      }
+    }
+    __syncthreads();
+  }
+  const int n_iter = use_list ? sched[0] : (B - cid + n_clusters - 1) / n_clusters;
+  auto vid = [&](int it) { return use_list ? sched[1 + it] : cid + it * n_clusters; };
+  auto vnt = [&](int it) { return use_list ? sched[1 + kMaxIter + it] : tiles_of(__ldg(num_frames + cid + it * n_clusters)); };
   const int nkb = D / 128;                      // 64-wide feature blocks of this CTA's half
   const int DH = nkb * 64;
   const int nmb = (nkb + 1) >> 1;               // 128-row accumulator blocks (the last one may be half valid)
-  const int total_tiles = n_iter * NT;
+  int total_tiles = 0;
+  for (int it = 0; it < n_iter; ++it) total_tiles += vnt(it);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x); tma_prefetch_desc(&tm_cw);
@@ -167,10 +200,11 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       mbar_init(&sum_ready[i], 4);
       mbar_init(&a_ready[i], 4); mbar_init(&a_free[i], 1);
     }
-    mbar_init(asum_ready, 4);
+    mbar_init(&asum_ready[0], 4); mbar_init(&asum_ready[1], 4);
     mbar_init(v_full, 1);
     for (int i = 0; i < kMaxMb; ++i) mbar_init(&v_free[i], 4);
     mbar_init(&ssq_full[0], 1); mbar_init(&ssq_full[1], 1);
+    mbar_init(&asum_free[0], 1); mbar_init(&asum_free[1], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -196,8 +230,9 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     int slot = 0;
     uint32_t phase = 0;
     for (int it = 0; it < n_iter; ++it) {
-      const int b = cid + it * n_clusters;
-      for (int i = 0; i < NT; ++i) {
+      const int b = vid(it);
+      const int ntv = vnt(it);
+      for (int i = 0; i < ntv; ++i) {
         mbar_wait(&x_empty[slot], phase ^ 1u);
         if (elect_one()) {
           mbar_arrive_expect_tx(&x_full[slot], nkb * kSubBytes);
@@ -215,6 +250,8 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     mbar_wait(cw_full, 0);
     // Tiles are numbered across this CTA's videos (G).  p0 / p1 = next tile whose phase 0 / phase 1 is to be issued.
     int p0 = 0, p1 = 0;
+    int it0 = 0, i0 = 0, nt0 = n_iter > 0 ? vnt(0) : 0;       // (video, tile, tiles of the video) of p0 and of p1
+    int it1 = 0, i1 = 0, nt1 = nt0;
     while (p1 < total_tiles) {
       if (p0 < total_tiles) {
         const int G = p0, sb = G & 1, u = G >> 1, slot = G % kSlots;
@@ -223,7 +260,7 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         ok = __all_sync(0xffffffffu, ok);
         if (ok) {
           tc_fence_after();
-          if (lane == 0 && (G % NT) < 10) NV4_T(G / NT, G % NT);
+          if (lane == 0 && i0 < 10) NV4_T(it0, i0);
           if (elect_one()) {
             const uint32_t x_addr = smem_u32(xs + slot * kXSlotBytes);
             const uint32_t c_addr = smem_u32(cws);
@@ -239,11 +276,12 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           }
           __syncwarp();
           ++p0;
+          if (++i0 == nt0) { ++it0; i0 = 0; nt0 = it0 < n_iter ? vnt(it0) : 0; }
         }
       }
       if (p1 < p0) {
         const int G = p1;
-        const int it = G / NT, i = G - it * NT;
+        const int it = it1, i = i1;
         const int ab = G & 1, u = G >> 1, slot = G % kSlots;
         const bool ok = __all_sync(0xffffffffu, mbar_test_wait(&a_ready[ab], u & 1));
         if (ok) {
@@ -283,10 +321,11 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           if (elect_one()) {
             umma_commit(&x_empty[slot]);
             umma_commit(&a_free[ab]);
-            if (i == NT - 1) umma_commit(v_full);
+            if (i == nt1 - 1) umma_commit(v_full);
           }
           __syncwarp();
           ++p1;
+          if (++i1 == nt1) { ++it1; i1 = 0; nt1 = it1 < n_iter ? vnt(it1) : 0; }
         }
       }
     }
@@ -300,13 +339,16 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + kSCol;
     const uint32_t peer_buf_remote = mapa_u32(smem_u32(peerbuf), peer);
     const uint32_t peer_full_remote = mapa_u32(smem_u32(peer_full), peer);
+    int itr = 0, ir = 0, ntr = n_iter > 0 ? vnt(0) : 0;       // (video, tile) of G, for the debug timeline only
     for (int G = 0; G < total_tiles; ++G) {
       const int sb = G & 1, u = G >> 1;
+      const int tl_it = itr, tl_i = ir;
+      if (++ir == ntr) { ++itr; ir = 0; ntr = itr < n_iter ? vnt(itr) : 0; }
       // this tile's incoming partial: 8 KB of st.async transaction bytes from the peer's readers
       if (warp == 12 && lane == 0) mbar_arrive_expect_tx(&peer_full[sb], kPeerBytes);
       mbar_wait(&s_full[sb], u & 1);
       tc_fence_after();
-      if (warp == 12 && lane == 0 && (G % NT) < 10) NV4_T(G / NT, 10 + G % NT);
+      if (warp == 12 && lane == 0 && tl_i < 10) NV4_T(tl_it, 10 + tl_i);
       float r[kFT];
       tmem_ld32(taddr + sb * kFT, reinterpret_cast<uint32_t*>(r));
       tmem_ld_wait();
@@ -323,7 +365,7 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
       // the peer's partial logits have landed in OUR buffer: add ours in place
       mbar_wait(&peer_full[sb], u & 1);
-      if (warp == 12 && lane == 0 && (G % NT) < 10) NV4_T(G / NT, 40 + G % NT);
+      if (warp == 12 && lane == 0 && tl_i < 10) NV4_T(tl_it, 40 + tl_i);
       uint8_t* pb = peerbuf + sb * kPeerBytes;
       if (act) {
 #pragma unroll
@@ -361,7 +403,7 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
     };
     for (int it = 0; it < n_iter; ++it) {
-      const int b = cid + it * n_clusters;
+      const int b = vid(it);
       const int p = it & 1;
       // the cw2 blocks of the first two pass-1 steps are in flight while we wait for the video to complete; after that the
       // fetch runs two steps ahead of its use (L2 latency ~ two steps of work)
@@ -369,7 +411,7 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       if (nsteps1 > 0) { fetch_c2(0, ga); fetch_c2(1, gb); }
       if (et == 0) mbar_arrive_expect_tx(&ssq_full[p], KC * 4);   // this video's 64 partial sums from the peer
       if (nsteps1 == 0) { ssq_w[wi * KC + lane] = 0.0f; ssq_w[wi * KC + 32 + lane] = 0.0f; }
-      mbar_wait(asum_ready, it & 1);
+      mbar_wait(&asum_ready[p], (it >> 1) & 1);
       mbar_wait(v_full, it & 1);
       tc_fence_after();
       if (et == 0) NV4_T(it, 50);
@@ -435,6 +477,9 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
         }
       }
       named_bar_sync(1, 128);
+      // every epilogue thread is done with asum_s[p]: the softmax warps may publish video it+2 into it (short videos --
+      // one or two tiles -- let them run that far ahead)
+      if (et == 0) mbar_arrive(&asum_free[p]);
       const float total = warp_sum(contrib_s[lane] + contrib_s[lane + 32]);     // same tree on every warp of both CTAs
       const float gs = rsqrtf(fmaxf(total, 1e-12f));
       if (stats && rank == 0 && et == 0) stats[static_cast<long long>(b) * (2 * KC + 1) + 2 * KC] = total;
@@ -500,9 +545,10 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
     int G = 0;
     for (int it = 0; it < n_iter; ++it) {
-      const int b = cid + it * n_clusters;
+      const int b = vid(it);
       const int nf = min(max(num_frames[b], 0), T);
-      for (int i = 0; i < NT; ++i, ++G) {
+      const int ntv = vnt(it);
+      for (int i = 0; i < ntv; ++i, ++G) {
         const int sb = G & 1, u = G >> 1;
         mbar_wait(&sum_ready[sb], u & 1);
         if (st == 0 && i < 10) NV4_T(it, 20 + i);
@@ -575,10 +621,11 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
       }
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+      if (it >= 2) mbar_wait(&asum_free[p], ((it >> 1) - 1) & 1);   // the epilogue has consumed a_sum of video it-2
       named_bar_sync(2, 128);
       if (st < KC) asum_s[p * KC + st] = (asum_w[st] + asum_w[KC + st]) + (asum_w[2 * KC + st] + asum_w[3 * KC + st]);
       named_bar_sync(2, 128);
-      if (lane == 0) mbar_arrive(asum_ready);
+      if (lane == 0) mbar_arrive(&asum_ready[p]);
       if (st == 0) NV4_T(it, 80);
     }
   }

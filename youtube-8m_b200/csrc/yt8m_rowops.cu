@@ -38,9 +38,12 @@ __device__ __forceinline__ void load8(const void* base, long long elem_off, floa
   }
 }
 
+// row_offsets != NULL: RAGGED source -- video b's frames are rows [row_offsets[b], row_offsets[b] + num_frames[b]) of x
+// (the reader's packed batch: padding never crosses PCIe); the output stays the padded [B, frames_per_video, dim].
 template <int SRC>
 __global__ void l2norm_rows_kernel(const void* __restrict__ x, long long rows, int dim, int normalize,
                                    const int* __restrict__ num_frames, int frames_per_video,
+                                   const long long* __restrict__ row_offsets,
                                    __nv_bfloat16* __restrict__ out_bf, float* __restrict__ out_f32) {
   const int lane = threadIdx.x & 31;
   const long long warp_global = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -48,17 +51,20 @@ __global__ void l2norm_rows_kernel(const void* __restrict__ x, long long rows, i
   const int chunks = dim >> 3;
   for (long long r = warp_global; r < rows; r += nwarps) {
     bool pad = false;
+    const long long base = r * dim;
+    long long src = base;
     if (num_frames) {
       const long long b = r / frames_per_video;
-      pad = (r - b * frames_per_video) >= num_frames[b];
+      const long long t = r - b * frames_per_video;
+      pad = t >= num_frames[b];
+      if (row_offsets) src = (row_offsets[b] + t) * dim;
     }
-    const long long base = r * dim;
     float scale = 1.0f;
     if (normalize && !pad) {
       float ss = 0.0f;
       for (int c = lane; c < chunks; c += 32) {
         float v[8];
-        load8<SRC>(x, base + c * 8, v);
+        load8<SRC>(x, src + c * 8, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) ss += v[j] * v[j];
       }
@@ -71,7 +77,7 @@ __global__ void l2norm_rows_kernel(const void* __restrict__ x, long long rows, i
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = 0.0f;
       } else {
-        load8<SRC>(x, base + c * 8, v);
+        load8<SRC>(x, src + c * 8, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] *= scale;
       }
@@ -325,11 +331,25 @@ int yt8m_l2norm_rows_fwd(const void* x, int src_dtype, long long rows, int dim, 
   const int blocks = grid_for(rows, threads / 32);
   __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out_bf16);
   switch (src_dtype) {
-    case YT8M_SRC_F32: l2norm_rows_kernel<YT8M_SRC_F32><<<blocks, threads, 0, stream>>>(x, rows, dim, normalize, num_frames, frames_per_video, ob, out_f32); break;
-    case YT8M_SRC_BF16: l2norm_rows_kernel<YT8M_SRC_BF16><<<blocks, threads, 0, stream>>>(x, rows, dim, normalize, num_frames, frames_per_video, ob, out_f32); break;
-    case YT8M_SRC_U8: l2norm_rows_kernel<YT8M_SRC_U8><<<blocks, threads, 0, stream>>>(x, rows, dim, normalize, num_frames, frames_per_video, ob, out_f32); break;
+    case YT8M_SRC_F32: l2norm_rows_kernel<YT8M_SRC_F32><<<blocks, threads, 0, stream>>>(x, rows, dim, normalize, num_frames, frames_per_video, nullptr, ob, out_f32); break;
+    case YT8M_SRC_BF16: l2norm_rows_kernel<YT8M_SRC_BF16><<<blocks, threads, 0, stream>>>(x, rows, dim, normalize, num_frames, frames_per_video, nullptr, ob, out_f32); break;
+    case YT8M_SRC_U8: l2norm_rows_kernel<YT8M_SRC_U8><<<blocks, threads, 0, stream>>>(x, rows, dim, normalize, num_frames, frames_per_video, nullptr, ob, out_f32); break;
     default: set_error("yt8m_l2norm_rows_fwd: unknown src_dtype %d", src_dtype); return YT8M_E_UNSUPPORTED;
   }
+  return check_launch("l2norm_rows_kernel");
+}
+
+int yt8m_frames_unpack_u8(const uint8_t* packed, const long long* row_offsets, const int* num_frames, int B, int T, int dim,
+                          int normalize, yt8m_bf16* out_bf16, float* out_f32, yt8m_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  YT8M_REQUIRE(packed && row_offsets && num_frames && (out_bf16 || out_f32), YT8M_E_BADPTR, "yt8m_frames_unpack_u8: null pointer");
+  YT8M_REQUIRE(B > 0 && T > 0 && dim > 0 && dim % 8 == 0, YT8M_E_BADSHAPE, "yt8m_frames_unpack_u8: bad shape B=%d T=%d dim=%d", B, T, dim);
+  YT8M_REQUIRE((reinterpret_cast<uintptr_t>(packed) & 7u) == 0, YT8M_E_BADPTR, "yt8m_frames_unpack_u8: packed must be 8-byte aligned");
+  const long long rows = static_cast<long long>(B) * T;
+  const int threads = 256;
+  const int blocks = grid_for(rows, threads / 32);
+  l2norm_rows_kernel<YT8M_SRC_U8><<<blocks, threads, 0, stream>>>(packed, rows, dim, normalize, num_frames, T, row_offsets,
+                                                                   reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32);
   return check_launch("l2norm_rows_kernel");
 }
 

@@ -63,7 +63,8 @@ def evaluation_loop(reader, model, checkpoint, last_global_step_val):
   loss_fn = utils.find_class_by_name(FLAGS.label_loss, [losses])()
   evl_metrics = eval_util.EvaluationMetrics(reader.num_classes, FLAGS.top_k)
   global_step_val, examples_processed = None, 0
-  for video_ids, feats, labels, num_frames in reader.prepare_reader(FLAGS.eval_data_pattern, FLAGS.batch_size, 1):
+  packed = {"packed": True} if FLAGS.frame_features else {}         # readers.PackedFrames: no padding over PCIe
+  for video_ids, feats, labels, num_frames in reader.prepare_reader(FLAGS.eval_data_pattern, FLAGS.batch_size, 1, **packed):
     t0 = time.time()
     nf = num_frames.cuda() if FLAGS.frame_features else None
     x, _ = transformer.transform(feats.cuda(non_blocking=True), nf)

@@ -46,7 +46,8 @@ def inference(reader, model, checkpoint, data_pattern, out_file_location, batch_
   restored, n, start = False, 0, time.time()
   with open(out_file_location, "w+") as out_file:
     out_file.write("VideoId,LabelConfidencePairs\n")
-    for video_ids, feats, _, num_frames in reader.prepare_reader(data_pattern, batch_size, 1):
+    packed = {"packed": True} if FLAGS.frame_features else {}       # readers.PackedFrames: no padding over PCIe
+    for video_ids, feats, _, num_frames in reader.prepare_reader(data_pattern, batch_size, 1, **packed):
       nf = num_frames.cuda() if FLAGS.frame_features else None
       x, _ = transformer.transform(feats.cuda(non_blocking=True), nf)
       if not restored:

@@ -268,6 +268,78 @@ class YT8MAggregatedFeatureReader(BaseReader):
       yield ids, torch.from_numpy(np.stack(feats)), torch.from_numpy(np.stack(labels)), torch.ones(len(ids), dtype=torch.int32)
 
 
+class PackedFrames(object):
+  """A frame-level batch WITHOUT the reader's zero padding: `data` uint8 [sum(num_frames), D] holds only the real
+  frames, video b = rows [offsets[b], offsets[b] + num_frames[b]).  It stands where the padded
+  [B, max_frames, D] tensor of wh/readers.py:186 stood (same .shape, slicing by video, .cuda()), but only the real
+  frames cross PCIe; DefaultTransformer.transform() expands it on the GPU (yt8m_frames_unpack_u8: de-quantise +
+  L2-normalise + zero padding in one pass)."""
+
+  dtype = torch.uint8
+
+  def __init__(self, data, num_frames, max_frames, offsets=None):
+    self.data, self.num_frames, self.max_frames = data, num_frames.to(torch.int32), int(max_frames)
+    if offsets is None:
+      offsets = torch.cumsum(self.num_frames.to(torch.int64), 0) - self.num_frames.to(torch.int64)
+    self.offsets = offsets
+
+  @property
+  def shape(self):
+    return (int(self.num_frames.shape[0]), self.max_frames, int(self.data.shape[1]))
+
+  @property
+  def is_cuda(self):
+    return self.data.is_cuda
+
+  def __len__(self):
+    return int(self.num_frames.shape[0])
+
+  def dim(self):
+    return 3
+
+  def __getitem__(self, idx):
+    """Slice by video (data-parallel sharding of a batch: rank r keeps videos [lo, hi))."""
+    if not isinstance(idx, slice):
+      raise TypeError("PackedFrames can only be sliced by a range of videos")
+    lo, hi, step = idx.indices(len(self))
+    assert step == 1
+    if hi <= lo:
+      return PackedFrames(self.data[:0], self.num_frames[:0], self.max_frames)
+    r0 = int(self.offsets[lo])
+    r1 = int(self.offsets[hi - 1]) + int(self.num_frames[hi - 1])
+    return PackedFrames(self.data[r0:r1], self.num_frames[lo:hi], self.max_frames, self.offsets[lo:hi] - r0)
+
+  def pin_memory(self):
+    return PackedFrames(self.data.pin_memory(), self.num_frames.pin_memory(), self.max_frames, self.offsets.pin_memory())
+
+  def cuda(self, non_blocking=False):
+    if self.is_cuda:
+      return self
+    return PackedFrames(self.data.cuda(non_blocking=non_blocking), self.num_frames.cuda(non_blocking=non_blocking), self.max_frames,
+                        self.offsets.cuda(non_blocking=non_blocking))
+
+  def nbytes(self):
+    return self.data.numel() + self.num_frames.numel() * 4 + self.offsets.numel() * 8
+
+  def to_padded(self):
+    """The reference reader's padded uint8 [B, max_frames, D] (host side; tests)."""
+    b, t, d = self.shape
+    out = torch.zeros((b, t, d), dtype=torch.uint8)
+    data, off, nf = self.data.cpu(), self.offsets.cpu(), self.num_frames.cpu()
+    for i in range(b):
+      n = int(nf[i])
+      out[i, :n] = data[int(off[i]):int(off[i]) + n]
+    return out
+
+  @staticmethod
+  def from_padded(u8, num_frames):
+    """Drop the padding of a [B, max_frames, D] uint8 batch (synthetic data)."""
+    b, t, d = u8.shape
+    nf = num_frames.to(torch.int64).clamp(0, t)
+    keep = (torch.arange(t).unsqueeze(0) < nf.unsqueeze(1))
+    return PackedFrames(u8[keep].contiguous(), nf.to(torch.int32), t)
+
+
 class YT8MFrameFeatureReader(BaseReader):
   """Frame-level SequenceExamples (wh/readers.py:128-259).  Batches keep the features uint8-quantised;
   frames beyond max_frames are dropped and shorter videos are zero padded (resize_axis, :21-56)."""
@@ -286,12 +358,18 @@ class YT8MFrameFeatureReader(BaseReader):
     out[:n] = mat[:n]
     return out, n
 
-  def prepare_reader(self, data_pattern, batch_size=1024, num_epochs=1, verify_crc=False):
-    """Generator of (video_ids, features uint8 [B, max_frames, D], labels bool [B, C], num_frames int32 [B])."""
+  def prepare_reader(self, data_pattern, batch_size=1024, num_epochs=1, verify_crc=False, packed=False):
+    """Generator of (video_ids, features uint8 [B, max_frames, D], labels bool [B, C], num_frames int32 [B]).
+    packed=True: the features come as a PackedFrames (real frames only; same .shape) instead of the padded tensor."""
     ids, mats, labels, nfs = [], [], [], []
 
     def flush():
-      return ids, torch.from_numpy(np.stack(mats)), torch.from_numpy(np.stack(labels)), torch.tensor(nfs, dtype=torch.int32)
+      nf = torch.tensor(nfs, dtype=torch.int32)
+      if packed:
+        feats = PackedFrames(torch.from_numpy(np.concatenate([m[:n] for m, n in zip(mats, nfs)], axis=0)), nf, self.max_frames)
+      else:
+        feats = torch.from_numpy(np.stack(mats))
+      return ids, feats, torch.from_numpy(np.stack(labels)), nf
 
     for _ in range(num_epochs):
       for path in _files(data_pattern):

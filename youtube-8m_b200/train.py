@@ -139,7 +139,10 @@ class Trainer(object):
       trainer.import_state({k: v.value for k, v in ops.get_store().vars.items()})
     logging.info("Entering training loop.")
     steps, last_save = 0, time.time()
-    for video_ids, feats, labels, num_frames in self.reader.prepare_reader(FLAGS.train_data_pattern, FLAGS.batch_size, FLAGS.num_epochs):
+    # frame-level batches travel as readers.PackedFrames: only the real frames cross PCIe (the padding is made on the GPU)
+    packed = {"packed": True} if FLAGS.frame_features else {}
+    for video_ids, feats, labels, num_frames in self.reader.prepare_reader(FLAGS.train_data_pattern, FLAGS.batch_size, FLAGS.num_epochs,
+                                                                           **packed):
       steps += 1
       t0 = time.time()
       lo, hi = yt8m_dp.shard_rows(feats.shape[0])

@@ -35,6 +35,7 @@ _SIGS = {
     "yt8m_last_error": (ctypes.c_char_p, []),
     "yt8m_launch_count": (c_ll, []),
     "yt8m_l2norm_rows_fwd": (c_int, [c_void_p, c_int, c_ll, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "yt8m_frames_unpack_u8": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "yt8m_linear_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "yt8m_linear_fwd": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
                                 c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_size_t, c_void_p]),
@@ -191,6 +192,18 @@ def l2norm_rows(x, normalize=True, num_frames=None, want_f32=False):
   _check(_lib.yt8m_l2norm_rows_fwd(_p(x), src, rows, dim, int(bool(normalize)), _p(num_frames), fpv, _p(out), _p(of),
                                    _stream()), "yt8m_l2norm_rows_fwd")
   return (out, of) if want_f32 else out
+
+
+def frames_unpack_u8(packed, row_offsets, num_frames, max_frames, normalize=True, out=None):
+  """packed uint8 [sum nf, D] (device), row_offsets int64 [B], num_frames int32 [B] -> padded bf16 [B, max_frames, D]."""
+  b, d = num_frames.shape[0], packed.shape[1]
+  if packed.shape[0] == 0:                       # a batch of empty videos: the kernel still needs a valid pointer
+    packed = torch.zeros((1, d), dtype=torch.uint8, device=packed.device)
+  if out is None:
+    out = _bf16((b, max_frames, d), packed.device)
+  _call("yt8m_frames_unpack_u8", _p(packed), _p(row_offsets), _p(num_frames), b, max_frames, d, 1 if normalize else 0, _p(out), None,
+        _stream())
+  return out
 
 
 def split_bf16(x, out_hi=None, out_lo=None, want_lo=True):
