@@ -58,6 +58,12 @@ vl16 = vl.to(torch.float16)
 wfc16 = wfc.to(torch.float16)
 ms = timeit(lambda: nat.linear(vl16, wfc16, act="relu6", out_f32=False, out_f16=True))
 res["fc_73728x1024_b256_f16"] = {"ms": ms}
+nat.debug_set_flags(16384)          # experiment: 128-wide tiles (32 KB stages, 6-deep ring) instead of 256-wide
+ms = timeit(lambda: nat.linear(vl16, wfc16, act="relu6", out_f32=False, out_f16=True))
+res["fc_73728x1024_b256_f16_bn128"] = {"ms": ms}
+nat.debug_set_flags(16384 | 256)
+ms = timeit(lambda: nat.linear(vl16, wfc16, act="relu6", out_f32=False, out_f16=True))
+res["fc_73728x1024_b256_f16_bn128_mt2"] = {"ms": ms}
 nat.debug_set_flags(256)            # experiment: pair the two M tiles in one CTA (W read once per CTA, twice the splits)
 ms = timeit(lambda: nat.linear(vl16, wfc16, act="relu6", out_f32=False, out_f16=True))
 res["fc_73728x1024_b256_f16_mt2"] = {"ms": ms}
@@ -74,6 +80,9 @@ for (d_in, m) in [(1024, 2), (4096, 4)]:
     if bb == 256:
       ms = timeit(lambda: nat.moe_fwd(h, wp, bp, V, m, x_lo=h))
       res["moe_d%d_m%d_b%d_hilo" % (d_in, m, bb)] = {"ms": ms}
+      nat.debug_set_flags(32768)      # A/B: both M tiles in one CTA (W tile read once), one CTA per SM
+      ms = timeit(lambda: nat.moe_fwd(h, wp, bp, V, m))
+      res["moe_d%d_m%d_b%d_mt2" % (d_in, m, bb)] = {"ms": ms}
       nat.debug_set_flags(1024)       # A/B: one CTA per SM
       ms = timeit(lambda: nat.moe_fwd(h, wp, bp, V, m))
       res["moe_d%d_m%d_b%d_1cta" % (d_in, m, bb)] = {"ms": ms}
@@ -97,7 +106,7 @@ res["lstm_l2_h1024_b64"] = {"ms": ms, "videos_per_s": Bl / ms * 1e3}
 
 # LSTM config 3 training step at B=64 and B=128: persistent forward + BPTT + MoE-4 head on the 4096-d state + Adam
 import yt8m_trainer  # noqa: E402
-for Bt in (64, 128):
+for Bt in ((64, 128) if "lstm" in sys.argv else ()):
   trn = yt8m_trainer.LstmTrainer(D, hidden=H, layers=2, vocab=V, mixtures=4)
   trn.param.normal_(0.0, 0.02)
   for l in range(2):

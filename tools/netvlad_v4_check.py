@@ -51,7 +51,7 @@ v3, st3 = run(True)
 print("  vs v3: l2 %.3e  max %.3e   stats: asum %.3e ssq %.3e" % (float((v4 - v3).norm() / v3.norm()), float((v4 - v3).abs().max()),
       float((st4[:, :K] - st3[:, :K]).abs().max()), float(((st4[:, K:] - st3[:, K:]).abs() / st3[:, K:].abs().clamp_min(1e-6)).max())))
 if do_time:
-  for name, flag in (("v4", 0), ("v3", 4096)):
+  for name, flag in (("v4", 0), ("v4 without the L2 prefetch", 65536), ("v3", 4096)):
     nat.debug_set_flags(flag)
     for _ in range(3):
       nat.netvlad_fwd(*args, out_f16=f16)

@@ -159,7 +159,8 @@ int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda,
   YT8M_REQUIRE(!(a_fmt == YT8M_FMT_F16 && a_lo) && !(out_fmt == YT8M_FMT_F16 && out_lo), YT8M_E_UNSUPPORTED,
                "yt8m_linear_fwd: an fp16 operand is a single tensor (no lo half)");
   const int a_f16 = a_fmt == YT8M_FMT_F16;
-  const int block_n = N <= 32 ? 32 : (N >= 512 && M > 128 ? 256 : 128);
+  int block_n = N <= 32 ? 32 : (N >= 512 && M > 128 ? 256 : 128);
+  if ((host_debug_flags() & 16384) && block_n == 256) block_n = 128;                     // experiment: narrower tiles, deeper ring
   // two accumulators per CTA share every W tile -- unless that would leave only two pipeline stages (hi/lo A with
   // 256-wide tiles: measured slower, the ring is latency-bound) or the grid cannot fill the SMs anyway (then
   // split-K takes over and pairing M tiles would only double the number of fp32 atomics per output element)
@@ -247,7 +248,7 @@ int yt8m_moe_fwd(const yt8m_bf16* x_hi, const yt8m_bf16* x_lo, long long ldx, co
   case NM: {                                                                                                \
     EpiMoe<NM>::Params ep;                                                                                  \
     ep.out = out; ep.ld_out = ld_out; ep.bias_packed = bias_packed; ep.vocab = vocab;                      \
-    if (B > 128 && (D >= 2048 || B > 256))   /* two accumulators per CTA pay off once the K loop is long */    \
+    if (B > 128 && (D >= 2048 || B > 256 || (host_debug_flags() & 32768)))   /* two accumulators per CTA pay off once the K loop is long */    \
       return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16) \
                   : launch_gemm<128, 1, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16); \
     if (D <= 2048 && !(host_debug_flags() & 1024))   /* short K loop: two co-resident CTAs per SM overlap epilogue and loads */ \

@@ -110,7 +110,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_cw, uint16_t* __restrict__ out,
                   const int* __restrict__ num_frames, int B, int T, int D, const float* __restrict__ scale,
                   const float* __restrict__ shift, const float* __restrict__ cw2, int out_f16, float* __restrict__ stats,
-                  unsigned long long* __restrict__ timeline) {
+                  unsigned long long* __restrict__ timeline, int dbg_flags) {
   // no static shared memory in this kernel: the dynamic window starts at the CTA's shared base (1024-byte aligned, checked
   // below), and pointers derived from the array keep their address space (LDS/STS instead of generic LD/ST)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -229,6 +229,19 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
     __syncwarp();
     int slot = 0;
     uint32_t phase = 0;
+    // L2 prefetch cursor: the ring holds only three tiles (a slot lives ~3 us from landing to the end of its phase 1), so a
+    // load issued when its slot frees pays the full HBM latency.  Every load therefore also asks L2 for the tile
+    // kAhead tiles further down this CTA's stream; the later shared-memory load then hits L2.
+    constexpr int kAhead = 3;
+    const bool do_pf = !(dbg_flags & 65536);
+    int itp = 0, ip = 0, ntp = n_iter > 0 ? vnt(0) : 0;
+    auto prefetch_next = [&]() {
+      if (itp >= n_iter) return;
+      if (do_pf && elect_one()) tma_prefetch_4d(&tm_x, 0, ip * kFT, static_cast<int>(rank) * nkb, vid(itp));
+      __syncwarp();
+      if (++ip == ntp) { ++itp; ip = 0; ntp = itp < n_iter ? vnt(itp) : 0; }
+    };
+    for (int j = 0; j < kSlots + kAhead; ++j) prefetch_next();      // the first tiles: (slots + kAhead) tiles ahead of consumption
     for (int it = 0; it < n_iter; ++it) {
       const int b = vid(it);
       const int ntv = vnt(it);
@@ -239,94 +252,90 @@ netvlad_v4_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constan
           tma_load_4d(xs + slot * kXSlotBytes, &tm_x, &x_full[slot], 0, i * kFT, static_cast<int>(rank) * nkb, b, kEvictFirst);
         }
         __syncwarp();
+        prefetch_next();
         if (++slot == kSlots) { slot = 0; phase ^= 1u; }
       }
     }
   } else if (warp == 1) {
-    // =================================== MMA issuer =====================================
+    // =================================== MMA issuer, phase 0 =============================
     // S^T = Cw . X^T (K-major x K-major), M = 64: cluster 16 j + i lands in TMEM lane 32 j + i (half of every lane quadrant)
     constexpr uint32_t idesc0 = make_idesc_bf16(64, kFT, 0, 0);
-    constexpr uint32_t idesc1 = make_idesc_bf16(128, KC, 1, 1);     // V^T += X^T . a    (MN-major x MN-major)
     mbar_wait(cw_full, 0);
-    // Tiles are numbered across this CTA's videos (G).  p0 / p1 = next tile whose phase 0 / phase 1 is to be issued.
-    int p0 = 0, p1 = 0;
-    int it0 = 0, i0 = 0, nt0 = n_iter > 0 ? vnt(0) : 0;       // (video, tile, tiles of the video) of p0 and of p1
-    int it1 = 0, i1 = 0, nt1 = nt0;
-    while (p1 < total_tiles) {
-      if (p0 < total_tiles) {
-        const int G = p0, sb = G & 1, u = G >> 1, slot = G % kSlots;
-        // S^T buffer drained by the readers (tile G-2) and X tile landed?  (the slot is recycled by phase 1 of tile G-3)
-        bool ok = mbar_test_wait(&s_free[sb], (u & 1) ^ 1u) && mbar_test_wait(&x_full[slot], (G / kSlots) & 1);
-        ok = __all_sync(0xffffffffu, ok);
-        if (ok) {
-          tc_fence_after();
-          if (lane == 0 && i0 < 10) NV4_T(it0, i0);
-          if (elect_one()) {
-            const uint32_t x_addr = smem_u32(xs + slot * kXSlotBytes);
-            const uint32_t c_addr = smem_u32(cws);
-            const uint32_t d_tmem = tmem_base + kSCol + sb * kFT;
-            for (int kb = 0; kb < nkb; ++kb) {
-              const uint64_t adesc0 = make_sdesc_sw128(c_addr + kb * kCwSubBytes, 16, 1024);
-              const uint64_t bdesc0 = make_sdesc_sw128(x_addr + kb * kSubBytes, 16, 1024);
+    // Tiles are numbered across this CTA's videos (G).
+    // Phase 0 (this warp) and phase 1 (warp 2) are issued by different warps: neither waits behind the other's
+    // barrier, and the tensor pipe executes the two instruction streams in arrival order.
+    int it0 = 0, i0 = 0, nt0 = n_iter > 0 ? vnt(0) : 0;       // (video, tile) of G, for the debug timeline only
+    for (int G = 0; G < total_tiles; ++G) {
+      const int sb = G & 1, u = G >> 1, slot = G % kSlots;
+      // S^T buffer drained by the readers (tile G-2) and X tile landed (the slot is recycled by phase 1 of tile G-3)
+      mbar_wait(&s_free[sb], (u & 1) ^ 1u);
+      mbar_wait(&x_full[slot], (G / kSlots) & 1);
+      tc_fence_after();
+      if (lane == 0 && i0 < 10) NV4_T(it0, i0);
+      if (elect_one()) {
+        const uint32_t x_addr = smem_u32(xs + slot * kXSlotBytes);
+        const uint32_t c_addr = smem_u32(cws);
+        const uint32_t d_tmem = tmem_base + kSCol + sb * kFT;
+        for (int kb = 0; kb < nkb; ++kb) {
+          const uint64_t adesc0 = make_sdesc_sw128(c_addr + kb * kCwSubBytes, 16, 1024);
+          const uint64_t bdesc0 = make_sdesc_sw128(x_addr + kb * kSubBytes, 16, 1024);
 #pragma unroll
-              for (int k = 0; k < 4; ++k)
-                umma_bf16(d_tmem, sdesc_advance(adesc0, k * 32), sdesc_advance(bdesc0, k * 32), idesc0, (kb > 0 || k > 0) ? 1u : 0u);
-            }
-            umma_commit(&s_full[sb]);
-          }
-          __syncwarp();
-          ++p0;
-          if (++i0 == nt0) { ++it0; i0 = 0; nt0 = it0 < n_iter ? vnt(it0) : 0; }
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, sdesc_advance(adesc0, k * 32), sdesc_advance(bdesc0, k * 32), idesc0, (kb > 0 || k > 0) ? 1u : 0u);
         }
+        umma_commit(&s_full[sb]);
       }
-      if (p1 < p0) {
-        const int G = p1;
-        const int it = it1, i = i1;
+      __syncwarp();
+      if (++i0 == nt0) { ++it0; i0 = 0; nt0 = it0 < n_iter ? vnt(it0) : 0; }
+    }
+  } else if (warp == 2) {
+    // =================================== MMA issuer, phase 1 =============================
+    constexpr uint32_t idesc1 = make_idesc_bf16(128, KC, 1, 1);     // V^T += X^T . a    (MN-major x MN-major)
+    int G = 0;
+    for (int it = 0; it < n_iter; ++it) {
+      const int ntv = vnt(it);
+      for (int i = 0; i < ntv; ++i, ++G) {
         const int ab = G & 1, u = G >> 1, slot = G % kSlots;
-        const bool ok = __all_sync(0xffffffffu, mbar_test_wait(&a_ready[ab], u & 1));
-        if (ok) {
-          tc_fence_after();
-          if (lane == 0 && i < 10) NV4_T(it, 30 + i);
-          const int valid = min(kFT, T - i * kFT);
-          const int nsteps = (valid + 15) >> 4;
-          const uint32_t x_addr = smem_u32(xs + slot * kXSlotBytes);
-          const uint64_t bdesc0 = make_sdesc_sw128(smem_u32(atile + ab * kATileBytes), kSubBytes, 1024);
-          const bool first = (i == 0 && it > 0);
-          if (!first) {
-            if (elect_one()) {
-              for (int m = 0; m < nmb; ++m) {
-                // rows m*128 .. +127 of this CTA's features = sub-tiles 2m and 2m+1, one box apart (LBO); the second
-                // sub-tile of a half-valid last block is whatever follows in shared memory (its 64 accumulator rows
-                // are never read)
-                const uint64_t adesc0 = make_sdesc_sw128(x_addr + m * 2 * kSubBytes, kSubBytes, 1024);
-                const uint32_t d_tmem = tmem_base + kVCol + m * KC;
-                for (int s = 0; s < nsteps; ++s)
-                  umma_bf16(d_tmem, sdesc_advance(adesc0, s * 2048), sdesc_advance(bdesc0, s * 2048), idesc1, (i > 0 || s > 0) ? 1u : 0u);
-              }
-            }
-          } else {
-            // first tile of a new video: follow the draining epilogue of the previous one block by block
-            for (int m = 0; m < nmb; ++m) {
-              mbar_wait(&v_free[m], (it - 1) & 1);
-              tc_fence_after();
-              if (elect_one()) {
-                const uint64_t adesc0 = make_sdesc_sw128(x_addr + m * 2 * kSubBytes, kSubBytes, 1024);
-                const uint32_t d_tmem = tmem_base + kVCol + m * KC;
-                for (int s = 0; s < nsteps; ++s)
-                  umma_bf16(d_tmem, sdesc_advance(adesc0, s * 2048), sdesc_advance(bdesc0, s * 2048), idesc1, s > 0 ? 1u : 0u);
-              }
-              __syncwarp();
-            }
-          }
+        mbar_wait(&a_ready[ab], u & 1);
+        tc_fence_after();
+        if (lane == 0 && i < 10) NV4_T(it, 30 + i);
+        const int valid = min(kFT, T - i * kFT);
+        const int nsteps = (valid + 15) >> 4;
+        const uint32_t x_addr = smem_u32(xs + slot * kXSlotBytes);
+        const uint64_t bdesc0 = make_sdesc_sw128(smem_u32(atile + ab * kATileBytes), kSubBytes, 1024);
+        const bool first = (i == 0 && it > 0);
+        if (!first) {
           if (elect_one()) {
-            umma_commit(&x_empty[slot]);
-            umma_commit(&a_free[ab]);
-            if (i == nt1 - 1) umma_commit(v_full);
+            for (int m = 0; m < nmb; ++m) {
+              // rows m*128 .. +127 of this CTA's features = sub-tiles 2m and 2m+1, one box apart (LBO); the second
+              // sub-tile of a half-valid last block is whatever follows in shared memory (its 64 accumulator rows
+              // are never read)
+              const uint64_t adesc0 = make_sdesc_sw128(x_addr + m * 2 * kSubBytes, kSubBytes, 1024);
+              const uint32_t d_tmem = tmem_base + kVCol + m * KC;
+              for (int s = 0; s < nsteps; ++s)
+                umma_bf16(d_tmem, sdesc_advance(adesc0, s * 2048), sdesc_advance(bdesc0, s * 2048), idesc1, (i > 0 || s > 0) ? 1u : 0u);
+            }
           }
-          __syncwarp();
-          ++p1;
-          if (++i1 == nt1) { ++it1; i1 = 0; nt1 = it1 < n_iter ? vnt(it1) : 0; }
+        } else {
+          // first tile of a new video: follow the draining epilogue of the previous one block by block
+          for (int m = 0; m < nmb; ++m) {
+            mbar_wait(&v_free[m], (it - 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t adesc0 = make_sdesc_sw128(x_addr + m * 2 * kSubBytes, kSubBytes, 1024);
+              const uint32_t d_tmem = tmem_base + kVCol + m * KC;
+              for (int s = 0; s < nsteps; ++s)
+                umma_bf16(d_tmem, sdesc_advance(adesc0, s * 2048), sdesc_advance(bdesc0, s * 2048), idesc1, s > 0 ? 1u : 0u);
+            }
+            __syncwarp();
+          }
         }
+        if (elect_one()) {
+          umma_commit(&x_empty[slot]);
+          umma_commit(&a_free[ab]);
+          if (i == ntv - 1) umma_commit(v_full);
+        }
+        __syncwarp();
       }
     }
   }
@@ -669,6 +678,6 @@ int yt8m::launch_netvlad_v4(const yt8m_bf16* x, const int* num_frames, int B, in
   }
   const int clusters = B < kSms / 2 ? B : kSms / 2;
   netvlad_v4_kernel<<<2 * clusters, kThreads, kSmemTotal, stream>>>(tm_x, tm_cw, reinterpret_cast<uint16_t*>(out), num_frames, B, T, D, scale, shift, cw2,
-                                                                    out_f16, stats, host_debug_timeline());
+                                                                    out_f16, stats, host_debug_timeline(), host_debug_flags());
   return check_launch("netvlad_v4_kernel");
 }
