@@ -190,6 +190,8 @@ def main():
   import synth
   from yt8m_flags import FLAGS
 
+  if os.environ.get("YT8M_DEBUG_FLAGS"):          # A/B switches of the kernels (tools/); unset in normal runs
+    nat.debug_set_flags(int(os.environ["YT8M_DEBUG_FLAGS"]))
   B = args.batch
   FLAGS.parse([], known_only=True)
   FLAGS.netvlad_cluster_size, FLAGS.netvlad_hidden_size, FLAGS.moe_num_mixtures = K_CLUSTERS, HIDDEN, MIXTURES

@@ -200,6 +200,9 @@ int yt8m_context_gate_bwd(const float* dy, const float* x, const float* g, const
                           long long rows, int cols, float* dx, float* dg, yt8m_bf16* dg_hi, yt8m_bf16* dg_lo, long long ld_dg,
                           yt8m_stream_t stream);
 
+/* y[i] += x[i]: where two gradient paths meet (e.g. the direct and the gate path of context gating) */
+int yt8m_add_inplace(float* y, const float* x, long long n, yt8m_stream_t stream);
+
 /* y = x * scale[c] + shift[c] on a contiguous [rows, cols] fp32 / bf16 matrix -> fp32 and/or bf16 hi (+lo):
  * inference-mode slim.batch_norm applied to a GEMM operand (wh/all_frame_models/dbof_model.py:64-70). */
 int yt8m_col_affine(const void* x, int src_dtype, long long rows, int cols, const float* scale, const float* shift,

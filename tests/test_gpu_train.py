@@ -385,3 +385,46 @@ def test_lstm_train_step_parity(tr, memory):
     assert float((got[kk] - sd[kk]).abs().max()) > 0, kk
   for l in range(layers):
     assert torch.equal(t_.w_bf16[l].float(), t_.p["w%d" % l].to(torch.bfloat16).float())
+
+
+def test_gated_netvlad_train_step_parity(tr):
+  """GatedNetVLADModel (K = 128 clusters, context gating, MoE-4: BASELINE config 4 at reduced sizes): predictions, loss
+  and every gradient of one step against autograd over the oracle; then two more steps move every tensor."""
+  g = torch.Generator().manual_seed(92)
+  b, t, d, k, h, v, mix = 5, 100, 256, 128, 256, 300, 4
+  x, nf, _ = synth.model_input(b, t, d, seed=36, min_frames=10)
+  y = synth.labels(b, v, seed=36, per_video=3.4)
+  sd = {"cluster_weights": synth.normal((d, k), g, 4.0), "cluster_biases": 0.1 * torch.randn(k, generator=g),
+        "cluster_weights2": synth.normal((d, k), g, 1 / math.sqrt(d)),
+        "hidden1_weights": synth.normal((k * d, h), g, 12.0 / math.sqrt(k)), "hidden1_biases": 0.1 * torch.randn(h, generator=g),
+        "gating_weights": synth.normal((h, h), g, 1.0 / math.sqrt(h)), "gating_biases": 0.1 * torch.randn(h, generator=g),
+        "gates/weights": synth.xavier((h, v * (mix + 1)), g, 2.0), "experts/weights": synth.xavier((h, v * mix), g, 2.0),
+        "experts/biases": 0.1 * torch.randn(v * mix, generator=g)}
+  t_ = tr.NetVLADTrainer(d, clusters=k, hidden=h, vocab=v, mixtures=mix, gating=True)
+  t_.import_state(sd)
+  t_.keep_grads = True
+  xd, nfd, yd = x.to(DEV).to(torch.bfloat16), nf.to(DEV), y.to(DEV)
+  p0 = t_.step(xd, nfd, yd)
+  grad0 = t_.grads_tf_layout(t_.last_grad)
+  loss0 = float(t_.last["label_loss_local"])
+  params = {kk: w.clone().requires_grad_(True) for kk, w in sd.items()}
+  vl = O.netvlad_pool(x, nf, params["cluster_weights"], torch.ones(k), params["cluster_biases"], params["cluster_weights2"])
+  hid = O.relu6(vl @ params["hidden1_weights"] + params["hidden1_biases"])
+  gated = O.context_gating(hid, params["gating_weights"], torch.ones(h), params["gating_biases"])
+  pw = O.moe_model(gated, params["gates/weights"], params["experts/weights"], params["experts/biases"], v, mix)
+  lw = O.cross_entropy_loss(pw, y)
+  gw = dict(zip(params, torch.autograd.grad(lw, list(params.values()))))
+  assert float((p0.cpu() - pw.detach()).abs().max()) < 1e-3
+  assert abs(loss0 - float(lw.detach())) / float(lw.detach()) < 1e-3
+  for kk in gw:
+    assert float(gw[kk].norm()) > 0, kk
+    err = _rel_l2(grad0[kk], gw[kk])
+    assert err < 2e-2, (kk, err)
+  for _ in range(2):
+    t_.step(xd, nfd, yd)
+  torch.cuda.synchronize()
+  got = t_.export_state()
+  for kk in sd:
+    assert bool(torch.isfinite(got[kk]).all()), kk
+    assert float((got[kk] - sd[kk]).abs().max()) > 0, kk
+  assert torch.equal(t_.wg_bf16.float(), t_.p["wg"].to(torch.bfloat16).float())

@@ -13,7 +13,7 @@ constexpr int kNumSms = 148;
 template <int BLOCK_N, int A_SPLIT, class Epi, int MT = 1, int CTAS = 1>
 int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, const yt8m_bf16* w, long long ldw, int M,
                 int N_rows_w, int N, int K, int split_k, const typename Epi::Params& ep, cudaStream_t stream,
-                int a_f16 = 0) {
+                int a_f16 = 0, unsigned long long hint_a = kEvictNormal, unsigned long long hint_w = kEvictNormal) {
   using S = GemmSmem<BLOCK_N, A_SPLIT, false, MT, CTAS>;
   CUtensorMap tm_a_hi, tm_a_lo, tm_b;
   int rc;
@@ -33,6 +33,7 @@ int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, con
   const int num_kb = (K + kBlockK - 1) / kBlockK;
   GemmShape shape;
   shape.M = M; shape.N = N; shape.K = K; shape.a_f16 = a_f16;
+  if (!(host_debug_flags() & 131072)) { shape.hint_a = hint_a; shape.hint_w = hint_w; }      // flag: A/B without the hints
   shape.kb_per_split = (num_kb + split_k - 1) / split_k;
   const int splits = (num_kb + shape.kb_per_split - 1) / shape.kb_per_split;
   const long long tiles = static_cast<long long>((N + BLOCK_N - 1) / BLOCK_N) * ((M + MT * kBlockM - 1) / (MT * kBlockM)) * splits;
@@ -182,11 +183,14 @@ int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda,
     ep.out_lo = reinterpret_cast<__nv_bfloat16*>(out_lo); ep.ld_out = ld_out;
   }
   int rc;
+  // a weight matrix larger than half of L2 (126 MB) that every step streams once: do not let it displace what is re-read
+  const unsigned long long hw = (static_cast<long long>(N) * K * 2 > (48ll << 20)) ? kEvictFirst : kEvictNormal;
+  const unsigned long long ha = kEvictNormal;
 #define YT8M_DISPATCH(BN)                                                                                              \
-  rc = mt == 2 ? (a_lo ? launch_gemm<BN, 2, EpiLinear, 2>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream, a_f16)    \
-                       : launch_gemm<BN, 1, EpiLinear, 2>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream, a_f16))   \
-               : (a_lo ? launch_gemm<BN, 2, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream, a_f16)    \
-                       : launch_gemm<BN, 1, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream, a_f16))
+  rc = mt == 2 ? (a_lo ? launch_gemm<BN, 2, EpiLinear, 2>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream, a_f16, ha, hw)    \
+                       : launch_gemm<BN, 1, EpiLinear, 2>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream, a_f16, ha, hw))   \
+               : (a_lo ? launch_gemm<BN, 2, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream, a_f16, ha, hw)    \
+                       : launch_gemm<BN, 1, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream, a_f16, ha, hw))
   if (block_n == 32) { YT8M_DISPATCH(32); }
   else if (block_n == 256) { YT8M_DISPATCH(256); }
   else { YT8M_DISPATCH(128); }
@@ -244,18 +248,20 @@ int yt8m_moe_fwd(const yt8m_bf16* x_hi, const yt8m_bf16* x_lo, long long ldx, co
                "yt8m_moe_fwd: x_fmt must be YT8M_FMT_BF16, or YT8M_FMT_F16 without a lo half");
   const int x_f16 = x_fmt == YT8M_FMT_F16;
   const int n = static_cast<int>(rows);
+  // the packed head (50 MB for MoE-2 on 1024-d) fits L2 beside the streams of the other kernels: keep it for the next step
+  const unsigned long long hw_moe = (rows * static_cast<long long>(D) * 2 <= (64ll << 20)) ? kEvictLast : kEvictNormal;
 #define YT8M_MOE_CASE(NM)                                                                                   \
   case NM: {                                                                                                \
     EpiMoe<NM>::Params ep;                                                                                  \
     ep.out = out; ep.ld_out = ld_out; ep.bias_packed = bias_packed; ep.vocab = vocab;                      \
     if (B > 128 && (D >= 2048 || B > 256 || (host_debug_flags() & 32768)))   /* two accumulators per CTA pay off once the K loop is long */    \
-      return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16) \
-                  : launch_gemm<128, 1, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16); \
+      return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16, kEvictLast, hw_moe) \
+                  : launch_gemm<128, 1, EpiMoe<NM>, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16, kEvictLast, hw_moe); \
     if (D <= 2048 && !(host_debug_flags() & 1024))   /* short K loop: two co-resident CTAs per SM overlap epilogue and loads */ \
-      return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 1, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16) \
-                  : launch_gemm<128, 1, EpiMoe<NM>, 1, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16); \
-    return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 1>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16) \
-                : launch_gemm<128, 1, EpiMoe<NM>, 1>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16); \
+      return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 1, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16, kEvictLast, hw_moe) \
+                  : launch_gemm<128, 1, EpiMoe<NM>, 1, 2>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16, kEvictLast, hw_moe); \
+    return x_lo ? launch_gemm<128, 2, EpiMoe<NM>, 1>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16, kEvictLast, hw_moe) \
+                : launch_gemm<128, 1, EpiMoe<NM>, 1>(x_hi, x_lo, ldx, w_packed, ldw, B, n, n, D, 1, ep, stream, x_f16, kEvictLast, hw_moe); \
   }
   switch (num_mixtures) {
     YT8M_MOE_CASE(1)

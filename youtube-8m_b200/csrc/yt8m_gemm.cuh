@@ -26,6 +26,11 @@ struct GemmShape {
   int kb_per_split;                    // K-blocks handled by one blockIdx.z
   int a_f16;                           // 1: A AND W hold IEEE fp16 (11 significant bits) instead of bf16 (fp16 x bf16 in one
                                        //    instruction is an illegal-instruction fault on sm_100a -- measured, tools/f16_diag.py)
+  // L2 eviction priority of the TMA loads: a weight matrix that is streamed once per step and is larger than L2 must
+  // not push out what the next kernel re-reads (evict-first); a head that fits (MoE: 50 MB) stays for the next step
+  // (evict-last)
+  unsigned long long hint_a = kEvictNormal;
+  unsigned long long hint_w = kEvictNormal;
 };
 
 // MN = false: operands stored [rows, K] with K contiguous (forward / dgrad): stage = 64 K-elements.
@@ -143,13 +148,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
               // two 64-column boxes of 128 contraction rows per operand half
 #pragma unroll
               for (int h = 0; h < 2; ++h) {
-                tma_load_2d(at + h * 16384, &tm_a_hi, &full_bar[stage], row0 + h * 64, kb * 128, kEvictNormal);
+                tma_load_2d(at + h * 16384, &tm_a_hi, &full_bar[stage], row0 + h * 64, kb * 128, shape.hint_a);
                 if (A_SPLIT == 2)
-                  tma_load_2d(at + S::kABytes + h * 16384, &tm_a_lo, &full_bar[stage], row0 + h * 64, kb * 128, kEvictNormal);
+                  tma_load_2d(at + S::kABytes + h * 16384, &tm_a_lo, &full_bar[stage], row0 + h * 64, kb * 128, shape.hint_a);
               }
             } else {
-              tma_load_2d(at, &tm_a_hi, &full_bar[stage], kb * kBlockK, row0, kEvictNormal);
-              if (A_SPLIT == 2) tma_load_2d(at + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, row0, kEvictNormal);
+              tma_load_2d(at, &tm_a_hi, &full_bar[stage], kb * kBlockK, row0, shape.hint_a);
+              if (A_SPLIT == 2) tma_load_2d(at + S::kABytes, &tm_a_lo, &full_bar[stage], kb * kBlockK, row0, shape.hint_a);
             }
           }
         }
@@ -172,9 +177,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
           if (MN) {
 #pragma unroll
             for (int h = 0; h < BLOCK_N / 64; ++h)
-              tma_load_2d(st + A_SPLIT * S::kABytes + h * 16384, &tm_b, &full_bar[stage], tl.n_tile * BLOCK_N + h * 64, kb * 128, kEvictNormal);
+              tma_load_2d(st + A_SPLIT * S::kABytes + h * 16384, &tm_b, &full_bar[stage], tl.n_tile * BLOCK_N + h * 64, kb * 128, shape.hint_w);
           } else {
-            tma_load_2d(st + A_SPLIT * S::kABytes, &tm_b, &full_bar[stage], kb * kBlockK, tl.n_tile * BLOCK_N, kEvictNormal);
+            tma_load_2d(st + A_SPLIT * S::kABytes, &tm_b, &full_bar[stage], kb * kBlockK, tl.n_tile * BLOCK_N, shape.hint_w);
           }
         }
         __syncwarp();

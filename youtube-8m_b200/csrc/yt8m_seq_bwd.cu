@@ -310,9 +310,25 @@ __global__ void context_gate_bwd_kernel(const float* __restrict__ dy, const floa
   }
 }
 
+__global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    y[i] += x[i];
+}
+
 }  // namespace
 
 extern "C" {
+
+int yt8m_add_inplace(float* y, const float* x, long long n, yt8m_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  YT8M_REQUIRE(y && x, YT8M_E_BADPTR, "yt8m_add_inplace: null pointer");
+  YT8M_REQUIRE(n >= 0, YT8M_E_BADSHAPE, "yt8m_add_inplace: n < 0");
+  if (n == 0) return YT8M_OK;
+  const int blocks = static_cast<int>(std::min<long long>((n + 255) / 256, kNumSms * 16));
+  add_inplace_kernel<<<blocks, 256, 0, stream>>>(y, x, n);
+  return check_launch("add_inplace_kernel");
+}
 
 size_t yt8m_lstm_bwd_workspace_bytes(int B, int T, int D, int H, int L) {
   if (B <= 0 || T <= 0 || D <= 0 || H <= 0 || L <= 0 || L > 8) return 0;

@@ -87,12 +87,13 @@ class Trainer(object):
       raise NotImplementedError("only --optimizer=AdamOptimizer (the reference default) is built")
     if FLAGS.label_loss != "CrossEntropyLoss":
       raise NotImplementedError("only --label_loss=CrossEntropyLoss (the reference default) is built")
-    if model_cls is frame_level_models.NetVLADModel:
+    if model_cls in (frame_level_models.NetVLADModel, frame_level_models.GatedNetVLADModel):
       if FLAGS.netvlad_add_batch_norm or FLAGS.video_level_classifier_model != "MoeModel":
-        raise NotImplementedError("train.py --model=NetVLADModel: the CUDA training step is built for "
-                                  "--netvlad_add_batch_norm=False with --video_level_classifier_model=MoeModel")
+        raise NotImplementedError("train.py --model=%s: the CUDA training step is built for "
+                                  "--netvlad_add_batch_norm=False with --video_level_classifier_model=MoeModel" % self.model_name)
       return yt8m_trainer.NetVLADTrainer(in_dim, clusters=FLAGS.netvlad_cluster_size, hidden=FLAGS.netvlad_hidden_size,
-                                         vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures, relu=FLAGS.netvlad_relu)
+                                         vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures, relu=FLAGS.netvlad_relu,
+                                         gating=model_cls is frame_level_models.GatedNetVLADModel)
     if model_cls in (frame_level_models.LstmModel, frame_level_models.LstmMemoryModel):
       if FLAGS.video_level_classifier_model != "MoeModel":
         raise NotImplementedError("train.py --model=%s: the CUDA training step is built for "
@@ -105,8 +106,8 @@ class Trainer(object):
       kind = "moe"
     else:
       raise NotImplementedError(
-          "train.py: the CUDA training step is built for LogisticModel, MoeModel, NetVLADModel, LstmModel and "
-          "LstmMemoryModel this round; "
+          "train.py: the CUDA training step is built for LogisticModel, MoeModel, NetVLADModel, GatedNetVLADModel, "
+          "LstmModel and LstmMemoryModel this round; "
           "%s runs forward-only (eval.py / inference.py)" % self.model_name)
     return yt8m_trainer.HeadTrainer(kind, in_dim, self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures)
 

@@ -58,6 +58,7 @@ _SIGS = {
                                    c_void_p, c_void_p]),
     "yt8m_context_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_ll, c_void_p]),
+    "yt8m_add_inplace": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
     "yt8m_attn_pool_fwd": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     "yt8m_netvlad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -417,6 +418,13 @@ def context_gate_bwd(dy, x, g, scale=None, shift=None, want_bf16=True):
   _call("yt8m_context_gate_bwd", _p(dy.contiguous()), _p(x.contiguous()), _p(g.contiguous()), _p(scale), _p(shift), rows, cols, _p(dx),
         _p(dg), _p(gh), _p(gl), ld, _stream())
   return dx, dg, (gh[:, :cols] if want_bf16 else None), (gl[:, :cols] if want_bf16 else None)
+
+
+def add_inplace(y, x):
+  """y += x (fp32, same shape, contiguous)."""
+  assert y.is_contiguous() and x.is_contiguous() and y.numel() == x.numel()
+  _call("yt8m_add_inplace", _p(y), _p(x), y.numel(), _stream())
+  return y
 
 
 def attn_pool(logits, feats, num_frames, heads, mode, want_bf16=True):

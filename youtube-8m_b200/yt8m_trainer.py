@@ -203,15 +203,20 @@ class NetVLADTrainer(object):
   hidden1_biases [H], then the packed MoE head.  import_state / export_state speak the model's TF names."""
 
   def __init__(self, feature_dim, clusters=64, hidden=1024, vocab=4716, mixtures=2, relu=True, l2_penalty=1e-8, device=None,
-               group=None):
+               group=None, gating=False):
+    """gating=True: GatedNetVLADModel -- context gating y = h * sigmoid(h . Wg + bg) between the hidden layer and the
+    classifier (BASELINE config 4; bias variant)."""
     self.d, self.k, self.h, self.v, self.m, self.relu = feature_dim, clusters, hidden, vocab, mixtures, relu
+    self.gating = gating
     self.dev = device or torch.device("cuda", torch.cuda.current_device())
     self.group = group
     self.world = yt8m_dp.world_size(group)
     kd = clusters * feature_dim
     self.kd = kd
-    sizes = [("cw", clusters * feature_dim), ("cb", clusters), ("c2", feature_dim * clusters), ("wfc", hidden * kd), ("bfc", hidden),
-             ("head", HeadTrainer.flat_size("moe", hidden, vocab, mixtures))]
+    sizes = [("cw", clusters * feature_dim), ("cb", clusters), ("c2", feature_dim * clusters), ("wfc", hidden * kd), ("bfc", hidden)]
+    if gating:
+      sizes += [("wg", hidden * hidden), ("bg", hidden)]
+    sizes.append(("head", HeadTrainer.flat_size("moe", hidden, vocab, mixtures)))
     total = sum(n for _, n in sizes)
     self.param = torch.zeros(total, dtype=torch.float32, device=self.dev)
     self.grad = torch.zeros_like(self.param)
@@ -223,6 +228,9 @@ class NetVLADTrainer(object):
       self._off[name] = (off, off + n)
       off += n
     shapes = {"cw": (clusters, feature_dim), "cb": (clusters, 1), "c2": (feature_dim, clusters), "wfc": (hidden, kd), "bfc": (hidden, 1)}
+    if gating:
+      shapes.update({"wg": (hidden, hidden), "bg": (hidden, 1)})            # Wg^T [out, in]
+    self._names = list(shapes)
     self.p, self.g, self.am, self.av = {}, {}, {}, {}
     for name, shp in shapes.items():
       a, b = self._off[name]
@@ -233,6 +241,7 @@ class NetVLADTrainer(object):
                             storage=(self.param[a:b], self.grad[a:b], self.adam_m[a:b], self.adam_v[a:b]))
     self.cw_bf16 = torch.zeros((clusters, feature_dim), dtype=torch.bfloat16, device=self.dev)
     self.wfc_bf16 = torch.zeros((hidden, kd), dtype=torch.bfloat16, device=self.dev)
+    self.wg_bf16 = torch.zeros((hidden, hidden), dtype=torch.bfloat16, device=self.dev) if gating else None
     self.global_step = 0
     self.keep_grads = False
     self.last = {}
@@ -248,11 +257,18 @@ class NetVLADTrainer(object):
     self.head.import_state({k: sd[k] for k in ("gates/weights", "experts/weights", "experts/biases")})
     self.cw_bf16.copy_(self.p["cw"])
     self.wfc_bf16.copy_(self.p["wfc"])
+    if self.gating:
+      self.p["wg"].copy_(sd["gating_weights"].t().to(dev))
+      self.p["bg"].copy_(sd["gating_biases"].view(-1, 1).to(dev))
+      self.wg_bf16.copy_(self.p["wg"])
 
   def _tf_layout(self, views, head_flat):
     out = {"cluster_weights": views["cw"].t().contiguous().cpu(), "cluster_biases": views["cb"].reshape(-1).cpu().clone(),
            "cluster_weights2": views["c2"].cpu().clone(), "hidden1_weights": views["wfc"].t().contiguous().cpu(),
            "hidden1_biases": views["bfc"].reshape(-1).cpu().clone()}
+    if self.gating:
+      out["gating_weights"] = views["wg"].t().contiguous().cpu()
+      out["gating_biases"] = views["bg"].reshape(-1).cpu().clone()
     out.update(self.head.grads_tf_layout(head_flat))
     return out
 
@@ -262,7 +278,7 @@ class NetVLADTrainer(object):
 
   def grads_tf_layout(self, flat):
     views = {}
-    for name in ("cw", "cb", "c2", "wfc", "bfc"):
+    for name in self._names:
       a, b = self._off[name]
       views[name] = flat[a:b].view(self.p[name].shape)
     a, b = self._off["head"]
@@ -276,8 +292,15 @@ class NetVLADTrainer(object):
     vh, vl, y32, stats = nat.netvlad_fwd(x, num_frames, self.cw_bf16, None, cb, c2, want_f32=True, want_lo=True, want_stats=True)
     hid = nat.linear(vh, self.wfc_bf16, a_lo=vl, n=self.h, k=self.kd, shift=self.p["bfc"].view(-1),
                      act="relu6" if self.relu else None, out_f32=True, out_bf16=True, out_lo=True)
-    p = nat.moe_fwd(hid["hi"], self.head.w_bf16, self.head.b, self.v, self.m, x_lo=hid["lo"], d=self.h)
-    return p, {"vh": vh, "vl": vl, "y32": y32, "stats": stats, "hid": hid}
+    sv = {"vh": vh, "vl": vl, "y32": y32, "stats": stats, "hid": hid}
+    top_hi, top_lo = hid["hi"], hid["lo"]
+    if self.gating:
+      g = nat.linear(hid["hi"], self.wg_bf16, a_lo=hid["lo"], n=self.h, k=self.h)["f32"]
+      _, top_hi, top_lo = nat.context_gate(hid["f32"], g, None, self.p["bg"].view(-1))
+      sv["g"] = g
+    sv["top"] = (top_hi, top_lo)
+    p = nat.moe_fwd(top_hi, self.head.w_bf16, self.head.b, self.v, self.m, x_lo=top_lo, d=self.h)
+    return p, sv
 
   def step(self, x, num_frames, labels, base_lr=0.01, lr_decay=0.95, lr_decay_examples=4000000, clip_gradient_norm=1.0,
            regularization_penalty=1.0, global_batch=None):
@@ -285,7 +308,14 @@ class NetVLADTrainer(object):
     global_batch = global_batch or b * self.world
     p, sv = self.forward(x, num_frames)
     hid = sv["hid"]
-    loss, dhid = self.head.backward(p, hid["hi"], hid["lo"], labels, global_batch, want_dx=True)
+    loss, dhid = self.head.backward(p, sv["top"][0], sv["top"][1], labels, global_batch, want_dx=True)
+    if self.gating:
+      # context gating y = h * sigmoid(h . Wg + bg): direct path + the path through the gate logits
+      dhid, _, dg_hi, dg_lo = nat.context_gate_bwd(dhid[:, :self.h].contiguous(), hid["f32"], sv["g"], None, self.p["bg"].view(-1))
+      nat.wgrad(dg_hi, dg_lo, hid["hi"], self.h, self.h, out=self.g["wg"])             # dWg^T [out, in]
+      nat.colsum_bf16(dg_hi, dg_lo, self.h, out=self.g["bg"].view(-1))
+      wg_t = nat.pack_transpose(self.p["wg"])                                           # bf16 [in, out]: the dgrad operand
+      nat.add_inplace(dhid, nat.linear(dg_hi, wg_t, a_lo=dg_lo, n=self.h, k=self.h)["f32"])
     # hidden FC: h = act(vlad . Wfc + b)
     dpre_hi, dpre_lo = nat.act_bwd(dhid, hid["f32"], act="relu6" if self.relu else None)
     nat.wgrad(dpre_hi, dpre_lo, sv["vh"], self.h, self.kd, out=self.g["wfc"])          # dWfc^T [H, K*D]
@@ -305,7 +335,10 @@ class NetVLADTrainer(object):
       self.last_grad = self.grad.clone()
     lr = exponential_decay(base_lr, self.global_step, global_batch, lr_decay_examples, lr_decay)
     lr_t = adam_lr_t(lr, self.global_step + 1)
-    for name, bf in (("cw", self.cw_bf16), ("cb", None), ("c2", None), ("wfc", self.wfc_bf16), ("bfc", None)):
+    tensors = [("cw", self.cw_bf16), ("cb", None), ("c2", None), ("wfc", self.wfc_bf16), ("bfc", None)]
+    if self.gating:
+      tensors += [("wg", self.wg_bf16), ("bg", None)]
+    for name, bf in tensors:
       sums = nat.grad_reg_sumsq(self.g[name], self.p[name], 0.0)
       nat.clip_adam_step(self.p[name], self.g[name], self.am[name], self.av[name], sums, clip_gradient_norm, lr_t, param_bf16=bf)
     self.head.apply(lr_t, clip_gradient_norm, regularization_penalty)
