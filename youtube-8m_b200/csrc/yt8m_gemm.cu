@@ -34,6 +34,7 @@ int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, con
   GemmShape shape;
   shape.M = M; shape.N = N; shape.K = K; shape.a_f16 = a_f16;
   if (!(host_debug_flags() & 131072)) { shape.hint_a = hint_a; shape.hint_w = hint_w; }      // flag: A/B without the hints
+  shape.timeline = host_debug_timeline();
   shape.kb_per_split = (num_kb + split_k - 1) / split_k;
   const int splits = (num_kb + shape.kb_per_split - 1) / shape.kb_per_split;
   const long long tiles = static_cast<long long>((N + BLOCK_N - 1) / BLOCK_N) * ((M + MT * kBlockM - 1) / (MT * kBlockM)) * splits;

@@ -31,6 +31,9 @@ struct GemmShape {
   // (evict-last)
   unsigned long long hint_a = kEvictNormal;
   unsigned long long hint_w = kEvictNormal;
+  // debug only (yt8m_debug_set_timeline; tools/gemm_timeline.py): globaltimer stamps of CTA 0 --
+  // [0, 48) MMA warp: k-block c landed   [48, 64) epilogue: tile start / end   [64, 112) A producer: slot of k-block c free
+  unsigned long long* timeline = nullptr;
 };
 
 // MN = false: operands stored [rows, K] with K contiguous (forward / dgrad): stage = 64 K-elements.
@@ -130,13 +133,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
 
   if (warp == 0) {
     // ------------------------------- TMA producer: A (hi [+ lo]) -------------------------------
-    int stage = 0;
+    int stage = 0, dbg_c = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const Tile tl = decode(t);
       for (int kbi = 0; kbi < tl.num_kb; ++kbi) {
         const int kb = tl.kb_begin + (kbi + tl.kb_rot >= tl.num_kb ? kbi + tl.kb_rot - tl.num_kb : kbi + tl.kb_rot);
         mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (shape.timeline && blockIdx.x == 0 && lane == 0 && dbg_c < 48) shape.timeline[64 + dbg_c] = global_timer_ns();
+        ++dbg_c;
         if (elect_one()) {
           uint8_t* st = tiles + stage * S::kStageBytes;
           mbar_arrive_expect_tx(&full_bar[stage], A_SPLIT * S::kABytes);
@@ -190,7 +195,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     // ------------------------------- MMA issuer ---------------------------------
     // a_format (bits 7..9) and b_format (bits 10..12): 1 = bf16, 0 = fp16; the hardware wants them equal
     const uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, MN ? 1 : 0, MN ? 1 : 0) ^ (shape.a_f16 ? ((1u << 7) | (1u << 10)) : 0u);
-    int stage = 0, it = 0;
+    int stage = 0, it = 0, dbg_c = 0;
     uint32_t phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const Tile tl = decode(t);
@@ -202,6 +207,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       for (int kb = 0; kb < tl.num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
+        if (shape.timeline && blockIdx.x == 0 && lane == 0 && dbg_c < 48) shape.timeline[dbg_c] = global_timer_ns();
+        ++dbg_c;
         if (elect_one()) {
           const uint32_t s_addr = smem_u32(tiles + stage * S::kStageBytes);
           const uint32_t b_addr = s_addr + A_SPLIT * S::kABytes;
@@ -248,8 +255,12 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
       const Tile tl = decode(t);
       const int buf = it % kAccBufs, use = it / kAccBufs;
+      // per-tile operands of the epilogue (e.g. the MoE expert biases) are staged in this warp's shared-memory quarter
+      // while the main loop of the tile is still running
+      Epi::stage(ep, tl.n_tile * BLOCK_N, epi_smem + q * (Epi::kSmemBytes / 4), lane);
       mbar_wait(&tmem_full_bar[buf], use & 1);
       tc_fence_after();
+      if (shape.timeline && blockIdx.x == 0 && threadIdx.x == 64 && it < 8) shape.timeline[48 + 2 * it] = global_timer_ns();
 #pragma unroll 1
       for (int mt = 0; mt < MT; ++mt) {
         const int row = (tl.m_tile * MT + mt) * kBlockM + row_in_tile;
@@ -259,6 +270,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
       }
       tc_fence_before();
       __syncwarp();
+      if (shape.timeline && blockIdx.x == 0 && threadIdx.x == 64 && it < 8) shape.timeline[48 + 2 * it + 1] = global_timer_ns();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[buf]);
     }
   }
@@ -288,6 +300,7 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 }
 
 struct EpiLinear {
+  template <class P> static __device__ __forceinline__ void stage(const P&, int, uint8_t*, int) {}
   // (a per-warp transpose through shared memory for 128-byte row stores was measured SLOWER: 8192^3 GEMM 1082 -> 894
   //  TFLOP/s, wgrad +14% -- the strided 16-byte stores are not what bounds these epilogues)
   static constexpr int kSmemBytes = 0;
@@ -401,7 +414,9 @@ struct EpiLinear {
 // ---------------------------------------------------------------------------------------------
 template <int NMIX>
 struct EpiMoe {
-  static constexpr int kSmemBytes = 0;
+  // the 128 packed biases of the tile, one copy per epilogue warp: loading them from global memory right where they are
+  // used put an exposed L2 round trip in front of every sigmoid (measured: 12-15 us per tile, tools/gemm_timeline.py)
+  static constexpr int kSmemBytes = 4 * 512;
   static constexpr int kPer = 2 * NMIX + 1;
   static constexpr int kCpt = 128 / kPer;
   struct Params {
@@ -410,32 +425,52 @@ struct EpiMoe {
     const float* bias_packed;   // [n_tiles * 128]: expert biases in packed order (0 for gates / padding)
     int vocab;
   };
+  static __device__ __forceinline__ void stage(const Params& p, int n0, uint8_t* smem, int lane) {
+    __syncwarp();                                    // the previous tile's reads of this quarter are done
+    reinterpret_cast<float4*>(smem)[lane] = __ldg(reinterpret_cast<const float4*>(p.bias_packed + n0) + lane);
+    __syncwarp();
+  }
   template <int BLOCK_N>
   static __device__ __forceinline__ void run(const Params& p, const GemmShape& /*s*/, int row, int n0, uint32_t taddr,
-                                             bool row_valid, bool /*have_acc*/, int /*split*/, uint8_t* /*smem*/) {
+                                             bool row_valid, bool /*have_acc*/, int /*split*/, uint8_t* smem) {
     static_assert(BLOCK_N == 128, "MoE epilogue expects 128-column tiles");
-    float acc[128];
-#pragma unroll
-    for (int c = 0; c < 128; c += 32) tmem_ld32(taddr + c, reinterpret_cast<uint32_t*>(acc) + c);
-    tmem_ld_wait();
-    if (!row_valid) return;
+    // 32 accumulator columns (= kCpc whole classes) at a time: with all 128 live the compiler had no registers left to
+    // overlap the exp / reciprocal chains of neighbouring classes (measured 8-15 us per tile)
+    constexpr int kCpc = 32 / kPer;                         // classes per chunk
+    constexpr int kChunks = (kCpt + kCpc - 1) / kCpc;
     const int v0 = (n0 / 128) * kCpt;
-    const float* bias = p.bias_packed + n0;
+    const float* bias = reinterpret_cast<const float*>(smem);
     float* out = p.out + static_cast<long long>(row) * p.ld_out + v0;
 #pragma unroll
-    for (int c = 0; c < kCpt; ++c) {
-      const int o = c * kPer;
-      float mx = acc[o];
+    for (int ch = 0; ch < kChunks; ++ch) {
+      const int c_first = ch * kCpc;
+      const int col_want = c_first * kPer;
+      const int col0 = col_want + 32 <= 128 ? col_want : 128 - 32;      // the last chunk is shifted back into the tile
+      const int loc = col_want - col0;
+      float a[32];
+      tmem_ld32(taddr + col0, reinterpret_cast<uint32_t*>(a));
+      tmem_ld_wait();
+      if (row_valid) {
 #pragma unroll
-      for (int m = 1; m <= NMIX; ++m) mx = fmaxf(mx, acc[o + m]);
-      float den = 0.0f, num = 0.0f;
+        for (int cc = 0; cc < kCpc; ++cc) {
+          const int c = c_first + cc;
+          if (c < kCpt) {
+            const int o = loc + cc * kPer;
+            const int ob = c * kPer;
+            float mx = a[o];
 #pragma unroll
-      for (int m = 0; m <= NMIX; ++m) {
-        const float e = __expf(acc[o + m] - mx);
-        den += e;
-        if (m < NMIX) num += e * sigmoidf_(acc[o + NMIX + 1 + m] + __ldg(bias + o + NMIX + 1 + m));
+            for (int m = 1; m <= NMIX; ++m) mx = fmaxf(mx, a[o + m]);
+            float den = 0.0f, num = 0.0f;
+#pragma unroll
+            for (int m = 0; m <= NMIX; ++m) {
+              const float e = __expf(a[o + m] - mx);
+              den += e;
+              if (m < NMIX) num += e * sigmoidf_(a[o + NMIX + 1 + m] + bias[ob + NMIX + 1 + m]);
+            }
+            if (v0 + c < p.vocab) out[c] = num / den;
+          }
+        }
       }
-      if (v0 + c < p.vocab) out[c] = num / den;
     }
   }
 };
@@ -450,6 +485,7 @@ struct EpiMoe {
 // ---------------------------------------------------------------------------------------------
 struct EpiLstm {
   static constexpr int kSmemBytes = 0;
+  template <class P> static __device__ __forceinline__ void stage(const P&, int, uint8_t*, int) {}
   struct Params {
     const float* xw;            // nullable: [B, 4H] slice for this t (row stride ld_xw), packed order
     long long ld_xw;

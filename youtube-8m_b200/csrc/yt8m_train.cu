@@ -163,6 +163,7 @@ namespace yt8m {
 template <int NMIX>
 struct EpiMoeBwd {
   static constexpr int kSmemBytes = 0;
+  template <class P> static __device__ __forceinline__ void stage(const P&, int, uint8_t*, int) {}
   static constexpr int kPer = 2 * NMIX + 1;
   static constexpr int kCpt = 128 / kPer;
   struct Params {
