@@ -115,6 +115,10 @@ int yt8m_moe_fwd(const yt8m_bf16* x_hi, const yt8m_bf16* x_lo, long long ldx, co
  * (wh/all_frame_models/lstm_attention_max_pooling_model.py:65-66, zt/video_level_models.py:2327-2328) */
 int yt8m_group_max_rows(const float* in, long long groups, int heads, int cols, float* out, yt8m_stream_t stream);
 
+/* backward of yt8m_group_max_rows: din[b*heads + a, :] = dout[b, :] where head a is the first to attain the maximum, else 0 */
+int yt8m_group_max_rows_bwd(const float* in, const float* dout, long long groups, int heads, int cols, float* din,
+                            yt8m_stream_t stream);
+
 /* ---- LstmModel / LstmMemoryModel: wh/all_frame_models/lstm_model.py:30-47 ------------------------
  * MultiRNNCell[BasicLSTMCell(H, forget_bias)] x L under dynamic_rnn(sequence_length = num_frames).
  * Per layer one packed matrix [4H, in_l + H] (in_0 = D, in_l = H): row 4u+g holds gate g (i, j, f, o) of

@@ -428,3 +428,59 @@ def test_gated_netvlad_train_step_parity(tr):
     assert bool(torch.isfinite(got[kk]).all()), kk
     assert float((got[kk] - sd[kk]).abs().max()) > 0, kk
   assert torch.equal(t_.wg_bf16.float(), t_.p["wg"].to(torch.bfloat16).float())
+
+
+def test_group_max_rows_bwd():
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  import yt8m_native as nat
+  g = torch.Generator().manual_seed(31)
+  groups, heads, cols = 7, 8, 45
+  x = torch.randn(groups * heads, cols, generator=g).requires_grad_(True)
+  dout = torch.randn(groups, cols, generator=g)
+  y = x.reshape(groups, heads, cols).max(dim=1).values
+  gx, = torch.autograd.grad((y * dout).sum(), [x])
+  got = nat.group_max_rows_bwd(x.detach().to(DEV), dout.to(DEV), heads)
+  assert torch.equal(got.cpu(), gx)
+
+
+def test_attention_train_step_parity(tr):
+  """zt AttentionModel (A = 8 heads over the raw frames) + MoeExtendModel (MoE on B*A rows, max over heads): predictions,
+  loss and every gradient of one step against autograd over the oracle (BASELINE config 5 pooling at reduced sizes)."""
+  g = torch.Generator().manual_seed(93)
+  b, t, d, a, v, mix = 5, 40, 128, 8, 300, 2
+  x, nf, _ = synth.model_input(b, t, d, seed=37, min_frames=5)
+  y = synth.labels(b, v, seed=37, per_video=3.4)
+  sd = {"Attention/W": synth.bf16r(torch.randn(2 * d, a, generator=g) * 3.0), "Attention/b": torch.full((a,), 0.1),
+        "gates/weights": synth.xavier((d, v * (mix + 1)), g, 6.0), "experts/weights": synth.xavier((d, v * mix), g, 6.0),
+        "experts/biases": 0.1 * torch.randn(v * mix, generator=g)}
+  t_ = tr.AttentionTrainer(d, heads=a, vocab=v, mixtures=mix)
+  t_.import_state(sd)
+  t_.keep_grads = True
+  xd, nfd, yd = x.to(DEV).to(torch.bfloat16), nf.to(DEV), y.to(DEV)
+  p0 = t_.step(xd, nfd, yd)
+  grad0 = t_.grads_tf_layout(t_.last_grad)
+  loss0 = float(t_.last["label_loss_local"])
+  params = {kk: w.clone().requires_grad_(True) for kk, w in sd.items()}
+  pooled = O.attention_model_pool(x, nf, params["Attention/W"], params["Attention/b"])
+  pw = O.moe_extend_model(pooled, params["gates/weights"], params["experts/weights"], params["experts/biases"], v, mix, a)
+  lw = O.cross_entropy_loss(pw, y)
+  gw = dict(zip(params, torch.autograd.grad(lw, list(params.values()))))
+  assert float((p0.cpu() - pw.detach()).abs().max()) < 1e-3
+  assert abs(loss0 - float(lw.detach())) / float(lw.detach()) < 1e-3
+  # softmax over T is shift invariant: the mean-pooled half of W and the bias get no label gradient
+  assert float(gw["Attention/b"].abs().max()) < 1e-6 and float(grad0["Attention/b"].abs().max()) == 0.0
+  assert float(gw["Attention/W"][d:].abs().max()) < 1e-6 and float(grad0["Attention/W"][d:].abs().max()) == 0.0
+  for kk in gw:
+    if kk == "Attention/b":
+      continue
+    assert float(gw[kk].norm()) > 0, kk
+    err = _rel_l2(grad0[kk], gw[kk])
+    assert err < 2e-2, (kk, err)
+  for _ in range(2):
+    t_.step(xd, nfd, yd)
+  torch.cuda.synchronize()
+  got = t_.export_state()
+  for kk in sd:                      # every tensor moves: the shift-invariant ones through their L2 regulariser + Adam
+    assert bool(torch.isfinite(got[kk]).all()), kk
+    assert float((got[kk] - sd[kk]).abs().max()) > 0, kk

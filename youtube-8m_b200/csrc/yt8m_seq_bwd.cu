@@ -310,6 +310,25 @@ __global__ void context_gate_bwd_kernel(const float* __restrict__ dy, const floa
   }
 }
 
+// backward of the max over `heads` consecutive rows: the gradient goes to the first head that attains the maximum
+__global__ void group_max_bwd_kernel(const float* __restrict__ in, const float* __restrict__ dout, long long groups, int heads,
+                                     int cols, float* __restrict__ din) {
+  const long long total = groups * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long g = i / cols;
+    const int c = static_cast<int>(i - g * cols);
+    int best = 0;
+    float m = in[(g * heads) * cols + c];
+    for (int a = 1; a < heads; ++a) {
+      const float v = in[(g * heads + a) * cols + c];
+      if (v > m) { m = v; best = a; }
+    }
+    const float d = dout[i];
+    for (int a = 0; a < heads; ++a) din[(g * heads + a) * cols + c] = a == best ? d : 0.0f;
+  }
+}
+
 __global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -319,6 +338,17 @@ __global__ void add_inplace_kernel(float* __restrict__ y, const float* __restric
 }  // namespace
 
 extern "C" {
+
+int yt8m_group_max_rows_bwd(const float* in, const float* dout, long long groups, int heads, int cols, float* din,
+                            yt8m_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  YT8M_REQUIRE(in && dout && din, YT8M_E_BADPTR, "yt8m_group_max_rows_bwd: null pointer");
+  YT8M_REQUIRE(groups > 0 && heads > 0 && cols > 0, YT8M_E_BADSHAPE, "yt8m_group_max_rows_bwd: bad shape");
+  const long long total = groups * cols;
+  const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, kNumSms * 8));
+  group_max_bwd_kernel<<<blocks, 256, 0, stream>>>(in, dout, groups, heads, cols, din);
+  return check_launch("group_max_bwd_kernel");
+}
 
 int yt8m_add_inplace(float* y, const float* x, long long n, yt8m_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

@@ -100,6 +100,12 @@ class Trainer(object):
                                   "--video_level_classifier_model=MoeModel" % self.model_name)
       return yt8m_trainer.LstmTrainer(in_dim, hidden=int(FLAGS.lstm_cells), layers=FLAGS.lstm_layers, vocab=self.reader.num_classes,
                                       mixtures=FLAGS.moe_num_mixtures, memory=model_cls is frame_level_models.LstmMemoryModel)
+    if model_cls is frame_level_models.AttentionModel:
+      if FLAGS.video_level_classifier_model != "MoeExtendModel":
+        raise NotImplementedError("train.py --model=AttentionModel: the CUDA training step is built for "
+                                  "--video_level_classifier_model=MoeExtendModel (the reference scripts' pairing)")
+      return yt8m_trainer.AttentionTrainer(in_dim, heads=FLAGS.moe_num_extend, vocab=self.reader.num_classes,
+                                           mixtures=FLAGS.moe_num_mixtures)
     if model_cls is video_level_models.LogisticModel:
       kind = "logistic"
     elif model_cls is video_level_models.MoeModel:
@@ -107,7 +113,7 @@ class Trainer(object):
     else:
       raise NotImplementedError(
           "train.py: the CUDA training step is built for LogisticModel, MoeModel, NetVLADModel, GatedNetVLADModel, "
-          "LstmModel and LstmMemoryModel this round; "
+          "LstmModel, LstmMemoryModel and AttentionModel (+ MoeExtendModel) this round; "
           "%s runs forward-only (eval.py / inference.py)" % self.model_name)
     return yt8m_trainer.HeadTrainer(kind, in_dim, self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures)
 

@@ -59,6 +59,7 @@ _SIGS = {
     "yt8m_context_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_ll, c_void_p]),
     "yt8m_add_inplace": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
+    "yt8m_group_max_rows_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p]),
     "yt8m_attn_pool_fwd": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
     "yt8m_netvlad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -418,6 +419,14 @@ def context_gate_bwd(dy, x, g, scale=None, shift=None, want_bf16=True):
   _call("yt8m_context_gate_bwd", _p(dy.contiguous()), _p(x.contiguous()), _p(g.contiguous()), _p(scale), _p(shift), rows, cols, _p(dx),
         _p(dg), _p(gh), _p(gl), ld, _stream())
   return dx, dg, (gh[:, :cols] if want_bf16 else None), (gl[:, :cols] if want_bf16 else None)
+
+
+def group_max_rows_bwd(x, dout, heads):
+  """Backward of group_max_rows: x [G*heads, C] (the forward's input), dout [G, C] -> dx [G*heads, C]."""
+  rows, cols = x.shape
+  dx = _f32((rows, cols), x.device)
+  _call("yt8m_group_max_rows_bwd", _p(x.contiguous()), _p(dout.contiguous()), rows // heads, heads, cols, _p(dx), _stream())
+  return dx
 
 
 def add_inplace(y, x):

@@ -132,6 +132,11 @@ class HeadTrainer(object):
     b_local = p.shape[0]
     # d(mean over the GLOBAL batch)/dp: xent divides by the local batch, so rescale by B_local / B_global
     loss, dp = nat.xent(p, labels, want_grad=True, grad_scale=b_local / float(global_batch))
+    return loss, self.backward_from_dp(dp, p, hi, lo, want_dx)
+
+  def backward_from_dp(self, dp, p, hi, lo, want_dx=False):
+    """Gradients of this head given dL/dp [rows, V] (the loss sits further up: e.g. after the max over attention heads).
+    Returns dx [rows, D] fp32 when want_dx."""
     if self.kind == "logistic":
       dz_hi, dz_lo = nat.logistic_bwd_dz(dp, p)
     else:
@@ -144,7 +149,7 @@ class HeadTrainer(object):
       # (same rounding as the forward's operand copy)
       wt = nat.pack_transpose(self.w)
       dx = nat.linear(dz_hi, wt, a_lo=dz_lo, n=self.d, k=self.rows)["f32"]
-    return loss, dx
+    return dx
 
   def apply(self, lr_t, clip_gradient_norm=1.0, regularization_penalty=1.0):
     """L2 regulariser gradient, per-tensor clip, TF-Adam on this head's tensors (self.grad already all-reduced)."""
@@ -473,6 +478,106 @@ class LstmTrainer(object):
       for name, bf in (("w%d" % l, self.w_bf16[l]), ("b%d" % l, None)):
         sums = nat.grad_reg_sumsq(self.g[name], self.p[name], 0.0)               # BasicLSTMCell carries no regulariser
         nat.clip_adam_step(self.p[name], self.g[name], self.am[name], self.av[name], sums, clip_gradient_norm, lr_t, param_bf16=bf)
+    self.head.apply(lr_t, clip_gradient_norm, regularization_penalty)
+    self.global_step += 1
+    self.head.global_step = self.global_step
+    self.last = {"label_loss_local": loss, "lr": lr}
+    return p
+
+
+class AttentionTrainer(object):
+  """The training step for zt's LSTM-free AttentionModel + MoeExtendModel (multi-head attention pooling over the raw
+  frames, MoE on the B*A pooled rows, max over the A heads; zt/frame_level_models.py:4355-4405 +
+  zt/video_level_models.py:2272-2330) on the GPU through the C ABI: logits GEMM over all B*T frame rows, attention
+  pooling, MoE head, max over heads, CrossEntropyLoss, and the backward of each (group-max routing, fused MoE backward,
+  yt8m_attn_pool_bwd, the logits weight gradient as one MN-major GEMM over B*T rows), per-tensor clip and TF-Adam.
+
+  softmax over T is shift invariant, so the mean-pooled half of Attention/W ([D:2D]) and Attention/b receive no label
+  gradient -- only their L2 regulariser (l2 * tf.nn.l2_loss, :4389-4392) moves them, exactly as in the reference graph.
+  Layouts: Attention/W^T [A, 2D], Attention/b [A], then the packed MoE head; one flat gradient buffer, one all-reduce."""
+
+  def __init__(self, feature_dim, heads=8, vocab=4716, mixtures=2, l2_penalty=1e-8, device=None, group=None):
+    self.d, self.a, self.v, self.m, self.l2 = feature_dim, heads, vocab, mixtures, l2_penalty
+    self.dev = device or torch.device("cuda", torch.cuda.current_device())
+    self.group = group
+    self.world = yt8m_dp.world_size(group)
+    sizes = [("aw", heads * 2 * feature_dim), ("ab", heads), ("head", HeadTrainer.flat_size("moe", feature_dim, vocab, mixtures))]
+    total = sum(n for _, n in sizes)
+    self.param = torch.zeros(total, dtype=torch.float32, device=self.dev)
+    self.grad = torch.zeros_like(self.param)
+    self.adam_m = torch.zeros_like(self.param)
+    self.adam_v = torch.zeros_like(self.param)
+    self._off, off = {}, 0
+    for name, n in sizes:
+      self._off[name] = (off, off + n)
+      off += n
+    self.p, self.g, self.am, self.av = {}, {}, {}, {}
+    for name, shp in (("aw", (heads, 2 * feature_dim)), ("ab", (heads, 1))):
+      a, b = self._off[name]
+      self.p[name], self.g[name] = self.param[a:b].view(shp), self.grad[a:b].view(shp)
+      self.am[name], self.av[name] = self.adam_m[a:b].view(shp), self.adam_v[a:b].view(shp)
+    a, b = self._off["head"]
+    self.head = HeadTrainer("moe", feature_dim, vocab, mixtures, l2_penalty, self.dev, group,
+                            storage=(self.param[a:b], self.grad[a:b], self.adam_m[a:b], self.adam_v[a:b]))
+    self.aw_bf16 = torch.zeros((heads, 2 * feature_dim), dtype=torch.bfloat16, device=self.dev)
+    self.global_step = 0
+    self.keep_grads = False
+    self.last = {}
+
+  # ---- TF names / layouts ----------------------------------------------------------------------------
+  def import_state(self, sd):
+    self.p["aw"].copy_(sd["Attention/W"].t().to(self.dev))
+    self.p["ab"].copy_(sd["Attention/b"].view(-1, 1).to(self.dev))
+    self.aw_bf16.copy_(self.p["aw"])
+    self.head.import_state({k: sd[k] for k in ("gates/weights", "experts/weights", "experts/biases")})
+
+  def _tf_layout(self, flat):
+    a, b = self._off["aw"]
+    out = {"Attention/W": flat[a:b].view(self.a, 2 * self.d).t().contiguous().cpu()}
+    a, b = self._off["ab"]
+    out["Attention/b"] = flat[a:b].cpu().clone()
+    a, b = self._off["head"]
+    out.update(self.head.grads_tf_layout(flat[a:b]))
+    return out
+
+  def export_state(self):
+    return self._tf_layout(self.param)
+
+  def grads_tf_layout(self, flat):
+    return self._tf_layout(flat)
+
+  # ---- forward / step --------------------------------------------------------------------------------
+  def forward(self, x, num_frames=None):
+    """x bf16 [B, T, D] (padded frames are all-zero rows: the mask of :4372-4375).  Returns predictions [B, V]."""
+    b, t, d = x.shape
+    logits = nat.linear(x.reshape(b * t, d), self.aw_bf16, n=self.a, k=d)["f32"]                # W[:D] only (shift invariance)
+    logits3 = logits.as_strided((b, t, self.a), (t * logits.stride(0), logits.stride(0), 1))
+    _, hi, lo = nat.attn_pool(logits3, x, None, self.a, 0)
+    hi, lo = hi.reshape(b * self.a, d), lo.reshape(b * self.a, d)
+    p_heads = nat.moe_fwd(hi, self.head.w_bf16, self.head.b, self.v, self.m, x_lo=lo, d=d)      # [B*A, V]
+    return nat.group_max_rows(p_heads, self.a), {"logits3": logits3, "hi": hi, "lo": lo, "p_heads": p_heads}
+
+  def step(self, x, num_frames, labels, base_lr=0.01, lr_decay=0.95, lr_decay_examples=4000000, clip_gradient_norm=1.0,
+           regularization_penalty=1.0, global_batch=None):
+    b, t, d = x.shape
+    global_batch = global_batch or b * self.world
+    p, sv = self.forward(x)
+    loss, dp = nat.xent(p, labels, want_grad=True, grad_scale=b / float(global_batch))
+    dp_heads = nat.group_max_rows_bwd(sv["p_heads"], dp, self.a)                                # gradient to the arg-max head
+    dpooled = self.head.backward_from_dp(dp_heads, sv["p_heads"], sv["hi"], sv["lo"], want_dx=True)
+    dlogits, _ = nat.attn_pool_bwd(sv["logits3"], x, None, self.a, 0, dpooled[:, :d].contiguous().view(b, self.a, d))
+    dl_hi, dl_lo = nat.split_bf16(dlogits.view(b * t, self.a))
+    self.g["aw"].zero_()                                                                        # the mean-pooled half: no label gradient
+    nat.wgrad(dl_hi, dl_lo, x.reshape(b * t, d), self.a, d, out=self.g["aw"])                   # dW[:D]^T [A, D] into the [A, 2D] rows
+    self.g["ab"].zero_()
+    yt8m_dp.all_reduce_sum_(self.grad, self.group)                                              # the ONE collective of the step
+    if self.keep_grads:
+      self.last_grad = self.grad.clone()
+    lr = exponential_decay(base_lr, self.global_step, global_batch, lr_decay_examples, lr_decay)
+    lr_t = adam_lr_t(lr, self.global_step + 1)
+    for name, bf in (("aw", self.aw_bf16), ("ab", None)):
+      sums = nat.grad_reg_sumsq(self.g[name], self.p[name], self.l2 * regularization_penalty)
+      nat.clip_adam_step(self.p[name], self.g[name], self.am[name], self.av[name], sums, clip_gradient_norm, lr_t, param_bf16=bf)
     self.head.apply(lr_t, clip_gradient_norm, regularization_penalty)
     self.global_step += 1
     self.head.global_step = self.global_step
