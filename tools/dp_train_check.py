@@ -86,5 +86,50 @@ if world > 1:
   torch.distributed.all_reduce(ferr, op=torch.distributed.ReduceOp.MAX)
 if rank == 0:
   print("NetVLAD step, DP world=%d vs single process: flat gradient rel L2 err %.2e -> %s" % (world, float(ferr), "OK" if float(ferr) < 2e-3 else "MISMATCH"))
+
+# ---- LstmModel step (persistent recurrence forward + BPTT) and AttentionModel + MoeExtend step: same check
+def run_generic(make, xs, nfs, ys, sd_, group_world, bsz):
+  t = make()
+  t.keep_grads = True
+  t.import_state(sd_)
+  import yt8m_dp as dp
+  saved = dp.all_reduce_sum_
+  if group_world == 1:
+    t.world = 1
+    if hasattr(t, "head"):
+      t.head.world = 1
+    dp.all_reduce_sum_ = lambda flat, group=None: flat
+    lo, hi = 0, bsz
+  else:
+    lo, hi = yt8m_dp.shard_rows(bsz)
+  t.step(xs[lo:hi].to(dev).to(torch.bfloat16), nfs[lo:hi].to(dev), ys[lo:hi].to(dev), global_batch=bsz)
+  dp.all_reduce_sum_ = saved
+  torch.cuda.synchronize()
+  return t.last_grad.clone()
+
+Bl, Tl, Dl, Hl, Ll, Vl = 16, 40, 128, 256, 2, 300
+xl, nfl, _ = synth.model_input(Bl, Tl, Dl, seed=6, min_frames=4)
+yl = synth.labels(Bl, Vl, seed=6, per_video=3.4)
+sdl = {"gates/weights": synth.xavier((Ll * 2 * Hl, Vl * (M + 1)), g, 2.0), "experts/weights": synth.xavier((Ll * 2 * Hl, Vl * M), g, 2.0),
+       "experts/biases": 0.1 * torch.randn(Vl * M, generator=g)}
+for l in range(Ll):
+  sdl[yt8m_trainer.LstmTrainer.SCOPE % l + "/weights"] = synth.xavier(((Dl if l == 0 else Hl) + Hl, 4 * Hl), g, 2.0)
+  sdl[yt8m_trainer.LstmTrainer.SCOPE % l + "/biases"] = synth.bf16r(0.1 * torch.randn(4 * Hl, generator=g))
+mk = lambda: yt8m_trainer.LstmTrainer(Dl, hidden=Hl, layers=Ll, vocab=Vl, mixtures=M, device=dev)
+gd, gs = run_generic(mk, xl, nfl, yl, sdl, world, Bl), run_generic(mk, xl, nfl, yl, sdl, 1, Bl)
+lerr = torch.tensor([float((gd - gs).norm() / gs.norm())], device=dev)
+A = 8
+sda = {"Attention/W": synth.bf16r(torch.randn(2 * Dl, A, generator=g) * 3.0), "Attention/b": torch.full((A,), 0.1),
+       "gates/weights": synth.xavier((Dl, Vl * (M + 1)), g, 6.0), "experts/weights": synth.xavier((Dl, Vl * M), g, 6.0),
+       "experts/biases": 0.1 * torch.randn(Vl * M, generator=g)}
+mka = lambda: yt8m_trainer.AttentionTrainer(Dl, heads=A, vocab=Vl, mixtures=M, device=dev)
+gd, gs = run_generic(mka, xl, nfl, yl, sda, world, Bl), run_generic(mka, xl, nfl, yl, sda, 1, Bl)
+aerr = torch.tensor([float((gd - gs).norm() / gs.norm())], device=dev)
+if world > 1:
+  torch.distributed.all_reduce(lerr, op=torch.distributed.ReduceOp.MAX)
+  torch.distributed.all_reduce(aerr, op=torch.distributed.ReduceOp.MAX)
+if rank == 0:
+  print("LSTM step, DP world=%d vs single process: flat gradient rel L2 err %.2e -> %s" % (world, float(lerr), "OK" if float(lerr) < 2e-3 else "MISMATCH"))
+  print("Attention step, DP world=%d vs single process: flat gradient rel L2 err %.2e -> %s" % (world, float(aerr), "OK" if float(aerr) < 2e-3 else "MISMATCH"))
 if world > 1:
   torch.distributed.destroy_process_group()
