@@ -484,3 +484,97 @@ def test_attention_train_step_parity(tr):
   for kk in sd:                      # every tensor moves: the shift-invariant ones through their L2 regulariser + Adam
     assert bool(torch.isfinite(got[kk]).all()), kk
     assert float((got[kk] - sd[kk]).abs().max()) > 0, kk
+
+
+def test_chain_moe_train_step_parity(tr):
+  """ChainMoeModel (support MoE -> concat -> main MoE, wh/all_video_models/chain_moe_model.py:9-49) without --multitask:
+  predictions, loss and the gradients of BOTH heads against autograd over the oracle; input width D + S = 153 is not a
+  multiple of 8 (padded operands)."""
+  g = torch.Generator().manual_seed(94)
+  b, d, v, s, mix = 12, 128, 300, 25, 2
+  x, y, _ = _data(b, d, v, 38)
+  sd = {"gates-support/weights": synth.xavier((d, s * (mix + 1)), g, 6.0), "experts-support/weights": synth.xavier((d, s * mix), g, 6.0),
+        "experts-support/biases": 0.1 * torch.randn(s * mix, generator=g),
+        "gates-main/weights": synth.xavier((d + s, v * (mix + 1)), g, 6.0), "experts-main/weights": synth.xavier((d + s, v * mix), g, 6.0),
+        "experts-main/biases": 0.1 * torch.randn(v * mix, generator=g)}
+  t_ = tr.ChainMoeTrainer(d, vocab=v, mixtures=mix, num_supports=s)
+  t_.import_state({k: w.to(DEV) for k, w in sd.items()})
+  t_.keep_grads = True
+  p0 = t_.step(x.to(DEV), y.to(DEV))
+  grad0 = t_.grads_tf_layout(t_.last_grad)
+  loss0 = float(t_.last["label_loss_local"])
+  params = {kk: w.clone().requires_grad_(True) for kk, w in sd.items()}
+  sup = {"gate_w": params["gates-support/weights"], "expert_w": params["experts-support/weights"], "expert_b": params["experts-support/biases"]}
+  main = {"gate_w": params["gates-main/weights"], "expert_w": params["experts-main/weights"], "expert_b": params["experts-main/biases"]}
+  pw, _ = O.chain_moe_model(x, sup, main, v, s, mix)
+  lw = O.cross_entropy_loss(pw, y)
+  gw = dict(zip(params, torch.autograd.grad(lw, list(params.values()))))
+  assert float((p0.cpu() - pw.detach()).abs().max()) < 1e-3
+  assert abs(loss0 - float(lw.detach())) / float(lw.detach()) < 1e-3
+  for kk in gw:
+    assert float(gw[kk].norm()) > 0, kk
+    err = _rel_l2(grad0[kk], gw[kk])
+    assert err < 2e-2, (kk, err)
+  for _ in range(2):
+    t_.step(x.to(DEV), y.to(DEV))
+  torch.cuda.synchronize()
+  got = t_.export_state()
+  for kk in sd:
+    assert bool(torch.isfinite(got[kk]).all()), kk
+    assert float((got[kk] - sd[kk]).abs().max()) > 0, kk
+
+
+@pytest.mark.parametrize("kind", ["max_pooling", "multi"])
+def test_lstm_attention_train_step_parity(tr, kind):
+  """LstmAttentionMaxPoolingModel / LstmMultiAttentionModel: one training step (LSTM forward that retains the sequences,
+  attention pooling, MoE per head, max over heads, and the whole backward incl. BPTT driven by the gradient of the
+  OUTPUT SEQUENCE) against autograd over the oracle's whole-model forward."""
+  from oracle import model_oracle as MO
+  g = torch.Generator().manual_seed(95)
+  b, t, d, h, layers, a, v, mix = 4, 16, 64, 256, 2, 8, 200, 2
+  x, nf, _ = synth.model_input(b, t, d, seed=39, min_frames=3)
+  y = synth.labels(b, v, seed=39, per_video=3.4)
+  sd = {}
+  for l, (w, bb) in enumerate(_lstm_layers(d, h, layers, g)):
+    sd[tr.LstmTrainer.SCOPE % l + "/weights"], sd[tr.LstmTrainer.SCOPE % l + "/biases"] = w, bb
+  if kind == "max_pooling":
+    att, gn, en, pool = "attention-", "gates-sub-moe", "experts-sub-moe", h
+    sd[att + "/weights"] = synth.xavier((d + h, a), g, 8.0)
+  else:
+    att, gn, en, pool = "fully_connected", "gates", "experts", d
+    sd[att + "/weights"] = synth.xavier((h, a), g, 8.0)
+  sd[att + "/biases"] = 0.1 * torch.randn(a, generator=g)
+  sd[gn + "/weights"] = synth.xavier((pool, v * (mix + 1)), g, 6.0)
+  sd[en + "/weights"] = synth.xavier((pool, v * mix), g, 6.0)
+  sd[en + "/biases"] = 0.1 * torch.randn(v * mix, generator=g)
+  t_ = tr.LstmAttentionTrainer(d, hidden=h, layers=layers, heads=a, vocab=v, mixtures=mix, kind=kind)
+  t_.import_state(sd)
+  t_.keep_grads = True
+  xd, nfd, yd = x.to(DEV).to(torch.bfloat16), nf.to(DEV), y.to(DEV)
+  p0 = t_.step(xd, nfd, yd)
+  grad0 = t_.grads_tf_layout(t_.last_grad)
+  loss0 = float(t_.last["label_loss_local"])
+  params = {kk: w.clone().requires_grad_(True) for kk, w in sd.items()}
+  fwd = MO.lstm_attention_max_pooling if kind == "max_pooling" else MO.lstm_multi_attention
+  pw = fwd(params, x, nf, v, mix, a, layers=layers)
+  lw = O.cross_entropy_loss(pw, y)
+  gw = dict(zip(params, torch.autograd.grad(lw, list(params.values()))))
+  assert float((p0.cpu() - pw.detach()).abs().max()) < 2e-3      # the attention reads the bf16 copy of h (as the forward plugin)
+  assert abs(loss0 - float(lw.detach())) / float(lw.detach()) < 2e-3
+  for kk in gw:
+    if kind == "max_pooling" and kk == att + "/biases":
+      # softmax over T is shift invariant: the bias gradient is zero up to rounding in both implementations
+      scale = float(gw[att + "/weights"].abs().max())
+      assert float(gw[kk].abs().max()) < 1e-5 * scale and float(grad0[kk].abs().max()) < 1e-3 * scale, kk
+      continue
+    assert float(gw[kk].norm()) > 0, kk
+    err = _rel_l2(grad0[kk], gw[kk])
+    assert err < 3e-2, (kk, err)
+  for _ in range(2):
+    t_.step(xd, nfd, yd)
+  torch.cuda.synchronize()
+  got = t_.export_state()
+  for kk in sd:
+    assert bool(torch.isfinite(got[kk]).all()), kk
+    if not (kind == "max_pooling" and kk == att + "/biases"):
+      assert float((got[kk] - sd[kk]).abs().max()) > 0, kk

@@ -100,12 +100,25 @@ class Trainer(object):
                                   "--video_level_classifier_model=MoeModel" % self.model_name)
       return yt8m_trainer.LstmTrainer(in_dim, hidden=int(FLAGS.lstm_cells), layers=FLAGS.lstm_layers, vocab=self.reader.num_classes,
                                       mixtures=FLAGS.moe_num_mixtures, memory=model_cls is frame_level_models.LstmMemoryModel)
+    if model_cls in (frame_level_models.LstmAttentionMaxPoolingModel, frame_level_models.LstmMultiAttentionModel):
+      multi = model_cls is frame_level_models.LstmMultiAttentionModel
+      if multi and FLAGS.video_level_classifier_model != "MoeModel":
+        raise NotImplementedError("train.py --model=LstmMultiAttentionModel: built for --video_level_classifier_model=MoeModel")
+      return yt8m_trainer.LstmAttentionTrainer(in_dim, hidden=int(FLAGS.lstm_cells), layers=FLAGS.lstm_layers,
+                                               heads=FLAGS.attention_size if multi else FLAGS.lstm_attentions,
+                                               vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures,
+                                               kind="multi" if multi else "max_pooling")
     if model_cls is frame_level_models.AttentionModel:
       if FLAGS.video_level_classifier_model != "MoeExtendModel":
         raise NotImplementedError("train.py --model=AttentionModel: the CUDA training step is built for "
                                   "--video_level_classifier_model=MoeExtendModel (the reference scripts' pairing)")
       return yt8m_trainer.AttentionTrainer(in_dim, heads=FLAGS.moe_num_extend, vocab=self.reader.num_classes,
                                            mixtures=FLAGS.moe_num_mixtures)
+    if model_cls is video_level_models.ChainMoeModel:
+      if FLAGS.multitask:
+        raise NotImplementedError("train.py --model=ChainMoeModel: --multitask (a separate loss on the support predictions) is not built")
+      return yt8m_trainer.ChainMoeTrainer(in_dim, vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures,
+                                          num_supports=FLAGS.num_supports)
     if model_cls is video_level_models.LogisticModel:
       kind = "logistic"
     elif model_cls is video_level_models.MoeModel:
@@ -113,7 +126,8 @@ class Trainer(object):
     else:
       raise NotImplementedError(
           "train.py: the CUDA training step is built for LogisticModel, MoeModel, NetVLADModel, GatedNetVLADModel, "
-          "LstmModel, LstmMemoryModel and AttentionModel (+ MoeExtendModel) this round; "
+          "LstmModel, LstmMemoryModel, LstmAttentionMaxPoolingModel, LstmMultiAttentionModel, AttentionModel (+ MoeExtendModel) "
+          "and ChainMoeModel this round; "
           "%s runs forward-only (eval.py / inference.py)" % self.model_name)
     return yt8m_trainer.HeadTrainer(kind, in_dim, self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures)
 

@@ -583,3 +583,232 @@ class AttentionTrainer(object):
     self.head.global_step = self.global_step
     self.last = {"label_loss_local": loss, "lr": lr}
     return p
+
+
+class ChainMoeTrainer(object):
+  """The training step for ChainMoeModel (wh/all_video_models/chain_moe_model.py:9-49) without --multitask: a support
+  MoE over `num_supports` categories, its predictions concatenated to the input, the main MoE on the concatenation;
+  the label loss sits on the main predictions and reaches the support head through the concatenated columns
+  (wh/train.py:412-413).  Two packed MoE heads in ONE flat gradient buffer: one all-reduce per step."""
+
+  def __init__(self, in_dim, vocab=4716, mixtures=2, num_supports=25, l2_penalty=1e-8, device=None, group=None):
+    self.d, self.v, self.m, self.s = in_dim, vocab, mixtures, num_supports
+    self.dev = device or torch.device("cuda", torch.cuda.current_device())
+    self.group = group
+    self.world = yt8m_dp.world_size(group)
+    n_sup = HeadTrainer.flat_size("moe", in_dim, num_supports, mixtures)
+    n_main = HeadTrainer.flat_size("moe", in_dim + num_supports, vocab, mixtures)
+    self.param = torch.zeros(n_sup + n_main, dtype=torch.float32, device=self.dev)
+    self.grad = torch.zeros_like(self.param)
+    self.adam_m = torch.zeros_like(self.param)
+    self.adam_v = torch.zeros_like(self.param)
+    sl = lambda t, a, b: t[a:b]
+    self.support = HeadTrainer("moe", in_dim, num_supports, mixtures, l2_penalty, self.dev, group,
+                               storage=tuple(sl(t, 0, n_sup) for t in (self.param, self.grad, self.adam_m, self.adam_v)))
+    self.main = HeadTrainer("moe", in_dim + num_supports, vocab, mixtures, l2_penalty, self.dev, group,
+                            storage=tuple(sl(t, n_sup, n_sup + n_main) for t in (self.param, self.grad, self.adam_m, self.adam_v)))
+    self._n_sup = n_sup
+    self.global_step = 0
+    self.keep_grads = False
+    self.last = {}
+
+  @staticmethod
+  def _sub(sd, scope):
+    return {"gates/weights": sd["gates%s/weights" % scope], "experts/weights": sd["experts%s/weights" % scope],
+            "experts/biases": sd["experts%s/biases" % scope]}
+
+  def import_state(self, sd):
+    self.support.import_state(self._sub(sd, "-support"))
+    self.main.import_state(self._sub(sd, "-main"))
+
+  def _tf_layout(self, flat):
+    out = {}
+    for scope, head, part in (("-support", self.support, flat[:self._n_sup]), ("-main", self.main, flat[self._n_sup:])):
+      for k, v in head.grads_tf_layout(part).items():
+        name, leaf = k.split("/")
+        out["%s%s/%s" % (name, scope, leaf)] = v
+    return out
+
+  def export_state(self):
+    return self._tf_layout(self.param)
+
+  def grads_tf_layout(self, flat):
+    return self._tf_layout(flat)
+
+  def step(self, x, labels, base_lr=0.01, lr_decay=0.95, lr_decay_examples=4000000, clip_gradient_norm=1.0,
+           regularization_penalty=1.0, global_batch=None):
+    b = x.shape[0]
+    global_batch = global_batch or b * self.world
+    sp, (s_hi, s_lo) = self.support.forward(x)                                        # [B, S] support predictions
+    main_in = torch.cat([x.float()[:, :self.d], sp[:, :self.s]], dim=1)               # tf.concat (device copy)
+    p, (m_hi, m_lo) = self.main.forward(main_in)
+    loss, d_in = self.main.backward(p, m_hi, m_lo, labels, global_batch, want_dx=True)
+    d_sp = d_in[:, self.d:self.d + self.s].contiguous()                               # the columns that came from the support head
+    self.support.backward_from_dp(d_sp, sp, s_hi, s_lo)
+    yt8m_dp.all_reduce_sum_(self.grad, self.group)                                    # the ONE collective of the step
+    if self.keep_grads:
+      self.last_grad = self.grad.clone()
+    lr = exponential_decay(base_lr, self.global_step, global_batch, lr_decay_examples, lr_decay)
+    lr_t = adam_lr_t(lr, self.global_step + 1)
+    self.support.apply(lr_t, clip_gradient_norm, regularization_penalty)
+    self.main.apply(lr_t, clip_gradient_norm, regularization_penalty)
+    self.global_step += 1
+    self.last = {"label_loss_local": loss, "lr": lr}
+    return p
+
+
+class LstmAttentionTrainer(object):
+  """The training step for the two LSTM + multi-head attention models of the reference, on the GPU through the C ABI:
+
+  kind="max_pooling": LstmAttentionMaxPoolingModel (wh/all_frame_models/lstm_attention_max_pooling_model.py:29-68) --
+      logits = [x_t, h_t] . Wa + ba, softmax over T (masked, renormalised), pooled = sum_t w . h_t, MoE ("sub-moe") on
+      the B*A rows, max over heads;
+  kind="multi": LstmMultiAttentionModel (wh/all_frame_models/lstm_multi_attention_model.py:30-91) --
+      att = sigmoid(h_t . Wa + ba) masked, / (sum + 1e-8), pooled = sum_t att . x_t (the RAW input), MoeModel, max over heads.
+
+  Backward: group-max routing, fused MoE backward, yt8m_attn_pool_bwd (d logits, and d h_t for "max_pooling"), the
+  attention weight gradient as one MN-major GEMM over B*T rows, d h_t through the logits GEMM, then back-propagation
+  through time with the gradient of the top layer's OUTPUT SEQUENCE (yt8m_lstm_bwd, dout_seq), clip + TF-Adam.
+  As in the forward plugins the attention reads the bf16 (hi) copy of the LSTM outputs."""
+
+  SCOPE = LstmTrainer.SCOPE
+
+  def __init__(self, feature_dim, hidden=1024, layers=2, heads=8, vocab=4716, mixtures=2, kind="max_pooling", l2_penalty=1e-8,
+               device=None, group=None):
+    assert kind in ("max_pooling", "multi")
+    self.d, self.h, self.l, self.a, self.v, self.m, self.kind, self.l2 = feature_dim, hidden, layers, heads, vocab, mixtures, kind, l2_penalty
+    self.dev = device or torch.device("cuda", torch.cuda.current_device())
+    self.group = group
+    self.world = yt8m_dp.world_size(group)
+    self.att_in = feature_dim + hidden if kind == "max_pooling" else hidden      # rows of the attention matrix
+    self.pool_dim = hidden if kind == "max_pooling" else feature_dim             # what the heads pool
+    sizes = []
+    for l in range(layers):
+      k = (feature_dim if l == 0 else hidden) + hidden
+      sizes += [("w%d" % l, 4 * hidden * k), ("b%d" % l, 4 * hidden)]
+    sizes += [("wa", heads * self.att_in), ("ba", heads), ("head", HeadTrainer.flat_size("moe", self.pool_dim, vocab, mixtures))]
+    total = sum(n for _, n in sizes)
+    self.param = torch.zeros(total, dtype=torch.float32, device=self.dev)
+    self.grad = torch.zeros_like(self.param)
+    self.adam_m = torch.zeros_like(self.param)
+    self.adam_v = torch.zeros_like(self.param)
+    self._off, off = {}, 0
+    for name, n in sizes:
+      self._off[name] = (off, off + n)
+      off += n
+    shapes = {"wa": (heads, self.att_in), "ba": (heads, 1)}
+    for l in range(layers):
+      k = (feature_dim if l == 0 else hidden) + hidden
+      shapes["w%d" % l], shapes["b%d" % l] = (4 * hidden, k), (4 * hidden, 1)
+    self.p, self.g, self.am, self.av = {}, {}, {}, {}
+    for name, shp in shapes.items():
+      a, b = self._off[name]
+      self.p[name], self.g[name] = self.param[a:b].view(shp), self.grad[a:b].view(shp)
+      self.am[name], self.av[name] = self.adam_m[a:b].view(shp), self.adam_v[a:b].view(shp)
+    a, b = self._off["head"]
+    self.head = HeadTrainer("moe", self.pool_dim, vocab, mixtures, l2_penalty, self.dev, group,
+                            storage=(self.param[a:b], self.grad[a:b], self.adam_m[a:b], self.adam_v[a:b]))
+    self.w_bf16 = [torch.zeros(self.p["w%d" % l].shape, dtype=torch.bfloat16, device=self.dev) for l in range(layers)]
+    self.wa_bf16 = torch.zeros((heads, self.att_in), dtype=torch.bfloat16, device=self.dev)
+    self.att_name = "attention-" if kind == "max_pooling" else "fully_connected"
+    self.moe_names = ("gates-sub-moe", "experts-sub-moe") if kind == "max_pooling" else ("gates", "experts")
+    self.global_step = 0
+    self.keep_grads = False
+    self.last = {}
+
+  # ---- TF names / layouts ----------------------------------------------------------------------------
+  def import_state(self, sd):
+    for l in range(self.l):
+      scope = self.SCOPE % l
+      self.p["w%d" % l].copy_(_lstm_tf_to_packed(sd[scope + "/weights"].to(self.dev), self.h))
+      self.p["b%d" % l].copy_(sd[scope + "/biases"].to(self.dev).reshape(4, self.h).t().reshape(-1, 1))
+      self.w_bf16[l].copy_(self.p["w%d" % l])
+    self.p["wa"].copy_(sd[self.att_name + "/weights"].t().to(self.dev))
+    self.p["ba"].copy_(sd[self.att_name + "/biases"].view(-1, 1).to(self.dev))
+    self.wa_bf16.copy_(self.p["wa"])
+    gn, en = self.moe_names
+    self.head.import_state({"gates/weights": sd[gn + "/weights"], "experts/weights": sd[en + "/weights"], "experts/biases": sd[en + "/biases"]})
+
+  def _tf_layout(self, flat):
+    out = {}
+    for l in range(self.l):
+      scope = self.SCOPE % l
+      a, b = self._off["w%d" % l]
+      out[scope + "/weights"] = _lstm_packed_to_tf(flat[a:b].view(self.p["w%d" % l].shape), self.h).cpu()
+      a, b = self._off["b%d" % l]
+      out[scope + "/biases"] = flat[a:b].view(self.h, 4).t().reshape(-1).cpu().clone()
+    a, b = self._off["wa"]
+    out[self.att_name + "/weights"] = flat[a:b].view(self.a, self.att_in).t().contiguous().cpu()
+    a, b = self._off["ba"]
+    out[self.att_name + "/biases"] = flat[a:b].cpu().clone()
+    a, b = self._off["head"]
+    gn, en = self.moe_names
+    for k, v in self.head.grads_tf_layout(flat[a:b]).items():
+      name, leaf = k.split("/")
+      out["%s/%s" % (gn if name == "gates" else en, leaf)] = v
+    return out
+
+  def export_state(self):
+    return self._tf_layout(self.param)
+
+  def grads_tf_layout(self, flat):
+    return self._tf_layout(flat)
+
+  # ---- step ------------------------------------------------------------------------------------------
+  def step(self, x, num_frames, labels, base_lr=0.01, lr_decay=0.95, lr_decay_examples=4000000, clip_gradient_norm=1.0,
+           regularization_penalty=1.0, global_batch=None):
+    b, t, d = x.shape
+    h, a = self.h, self.a
+    global_batch = global_batch or b * self.world
+    bs = [self.p["b%d" % l].view(-1) for l in range(self.l)]
+    _, _, seq_hi, seq_lo = nat.lstm_fwd_train(x, num_frames, self.w_bf16, bs, h)
+    out_bf = seq_hi[-1]                                                            # bf16 outputs of the top layer [B, T, H]
+    if self.kind == "max_pooling":
+      att_op = torch.cat([x, out_bf], dim=2).reshape(b * t, d + h)                 # tf.concat (device copy)
+      feats, mode = out_bf, 0
+    else:
+      att_op = out_bf.reshape(b * t, h)
+      feats, mode = x, 1
+    logits = nat.linear(att_op, self.wa_bf16, n=a, k=self.att_in, shift=self.p["ba"].view(-1))["f32"]
+    logits3 = logits.as_strided((b, t, a), (t * logits.stride(0), logits.stride(0), 1))
+    _, hi, lo = nat.attn_pool(logits3, feats, num_frames, a, mode)
+    hi, lo = hi.reshape(b * a, self.pool_dim), lo.reshape(b * a, self.pool_dim)
+    p_heads = nat.moe_fwd(hi, self.head.w_bf16, self.head.b, self.v, self.m, x_lo=lo, d=self.pool_dim)
+    p = nat.group_max_rows(p_heads, a)
+    # ---- backward
+    loss, dp = nat.xent(p, labels, want_grad=True, grad_scale=b / float(global_batch))
+    dp_heads = nat.group_max_rows_bwd(p_heads, dp, a)
+    dpooled = self.head.backward_from_dp(dp_heads, p_heads, hi, lo, want_dx=True)
+    dlogits, dfeats = nat.attn_pool_bwd(logits3, feats, num_frames, a, mode,
+                                        dpooled[:, :self.pool_dim].contiguous().view(b, a, self.pool_dim),
+                                        want_dfeats=(self.kind == "max_pooling"))
+    dl_hi, dl_lo = nat.split_bf16(dlogits.view(b * t, a))
+    nat.wgrad(dl_hi, dl_lo, att_op, a, self.att_in, out=self.g["wa"])              # dWa^T [A, att_in]
+    nat.colsum_bf16(dl_hi, dl_lo, a, out=self.g["ba"].view(-1))
+    wa_t = nat.pack_transpose(self.p["wa"])                                        # bf16 [att_in, 8]: rows of Wa, K = A contiguous
+    wa_h = wa_t[d:] if self.kind == "max_pooling" else wa_t                        # the rows that multiply h_t
+    dseq = nat.linear(dl_hi, wa_h, a_lo=dl_lo, n=h, k=a)["f32"]                    # d h_t through the logits [B*T, H]
+    if dfeats is not None:
+      nat.add_inplace(dseq, dfeats.view(b * t, h))                                 # + d h_t through the pooling
+    wt = [nat.pack_transpose(self.p["w%d" % l]) for l in range(self.l)]
+    nat.lstm_bwd(x, num_frames, self.w_bf16, bs, wt, h, seq_hi, seq_lo, dstate=None, dout_seq=dseq.view(b, t, h),
+                 dw=[self.g["w%d" % l] for l in range(self.l)], db=[self.g["b%d" % l].view(-1) for l in range(self.l)])
+    del wt
+    yt8m_dp.all_reduce_sum_(self.grad, self.group)                                 # the ONE collective of the step
+    if self.keep_grads:
+      self.last_grad = self.grad.clone()
+    lr = exponential_decay(base_lr, self.global_step, global_batch, lr_decay_examples, lr_decay)
+    lr_t = adam_lr_t(lr, self.global_step + 1)
+    for l in range(self.l):
+      for name, bf in (("w%d" % l, self.w_bf16[l]), ("b%d" % l, None)):
+        sums = nat.grad_reg_sumsq(self.g[name], self.p[name], 0.0)
+        nat.clip_adam_step(self.p[name], self.g[name], self.am[name], self.av[name], sums, clip_gradient_norm, lr_t, param_bf16=bf)
+    sums = nat.grad_reg_sumsq(self.g["wa"], self.p["wa"], self.l2 * regularization_penalty)   # slim l2_regularizer on the weights
+    nat.clip_adam_step(self.p["wa"], self.g["wa"], self.am["wa"], self.av["wa"], sums, clip_gradient_norm, lr_t, param_bf16=self.wa_bf16)
+    sums = nat.grad_reg_sumsq(self.g["ba"], self.p["ba"], 0.0)
+    nat.clip_adam_step(self.p["ba"], self.g["ba"], self.am["ba"], self.av["ba"], sums, clip_gradient_norm, lr_t)
+    self.head.apply(lr_t, clip_gradient_norm, regularization_penalty)
+    self.global_step += 1
+    self.head.global_step = self.global_step
+    self.last = {"label_loss_local": loss, "lr": lr}
+    return p
