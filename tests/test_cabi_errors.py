@@ -60,3 +60,32 @@ def test_row_kernel_argument_checks():
   assert lib.yt8m_xent_fwd_bwd(P, None, 4, 10, P, None, 1.0, None) == BADPTR
   assert lib.yt8m_wgrad(P, None, 60, P, 64, 8, 8, 8, P, 8, None) == BADSHAPE
   assert lib.yt8m_group_max_rows(P, 0, 8, 10, P, None) == BADSHAPE
+
+
+def test_backward_and_ingest_argument_checks():
+  """The entry points added for the training step and the ragged ingest validate before touching CUDA as well."""
+  # ragged ingest
+  assert lib.yt8m_frames_unpack_u8(None, P, P, 4, 300, 1152, 1, P, None, None) == BADPTR
+  assert lib.yt8m_frames_unpack_u8(P, P, P, 4, 300, 1150, 1, P, None, None) == BADSHAPE                   # dim % 8
+  assert lib.yt8m_frames_unpack_u8(P + 4, P, P, 4, 300, 1152, 1, P, None, None) == BADPTR                 # 8-byte alignment
+  assert "aligned" in err()
+  assert lib.yt8m_frames_unpack_u8(P, P, P, 0, 300, 1152, 1, P, None, None) == BADSHAPE
+  # LSTM backward
+  assert lib.yt8m_lstm_bwd_workspace_bytes(4, 10, 64, 32, 0) == 0
+  assert lib.yt8m_lstm_bwd_workspace_bytes(64, 300, 1152, 1024, 2) > 64 * 300 * 4096 * (4 + 2 + 2)
+  assert lib.yt8m_lstm_bwd(P, P, 4, 10, 64, 256, 1, P, P, P, 1.0, P, P, None, None, P, P, P, 1 << 40, None) == BADPTR   # no gradient given
+  assert "neither" in err()
+  assert lib.yt8m_lstm_bwd(P, P, 4, 10, 60, 256, 1, P, P, P, 1.0, P, P, P, None, P, P, P, 1 << 40, None) == BADSHAPE    # D % 8
+  assert lib.yt8m_lstm_bwd(P, P, 4, 10, 64, 256, 1, P, P, P, 1.0, P, P, P, None, P, P, P, 16, None) == BADSHAPE         # workspace
+  assert "workspace" in err()
+  assert lib.yt8m_lstm_fwd_train(P, P, 4, 10, 64, 256, 1, P, P, 1.0, P, None, None, None, P, 1 << 40, None) == BADPTR   # no sequence buffers
+  # attention pooling / context gate / group max backward
+  assert lib.yt8m_attn_pool_bwd(P, 8, P, None, 2, 300, 17, 1152, 0, P, P, 17, None, None) == BADSHAPE                  # A > 16
+  assert lib.yt8m_attn_pool_bwd(P, 8, P, None, 2, 300, 8, 1150, 0, P, P, 8, None, None) == BADSHAPE                    # F % 8
+  assert lib.yt8m_attn_pool_bwd(P, 8, P, None, 2, 300, 8, 1152, 0, P, P, 4, None, None) == BADSHAPE                    # ld_dl < A
+  assert lib.yt8m_attn_pool_bwd(P, 8, P, None, 2, 300, 8, 1152, 0, None, P, 8, None, None) == BADPTR
+  assert lib.yt8m_context_gate_bwd(P, P, P, None, None, 4, 16, None, None, None, None, 16, None) == BADPTR             # no output
+  assert lib.yt8m_context_gate_bwd(P, P, P, None, None, 4, 16, None, None, P, P, 8, None) == BADSHAPE                  # ld_dg < cols
+  assert lib.yt8m_group_max_rows_bwd(P, P, 0, 8, 10, P, None) == BADSHAPE
+  assert lib.yt8m_group_max_rows_bwd(P, None, 4, 8, 10, P, None) == BADPTR
+  assert lib.yt8m_add_inplace(P, None, 10, None) == BADPTR and lib.yt8m_add_inplace(P, P, 0, None) == OK
