@@ -73,3 +73,30 @@ def test_gap_edge_cases():
     eval_util.top_k_by_class(p, y, 0)
   with pytest.raises(ValueError):
     eval_util.EvaluationMetrics(10, 20).get()
+
+
+def test_step_metrics_from_topk_equal_the_full_metrics():
+  """eval_util.step_metrics_from_topk (the GPU top-32 path of train.py's log line) == the three calculate_* functions on
+  the full predictions, including a video without labels (PERR nan convention) and the fallback signal for a video with
+  more positives than extracted entries."""
+  import numpy as np
+  import eval_util
+  rs = np.random.RandomState(7)
+  n, v, kp = 40, 300, 32
+  pred = rs.rand(n, v).astype(np.float32)
+  act = (rs.rand(n, v) < 0.02).astype(np.float32)
+  act[3] = 0
+  act[5, :20] = 1                                   # 20 positives: still within the 32 extracted entries
+  order = np.argsort(-pred, axis=1, kind="stable")[:, :kp]
+  tv = np.take_along_axis(pred, order, axis=1)
+  h1, perr, gap = eval_util.step_metrics_from_topk(tv, order.astype(np.int32), act, top_k=20)
+  assert abs(h1 - eval_util.calculate_hit_at_one(pred, act)) < 1e-6       # float32 vs float64 averaging
+  want_perr = eval_util.calculate_precision_at_equal_recall_rate(pred, act)
+  assert (np.isnan(perr) and np.isnan(want_perr)) or abs(perr - want_perr) < 1e-6
+  assert abs(gap - eval_util.calculate_gap(pred, act, 20)) < 1e-9
+  act2 = act.copy()
+  act2[3, 0] = 1                                    # no empty video: PERR is a number
+  _, perr2, _ = eval_util.step_metrics_from_topk(tv, order, act2, top_k=20)
+  assert abs(perr2 - eval_util.calculate_precision_at_equal_recall_rate(pred, act2)) < 1e-6
+  act2[7, :40] = 1                                  # 40 positives > 32 extracted: the caller must fall back
+  assert eval_util.step_metrics_from_topk(tv, order, act2, top_k=20)[1] is None

@@ -80,6 +80,33 @@ def calculate_gap(predictions, actuals, top_k=20):
   return _ap(p, l, float(pos.sum()))
 
 
+def step_metrics_from_topk(top_val, top_idx, actuals, top_k=20):
+  """Hit@1, PERR and GAP@top_k of one step from the per-video top-K' entries (K' >= top_k, descending) that the GPU
+  extracted (yt8m_topk_rows) -- the per-step metrics of the training log line (wh/train.py:578-591) without fetching
+  the B x 4716 predictions: 2 * K' numbers per video cross PCIe and the host work is O(B * K') instead of O(B * V).
+
+  Equal to calculate_hit_at_one / calculate_precision_at_equal_recall_rate / calculate_gap on the full predictions up to
+  ties between equal scores.  Returns (hit_at_one, perr, gap); perr is None when some video has more than K' positive
+  labels (the caller then falls back to the full predictions for that step)."""
+  top_val, top_idx = numpy.asarray(top_val), numpy.asarray(top_idx).astype(numpy.int64)
+  n_videos, kp = top_idx.shape
+  if top_k > kp:
+    raise ValueError("top_k (%d) exceeds the %d entries extracted per video" % (top_k, kp))
+  r = numpy.arange(n_videos)[:, None]
+  hit_lab = actuals[r, top_idx].astype(numpy.float64)            # label of every extracted class
+  hit_at_one = float(numpy.average(hit_lab[:, 0]))
+  counts = actuals.sum(axis=1).astype(numpy.int64)
+  perr = None
+  if counts.max(initial=0) <= kp:
+    within = numpy.arange(kp)[None, :] < counts[:, None]         # the num_labels best classes of every video
+    hits = (hit_lab * (top_val > 0) * within).sum(axis=1)
+    with numpy.errstate(divide="ignore", invalid="ignore"):
+      perr = float(numpy.where(counts > 0, hits / counts, numpy.nan).sum() / n_videos)
+  k = min(top_k, actuals.shape[1])
+  gap = _ap(top_val[:, :k].ravel(), hit_lab[:, :k].ravel(), float(actuals.sum()))
+  return hit_at_one, perr, gap
+
+
 class EvaluationMetrics(object):
   """A class to store the evaluation metrics (wh/eval_util.py:167-254)."""
 
