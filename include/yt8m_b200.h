@@ -81,6 +81,10 @@ int yt8m_l2norm_rows_fwd(const void* x, int src_dtype, long long rows, int dim, 
 int yt8m_frames_unpack_u8(const uint8_t* packed, const long long* row_offsets, const int* num_frames, int B, int T,
                           int dim, int normalize, yt8m_bf16* out_bf16, float* out_f32, yt8m_stream_t stream);
 
+/* backward of the row L2 normalisation y = x * rsqrt(max(sum x^2, 1e-12)) (tf.nn.l2_normalize, e.g.
+ * wh/all_video_models/deep_combine_chain_model.py:41): dx = dy / ||x|| - x (x . dy) / ||x||^3; x, dy, dx fp32 [rows, dim]. */
+int yt8m_l2norm_rows_bwd(const float* x, const float* dy, long long rows, int dim, float* dx, yt8m_stream_t stream);
+
 /* ---- dense layer (slim.fully_connected / tf.matmul + bias / folded batch-norm + activation) ----
  * out[M, N] = act((A[M, K] . W[N, K]^T) * col_scale[N] + col_shift[N]);  A = a_hi (+ a_lo).
  * Replaces e.g. wh/all_video_models/logistic_model.py:23-25, wh/all_frame_models/dbof_model.py:76-115,

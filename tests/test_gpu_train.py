@@ -578,3 +578,61 @@ def test_lstm_attention_train_step_parity(tr, kind):
     assert bool(torch.isfinite(got[kk]).all()), kk
     if not (kind == "max_pooling" and kk == att + "/biases"):
       assert float((got[kk] - sd[kk]).abs().max()) > 0, kk
+
+
+def test_l2norm_rows_bwd():
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  import yt8m_native as nat
+  g = torch.Generator().manual_seed(41)
+  x = torch.randn(9, 72, generator=g).requires_grad_(True)
+  dy = torch.randn(9, 72, generator=g)
+  y = O.l2_normalize(x, dim=1)
+  gx, = torch.autograd.grad((y * dy).sum(), [x])
+  got = nat.l2norm_rows_bwd(x.detach().to(DEV), dy.to(DEV))
+  assert float((got.cpu() - gx).abs().max()) < 1e-5 * float(gx.abs().max())
+
+
+def test_deep_combine_chain_train_step_parity(tr):
+  """DeepCombineChainModel (wh/all_video_models/deep_combine_chain_model.py:24-49) without --multitask: 2 stacked MoE
+  sub-predictions -> projection -> ReLU -> L2-normalise -> concat, main MoE; every gradient against autograd over the oracle."""
+  g = torch.Generator().manual_seed(96)
+  b, d, v, mix, layers, r = 10, 128, 300, 2, 2, 64
+  x, y, _ = _data(b, d, v, 40)
+  sd = {}
+  for i in range(layers + 1):
+    sc = "-prediction-%d" % i if i < layers else "--main"
+    din = d + i * r
+    sd["gates%s/weights" % sc] = synth.xavier((din, v * (mix + 1)), g, 6.0)
+    sd["experts%s/weights" % sc] = synth.xavier((din, v * mix), g, 6.0)
+    sd["experts%s/biases" % sc] = 0.1 * torch.randn(v * mix, generator=g)
+  for i in range(layers):
+    sd["relu-%d/weights" % i] = synth.xavier((v, r), g, 4.0)
+    sd["relu-%d/biases" % i] = 0.1 * torch.randn(r, generator=g)
+  t_ = tr.DeepCombineChainTrainer(d, vocab=v, mixtures=mix, layers=layers, relu_cells=r)
+  t_.import_state({k: w.to(DEV) for k, w in sd.items()})
+  t_.keep_grads = True
+  p0 = t_.step(x.to(DEV), y.to(DEV))
+  grad0 = t_.grads_tf_layout(t_.last_grad)
+  loss0 = float(t_.last["label_loss_local"])
+  params = {kk: w.clone().requires_grad_(True) for kk, w in sd.items()}
+  lyr = [{"gate_w": params["gates-prediction-%d/weights" % i], "expert_w": params["experts-prediction-%d/weights" % i],
+          "expert_b": params["experts-prediction-%d/biases" % i], "relu_w": params["relu-%d/weights" % i],
+          "relu_b": params["relu-%d/biases" % i]} for i in range(layers)]
+  main = {"gate_w": params["gates--main/weights"], "expert_w": params["experts--main/weights"], "expert_b": params["experts--main/biases"]}
+  pw, _ = O.deep_combine_chain_model(x, lyr, main, v, mix)
+  lw = O.cross_entropy_loss(pw, y)
+  gw = dict(zip(params, torch.autograd.grad(lw, list(params.values()))))
+  assert float((p0.cpu() - pw.detach()).abs().max()) < 1e-3
+  assert abs(loss0 - float(lw.detach())) / float(lw.detach()) < 1e-3
+  for kk in gw:
+    assert float(gw[kk].norm()) > 0, kk
+    err = _rel_l2(grad0[kk], gw[kk])
+    assert err < 2e-2, (kk, err)
+  for _ in range(2):
+    t_.step(x.to(DEV), y.to(DEV))
+  torch.cuda.synchronize()
+  got = t_.export_state()
+  for kk in sd:
+    assert bool(torch.isfinite(got[kk]).all()), kk
+    assert float((got[kk] - sd[kk]).abs().max()) > 0, kk

@@ -329,6 +329,30 @@ __global__ void group_max_bwd_kernel(const float* __restrict__ in, const float* 
   }
 }
 
+// backward of y = x * rsqrt(max(sum x^2, 1e-12)) (tf.nn.l2_normalize): one warp per row
+__global__ void l2norm_rows_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy, long long rows, int dim,
+                                       float* __restrict__ dx) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const float* xr = x + r * dim;
+    const float* dr = dy + r * dim;
+    float ss = 0.0f, dot = 0.0f;
+    for (int c = lane; c < dim; c += 32) {
+      const float v = xr[c];
+      ss += v * v;
+      dot += v * dr[c];
+    }
+    ss = warp_sum(ss);
+    dot = warp_sum(dot);
+    const float inv = rsqrtf(fmaxf(ss, 1e-12f));
+    // d/dx [x * inv(ss)]: inv is constant below the epsilon clamp
+    const float k = ss > 1e-12f ? dot * inv * inv * inv : 0.0f;
+    for (int c = lane; c < dim; c += 32) dx[r * dim + c] = dr[c] * inv - xr[c] * k;
+  }
+}
+
 __global__ void add_inplace_kernel(float* __restrict__ y, const float* __restrict__ x, long long n) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
        i += static_cast<long long>(gridDim.x) * blockDim.x)
@@ -348,6 +372,16 @@ int yt8m_group_max_rows_bwd(const float* in, const float* dout, long long groups
   const int blocks = static_cast<int>(std::min<long long>((total + 255) / 256, kNumSms * 8));
   group_max_bwd_kernel<<<blocks, 256, 0, stream>>>(in, dout, groups, heads, cols, din);
   return check_launch("group_max_bwd_kernel");
+}
+
+int yt8m_l2norm_rows_bwd(const float* x, const float* dy, long long rows, int dim, float* dx, yt8m_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  YT8M_REQUIRE(x && dy && dx, YT8M_E_BADPTR, "yt8m_l2norm_rows_bwd: null pointer");
+  YT8M_REQUIRE(rows >= 0 && dim > 0, YT8M_E_BADSHAPE, "yt8m_l2norm_rows_bwd: bad shape");
+  if (rows == 0) return YT8M_OK;
+  const int blocks = static_cast<int>(std::min<long long>((rows + 7) / 8, kNumSms * 16));
+  l2norm_rows_bwd_kernel<<<blocks, 256, 0, stream>>>(x, dy, rows, dim, dx);
+  return check_launch("l2norm_rows_bwd_kernel");
 }
 
 int yt8m_add_inplace(float* y, const float* x, long long n, yt8m_stream_t stream_) {

@@ -120,6 +120,11 @@ class Trainer(object):
         raise NotImplementedError("train.py --model=ChainMoeModel: --multitask (a separate loss on the support predictions) is not built")
       return yt8m_trainer.ChainMoeTrainer(in_dim, vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures,
                                           num_supports=FLAGS.num_supports)
+    if model_cls is video_level_models.DeepCombineChainModel:
+      if FLAGS.multitask or FLAGS.deep_chain_relu_type != "relu":
+        raise NotImplementedError("train.py --model=DeepCombineChainModel: built without --multitask and with --deep_chain_relu_type=relu")
+      return yt8m_trainer.DeepCombineChainTrainer(in_dim, vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures,
+                                                  layers=FLAGS.deep_chain_layers, relu_cells=FLAGS.deep_chain_relu_cells)
     if model_cls is video_level_models.LogisticModel:
       kind = "logistic"
     elif model_cls is video_level_models.MoeModel:
@@ -128,7 +133,7 @@ class Trainer(object):
       raise NotImplementedError(
           "train.py: the CUDA training step is built for LogisticModel, MoeModel, NetVLADModel, GatedNetVLADModel, "
           "LstmModel, LstmMemoryModel, LstmAttentionMaxPoolingModel, LstmMultiAttentionModel, AttentionModel (+ MoeExtendModel) "
-          "and ChainMoeModel this round; "
+          "ChainMoeModel and DeepCombineChainModel this round; "
           "%s runs forward-only (eval.py / inference.py)" % self.model_name)
     return yt8m_trainer.HeadTrainer(kind, in_dim, self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures)
 

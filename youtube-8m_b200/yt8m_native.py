@@ -59,6 +59,7 @@ _SIGS = {
     "yt8m_context_gate_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_ll, c_void_p]),
     "yt8m_add_inplace": (c_int, [c_void_p, c_void_p, c_ll, c_void_p]),
+    "yt8m_l2norm_rows_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "yt8m_group_max_rows_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p]),
     "yt8m_attn_pool_fwd": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
@@ -426,6 +427,14 @@ def group_max_rows_bwd(x, dout, heads):
   rows, cols = x.shape
   dx = _f32((rows, cols), x.device)
   _call("yt8m_group_max_rows_bwd", _p(x.contiguous()), _p(dout.contiguous()), rows // heads, heads, cols, _p(dx), _stream())
+  return dx
+
+
+def l2norm_rows_bwd(x, dy):
+  """Backward of l2norm_rows on fp32 [rows, dim]: x = the un-normalised input, dy = dL/dy -> dL/dx."""
+  rows, dim = x.shape
+  dx = _f32((rows, dim), x.device)
+  _call("yt8m_l2norm_rows_bwd", _p(x.contiguous()), _p(dy.contiguous()), rows, dim, _p(dx), _stream())
   return dx
 
 

@@ -812,3 +812,132 @@ class LstmAttentionTrainer(object):
     self.head.global_step = self.global_step
     self.last = {"label_loss_local": loss, "lr": lr}
     return p
+
+
+class DeepCombineChainTrainer(object):
+  """The training step for DeepCombineChainModel (wh/all_video_models/deep_combine_chain_model.py:9-85) without
+  --multitask: `layers` stacked MoE sub-predictions, each projected (V -> relu_cells), ReLU, L2-normalised and
+  concatenated to the next MoE's input; the main MoE on the last concatenation carries the label loss.  Backward walks
+  the chain in reverse: the gradient of a concatenation splits into the part that continues down the chain and the part
+  that goes through L2-normalise (yt8m_l2norm_rows_bwd), ReLU, the projection (wgrad + dgrad) and the layer's MoE."""
+
+  def __init__(self, in_dim, vocab=4716, mixtures=2, layers=3, relu_cells=256, l2_penalty=1e-8, device=None, group=None):
+    self.d, self.v, self.m, self.nl, self.r, self.l2 = in_dim, vocab, mixtures, layers, relu_cells, l2_penalty
+    self.dev = device or torch.device("cuda", torch.cuda.current_device())
+    self.group = group
+    self.world = yt8m_dp.world_size(group)
+    self.vpad = nat.pad8(vocab)
+    dims = [in_dim + i * relu_cells for i in range(layers + 1)]               # input width of layer i (the last: the main head)
+    sizes = []
+    for i in range(layers):
+      sizes += [("moe%d" % i, HeadTrainer.flat_size("moe", dims[i], vocab, mixtures)), ("wr%d" % i, relu_cells * self.vpad),
+                ("br%d" % i, relu_cells)]
+    sizes.append(("main", HeadTrainer.flat_size("moe", dims[layers], vocab, mixtures)))
+    total = sum(n for _, n in sizes)
+    self.param = torch.zeros(total, dtype=torch.float32, device=self.dev)
+    self.grad = torch.zeros_like(self.param)
+    self.adam_m = torch.zeros_like(self.param)
+    self.adam_v = torch.zeros_like(self.param)
+    self._off, off = {}, 0
+    for name, n in sizes:
+      self._off[name] = (off, off + n)
+      off += n
+    bufs = (self.param, self.grad, self.adam_m, self.adam_v)
+    self.heads, self.p, self.g, self.am, self.av, self.wr_bf16 = [], {}, {}, {}, {}, []
+    for i in range(layers + 1):
+      a, b = self._off["moe%d" % i if i < layers else "main"]
+      self.heads.append(HeadTrainer("moe", dims[i], vocab, mixtures, l2_penalty, self.dev, group, storage=tuple(t[a:b] for t in bufs)))
+    for i in range(layers):
+      for name, shp in (("wr%d" % i, (relu_cells, self.vpad)), ("br%d" % i, (relu_cells, 1))):   # Wr^T [relu_cells, V] (K-major)
+        a, b = self._off[name]
+        self.p[name], self.g[name] = self.param[a:b].view(shp), self.grad[a:b].view(shp)
+        self.am[name], self.av[name] = self.adam_m[a:b].view(shp), self.adam_v[a:b].view(shp)
+      self.wr_bf16.append(torch.zeros((relu_cells, self.vpad), dtype=torch.bfloat16, device=self.dev))
+    self.dims = dims
+    self.global_step = 0
+    self.keep_grads = False
+    self.last = {}
+
+  # ---- TF names / layouts ----------------------------------------------------------------------------
+  @staticmethod
+  def _scope(i, layers):
+    return "-prediction-%d" % i if i < layers else "--main"
+
+  def import_state(self, sd):
+    for i, head in enumerate(self.heads):
+      sc = self._scope(i, self.nl)
+      head.import_state({"gates/weights": sd["gates%s/weights" % sc], "experts/weights": sd["experts%s/weights" % sc],
+                         "experts/biases": sd["experts%s/biases" % sc]})
+    for i in range(self.nl):
+      self.p["wr%d" % i].zero_()
+      self.p["wr%d" % i][:, :self.v].copy_(sd["relu-%d/weights" % i].t().to(self.dev))
+      self.p["br%d" % i].copy_(sd["relu-%d/biases" % i].view(-1, 1).to(self.dev))
+      self.wr_bf16[i].copy_(self.p["wr%d" % i])
+
+  def _tf_layout(self, flat):
+    out = {}
+    for i, head in enumerate(self.heads):
+      sc = self._scope(i, self.nl)
+      a, b = self._off["moe%d" % i if i < self.nl else "main"]
+      for k, v in head.grads_tf_layout(flat[a:b]).items():
+        name, leaf = k.split("/")
+        out["%s%s/%s" % (name, sc, leaf)] = v
+    for i in range(self.nl):
+      a, b = self._off["wr%d" % i]
+      out["relu-%d/weights" % i] = flat[a:b].view(self.r, self.vpad)[:, :self.v].t().contiguous().cpu()
+      a, b = self._off["br%d" % i]
+      out["relu-%d/biases" % i] = flat[a:b].cpu().clone()
+    return out
+
+  def export_state(self):
+    return self._tf_layout(self.param)
+
+  def grads_tf_layout(self, flat):
+    return self._tf_layout(flat)
+
+  # ---- step ------------------------------------------------------------------------------------------
+  def step(self, x, labels, base_lr=0.01, lr_decay=0.95, lr_decay_examples=4000000, clip_gradient_norm=1.0,
+           regularization_penalty=1.0, global_batch=None):
+    b = x.shape[0]
+    global_batch = global_batch or b * self.world
+    cur = x.float()[:, :self.d].contiguous()
+    saved = []
+    for i in range(self.nl):
+      sub, (s_hi, s_lo) = self.heads[i].forward(cur)                                   # [B, V] sub-prediction
+      p_hi, p_lo = nat.split_bf16(sub[:, :self.v])
+      z = nat.linear(p_hi, self.wr_bf16[i], a_lo=p_lo, n=self.r, k=self.vpad, shift=self.p["br%d" % i].view(-1), act="relu")["f32"]
+      _, n32 = nat.l2norm_rows(z.contiguous(), want_f32=True)
+      saved.append((sub, s_hi, s_lo, p_hi, z))
+      cur = torch.cat([cur, n32], dim=1)                                               # tf.concat (device copy)
+    p, (m_hi, m_lo) = self.heads[self.nl].forward(cur)
+    loss, dcur = self.heads[self.nl].backward(p, m_hi, m_lo, labels, global_batch, want_dx=True)
+    for i in range(self.nl - 1, -1, -1):
+      sub, s_hi, s_lo, p_hi, z = saved[i]
+      dn = dcur[:, self.dims[i]:self.dims[i] + self.r].contiguous()                    # the columns that came from this layer
+      dz = nat.l2norm_rows_bwd(z, dn)
+      dzr_hi, dzr_lo = nat.act_bwd(dz, z, act="relu")
+      nat.wgrad(dzr_hi, dzr_lo, p_hi, self.r, self.v, out=self.g["wr%d" % i])          # dWr^T [relu_cells, V]
+      nat.colsum_bf16(dzr_hi, dzr_lo, self.r, out=self.g["br%d" % i].view(-1))
+      wr_t = nat.pack_transpose(self.p["wr%d" % i])                                    # bf16 [V(pad), relu_cells]: dgrad operand
+      dsub = nat.linear(dzr_hi, wr_t, a_lo=dzr_lo, n=self.v, k=self.r)["f32"]          # dL/d sub-prediction [B, V]
+      dx_i = self.heads[i].backward_from_dp(dsub.contiguous(), sub, s_hi, s_lo, want_dx=(i > 0))
+      if i > 0:
+        dnext = dcur[:, :self.dims[i]].contiguous()                                    # what continues down the chain ...
+        nat.add_inplace(dnext, dx_i[:, :self.dims[i]].contiguous())                    # ... + the path through this layer's MoE
+        dcur = dnext
+    yt8m_dp.all_reduce_sum_(self.grad, self.group)                                     # the ONE collective of the step
+    if self.keep_grads:
+      self.last_grad = self.grad.clone()
+    lr = exponential_decay(base_lr, self.global_step, global_batch, lr_decay_examples, lr_decay)
+    lr_t = adam_lr_t(lr, self.global_step + 1)
+    for i in range(self.nl):
+      sums = nat.grad_reg_sumsq(self.g["wr%d" % i], self.p["wr%d" % i], self.l2 * regularization_penalty)
+      nat.clip_adam_step(self.p["wr%d" % i], self.g["wr%d" % i], self.am["wr%d" % i], self.av["wr%d" % i], sums, clip_gradient_norm,
+                         lr_t, param_bf16=self.wr_bf16[i])
+      sums = nat.grad_reg_sumsq(self.g["br%d" % i], self.p["br%d" % i], 0.0)
+      nat.clip_adam_step(self.p["br%d" % i], self.g["br%d" % i], self.am["br%d" % i], self.av["br%d" % i], sums, clip_gradient_norm, lr_t)
+    for head in self.heads:
+      head.apply(lr_t, clip_gradient_norm, regularization_penalty)
+    self.global_step += 1
+    self.last = {"label_loss_local": loss, "lr": lr}
+    return p
