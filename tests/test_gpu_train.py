@@ -636,3 +636,44 @@ def test_deep_combine_chain_train_step_parity(tr):
   for kk in sd:
     assert bool(torch.isfinite(got[kk]).all()), kk
     assert float((got[kk] - sd[kk]).abs().max()) > 0, kk
+
+
+def test_dbof_train_step_parity(tr):
+  """DbofModel in its bias form (--dbof_add_batch_norm=False, max pooling) + MoE: pinned frame sample, every gradient of one
+  step against autograd over the oracle (wh/all_frame_models/dbof_model.py:62-123)."""
+  g = torch.Generator().manual_seed(97)
+  b, t, d, c, h, n, v, mix = 6, 50, 128, 512, 256, 10, 300, 2
+  x, nf, _ = synth.model_input(b, t, d, seed=41, min_frames=12)
+  y = synth.labels(b, v, seed=41, per_video=3.4)
+  fidx = (torch.rand(b, n, generator=g) * nf.float().unsqueeze(1)).to(torch.int64)
+  sd = {"cluster_weights": synth.normal((d, c), g, 3.0), "cluster_biases": 0.1 * torch.randn(c, generator=g),
+        "hidden1_weights": synth.normal((c, h), g, 1.5 / math.sqrt(c)), "hidden1_biases": 0.1 * torch.randn(h, generator=g),
+        "gates/weights": synth.xavier((h, v * (mix + 1)), g, 4.0), "experts/weights": synth.xavier((h, v * mix), g, 4.0),
+        "experts/biases": 0.1 * torch.randn(v * mix, generator=g)}
+  t_ = tr.DbofTrainer(d, cluster_size=c, hidden=h, iterations=n, vocab=v, mixtures=mix)
+  t_.import_state(sd)
+  t_.keep_grads = True
+  xd, nfd, yd = x.to(DEV).to(torch.bfloat16), nf.to(DEV), y.to(DEV)
+  p0 = t_.step(xd, nfd, yd, frame_index=fidx)
+  grad0 = t_.grads_tf_layout(t_.last_grad)
+  loss0 = float(t_.last["label_loss_local"])
+  params = {kk: w.clone().requires_grad_(True) for kk, w in sd.items()}
+  pp = {"cluster_w": params["cluster_weights"], "cluster_b": params["cluster_biases"], "hidden_w": params["hidden1_weights"],
+        "hidden_b": params["hidden1_biases"]}
+  hid = O.dbof_pool(x, fidx, pp, add_batch_norm=False, pooling="max")
+  pw = O.moe_model(hid, params["gates/weights"], params["experts/weights"], params["experts/biases"], v, mix)
+  lw = O.cross_entropy_loss(pw, y)
+  gw = dict(zip(params, torch.autograd.grad(lw, list(params.values()))))
+  assert float((p0.cpu() - pw.detach()).abs().max()) < 1e-3
+  assert abs(loss0 - float(lw.detach())) / float(lw.detach()) < 1e-3
+  for kk in gw:
+    assert float(gw[kk].norm()) > 0, kk
+    err = _rel_l2(grad0[kk], gw[kk])
+    assert err < 2e-2, (kk, err)
+  for _ in range(2):
+    t_.step(xd, nfd, yd, frame_index=fidx)
+  torch.cuda.synchronize()
+  got = t_.export_state()
+  for kk in sd:
+    assert bool(torch.isfinite(got[kk]).all()), kk
+    assert float((got[kk] - sd[kk]).abs().max()) > 0, kk

@@ -109,6 +109,14 @@ class Trainer(object):
                                                heads=FLAGS.attention_size if multi else FLAGS.lstm_attentions,
                                                vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures,
                                                kind="multi" if multi else "max_pooling")
+    if model_cls is frame_level_models.DbofModel:
+      if FLAGS.dbof_add_batch_norm or FLAGS.dbof_pooling_method != "max" or FLAGS.video_level_classifier_model != "MoeModel":
+        raise NotImplementedError("train.py --model=DbofModel: the CUDA training step is built for --dbof_add_batch_norm=False, "
+                                  "--dbof_pooling_method=max and --video_level_classifier_model=MoeModel")
+      t = yt8m_trainer.DbofTrainer(in_dim, cluster_size=FLAGS.dbof_cluster_size, hidden=FLAGS.dbof_hidden_size,
+                                   iterations=FLAGS.iterations, vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures)
+      t.sample_random_frames = FLAGS.sample_random_frames
+      return t
     if model_cls is frame_level_models.AttentionModel:
       if FLAGS.video_level_classifier_model != "MoeExtendModel":
         raise NotImplementedError("train.py --model=AttentionModel: the CUDA training step is built for "
@@ -133,7 +141,7 @@ class Trainer(object):
       raise NotImplementedError(
           "train.py: the CUDA training step is built for LogisticModel, MoeModel, NetVLADModel, GatedNetVLADModel, "
           "LstmModel, LstmMemoryModel, LstmAttentionMaxPoolingModel, LstmMultiAttentionModel, AttentionModel (+ MoeExtendModel) "
-          "ChainMoeModel and DeepCombineChainModel this round; "
+          "DbofModel (bias form), ChainMoeModel and DeepCombineChainModel this round; "
           "%s runs forward-only (eval.py / inference.py)" % self.model_name)
     return yt8m_trainer.HeadTrainer(kind, in_dim, self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures)
 

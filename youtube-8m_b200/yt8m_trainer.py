@@ -941,3 +941,115 @@ class DeepCombineChainTrainer(object):
     self.global_step += 1
     self.last = {"label_loss_local": loss, "lr": lr}
     return p
+
+
+class DbofTrainer(object):
+  """The training step for DbofModel (wh/all_frame_models/dbof_model.py:62-123) in its bias form
+  (--dbof_add_batch_norm=False, --dbof_pooling_method=max) + MoeModel: sample `iterations` frames per video, cluster
+  projection D -> cluster_size + bias + ReLU6, max over the sampled frames, hidden FC + bias + ReLU6, MoE head; the
+  backward routes the pooled gradient to the arg-max frame of every (video, cluster) (yt8m_group_max_rows_bwd) and
+  computes the cluster-weight gradient as one MN-major GEMM over all B*iterations sampled rows.
+  The batch-norm form needs batch statistics and their backward, which are not built."""
+
+  def __init__(self, feature_dim, cluster_size=8192, hidden=1024, iterations=30, vocab=4716, mixtures=2, l2_penalty=1e-8,
+               device=None, group=None):
+    self.d, self.c, self.h, self.n, self.v, self.m = feature_dim, cluster_size, hidden, iterations, vocab, mixtures
+    self.dev = device or torch.device("cuda", torch.cuda.current_device())
+    self.group = group
+    self.world = yt8m_dp.world_size(group)
+    sizes = [("cw", cluster_size * feature_dim), ("cb", cluster_size), ("wh", hidden * cluster_size), ("bh", hidden),
+             ("head", HeadTrainer.flat_size("moe", hidden, vocab, mixtures))]
+    total = sum(n for _, n in sizes)
+    self.param = torch.zeros(total, dtype=torch.float32, device=self.dev)
+    self.grad = torch.zeros_like(self.param)
+    self.adam_m = torch.zeros_like(self.param)
+    self.adam_v = torch.zeros_like(self.param)
+    self._off, off = {}, 0
+    for name, n in sizes:
+      self._off[name] = (off, off + n)
+      off += n
+    shapes = {"cw": (cluster_size, feature_dim), "cb": (cluster_size, 1), "wh": (hidden, cluster_size), "bh": (hidden, 1)}
+    self.p, self.g, self.am, self.av = {}, {}, {}, {}
+    for name, shp in shapes.items():
+      a, b = self._off[name]
+      self.p[name], self.g[name] = self.param[a:b].view(shp), self.grad[a:b].view(shp)
+      self.am[name], self.av[name] = self.adam_m[a:b].view(shp), self.adam_v[a:b].view(shp)
+    a, b = self._off["head"]
+    self.head = HeadTrainer("moe", hidden, vocab, mixtures, l2_penalty, self.dev, group,
+                            storage=(self.param[a:b], self.grad[a:b], self.adam_m[a:b], self.adam_v[a:b]))
+    self.cw_bf16 = torch.zeros((cluster_size, feature_dim), dtype=torch.bfloat16, device=self.dev)
+    self.wh_bf16 = torch.zeros((hidden, cluster_size), dtype=torch.bfloat16, device=self.dev)
+    self.sample_random_frames = True
+    self.global_step = 0
+    self.keep_grads = False
+    self.last = {}
+
+  def import_state(self, sd):
+    dev = self.dev
+    self.p["cw"].copy_(sd["cluster_weights"].t().to(dev))
+    self.p["cb"].copy_(sd["cluster_biases"].view(-1, 1).to(dev))
+    self.p["wh"].copy_(sd["hidden1_weights"].t().to(dev))
+    self.p["bh"].copy_(sd["hidden1_biases"].view(-1, 1).to(dev))
+    self.cw_bf16.copy_(self.p["cw"])
+    self.wh_bf16.copy_(self.p["wh"])
+    self.head.import_state({k: sd[k] for k in ("gates/weights", "experts/weights", "experts/biases")})
+
+  def _tf_layout(self, flat):
+    v = {}
+    for name in ("cw", "cb", "wh", "bh"):
+      a, b = self._off[name]
+      v[name] = flat[a:b].view(self.p[name].shape)
+    out = {"cluster_weights": v["cw"].t().contiguous().cpu(), "cluster_biases": v["cb"].reshape(-1).cpu().clone(),
+           "hidden1_weights": v["wh"].t().contiguous().cpu(), "hidden1_biases": v["bh"].reshape(-1).cpu().clone()}
+    a, b = self._off["head"]
+    out.update(self.head.grads_tf_layout(flat[a:b]))
+    return out
+
+  def export_state(self):
+    return self._tf_layout(self.param)
+
+  def grads_tf_layout(self, flat):
+    return self._tf_layout(flat)
+
+  def step(self, x, num_frames, labels, base_lr=0.01, lr_decay=0.95, lr_decay_examples=4000000, clip_gradient_norm=1.0,
+           regularization_penalty=1.0, global_batch=None, frame_index=None):
+    """frame_index ([B, iterations] int64) pins the sampled frames (tests); by default they are drawn like
+    wh/model_utils.py:56-74."""
+    import frame_level_models
+    b, t, d = x.shape
+    n = self.n
+    global_batch = global_batch or b * self.world
+    if frame_index is None:
+      frame_index = frame_level_models.sample_frames(num_frames, n, self.sample_random_frames)
+    rows = x[torch.arange(b, device=x.device).unsqueeze(1), frame_index.to(x.device)].reshape(b * n, d).contiguous()   # gather_nd
+    act = nat.linear(rows, self.cw_bf16, n=self.c, k=d, shift=self.p["cb"].view(-1), act="relu6")["f32"]               # [B*n, C]
+    pooled = nat.group_max_rows(act, n)                                                                                # [B, C]
+    q_hi, q_lo = nat.split_bf16(pooled)
+    hid = nat.linear(q_hi, self.wh_bf16, a_lo=q_lo, n=self.h, k=self.c, shift=self.p["bh"].view(-1), act="relu6", out_f32=True,
+                     out_bf16=True, out_lo=True)
+    p = nat.moe_fwd(hid["hi"], self.head.w_bf16, self.head.b, self.v, self.m, x_lo=hid["lo"], d=self.h)
+    # ---- backward
+    loss, dhid = self.head.backward(p, hid["hi"], hid["lo"], labels, global_batch, want_dx=True)
+    dpre_hi, dpre_lo = nat.act_bwd(dhid[:, :self.h].contiguous(), hid["f32"], act="relu6")
+    nat.wgrad(dpre_hi, dpre_lo, q_hi, self.h, self.c, out=self.g["wh"])                  # d hidden1_weights^T [H, C]
+    nat.colsum_bf16(dpre_hi, dpre_lo, self.h, out=self.g["bh"].view(-1))
+    wh_t = nat.pack_transpose(self.p["wh"])                                              # bf16 [C, H]: the dgrad operand
+    dpooled = nat.linear(dpre_hi, wh_t, a_lo=dpre_lo, n=self.c, k=self.h)["f32"]
+    del wh_t
+    dact = nat.group_max_rows_bwd(act, dpooled.contiguous(), n)                          # to the arg-max frame of every (video, cluster)
+    dz_hi, dz_lo = nat.act_bwd(dact, act, act="relu6")
+    nat.wgrad(dz_hi, dz_lo, rows, self.c, d, out=self.g["cw"])                           # d cluster_weights^T [C, D]
+    nat.colsum_bf16(dz_hi, dz_lo, self.c, out=self.g["cb"].view(-1))
+    yt8m_dp.all_reduce_sum_(self.grad, self.group)                                       # the ONE collective of the step
+    if self.keep_grads:
+      self.last_grad = self.grad.clone()
+    lr = exponential_decay(base_lr, self.global_step, global_batch, lr_decay_examples, lr_decay)
+    lr_t = adam_lr_t(lr, self.global_step + 1)
+    for name, bf in (("cw", self.cw_bf16), ("cb", None), ("wh", self.wh_bf16), ("bh", None)):
+      sums = nat.grad_reg_sumsq(self.g[name], self.p[name], 0.0)
+      nat.clip_adam_step(self.p[name], self.g[name], self.am[name], self.av[name], sums, clip_gradient_norm, lr_t, param_bf16=bf)
+    self.head.apply(lr_t, clip_gradient_norm, regularization_penalty)
+    self.global_step += 1
+    self.head.global_step = self.global_step
+    self.last = {"label_loss_local": loss, "lr": lr}
+    return p
