@@ -60,6 +60,21 @@ def test_train_eval_inference_video_level(tmp_path):
   assert vid == "vid000" and len(toks) == 10
   confs = [float(c) for c in toks[1::2]]
   assert confs == sorted(confs, reverse=True) and all(0 <= c <= 1 for c in confs)
+  # pre-ensemble prediction records (wh/inference-pre-ensemble.py:291-308): full vectors, file_size examples per file,
+  # batches that do not divide file_size; the top-5 of the CSV are the 5 largest entries of the stored vector
+  pdir = str(tmp_path / "pre")
+  _run("inference-pre-ensemble.py", "--input_data_pattern=" + data, "--train_dir=" + train_dir, "--output_dir=" + pdir,
+       "--batch_size=50", "--file_size=40", *common)
+  files = sorted(os.listdir(pdir))
+  assert files == ["predictions-0000.tfrecord", "predictions-0001.tfrecord", "predictions-0002.tfrecord"]
+  counts = [len(list(readers.tfrecord_iterator(os.path.join(pdir, f), True))) for f in files]
+  assert counts == [40, 40, 16]
+  ex = readers.parse_example(next(readers.tfrecord_iterator(os.path.join(pdir, files[0]), True)))
+  assert ex["video_id"][1][0] == b"vid000" and len(ex["predictions"][1]) == V
+  vec = np.asarray(ex["predictions"][1], dtype=np.float32)
+  top5 = np.argsort(-vec)[:5]
+  assert [int(c) for c in toks[0::2]] == top5.tolist()
+  assert np.allclose(vec[top5], confs, atol=1e-6)
 
 
 def test_eval_frame_level_netvlad(tmp_path):

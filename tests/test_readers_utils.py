@@ -120,3 +120,30 @@ def test_packed_frames_equal_the_padded_batch(tmp_path):
   # synthetic batches: dropping the padding and restoring it is the identity
   again = readers.PackedFrames.from_padded(padded, nf_a)
   assert torch.equal(again.data, packed.data) and torch.equal(again.offsets, packed.offsets)
+
+
+def test_pre_ensemble_prediction_records(tmp_path):
+  """The wire format of wh/inference-pre-ensemble.py:291-308: predictions-%04d.tfrecord files whose Examples hold video_id,
+  the indices of the positive labels and the full float prediction vector -- written with our codecs, read back."""
+  import importlib.util
+  spec = importlib.util.spec_from_file_location(
+      "inference_pre_ensemble", os.path.join(os.path.dirname(readers.__file__), "inference-pre-ensemble.py"))
+  mod = importlib.util.module_from_spec(spec)
+  try:
+    spec.loader.exec_module(mod)
+  except ImportError as e:                      # the module imports the CUDA binding (built library required)
+    pytest.skip(str(e))
+  rs = np.random.RandomState(9)
+  n, v = 5, 12
+  ids = [b"vid%d" % i for i in range(n)]
+  labels = rs.rand(n, v) < 0.3
+  preds = rs.rand(n, v).astype(np.float32)
+  path = mod.write_to_record(str(tmp_path), ids, labels, preds, 3, n)
+  assert path.endswith("predictions-0003.tfrecord")
+  recs = list(readers.tfrecord_iterator(path, True))
+  assert len(recs) == n
+  for i, rec in enumerate(recs):
+    ex = readers.parse_example(rec)
+    assert ex["video_id"][1][0] == ids[i]
+    assert list(ex["labels"][1]) == list(np.nonzero(labels[i])[0])
+    assert np.array_equal(np.asarray(ex["predictions"][1], dtype=np.float32), preds[i])
