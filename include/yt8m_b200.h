@@ -88,7 +88,8 @@ int yt8m_l2norm_rows_bwd(const float* x, const float* dy, long long rows, int di
 /* ---- dense layer (slim.fully_connected / tf.matmul + bias / folded batch-norm + activation) ----
  * out[M, N] = act((A[M, K] . W[N, K]^T) * col_scale[N] + col_shift[N]);  A = a_hi (+ a_lo).
  * Replaces e.g. wh/all_video_models/logistic_model.py:23-25, wh/all_frame_models/dbof_model.py:76-115,
- * wh/all_video_models/deep_combine_chain_model.py:31-36.  K, lda, ldw must be multiples of 8.
+ * wh/all_video_models/deep_combine_chain_model.py:31-36.  lda and ldw must be multiples of 8 elements (16-byte TMA
+ * strides) and >= K; K itself is free (out-of-range columns are zero-filled by the tensor map).
  * Outputs (any subset non-NULL): fp32, bf16 hi, bf16 lo, all with row stride ld_out.
  * workspace: optional split-K scratch (>= yt8m_linear_workspace_bytes) -- used when the tile grid
  * alone cannot fill the GPU. */
@@ -183,6 +184,10 @@ int yt8m_attn_pool_bwd(const float* logits, long long ld_logits, const yt8m_bf16
  * output (ld_out = D*K) the residual runs on the tensor cores and the descriptor is written through TMA.
  * out: [B, D*K] (D-major, K-minor).  K in {32, 64, 128}, D % 128 == 0, T <= 384.
  * out_fmt = YT8M_FMT_F16: out_hi receives fp16 (out_lo must be NULL).
+ * With K = 64, a single 16-bit output (no out_lo, no out_f32), a dense output (ld_out = D*K), D <= 1152 and T > 64 the
+ * ONE-PASS cluster kernel runs (csrc/yt8m_netvlad_v4.cu): every frame is read from HBM once, only the
+ * ceil(num_frames[b] / 32) tiles that hold real frames are streamed, and videos are scheduled longest first; frame rows
+ * inside the last streamed tile but at or beyond num_frames[b] must be finite (the reader's zero padding).
  * out_hi (+ out_lo) double as the stash of the un-normalised descriptor, which the final rescale reads back: out_f32
  * therefore carries the precision of the stash (bf16 hi alone: 8 bits; hi + lo: ~16 bits; fp16: 11 bits).
  * stats (nullable): fp32 [B, 2K+1] = {a_sum[K], ||V[:,k]||^2 [K], ||U||_F^2} saved for yt8m_netvlad_bwd_norm. */
