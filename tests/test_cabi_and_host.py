@@ -95,3 +95,29 @@ def test_sample_frames_host_logic():
   seq = flm.sample_frames(nf, 30, False, generator=g)
   assert bool((seq[0, 1:] - seq[0, :-1] == 1).all())            # a contiguous run when the video is long enough
   assert bool((seq[1] <= 4).all()) and int(seq[2].max()) == 0     # clamped to the last valid frame
+
+
+def test_trainer_layout_helpers_roundtrip():
+  """Host-side layout maps of the trainers (no GPU): TF BasicLSTMCell kernel [in+H, 4H] (columns g*H + u) <-> packed
+  [4H, in+H] (rows 4u + g, the layout of yt8m_lstm_pack_weights); MoE reference columns <-> packed class-major rows."""
+  import torch
+  import yt8m_trainer as tr
+  g = torch.Generator().manual_seed(1)
+  h, k = 8, 5
+  w_tf = torch.randn(k, 4 * h, generator=g)
+  wp = tr._lstm_tf_to_packed(w_tf, h)
+  assert wp.shape == (4 * h, k)
+  for u in (0, 3, 7):
+    for gate in range(4):
+      assert torch.equal(wp[4 * u + gate], w_tf[:, gate * h + u])
+  assert torch.equal(tr._lstm_packed_to_tf(wp, h), w_tf)
+  # MoE: vocab 7, 2 mixtures -> 5 rows per class, 25 classes per 128-row tile
+  gates, experts = tr._moe_row_index(7, 2)
+  assert gates.tolist()[:6] == [0, 1, 2, 5, 6, 7] and experts.tolist()[:4] == [3, 4, 8, 9]
+  assert len(set(gates.tolist()) | set(experts.tolist())) == 7 * 5
+  gates, experts = tr._moe_row_index(30, 2)              # class 25 starts the second tile
+  assert gates.tolist()[25 * 3] == 128 and experts.tolist()[25 * 2] == 131
+  # learning-rate schedule and Adam bias correction (wh/train.py:303-308; TF-1.0 AdamOptimizer)
+  assert tr.exponential_decay(0.01, 0, 1024, 4000000, 0.95) == 0.01
+  assert abs(tr.exponential_decay(0.01, 3907, 1024, 4000000, 0.95) - 0.0095) < 1e-12      # 3907 * 1024 > 4e6: one decay
+  assert abs(tr.adam_lr_t(0.01, 1) - 0.01 * (1 - 0.999) ** 0.5 / (1 - 0.9)) < 1e-15
