@@ -138,6 +138,70 @@ def time_cpu(sample, min_seconds=10.0, max_reps=100000):
           "sample": "%d forwards of %d videos (fp32 torch-CPU restatement of the reference ops, %.1f s)" % (reps, n, dt)}
 
 
+def config1_pair(dev, seconds=3.0):
+  """BASELINE.json configs[0]: LogisticModel on mean-pooled 1152-d features, batch 128, one FULL train.py step including
+  the per-step Hit@1 / PERR / GAP of the log line (wh/train.py:578-591) -- the reference's own CPU-runnable case.  Timed
+  on the host cores with the oracle port (torch autograd + oracle clip / TF-Adam + eval_util on the full predictions) and
+  on the GPU through HeadTrainer (+ the top-32 metrics path of our train.py).  A side measurement: never fatal."""
+  try:
+    import synth
+    import eval_util
+    import yt8m_native as nat
+    import yt8m_trainer
+    from oracle import yt8m_oracle as O
+    b1 = 128
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(b1, D, generator=g)
+    x = synth.bf16r(x * torch.rsqrt((x * x).sum(1, keepdim=True)))
+    y = synth.labels(b1, V, seed=8)
+    w0, b0 = synth.xavier((D, V), g), torch.zeros(V)
+    lv = y.numpy()
+    params = [w0.clone().requires_grad_(True), b0.clone().requires_grad_(True)]
+    m, v = [torch.zeros_like(t) for t in params], [torch.zeros_like(t) for t in params]
+
+    def cpu_step(step):
+      p = O.logistic_model(x, params[0], params[1])
+      loss = O.cross_entropy_loss(p, y) + O.l2_regularizer(params[0], 1e-8)
+      grads = torch.autograd.grad(loss, params)
+      lr = O.exponential_decay(0.01, step, b1, 4000000, 0.95)
+      with torch.no_grad():
+        for i, (t, gr) in enumerate(zip(params, grads)):
+          new, m[i], v[i] = O.adam_step(t, O.clip_by_norm(gr, 1.0), m[i], v[i], step + 1, lr)
+          t.copy_(new)
+      pv = p.detach().numpy()
+      return eval_util.calculate_hit_at_one(pv, lv), eval_util.calculate_precision_at_equal_recall_rate(pv, lv), eval_util.calculate_gap(pv, lv)
+
+    cpu_step(0)
+    n, t0 = 0, time.perf_counter()
+    while n < 3 or time.perf_counter() - t0 < seconds:
+      n += 1
+      cpu_step(n)
+    cpu = b1 * n / (time.perf_counter() - t0)
+
+    tr = yt8m_trainer.HeadTrainer("logistic", D, V, device=dev)
+    tr.import_state({"fully_connected/weights": w0.to(dev), "fully_connected/biases": b0.to(dev)})
+    xd, yd = x.to(dev).to(torch.bfloat16), y.to(dev)
+
+    def gpu_step():
+      p = tr.step(xd, yd)
+      ti, tv = nat.topk_rows(p, 32)
+      return eval_util.step_metrics_from_topk(tv.cpu().numpy(), ti.cpu().numpy(), lv, 20)
+
+    for _ in range(3):
+      gpu_step()
+    torch.cuda.synchronize()
+    k, t0 = 50, time.perf_counter()
+    for _ in range(k):
+      gpu_step()
+    torch.cuda.synchronize()
+    gpu = b1 * k / (time.perf_counter() - t0)
+    return {"workload": "LogisticModel video-level, batch 128, full train step + per-step Hit@1/PERR/GAP (BASELINE configs[0])",
+            "gpu": {"value": gpu, "unit": "videos/s", "steps": k, "timing": "wall clock incl. the host metrics"},
+            "cpu_port": {"value": cpu, "unit": "videos/s", "steps": n, "cores": torch.get_num_threads(), "kind": "port"}}
+  except Exception as e:                                     # side measurement only
+    return {"error": "%s: %s" % (type(e).__name__, e)}
+
+
 def run_reference(args, rank):
   """--impl reference: the reference's own path is TF-1.0 / python2 and cannot run; the arm
   times the oracle port (kind "port") on the host cores, rank 0 only."""
@@ -380,6 +444,7 @@ def main():
   }
   if world == 1 and not args.no_cpu_baseline:
     line["cpu_baseline"] = time_cpu(args.cpu_sample)
+    line["config1_logistic_train"] = config1_pair(dev)
   print(json.dumps(line))
   if world > 1:
     dist.destroy_process_group()
