@@ -146,3 +146,35 @@ def test_chain_models_shapes():
   p, sp = O.deep_combine_chain_model(torch.randn(b, d), layers, mk(din, v), v, m)
   assert p.shape == (b, v) and sp.shape == (b, 2 * v)
   assert float(p.min()) >= 0 and float(p.max()) <= 1
+
+
+def test_lstm_oracle_against_torch_nn_lstm():
+  """Independent cross-check of the BasicLSTMCell / dynamic_rnn restatement (TF-1.0 semantics): torch.nn.LSTM
+  computes the same recurrence with gate order (i, f, g, o) and separate input / hidden matrices.  Mapping: TF kernel
+  [x; h] x [i | j | f | o], forget_bias added to f  ->  torch weight_ih / weight_hh rows [i; f; g = j; o], bias_f += 1.
+  Sequences are cut at num_frames: outputs past the end are zero and the state is the one at the last real frame."""
+  import torch
+  from oracle import yt8m_oracle as O
+  g = torch.Generator().manual_seed(11)
+  b, t, d, h = 3, 7, 5, 4
+  x = torch.randn(b, t, d, generator=g, dtype=torch.float64)
+  nf = torch.tensor([7, 3, 1])
+  w = torch.randn(d + h, 4 * h, generator=g, dtype=torch.float64) * 0.5
+  bias = torch.randn(4 * h, generator=g, dtype=torch.float64) * 0.1
+  outs, states = O.dynamic_rnn_lstm(x, nf, [(w, bias)], forget_bias=1.0)
+  lstm = torch.nn.LSTM(d, h, batch_first=True).double()
+  wi, wj, wf, wo = w.chunk(4, dim=1)
+  bi, bj, bf, bo = bias.chunk(4)
+  with torch.no_grad():
+    tw = torch.cat([wi, wf, wj, wo], dim=1).t()                # torch rows: i, f, g, o
+    lstm.weight_ih_l0.copy_(tw[:, :d])
+    lstm.weight_hh_l0.copy_(tw[:, d:])
+    lstm.bias_ih_l0.copy_(torch.cat([bi, bf + 1.0, bj, bo]))
+    lstm.bias_hh_l0.zero_()
+  for i in range(b):
+    n = int(nf[i])
+    y, (hn, cn) = lstm(x[i:i + 1, :n])
+    assert float((outs[i, :n] - y[0]).abs().max()) < 1e-12
+    assert float(outs[i, n:].abs().max()) == 0.0 if n < t else True
+    c_fin, h_fin = states[0]
+    assert float((c_fin[i] - cn[0, 0]).abs().max()) < 1e-12 and float((h_fin[i] - hn[0, 0]).abs().max()) < 1e-12
