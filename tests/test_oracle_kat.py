@@ -178,3 +178,52 @@ def test_lstm_oracle_against_torch_nn_lstm():
     assert float(outs[i, n:].abs().max()) == 0.0 if n < t else True
     c_fin, h_fin = states[0]
     assert float((c_fin[i] - cn[0, 0]).abs().max()) < 1e-12 and float((h_fin[i] - hn[0, 0]).abs().max()) < 1e-12
+
+
+def test_netvlad_and_attention_oracles_against_explicit_loops():
+  """The vectorised oracle restatements against plain Python loops over the published definitions (small cases):
+  NetVLAD (soft assignment over K, residual against cluster_w2, intra-norm per cluster, flatten D-major / K-minor, L2)
+  and the softmax-over-T attention pooling with mask and renormalisation (lstm_attention_max_pooling_model.py:58-63)."""
+  import numpy as np
+  g = torch.Generator().manual_seed(13)
+  b, t, d, k = 2, 6, 5, 3
+  x = torch.randn(b, t, d, generator=g, dtype=torch.float64)
+  nf = torch.tensor([6, 4])
+  cw = torch.randn(d, k, generator=g, dtype=torch.float64)
+  sc = 1 + 0.1 * torch.randn(k, generator=g, dtype=torch.float64)
+  sh = 0.1 * torch.randn(k, generator=g, dtype=torch.float64)
+  c2 = torch.randn(d, k, generator=g, dtype=torch.float64)
+  got = O.netvlad_pool(x, nf, cw, sc, sh, c2).numpy()
+  xs, cwn, scn, shn, c2n = x.numpy(), cw.numpy(), sc.numpy(), sh.numpy(), c2.numpy()
+  for i in range(b):
+    v = np.zeros((d, k))
+    asum = np.zeros(k)
+    for tt in range(int(nf[i])):
+      logit = np.array([sum(xs[i, tt, dd] * cwn[dd, kk] for dd in range(d)) * scn[kk] + shn[kk] for kk in range(k)])
+      e = np.exp(logit - logit.max())
+      a = e / e.sum()
+      asum += a
+      for dd in range(d):
+        for kk in range(k):
+          v[dd, kk] += a[kk] * xs[i, tt, dd]
+    v -= asum[None, :] * c2n
+    for kk in range(k):
+      v[:, kk] /= max(np.sqrt((v[:, kk] ** 2).sum()), 1e-6)
+    flat = v.reshape(-1)                                   # index d * K + k
+    flat = flat / np.sqrt((flat ** 2).sum())
+    assert np.abs(got[i] - flat).max() < 1e-12
+  # attention: weights = softmax over ALL T, times mask, renormalised; pooled[a] = sum_t w[t, a] * outputs[t]
+  a_heads, hdim = 2, 4
+  outs = torch.randn(b, t, hdim, generator=g, dtype=torch.float64)
+  wa = torch.randn(d + hdim, a_heads, generator=g, dtype=torch.float64)
+  ba = torch.randn(a_heads, generator=g, dtype=torch.float64)
+  pooled = O.attention_softmax_pool(x, outs, nf, wa, ba).numpy()
+  for i in range(b):
+    logits = np.concatenate([xs[i], outs[i].numpy()], axis=1) @ wa.numpy() + ba.numpy()          # [T, A]
+    for a in range(a_heads):
+      e = np.exp(logits[:, a] - logits[:, a].max())
+      w = e / e.sum()
+      w = np.array([w[tt] if tt < int(nf[i]) else 0.0 for tt in range(t)])
+      w = w / w.sum()
+      want = sum(w[tt] * outs[i, tt].numpy() for tt in range(t))
+      assert np.abs(pooled[i, a] - want).max() < 1e-12
