@@ -121,3 +121,39 @@ def test_trainer_layout_helpers_roundtrip():
   assert tr.exponential_decay(0.01, 0, 1024, 4000000, 0.95) == 0.01
   assert abs(tr.exponential_decay(0.01, 3907, 1024, 4000000, 0.95) - 0.0095) < 1e-12      # 3907 * 1024 > 4e6: one decay
   assert abs(tr.adam_lr_t(0.01, 1) - 0.01 * (1 - 0.999) ** 0.5 / (1 - 0.9)) < 1e-15
+
+
+def test_cli_and_model_flags_match_the_reference():
+  """SURVEY.md §8b "CLI flags that must survive": every flags.DEFINE_* of the reference's train.py / eval.py / inference.py /
+  inference-pre-ensemble.py and of its model / loss / transform flag modules (read from the reference SOURCE by
+  oracle/make_flag_golden.py -> tests/golden/flags_golden.json) exists here with the same kind and default.  Our files are
+  read the same way (ast), so the `if __name__ == "__main__"` blocks of the command lines are covered too."""
+  import ast
+  import json
+  import os
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  golden = json.load(open(os.path.join(root, "tests", "golden", "flags_golden.json")))
+
+  def defines(path):
+    found = {}
+    for node in ast.walk(ast.parse(open(path).read())):
+      if isinstance(node, ast.Call) and isinstance(node.func, ast.Attribute) and node.func.attr.startswith("DEFINE_"):
+        try:
+          found[ast.literal_eval(node.args[0])] = [node.func.attr[7:].replace("boolean", "bool"), ast.literal_eval(node.args[1])]
+        except Exception:
+          pass
+    return found
+
+  pkg = os.path.join(root, "youtube-8m_b200")
+  modules = {}
+  for f in ("frame_level_models.py", "video_level_models.py", "losses.py", "feature_transform.py"):
+    modules.update(defines(os.path.join(pkg, f)))                        # module-level flags share one registry
+  assert len(golden) == 8
+  for fname, ref in golden.items():
+    mine = defines(os.path.join(pkg, fname))
+    scope = dict(modules, **mine) if fname in ("frame_level_models.py", "video_level_models.py", "losses.py", "feature_transform.py") else mine
+    for name, (kind, default) in ref.items():
+      assert name in scope, "%s: reference flag --%s is not defined" % (fname, name)
+      k2, d2 = scope[name]
+      assert k2 == kind.replace("boolean", "bool"), (fname, name, kind, k2)
+      assert d2 == default and type(d2) == type(default), "%s: --%s default %r != reference %r" % (fname, name, d2, default)

@@ -21,7 +21,8 @@ FLAGS = flags.FLAGS
 
 if __name__ == "__main__":
   flags.DEFINE_string("train_dir", "/tmp/yt8m_model/", "The directory to load the model files from.")
-  flags.DEFINE_string("model_checkpoint_path", None, "The file path to load the model from.")
+  flags.DEFINE_string("model_checkpoint_path", "", "The file path to load the model from.")
+  flags.DEFINE_string("distill_data_pattern", None, "File glob defining the distillation data pattern (accepted, unused)")
   flags.DEFINE_string("eval_data_pattern", "", "File glob defining the evaluation dataset in tensorflow.SequenceExample format.")
   flags.DEFINE_string("feature_names", "mean_rgb", "Name of the feature to use for training.")
   flags.DEFINE_string("feature_sizes", "1024", "Length of the feature vectors.")

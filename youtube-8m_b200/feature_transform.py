@@ -10,6 +10,9 @@ import yt8m_native as nat
 
 flags.DEFINE_string("feature_transformer", "DefaultTransformer",
                     "how to preprocess feature, defaults to identical, which means no transform")
+# flags of the reference's EngineerTransformer / ResolutionTransformer (outside SURVEY.md §8): accepted so that command lines parse
+flags.DEFINE_string("engineer_types", "identical,avg,std,diff", "how to preprocess feature (EngineerTransformer; not built)")
+flags.DEFINE_integer("time_resolution", 8, "how many frames are merged into one (ResolutionTransformer; not built)")
 
 
 class DefaultTransformer(object):

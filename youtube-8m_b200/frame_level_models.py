@@ -47,6 +47,26 @@ flags.DEFINE_string("netvlad_operand_format", "f16",
                     "How the descriptor and the hidden layer travel to the next GEMM: 'f16' = one IEEE fp16 tensor "
                     "(11 significant bits, one MMA per weight tile), 'bf16x2' = bf16 hi + lo pair (~16 bits, two MMAs).")
 
+# flags of the reference's other 50 frame-level models (wh/frame_level_models.py:20-83, outside SURVEY.md §8): accepted so that
+# command lines parse; the models themselves are not built (find_class_by_name raises StopIteration for them)
+flags.DEFINE_string("cnn_filter_nums", '256,256,256', "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_string("cnn_filter_sizes", '1,2,3', "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("cnn_num_filters", 512, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("cnn_pooling_k", 4, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("deep_cnn_base_size", 128, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("distillchain_relu_cells", 256, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("frame_seg_relu_cells", 256, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("gru_cells", 1024, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("gru_layers", 2, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("lstm_look_back", 3, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_string("lstm_normalization", 'identical', "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("mm_label_embedding", 256, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("multiscale_cnn_lstm_layers", 1, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("num_attentions", 5, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("positional_embedding_size", 32, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_string("video_level_classifier_support_model", 'MoeModel', "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_string("wide_and_deep_models", 'FrameLevelLogisticModel,LstmMemoryModel', "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+
 BN_EPS = 1e-3      # slim.batch_norm default epsilon
 
 

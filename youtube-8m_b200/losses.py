@@ -5,6 +5,17 @@ import yt8m_native as nat
 flags.DEFINE_integer("num_classes", 4716, "number of classes")
 flags.DEFINE_bool("label_smoothing", False, "whether do label smoothing")
 
+# flags of the reference's other losses (wh/losses.py:22-44): accepted so that its command lines parse; only CrossEntropyLoss is built
+flags.DEFINE_float("label_smoothing_epsilon", 0.1, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_float("batch_agreement", 0.1, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_float("false_positive_punishment", 1.0, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_float("false_negative_punishment", 1.0, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("num_frequents", 200, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("num_verticals", 25, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_float("support_loss_percent", 0.1, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_string("support_type", 'vertical', "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_string("vertical_file", 'resources/vertical.tsv', "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+
 
 class BaseLoss(object):
   """Inherit from this class when implementing new losses (wh/losses.py:56-74)."""

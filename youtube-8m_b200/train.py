@@ -56,6 +56,16 @@ if __name__ == "__main__":
   flags.DEFINE_bool("dropout", False, "Whether to consider dropout")
   flags.DEFINE_float("keep_prob", 1.0, "probability to keep output (used in dropout, keep it unchanged in validationg and test)")
   flags.DEFINE_float("noise_level", 0.0, "standard deviation of noise (added to hidden nodes)")
+  # the boosting / distillation pipeline of the reference (wh/train.py:104-137): accepted so that its command lines parse;
+  # enabling any of them is refused (outside SURVEY.md §8)
+  flags.DEFINE_bool("reweight", False, "Whether to reweight samples (boosting pipeline; not built)")
+  flags.DEFINE_string("sample_vocab_file", "", "Where the vocabulary of the sample weights is (boosting pipeline; not built)")
+  flags.DEFINE_string("sample_freq_file", "", "Where the sample weights are (boosting pipeline; not built)")
+  flags.DEFINE_bool("distillation_features", False, "If set, *DistillationFeatureReader will be used (not built)")
+  flags.DEFINE_bool("distillation_as_input", False, "If set, distillation_predictions will be given to the model (not built)")
+  flags.DEFINE_bool("distillation_as_boosting", False, "If set, boosting via distillation predictions (not built)")
+  flags.DEFINE_integer("distillation_type", 0, "Type of distillation, options are 0, 1 and 2 (not built)")
+  flags.DEFINE_float("distillation_percent", 0.0, "If larger than 0, final_loss = distillation_loss * percent + normal_loss * (1.0 - percent) (not built)")
 
 
 def get_reader():
@@ -227,6 +237,9 @@ def main(unused_argv=None):
   rest = FLAGS.parse()
   if rest:
     logging.warning("ignoring positional arguments %s", rest)
+  off = [n for n in ("reweight", "distillation_features", "distillation_as_input", "distillation_as_boosting") if getattr(FLAGS, n)]
+  if off or FLAGS.distillation_percent > 0 or FLAGS.distillation_type != 0:
+    raise NotImplementedError("train.py: the boosting / distillation pipeline (--reweight, --distillation_*) is outside the hot path")
   if not torch.cuda.is_available():
     raise SystemExit("train.py: no CUDA device; the yt8m_b200 path has no CPU fallback")
   rank, world, local_rank = yt8m_dp.init_from_env()

@@ -23,6 +23,11 @@ flags.DEFINE_bool("deep_chain_use_length", False, "The number of relu cells used
 flags.DEFINE_integer("num_supports", 25, "Number of total support categories.")
 flags.DEFINE_integer("moe_num_extend", 8, "The number of attention outputs, used for MoeExtendModel.")
 
+# flags of reference video-level models outside SURVEY.md §8 (wh/video_level_models.py:19-46): accepted so that command lines parse
+flags.DEFINE_integer("divergence_model_count", 8, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("hidden_chain_layers", 4, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+flags.DEFINE_integer("hidden_chain_relu_cells", 256, "reference flag of a model / loss outside SURVEY.md §8 (accepted, unused)")
+
 
 class LogisticModel(models.BaseModel):
   """Logistic model with L2 regularization (wh/all_video_models/logistic_model.py:9-26)."""
