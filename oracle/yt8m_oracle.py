@@ -12,8 +12,12 @@ executes these inside TensorFlow 1.0, which is NOT vendored under ``/root/refere
 installable here, and the reference holds no tests or golden vectors for this path
 (SURVEY.md §4).  So for the model arithmetic:
 
-    PARITY UNPINNED -- pinned only by closed-form known-answer tests (tests/test_oracle_kat.py)
-    and by TF-1.0's documented op semantics recorded in SURVEY.md §8(c).
+    PINNED TO THE REFERENCE SOURCE, NOT TO A TENSORFLOW RUN -- ``oracle/make_model_golden.py`` exec's the reference's
+    own create_model() / calculate_loss() / Dequantize code against ``oracle/tf_numpy_shim.py`` (a numpy stand-in for
+    the TF / slim ops it calls, following TF-1.0's documented semantics) and
+    ``tests/test_oracle_golden_models.py`` holds this module to those outputs (13 cases, 3e-6); TensorFlow's own
+    kernels are not in the loop, so closed-form known-answer tests (tests/test_oracle_kat.py) and a torch.nn.LSTM
+    cross-check back the shim's op semantics.  NetVLAD / context gating: PARITY UNPINNED (no upstream definition).
 
 The metric path (GAP@20 / Hit@1 / PERR) IS pinned: ``oracle/gap_oracle.py`` is checked against
 golden vectors produced by the reference's own ``average_precision_calculator.py`` /

@@ -1,0 +1,108 @@
+"""The torch-CPU oracle (oracle/yt8m_oracle.py, oracle/model_oracle.py) against golden vectors produced by EXECUTING THE
+REFERENCE'S OWN create_model() / calculate_loss() / Dequantize code (oracle/make_model_golden.py: the reference files are
+exec'd against a numpy stand-in for the TF / slim ops they call -- see that script for what is the reference's and what
+is the shim's).  This pins the restatement's variable names, the class-major / mixture-minor MoE layout, the concat
+orders, einsum subscripts, masking / renormalisation and max-over-heads to the reference source; inputs and weights are
+regenerated from seeds, the fixture tests/golden/model_golden.json holds only the reference's outputs."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import make_model_golden as G
+from oracle import model_oracle as MO
+from oracle import yt8m_oracle as O
+
+GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "model_golden.json")))
+TOL = 3e-6
+
+
+def _t(d):
+  return {k: torch.from_numpy(np.asarray(v)) for k, v in d.items()}
+
+
+def _close(got, want):
+  want = torch.tensor(want, dtype=torch.float64)
+  assert tuple(got.shape) == tuple(want.shape), (got.shape, want.shape)
+  err = float((got.double() - want).abs().max())
+  assert err < TOL, err
+
+
+def test_moe_and_logistic_against_reference_code():
+  inp, w, fl = G.case_inputs("moe")
+  w = _t(w)
+  _close(O.moe_model(torch.from_numpy(inp["x"]), w["gates/weights"], w["experts/weights"], w["experts/biases"], fl["vocab"],
+                     fl["moe_num_mixtures"]), GOLDEN["moe"]["predictions"])
+  inp, w, fl = G.case_inputs("logistic")
+  w = _t(w)
+  _close(O.logistic_model(torch.from_numpy(inp["x"]), w["fully_connected/weights"], w["fully_connected/biases"]),
+         GOLDEN["logistic"]["predictions"])
+
+
+def test_chain_models_against_reference_code():
+  inp, w, fl = G.case_inputs("chain")
+  p, sp = MO.chain_moe(_t(w), torch.from_numpy(inp["x"]), fl["vocab"], fl["moe_num_mixtures"], fl["num_supports"])
+  _close(p, GOLDEN["chain"]["predictions"])
+  _close(sp, GOLDEN["chain"]["support_predictions"])
+  inp, w, fl = G.case_inputs("deep_chain")
+  p, sup = MO.deep_combine_chain(_t(w), torch.from_numpy(inp["x"]), fl["vocab"], fl["moe_num_mixtures"], fl["deep_chain_layers"])
+  _close(p, GOLDEN["deep_chain"]["predictions"])
+  _close(sup, GOLDEN["deep_chain"]["support_predictions"])
+
+
+def test_cross_entropy_and_dequantize_against_reference_code():
+  inp, _, _ = G.case_inputs("xent")
+  loss = O.cross_entropy_loss(torch.from_numpy(inp["p"]), torch.from_numpy(inp["labels"]).float())
+  assert abs(float(loss) - GOLDEN["xent"]["loss"]) < 2e-5 * GOLDEN["xent"]["loss"]
+  inp, _, _ = G.case_inputs("dequantize")
+  _close(O.dequantize(torch.from_numpy(inp["u8"])), GOLDEN["dequantize"]["predictions"])
+
+
+@pytest.mark.parametrize("case", ["lstm_att_max", "lstm_multi_att"])
+def test_lstm_attention_models_against_reference_code(case):
+  inp, w, fl = G.case_inputs(case)
+  fwd = MO.lstm_attention_max_pooling if case == "lstm_att_max" else MO.lstm_multi_attention
+  heads = fl["lstm_attentions"] if case == "lstm_att_max" else fl["attention_size"]
+  p = fwd(_t(w), torch.from_numpy(inp["x"]), torch.from_numpy(inp["num_frames"]), fl["vocab"], fl["moe_num_mixtures"], heads,
+          layers=fl["lstm_layers"])
+  _close(p, GOLDEN[case]["predictions"])
+
+
+@pytest.mark.parametrize("case", ["lstm", "lstm_memory"])
+def test_lstm_models_against_reference_code(case):
+  """LstmModel feeds the NON-tuple MultiRNNCell state [c0, h0, c1, h1] to the classifier (lstm_model.py:34-52), LstmMemoryModel the
+  concatenated c states (lstm_memory_model.py:61)."""
+  inp, w, fl = G.case_inputs(case)
+  fwd = MO.lstm_model if case == "lstm" else MO.lstm_memory_model
+  p = fwd(_t(w), torch.from_numpy(inp["x"]), torch.from_numpy(inp["num_frames"]), fl["vocab"], fl["moe_num_mixtures"], layers=fl["lstm_layers"])
+  _close(p, GOLDEN[case]["predictions"])
+
+
+def test_zt_attention_model_against_reference_code():
+  """zt AttentionModel + MoeExtendModel (zt/frame_level_models.py:4355-4405, zt/video_level_models.py:2272-2330): the two classes
+  are cut out of the reference files and executed; mask from all-zero rows, mean pooling by num_frames, softmax over T of
+  [x_t, mean] . W + b, renormalisation, MoE on B*A rows, max over the A heads."""
+  inp, w, fl = G.case_inputs("zt_attention")
+  p = MO.attention_model(_t(w), torch.from_numpy(inp["x"]), torch.from_numpy(inp["num_frames"]), fl["vocab"], fl["moe_num_mixtures"],
+                         fl["moe_num_extend"])
+  _close(p, GOLDEN["zt_attention"]["predictions"])
+
+
+@pytest.mark.parametrize("case", ["dbof_bn", "dbof_bias"])
+def test_dbof_model_against_reference_code(case):
+  """DbofModel + model_utils.SampleRandomFrames / FramePooling (wh/all_frame_models/dbof_model.py:62-123, wh/model_utils.py:56-94)
+  executed from the reference files; the tf.random_uniform draw is pinned by the harness, so the frame index arithmetic
+  (int(uniform * num_frames)) is checked too.  Batch-norm in inference form and the bias form."""
+  inp, w, fl = G.case_inputs(case)
+  x, nf = torch.from_numpy(inp["x"]), torch.from_numpy(inp["num_frames"])
+  fidx = (torch.from_numpy(inp["uniform"]) * nf.float().unsqueeze(1)).to(torch.int64)
+  sd = _t(w)
+  if case == "dbof_bn":
+    p = MO.dbof(sd, x, fidx, fl["vocab"], fl["moe_num_mixtures"], pooling="max")
+  else:
+    hid = O.dbof_pool(x, fidx, {"cluster_w": sd["cluster_weights"], "cluster_b": sd["cluster_biases"], "hidden_w": sd["hidden1_weights"],
+                                "hidden_b": sd["hidden1_biases"]}, add_batch_norm=False, pooling="max")
+    p = O.moe_model(hid, sd["gates/weights"], sd["experts/weights"], sd["experts/biases"], fl["vocab"], fl["moe_num_mixtures"])
+  _close(p, GOLDEN[case]["predictions"])
