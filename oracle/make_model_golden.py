@@ -71,7 +71,7 @@ def rnd(rs, shape, scale=1.0):
 def case_inputs(case):
   """Returns (inputs dict, weights dict by TF variable name, flags dict) for a named case."""
   rs = np.random.RandomState({"moe": 1, "logistic": 2, "chain": 3, "deep_chain": 4, "xent": 5, "lstm_att_max": 6, "lstm_multi_att": 7,
-                              "dequantize": 8, "lstm": 9, "lstm_memory": 10, "zt_attention": 11, "dbof_bn": 12, "dbof_bias": 13}[case])
+                              "dequantize": 8, "lstm": 9, "lstm_memory": 10, "zt_attention": 11, "dbof_bn": 12, "dbof_bias": 13, "video_matrix": 14}[case])
   b, d, v, m = 4, 8, 6, 2
   if case == "moe":
     return ({"x": rnd(rs, (b, d))}, {"gates/weights": rnd(rs, (d, v * (m + 1))), "experts/weights": rnd(rs, (d, v * m)),
@@ -168,6 +168,11 @@ def case_inputs(case):
          "experts/weights": rnd(rs, (dd, v * m)), "experts/biases": rnd(rs, (v * m,), 0.3)}
     return ({"x": x.astype(np.float32), "num_frames": nf}, w,
             {"moe_num_extend": a, "moe_num_mixtures": m, "video_level_classifier_model": "MoeExtendModel", "vocab": v})
+  if case == "video_matrix":
+    # two videos: 5 frames (padded to max_frames = 8) and 11 frames (truncated to 8); one byte string per frame
+    fs = 6
+    return ({"frames_short": rs.randint(0, 256, (5, fs)).astype(np.uint8), "frames_long": rs.randint(0, 256, (11, fs)).astype(np.uint8)},
+            {}, {"max_frames": 8, "feature_size": fs})
   if case == "dequantize":
     return ({"u8": np.arange(256, dtype=np.float32)}, {}, {})
   raise KeyError(case)
@@ -234,6 +239,15 @@ def run_reference(case):
     vlm.MoeExtendModel = load_class(os.path.join(REF_ZT, "video_level_models.py"), "MoeExtendModel", base)
     cls = load_class(os.path.join(REF_ZT, "frame_level_models.py"), "AttentionModel", dict(base, video_level_models=vlm))
     out = cls().create_model(shim.t(inputs["x"]), v, inputs["num_frames"])["predictions"]
+  elif case == "video_matrix":
+    sys.modules["utils"] = load("utils.py", "ref_utils")
+    readers = load("readers.py", "ref_readers")
+    res = {}
+    for key in ("frames_short", "frames_long"):
+      reader = readers.YT8MFrameFeatureReader.__new__(readers.YT8MFrameFeatureReader)
+      mat, n = reader.get_video_matrix([row.tobytes() for row in inputs[key]], flag_dict["feature_size"], flag_dict["max_frames"], 2, -2)
+      res[key] = {"matrix": np.asarray(mat, dtype=np.float64).tolist(), "num_frames": int(n)}
+    return res
   elif case == "dequantize":
     utils = load("utils.py", "ref_utils", extra={})
     out = utils.Dequantize(inputs["u8"], 2, -2)
@@ -241,14 +255,14 @@ def run_reference(case):
 
 
 CASES = ["moe", "logistic", "chain", "deep_chain", "xent", "lstm", "lstm_memory", "lstm_att_max", "lstm_multi_att", "zt_attention",
-         "dbof_bn", "dbof_bias", "dequantize"]
+         "dbof_bn", "dbof_bias", "video_matrix", "dequantize"]
 
 
 def main():
   golden = {c: run_reference(c) for c in CASES}
   json.dump(golden, open(OUT, "w"), indent=0, sort_keys=True)
   for c in CASES:
-    print(c, {k: (np.asarray(val).shape if not isinstance(val, float) else val) for k, val in golden[c].items()})
+    print(c, {k: (np.asarray(val).shape if isinstance(val, list) else val if isinstance(val, float) else "...") for k, val in golden[c].items()})
 
 
 if __name__ == "__main__":

@@ -33,6 +33,9 @@ class T(np.ndarray):
         return list(shape)
     return _S()
 
+  def set_shape(self, shape):
+    assert list(self.shape) == list(shape), (self.shape, shape)
+
 
 def t(x, dtype=np.float32):
   return np.asarray(x, dtype=dtype).view(T)
@@ -170,11 +173,11 @@ def install(flag_values):
   tf.reshape = lambda x, shape, name=None: t(np.reshape(np.asarray(x, dtype=np.float32), shape))
   tf.reduce_sum, tf.reduce_mean, tf.reduce_max = _reduce(np.sum), _reduce(np.mean), _reduce(np.max)
   tf.concat = lambda values, axis, name=None: t(np.concatenate([np.asarray(v, dtype=np.float32) for v in values], axis=axis))
-  tf.cast = lambda x, dtype, name=None: t(np.asarray(x).astype(np.float32)) if dtype is np.float32 else np.asarray(x).astype(dtype)
+  tf.cast = lambda x, dtype, name=None: t(np.asarray(x).astype(np.float32)) if np.dtype(dtype) == np.float32 else np.asarray(x).astype(dtype)
   tf.log = lambda x, name=None: t(np.log(np.asarray(x, dtype=np.float32)))
   tf.negative = lambda x, name=None: t(-np.asarray(x, dtype=np.float32))
   tf.square = lambda x, name=None: t(np.square(np.asarray(x, dtype=np.float32)))
-  tf.maximum = lambda a, b, name=None: t(np.maximum(a, b))
+  tf.maximum = lambda a, b, name=None: (max(a, b) if isinstance(a, int) and isinstance(b, int) else t(np.maximum(a, b)))
   tf.expand_dims = lambda x, axis, name=None: np.expand_dims(np.asarray(x), axis).view(T)
   tf.einsum = lambda eq, *ops: t(np.einsum(eq, *[np.asarray(o, dtype=np.float32) for o in ops]))
   tf.sequence_mask = _sequence_mask
@@ -201,7 +204,7 @@ def install(flag_values):
   tf.random_uniform = lambda shape, **kw: t(np.reshape(STORE["__random_uniform__"], shape))    # pinned by the harness
   tf.range = lambda n, name=None: np.arange(n)
   tf.multiply = lambda a, b, name=None: t(np.asarray(a, dtype=np.float32) * np.asarray(b, dtype=np.float32))
-  tf.minimum = lambda a, b, name=None: np.minimum(a, b)
+  tf.minimum = lambda a, b, name=None: (min(a, b) if isinstance(a, int) and isinstance(b, int) else np.minimum(a, b))
   tf.stack = lambda values, axis=0, name=None: np.stack([np.asarray(v) for v in values], axis=axis)
   tf.gather_nd = lambda params, indices, name=None: t(np.asarray(params)[tuple(np.moveaxis(np.asarray(indices).astype(np.int64), -1, 0))])
   tf.matmul = lambda a, b, name=None: t(np.asarray(a, dtype=np.float32) @ np.asarray(b, dtype=np.float32))
@@ -211,6 +214,14 @@ def install(flag_values):
   tf.GraphKeys = types.SimpleNamespace(REGULARIZATION_LOSSES="regularization_losses")
   nn.l2_loss = lambda x, name=None: float((np.asarray(x, dtype=np.float32) ** 2).sum() / 2)
   nn.xw_plus_b = lambda x, w, b, name=None: t(np.asarray(x, dtype=np.float32) @ np.asarray(w, dtype=np.float32) + np.asarray(b, dtype=np.float32))
+  # ops used by the frame reader (wh/readers.py:21-56 resize_axis, :159-186 get_video_matrix)
+  tf.uint8 = np.uint8
+  tf.decode_raw = lambda strings, dtype, name=None: np.stack([np.frombuffer(bytes(b_), dtype=dtype) for b_ in strings])
+  tf.convert_to_tensor = lambda x, **kw: t(x)
+  tf.unstack = lambda x, **kw: [int(v) for v in x]
+  tf.zeros_like = lambda x, **kw: np.zeros_like(np.asarray(x))
+  tf.slice = lambda x, begin, size, name=None: t(np.asarray(x)[tuple(slice(int(b_), int(b_) + int(n_)) for b_, n_ in zip(begin, size))])
+  tf.fill = lambda dims, value, name=None: t(np.full([int(d_) for d_ in dims], value, dtype=np.float32))
   contrib = types.ModuleType("tensorflow.contrib")
   rnn = types.ModuleType("tensorflow.contrib.rnn")
   rnn.BasicLSTMCell, rnn.MultiRNNCell = _BasicLSTMCell, _MultiRNNCell

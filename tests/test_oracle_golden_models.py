@@ -106,3 +106,24 @@ def test_dbof_model_against_reference_code(case):
                                 "hidden_b": sd["hidden1_biases"]}, add_batch_norm=False, pooling="max")
     p = O.moe_model(hid, sd["gates/weights"], sd["experts/weights"], sd["experts/biases"], fl["vocab"], fl["moe_num_mixtures"])
   _close(p, GOLDEN[case]["predictions"])
+
+
+def test_frame_reader_video_matrix_against_reference_code():
+  """wh/readers.py:159-186 get_video_matrix + :21-56 resize_axis executed from the reference file: decode_raw, Dequantize FIRST,
+  then zero padding / truncation to max_frames (padded rows are 0.0, not Dequantize(0)).  Our reader keeps uint8 and
+  de-quantises + pads on the GPU; the host half (get_video_matrix -> uint8 [max_frames, D] + n) and the oracle's dequantize
+  reproduce the reference matrix exactly."""
+  import sys
+  pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "youtube-8m_b200")
+  if pkg not in sys.path:
+    sys.path.insert(0, pkg)
+  import readers
+  inp, _, fl = G.case_inputs("video_matrix")
+  r = readers.YT8MFrameFeatureReader(feature_names=["rgb"], feature_sizes=[fl["feature_size"]], max_frames=fl["max_frames"])
+  for key in ("frames_short", "frames_long"):
+    u8, n = r.get_video_matrix([row.tobytes() for row in inp[key]], fl["feature_size"])
+    want = GOLDEN["video_matrix"][key]
+    assert n == want["num_frames"]
+    got = O.dequantize(torch.from_numpy(u8.astype(np.float32)))
+    got[n:] = 0.0                                                   # what yt8m_l2norm_rows_fwd / yt8m_frames_unpack_u8 write past num_frames
+    _close(got, want["matrix"])
