@@ -51,6 +51,16 @@ def load(rel, name, extra=None):
   return mod
 
 
+def load_function(path, func_name, namespace):
+  """exec ONE top-level function of a reference file."""
+  import ast
+  src = py3ify(open(path, errors="ignore").read())
+  node = next(n for n in ast.parse(src).body if isinstance(n, ast.FunctionDef) and n.name == func_name)
+  ns = dict(namespace)
+  exec(compile(ast.get_source_segment(src, node), path, "exec"), ns)
+  return ns[func_name]
+
+
 def load_class(path, class_name, namespace):
   """exec ONE class of a reference file (zt's model files are thousands of lines of other models): the class source is cut
   out with the ast module and run in `namespace`."""
@@ -71,7 +81,7 @@ def rnd(rs, shape, scale=1.0):
 def case_inputs(case):
   """Returns (inputs dict, weights dict by TF variable name, flags dict) for a named case."""
   rs = np.random.RandomState({"moe": 1, "logistic": 2, "chain": 3, "deep_chain": 4, "xent": 5, "lstm_att_max": 6, "lstm_multi_att": 7,
-                              "dequantize": 8, "lstm": 9, "lstm_memory": 10, "zt_attention": 11, "dbof_bn": 12, "dbof_bias": 13, "video_matrix": 14}[case])
+                              "dequantize": 8, "lstm": 9, "lstm_memory": 10, "zt_attention": 11, "dbof_bn": 12, "dbof_bias": 13, "video_matrix": 14, "format_lines": 15}[case])
   b, d, v, m = 4, 8, 6, 2
   if case == "moe":
     return ({"x": rnd(rs, (b, d))}, {"gates/weights": rnd(rs, (d, v * (m + 1))), "experts/weights": rnd(rs, (d, v * m)),
@@ -168,6 +178,8 @@ def case_inputs(case):
          "experts/weights": rnd(rs, (dd, v * m)), "experts/biases": rnd(rs, (v * m,), 0.3)}
     return ({"x": x.astype(np.float32), "num_frames": nf}, w,
             {"moe_num_extend": a, "moe_num_mixtures": m, "video_level_classifier_model": "MoeExtendModel", "vocab": v})
+  if case == "format_lines":
+    return ({"video_ids": [b"abc", b"vid-2", b"x"], "predictions": rs.random_sample((3, 30)).astype(np.float32)}, {}, {"top_k": 5})
   if case == "video_matrix":
     # two videos: 5 frames (padded to max_frames = 8) and 11 frames (truncated to 8); one byte string per frame
     fs = 6
@@ -239,6 +251,9 @@ def run_reference(case):
     vlm.MoeExtendModel = load_class(os.path.join(REF_ZT, "video_level_models.py"), "MoeExtendModel", base)
     cls = load_class(os.path.join(REF_ZT, "frame_level_models.py"), "AttentionModel", dict(base, video_level_models=vlm))
     out = cls().create_model(shim.t(inputs["x"]), v, inputs["num_frames"])["predictions"]
+  elif case == "format_lines":
+    fn = load_function(os.path.join(REF, "inference.py"), "format_lines", {"numpy": np})
+    return {"lines": list(fn(inputs["video_ids"], inputs["predictions"], flag_dict["top_k"]))}
   elif case == "video_matrix":
     sys.modules["utils"] = load("utils.py", "ref_utils")
     readers = load("readers.py", "ref_readers")
@@ -255,7 +270,7 @@ def run_reference(case):
 
 
 CASES = ["moe", "logistic", "chain", "deep_chain", "xent", "lstm", "lstm_memory", "lstm_att_max", "lstm_multi_att", "zt_attention",
-         "dbof_bn", "dbof_bias", "video_matrix", "dequantize"]
+         "dbof_bn", "dbof_bias", "video_matrix", "format_lines", "dequantize"]
 
 
 def main():

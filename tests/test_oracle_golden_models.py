@@ -127,3 +127,22 @@ def test_frame_reader_video_matrix_against_reference_code():
     got = O.dequantize(torch.from_numpy(u8.astype(np.float32)))
     got[n:] = 0.0                                                   # what yt8m_l2norm_rows_fwd / yt8m_frames_unpack_u8 write past num_frames
     _close(got, want["matrix"])
+
+
+def test_inference_csv_lines_against_reference_code():
+  """wh/inference.py:76-87 format_lines executed from the reference file: 'id,cls conf cls conf ...' with the top_k classes by
+  descending confidence and '%i %f' pairs.  Our inference.format_lines takes the per-video top-k that yt8m_topk_rows
+  extracts on the GPU (here: numpy's descending sort) and must emit the same lines."""
+  import importlib.util
+  import sys
+  pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "youtube-8m_b200")
+  if pkg not in sys.path:
+    sys.path.insert(0, pkg)
+  try:
+    import inference
+  except ImportError as e:                      # imports the CUDA binding (built library required)
+    pytest.skip(str(e))
+  inp, _, fl = G.case_inputs("format_lines")
+  order = np.argsort(-inp["predictions"], axis=1, kind="stable")[:, :fl["top_k"]]
+  vals = np.take_along_axis(inp["predictions"], order, axis=1)
+  assert list(inference.format_lines(inp["video_ids"], order, vals)) == GOLDEN["format_lines"]["lines"]
