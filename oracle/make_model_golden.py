@@ -81,7 +81,7 @@ def rnd(rs, shape, scale=1.0):
 def case_inputs(case):
   """Returns (inputs dict, weights dict by TF variable name, flags dict) for a named case."""
   rs = np.random.RandomState({"moe": 1, "logistic": 2, "chain": 3, "deep_chain": 4, "xent": 5, "lstm_att_max": 6, "lstm_multi_att": 7,
-                              "dequantize": 8, "lstm": 9, "lstm_memory": 10, "zt_attention": 11, "dbof_bn": 12, "dbof_bias": 13, "video_matrix": 14, "format_lines": 15}[case])
+                              "dequantize": 8, "lstm": 9, "lstm_memory": 10, "zt_attention": 11, "dbof_bn": 12, "dbof_bias": 13, "video_matrix": 14, "format_lines": 15, "log_lines": 16}[case])
   b, d, v, m = 4, 8, 6, 2
   if case == "moe":
     return ({"x": rnd(rs, (b, d))}, {"gates/weights": rnd(rs, (d, v * (m + 1))), "experts/weights": rnd(rs, (d, v * m)),
@@ -178,6 +178,10 @@ def case_inputs(case):
          "experts/weights": rnd(rs, (dd, v * m)), "experts/biases": rnd(rs, (v * m,), 0.3)}
     return ({"x": x.astype(np.float32), "num_frames": nf}, w,
             {"moe_num_extend": a, "moe_num_mixtures": m, "video_level_classifier_model": "MoeExtendModel", "vocab": v})
+  if case == "log_lines":
+    return ({"epoch": {"epoch_id": 1234, "avg_hit_at_one": 0.87654, "avg_perr": 0.71234, "avg_loss": 4.56789123,
+                       "aps": [0.5, 0.25, 0.8], "gap": 0.81234},
+             "step": {"hit_at_one": 0.9, "perr": 0.75, "loss": 3.25, "examples_per_second": 1234.5678}}, {}, {})
   if case == "format_lines":
     return ({"video_ids": [b"abc", b"vid-2", b"x"], "predictions": rs.random_sample((3, 30)).astype(np.float32)}, {}, {"top_k": 5})
   if case == "video_matrix":
@@ -251,6 +255,17 @@ def run_reference(case):
     vlm.MoeExtendModel = load_class(os.path.join(REF_ZT, "video_level_models.py"), "MoeExtendModel", base)
     cls = load_class(os.path.join(REF_ZT, "frame_level_models.py"), "AttentionModel", dict(base, video_level_models=vlm))
     out = cls().create_model(shim.t(inputs["x"]), v, inputs["num_frames"])["predictions"]
+  elif case == "log_lines":
+    class _Writer(object):
+      def add_summary(self, *a, **k):
+        pass
+
+      def flush(self):
+        pass
+    ns = {"numpy": np, "MakeSummary": lambda name, value: None}
+    epoch = load_function(os.path.join(REF, "utils.py"), "AddEpochSummary", ns)(_Writer(), 1234, inputs["epoch"])
+    step = load_function(os.path.join(REF, "utils.py"), "AddGlobalStepSummary", ns)(_Writer(), 77, inputs["step"])
+    return {"epoch": epoch, "step": step}
   elif case == "format_lines":
     fn = load_function(os.path.join(REF, "inference.py"), "format_lines", {"numpy": np})
     return {"lines": list(fn(inputs["video_ids"], inputs["predictions"], flag_dict["top_k"]))}
@@ -270,7 +285,7 @@ def run_reference(case):
 
 
 CASES = ["moe", "logistic", "chain", "deep_chain", "xent", "lstm", "lstm_memory", "lstm_att_max", "lstm_multi_att", "zt_attention",
-         "dbof_bn", "dbof_bias", "video_matrix", "format_lines", "dequantize"]
+         "dbof_bn", "dbof_bias", "video_matrix", "format_lines", "log_lines", "dequantize"]
 
 
 def main():

@@ -15,7 +15,7 @@ installable here, and the reference holds no tests or golden vectors for this pa
     PINNED TO THE REFERENCE SOURCE, NOT TO A TENSORFLOW RUN -- ``oracle/make_model_golden.py`` exec's the reference's
     own create_model() / calculate_loss() / Dequantize code against ``oracle/tf_numpy_shim.py`` (a numpy stand-in for
     the TF / slim ops it calls, following TF-1.0's documented semantics) and
-    ``tests/test_oracle_golden_models.py`` holds this module to those outputs (15 cases, 3e-6); TensorFlow's own
+    ``tests/test_oracle_golden_models.py`` holds this module to those outputs (16 cases, 3e-6); TensorFlow's own
     kernels are not in the loop, so closed-form known-answer tests (tests/test_oracle_kat.py) and a torch.nn.LSTM
     cross-check back the shim's op semantics.  NetVLAD / context gating: PARITY UNPINNED (no upstream definition).
 

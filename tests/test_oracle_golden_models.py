@@ -146,3 +146,15 @@ def test_inference_csv_lines_against_reference_code():
   order = np.argsort(-inp["predictions"], axis=1, kind="stable")[:, :fl["top_k"]]
   vals = np.take_along_axis(inp["predictions"], order, axis=1)
   assert list(inference.format_lines(inp["video_ids"], order, vals)) == GOLDEN["format_lines"]["lines"]
+
+
+def test_epoch_log_line_against_reference_code():
+  """wh/utils.py:100-138 AddEpochSummary executed from the reference file (TensorBoard writer stubbed): the
+  'epoch/eval number ...' line that eval.py prints, incl. its '{5:3f}' (sic) loss format."""
+  import sys
+  pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "youtube-8m_b200")
+  if pkg not in sys.path:
+    sys.path.insert(0, pkg)
+  import utils
+  inp, _, _ = G.case_inputs("log_lines")
+  assert utils.FormatEpochInfo(inp["epoch"]) == GOLDEN["log_lines"]["epoch"]
