@@ -241,12 +241,15 @@ int yt8m_xent_fwd_bwd(const float* pred, const float* labels, int B, int V, floa
  * yt8m_colsum_bf16: out[n] = sum_rows (hi + lo)[r, n]   (bias gradients).
  * yt8m_moe_bwd_dlogits: recomputes the MoE logits tile and writes dL/dlogits (packed column order, bf16
  *   hi/lo) from dL/dp -- backward of wh/all_video_models/moe_model.py:54-64.  num_mixtures in {1, 2, 4}.
- * yt8m_grad_reg_sumsq: grad += l2 * param; sums4 = {sum g^2 seg0, seg1, sum w^2 seg0, seg1}; for MoE packed
+ * yt8m_grad_reg_sumsq: grad += l2 * param; sums4[0..3] = {sum g^2 seg0, seg1, sum w^2 seg0, seg1}; for MoE packed
  *   weights (moe_per = 2M+1, moe_nmix = M) segment 0 = gate rows, 1 = expert rows (two tensors in the
- *   reference, hence two norms); moe_per = 0 -> one segment.
+ *   reference, hence two norms); moe_per = 0 -> one segment.  sums4 must hold YT8M_SUMS_FLOATS floats: beyond the four
+ *   results it is the scratch of a fixed-order two-stage reduction (no floating-point atomics), so the sums -- and with them
+ *   the clip scales -- are bit-identical from launch to launch and on every data-parallel rank.
  * yt8m_clip_adam_step: g *= clip / max(||g||_seg, clip)  (tf.clip_by_norm per tensor), then TF-1.0 Adam
  *   (theta -= lr_t * m / (sqrt(v) + eps), lr_t = lr*sqrt(1-b2^t)/(1-b1^t) computed by the caller), and the
  *   bf16 operand copy is refreshed in place.  only_segment >= 0 restricts the update (MoE bias rows). */
+#define YT8M_SUMS_FLOATS 4104 /* 8 + 4 * 1024 partial sums */
 int yt8m_logistic_bwd_dz(const float* dp, const float* p, int B, int V, yt8m_bf16* dz_hi, yt8m_bf16* dz_lo, long long ld,
                          yt8m_stream_t stream);
 int yt8m_wgrad(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, const yt8m_bf16* b, long long ldb, int M, int N,

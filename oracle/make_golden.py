@@ -27,11 +27,14 @@ CASES = [
     ("yt8m_shape", 3, 64, 4716, 3.4, 20, 0),
     ("topk_gt_classes", 4, 8, 12, 2.0, 20, 0),
     ("k5", 5, 48, 300, 3.0, 5, 0),
+    ("empty_label_rows", 6, 12, 60, 2.0, 20, 0),   # rows 3 and 7 carry no label at all (wh/eval_util.py:87-96: PERR counts them as 0)
 ]
+ZERO_ROWS = {"empty_label_rows": [3, 7]}
 
 
-def golden_case(seed, batch, classes, labels_per_video, quant):
-  """Deterministic synthetic (predictions, labels); shared with tests/test_gap_oracle.py."""
+def golden_case(seed, batch, classes, labels_per_video, quant, zero_rows=()):
+  """Deterministic synthetic (predictions, labels); shared with tests/test_gap_oracle.py.
+  zero_rows: videos whose labels are all cleared afterwards (label-free videos)."""
   rs = np.random.RandomState(seed)
   labels = (rs.random_sample((batch, classes)) < labels_per_video / classes)
   for b in range(batch):                                  # force >= 1 positive per video
@@ -41,7 +44,10 @@ def golden_case(seed, batch, classes, labels_per_video, quant):
   preds = np.clip(scores, 0.0, 1.0).astype(np.float32)
   if quant:
     preds = (np.round(preds * quant) / quant).astype(np.float32)
-  return preds, labels.astype(np.float32)
+  labels = labels.astype(np.float32)
+  for r in zero_rows:
+    labels[r] = 0.0
+  return preds, labels
 
 
 def _load_reference():
@@ -61,9 +67,9 @@ def main():
   out = {"generator": "oracle/make_golden.py", "reference": "wh/eval_util.py + wh/average_precision_calculator.py",
          "cases": []}
   for name, seed, b, v, lpv, k, quant in CASES:
-    preds, labels = golden_case(seed, b, v, lpv, quant)
+    preds, labels = golden_case(seed, b, v, lpv, quant, ZERO_ROWS.get(name, ()))
     rec = {"name": name, "seed": seed, "batch": b, "classes": v, "labels_per_video": lpv,
-           "top_k": k, "quant": quant}
+           "top_k": k, "quant": quant, "zero_rows": ZERO_ROWS.get(name, [])}
     rec["hit_at_one"] = float(eval_util.calculate_hit_at_one(preds, labels))
     rec["perr"] = float(eval_util.calculate_precision_at_equal_recall_rate(preds, labels))
     rec["gap"] = float(eval_util.calculate_gap(preds, labels, top_k=k))

@@ -90,6 +90,15 @@ def attention_model(sd, x, nf, vocab, mixtures, heads):
   return O.moe_extend_model(state, sd["gates/weights"], sd["experts/weights"], sd["experts/biases"], vocab, mixtures, heads)
 
 
+def attention_chain(sd, x, nf, vocab, mixtures, heads, layers):
+  """zt/frame_level_models.py:4355-4405 pooling with --video_level_classifier_model=DeepCombineChainModel
+  (wh/all_video_models/deep_combine_chain_model.py:24-49) applied to each of the B*A pooled rows, then the max over the A
+  heads that MoeExtendModel takes (zt/video_level_models.py:2327-2328) -- BASELINE.json configs[4]."""
+  state = O.attention_model_pool(x, nf, sd["Attention/W"], sd["Attention/b"])
+  p, _ = deep_combine_chain(sd, state, vocab, mixtures, layers)
+  return p.reshape(-1, heads, vocab).max(dim=1).values
+
+
 def dbof(sd, x, frame_index, vocab, mixtures, pooling="max"):
   """wh/all_frame_models/dbof_model.py:62-123 (inference-mode batch norm) + MoeModel."""
   def bn(scope):

@@ -16,7 +16,7 @@ CASES = {c["name"]: c for c in GOLD["cases"]}
 
 
 def _inputs(c):
-  return golden_case(c["seed"], c["batch"], c["classes"], c["labels_per_video"], c["quant"])
+  return golden_case(c["seed"], c["batch"], c["classes"], c["labels_per_video"], c["quant"], c.get("zero_rows", ()))
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -100,3 +100,16 @@ def test_step_metrics_from_topk_equal_the_full_metrics():
   assert abs(perr2 - eval_util.calculate_precision_at_equal_recall_rate(pred, act2)) < 1e-6
   act2[7, :40] = 1                                  # 40 positives > 32 extracted: the caller must fall back
   assert eval_util.step_metrics_from_topk(tv, order, act2, top_k=20)[1] is None
+
+
+def test_label_free_video_counts_zero_in_perr():
+  """a video without labels contributes 0 to PERR (the reference's behaviour, golden case empty_label_rows) in
+  both the full-prediction function and the GPU top-k path -- never NaN."""
+  import eval_util
+  c = CASES["empty_label_rows"]
+  preds, act = _inputs(c)
+  assert abs(eval_util.calculate_precision_at_equal_recall_rate(preds, act) - c["perr"]) < 1e-6
+  order = np.argsort(-preds, axis=1, kind="stable")[:, :32]
+  tv = np.take_along_axis(preds, order, axis=1)
+  h1, perr, gap = eval_util.step_metrics_from_topk(tv, order, act, top_k=20)
+  assert abs(perr - c["perr"]) < 1e-6 and abs(h1 - c["hit_at_one"]) < 1e-6 and np.isfinite(gap)

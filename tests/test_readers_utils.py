@@ -147,3 +147,55 @@ def test_pre_ensemble_prediction_records(tmp_path):
     assert ex["video_id"][1][0] == ids[i]
     assert list(ex["labels"][1]) == list(np.nonzero(labels[i])[0])
     assert np.array_equal(np.asarray(ex["predictions"][1], dtype=np.float32), preds[i])
+
+
+def test_shuffled_sharded_input_pipeline(tmp_path):
+  """ADVICE r1 (train.py input): the record order is shuffled per epoch through a 5 * batch buffer, is a pure function of
+  the seed (every data-parallel rank derives the same global batches), differs between epochs and from the file order; a
+  rank parses only its own rows and the ranks' shards tile every batch; the short tail is dropped on request."""
+  for f in range(3):
+    readers.write_tfrecord(str(tmp_path / ("s%d.tfrecord" % f)), _video_records(40)[f * 13:(f + 1) * 13])
+  pat = str(tmp_path / "s*.tfrecord")
+  r = readers.YT8MAggregatedFeatureReader(num_classes=20, feature_names=["mean_rgb", "mean_audio"], feature_sizes=[8, 4])
+  plain = [i for b in r.prepare_reader(pat, batch_size=8) for i in b[0]]
+  a = [b[0] for b in r.prepare_reader(pat, batch_size=8, num_epochs=2, shuffle=True, seed=3)]
+  b = [b[0] for b in r.prepare_reader(pat, batch_size=8, num_epochs=2, shuffle=True, seed=3)]
+  c = [b[0] for b in r.prepare_reader(pat, batch_size=8, num_epochs=2, shuffle=True, seed=4)]
+  flat = [i for ids in a for i in ids]
+  assert a == b and a != c                                           # a function of the seed only
+  assert sorted(flat) == sorted(plain * 2)                           # every record exactly once per epoch
+  assert flat[:39] != plain and flat[:39] != flat[39:]               # shuffled, and differently in the second epoch
+  assert [len(x) for x in a] == [8] * 9 + [6]
+  assert [len(x[0]) for x in r.prepare_reader(pat, batch_size=8, num_epochs=2, shuffle=True, seed=3, drop_remainder=True)] == [8] * 9
+  world = 4
+  per_rank = [list(r.prepare_reader(pat, batch_size=8, num_epochs=2, shuffle=True, seed=3, shard=(k, world))) for k in range(world)]
+  for step, ids in enumerate(a):
+    got = [i for k in range(world) for i in per_rank[k][step][0]]
+    assert got == ids and all(per_rank[k][step][4] == len(ids) for k in range(world))
+  # a tail batch with fewer videos than ranks: some shards are EMPTY but well-formed, and every rank sees n_global
+  tail = [list(r.prepare_reader(pat, batch_size=37, shard=(k, 8)))[-1] for k in range(8)]
+  assert [len(t[0]) for t in tail] == [1, 1, 0, 0, 0, 0, 0, 0] and all(t[4] == 2 for t in tail)
+  assert tail[5][1].shape == (0, 12) and tail[5][2].shape == (0, 20)
+  assert readers.shard_range(9, (7, 8)) == (8, 9) and readers.shard_range(3, (5, 8)) == (3, 3)
+
+
+def test_prefetch_thread_and_missing_labels(tmp_path):
+  recs = [readers.encode_example({"video_id": ("bytes", [b"u%d" % i]), "mean_rgb": ("float", np.ones(8, dtype=np.float32)),
+                                  "mean_audio": ("float", np.zeros(4, dtype=np.float32))}) for i in range(5)]   # no `labels` feature
+  p = str(tmp_path / "u.tfrecord")
+  readers.write_tfrecord(p, recs)
+  r = readers.YT8MAggregatedFeatureReader(num_classes=20, feature_names=["mean_rgb", "mean_audio"], feature_sizes=[8, 4])
+  out = list(readers.prefetch(r.prepare_reader(p, batch_size=2), depth=2))
+  assert [len(b[0]) for b in out] == [2, 2, 1] and all(int(b[2].sum()) == 0 for b in out)   # tf.VarLenFeature: missing = empty
+  seq = [readers.encode_sequence_example({"video_id": ("bytes", [b"w"])}, {"rgb": [("bytes", [bytes([1] * 6)])] * 3})]
+  p2 = str(tmp_path / "w.tfrecord")
+  readers.write_tfrecord(p2, seq)
+  fr = readers.YT8MFrameFeatureReader(num_classes=20, feature_names=["rgb"], feature_sizes=[6], max_frames=4)
+  (ids, f, l, nf), = list(fr.prepare_reader(p2, batch_size=4))
+  assert nf.tolist() == [3] and int(l.sum()) == 0
+
+  def boom():
+    yield 1
+    raise ValueError("reader failed")
+  with pytest.raises(ValueError):
+    list(readers.prefetch(boom()))

@@ -371,11 +371,12 @@ static int lstm_fwd_impl(const yt8m_bf16* x, const int* num_frames, int B, int T
   YT8M_REQUIRE(workspace_bytes >= yt8m_lstm_workspace_bytes(B, T, D, H, L), YT8M_E_BADSHAPE,
                "yt8m_lstm_fwd: workspace too small");
   LstmWs ws = carve_lstm_ws(workspace, B, T, H, L);
+  bool rec_refused = false;
   if (!(host_debug_flags() & 8192) && lstm_rec_available(H)) {
     // one persistent launch per layer (and per 64 videos); the input projection of EVERY layer is one big GEMM
     const int chunk = lstm_rec_batch_chunk();
     const int n_chunks = (B + chunk - 1) / chunk;
-    for (int l = 0; l < L; ++l) {
+    for (int l = 0; l < L && !rec_refused; ++l) {
       const bool top = (l == L - 1);
       int rc;
       if (l == 0)
@@ -396,9 +397,10 @@ static int lstm_fwd_impl(const yt8m_bf16* x, const int* num_frames, int B, int T
                            top ? out_seq : nullptr, state_out + static_cast<long long>(l) * 2 * H,
                            state_out + static_cast<long long>(l) * 2 * H + H, static_cast<long long>(L) * 2 * H,
                            ws.counters + l * n_chunks, stream);
+      if (rc == YT8M_E_UNSUPPORTED && l == 0 && !seq_hi_all) { rec_refused = true; break; }   // cooperative launch refused: per-step path
       if (rc != YT8M_OK) return rc;
     }
-    return YT8M_OK;
+    if (!rec_refused) return YT8M_OK;
   }
   YT8M_REQUIRE(!seq_hi_all, YT8M_E_UNSUPPORTED,
                "yt8m_lstm_fwd_train: needs the persistent recurrence (H in {256, 512, 768, 1024} and an idle GPU), H=%d", H);

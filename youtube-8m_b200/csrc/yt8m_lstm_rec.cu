@@ -387,11 +387,13 @@ int yt8m::launch_lstm_rec(const float* xw, const int* num_frames, int B, int T, 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, lstm_rec_kernel, tm_w, tm_hhi, tm_hlo, p);
-    if (e != cudaSuccess) {
-      // cooperative + cluster launch refused: the occupancy query above already says the grid fits an idle GPU
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+      // The CTAs spin on a grid-wide barrier, so a launch WITHOUT the co-residency guarantee could deadlock a busy GPU: never
+      // retry non-cooperatively.  The first chunk of the first layer reports "unsupported" and the caller runs the per-step
+      // GEMM recurrence instead.
       (void)cudaGetLastError();
-      cfg.numAttrs = 0;
-      e = cudaLaunchKernelEx(&cfg, lstm_rec_kernel, tm_w, tm_hhi, tm_hlo, p);
+      set_error("lstm_rec_kernel: cooperative launch refused (%s)", cudaGetErrorString(e));
+      return YT8M_E_UNSUPPORTED;
     }
     if (e != cudaSuccess) {
       set_error("lstm_rec_kernel: launch failed: %s", cudaGetErrorString(e));

@@ -89,17 +89,37 @@ __global__ void grad_reg_sumsq_kernel(float* __restrict__ g, const float* __rest
     }
   }
   __shared__ float red[4][8];
+  __shared__ bool is_last;
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
     const float a = warp_sum(sg[s]), b = warp_sum(sw[s]);
     if ((threadIdx.x & 31) == 0) { red[s][threadIdx.x >> 5] = a; red[2 + s][threadIdx.x >> 5] = b; }
   }
   __syncthreads();
+  // DETERMINISTIC across launches and across data-parallel ranks (replicas must apply bit-identical clip scales): every
+  // block parks its four partial sums in sums[8 + 4 * block ..] and the LAST block to finish (ticket at sums[4]) adds them up
+  // in block order -- no floating-point atomics.
   if (threadIdx.x < 4) {
     float t = 0.0f;
     for (int wq = 0; wq < (blockDim.x >> 5); ++wq) t += red[threadIdx.x][wq];
-    if (t != 0.0f) atomicAdd(&sums[threadIdx.x], t);
+    sums[8 + 4 * blockIdx.x + threadIdx.x] = t;
   }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(reinterpret_cast<unsigned int*>(sums + 4), 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (is_last && threadIdx.x < 128) {
+    __threadfence();
+    const int j = threadIdx.x & 3, part = threadIdx.x >> 2;          // 32 partial chains per sum, then a fixed tree
+    float t = 0.0f;
+    for (unsigned int b = part; b < gridDim.x; b += 32) t += __ldcg(sums + 8 + 4 * b + j);
+    // lanes j, j+4, ..., j+28 of a warp hold 8 of the 32 chains of sum j: fixed butterfly, then the 4 warps through shared memory
+#pragma unroll
+    for (int o = 16; o >= 4; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if ((threadIdx.x & 31) < 4) red[threadIdx.x & 3][threadIdx.x >> 5] = t;
+  }
+  __syncthreads();
+  if (is_last && threadIdx.x < 4) sums[threadIdx.x] = (red[threadIdx.x][0] + red[threadIdx.x][1]) + (red[threadIdx.x][2] + red[threadIdx.x][3]);
 }
 
 // per-tensor clip_by_norm (g * c / max(||g||, c)) + TF-1.0 Adam (epsilon outside the sqrt, lr_t carries the bias
@@ -341,10 +361,12 @@ int yt8m_grad_reg_sumsq(float* grad, const float* param, long long rows, int row
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   YT8M_REQUIRE(grad && param && sums4, YT8M_E_BADPTR, "yt8m_grad_reg_sumsq: null pointer");
   YT8M_REQUIRE(rows > 0 && row_len > 0, YT8M_E_BADSHAPE, "yt8m_grad_reg_sumsq: bad shape");
-  YT8M_CUDA(cudaMemsetAsync(sums4, 0, 4 * sizeof(float), stream));
+  YT8M_CUDA(cudaMemsetAsync(sums4, 0, 8 * sizeof(float), stream));       // the four sums + the block ticket
   const bool vec = row_len % 4 == 0 && aligned16(grad) && aligned16(param);
-  if (vec) grad_reg_sumsq_kernel<true><<<grid_for(rows * row_len / 4, 2048), 256, 0, stream>>>(grad, param, rows, row_len, l2, moe_per, moe_nmix, sums4);
-  else grad_reg_sumsq_kernel<false><<<grid_for(rows * row_len, 2048), 256, 0, stream>>>(grad, param, rows, row_len, l2, moe_per, moe_nmix, sums4);
+  // at most (YT8M_SUMS_FLOATS - 8) / 4 blocks: each parks four partials in the caller's buffer
+  constexpr int kMaxBlocks = (YT8M_SUMS_FLOATS - 8) / 4;
+  if (vec) grad_reg_sumsq_kernel<true><<<min(grid_for(rows * row_len / 4, 2048), kMaxBlocks), 256, 0, stream>>>(grad, param, rows, row_len, l2, moe_per, moe_nmix, sums4);
+  else grad_reg_sumsq_kernel<false><<<min(grid_for(rows * row_len, 2048), kMaxBlocks), 256, 0, stream>>>(grad, param, rows, row_len, l2, moe_per, moe_nmix, sums4);
   return check_launch("grad_reg_sumsq_kernel");
 }
 

@@ -24,7 +24,8 @@ def calculate_precision_at_equal_recall_rate(predictions, actuals):
   for n in numpy.unique(counts):
     rows = numpy.nonzero(counts == n)[0]
     if n <= 0:
-      total += float("nan") * len(rows)
+      # a label-free video contributes 0: the reference's argpartition(..., -0)[-0:] selects every class and none is a hit
+      # (wh/eval_util.py:87-96; golden case "empty_label_rows")
       continue
     # same selection rule as the reference (numpy.argpartition per row), batched over equal n
     idx = numpy.argpartition(predictions[rows], -n, axis=1)[:, -n:]
@@ -101,7 +102,7 @@ def step_metrics_from_topk(top_val, top_idx, actuals, top_k=20):
     within = numpy.arange(kp)[None, :] < counts[:, None]         # the num_labels best classes of every video
     hits = (hit_lab * (top_val > 0) * within).sum(axis=1)
     with numpy.errstate(divide="ignore", invalid="ignore"):
-      perr = float(numpy.where(counts > 0, hits / counts, numpy.nan).sum() / n_videos)
+      perr = float(numpy.where(counts > 0, hits / numpy.maximum(counts, 1), 0.0).sum() / n_videos)   # label-free video: 0
   k = min(top_k, actuals.shape[1])
   gap = _ap(top_val[:, :k].ravel(), hit_lab[:, :k].ravel(), float(actuals.sum()))
   return hit_at_one, perr, gap

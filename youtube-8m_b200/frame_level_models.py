@@ -244,12 +244,21 @@ class AttentionModel(models.BaseModel):
     w = st.get("Attention/W", (2 * d, num_extend), ops.truncated_normal(0.1), l2=l2_penalty)
     st.get("Attention/b", (num_extend,), ops.constant_init(0.1), l2=l2_penalty, round_bf16=False)
     wp = st.packed(w, "kmajor_top", lambda: nat.pack_transpose(w.value[:d].contiguous()))
-    logits = nat.linear(x.reshape(b * t, d), wp, n=num_extend, k=d)["f32"]
-    logits3 = logits.as_strided((b, t, num_extend), (t * logits.stride(0), logits.stride(0), 1))
-    pooled, hi, lo = nat.attn_pool(logits3, x, None, num_extend, 0)
+    with nat.region("attention_pool"):
+      logits = nat.linear(x.reshape(b * t, d), wp, n=num_extend, k=d)["f32"]
+      logits3 = logits.as_strided((b, t, num_extend), (t * logits.stride(0), logits.stride(0), 1))
+      pooled, hi, lo = nat.attn_pool(logits3, x, None, num_extend, 0)
     act = ops.Act(f32=pooled.reshape(b * num_extend, d), hi=hi.reshape(b * num_extend, d),
                   lo=lo.reshape(b * num_extend, d))
-    return _classifier().create_model(model_input=act, vocab_size=vocab_size, **unused_params)
+    out = _classifier().create_model(model_input=act, vocab_size=vocab_size, **unused_params)
+    if out["predictions"].shape[0] == b * num_extend and num_extend > 1:
+      # a row-wise classifier (MoeModel, ChainMoeModel, DeepCombineChainModel -- BASELINE configs[4] "attention pool +
+      # chained MoE") scored every head: reduce with the max over heads MoeExtendModel takes (zt/video_level_models.py:2327-2328)
+      out = dict(out)
+      out["predictions"] = nat.group_max_rows(out["predictions"], num_extend)
+      if "support_predictions" in out:
+        out["support_predictions"] = nat.group_max_rows(out["support_predictions"].contiguous(), num_extend)
+    return out
 
 
 class DbofModel(models.BaseModel):

@@ -8,6 +8,7 @@ the GPU still QUANTISED (uint8 [B, max_frames, D], zero padded -- wh/readers.py:
 (wh/utils.py:23-38) and the L2 normalisation are fused into one kernel behind DefaultTransformer.
 """
 import glob
+import random
 import struct
 
 import numpy as np
@@ -241,6 +242,89 @@ def _files(pattern):
   return files
 
 
+def _label_vector(feature, num_classes):
+  """tf.VarLenFeature + sparse_to_indicator (wh/readers.py:101-107, 225-228): a missing or empty `labels` feature is an
+  empty label set (unlabeled test-set records); ids at or beyond num_classes are dropped."""
+  lab = np.zeros(num_classes, dtype=bool)
+  if feature is not None and feature[1] is not None and len(feature[1]):
+    idx = np.asarray(feature[1], dtype=np.int64)
+    lab[idx[(idx >= 0) & (idx < num_classes)]] = True
+  return lab
+
+
+def record_batches(data_pattern, batch_size, num_epochs=1, verify_crc=False, shuffle=False, seed=0, shuffle_buffer=None,
+                   drop_remainder=False):
+  """Batches of RAW records.  shuffle=True reproduces the reference's input randomisation (wh/train.py:199-209 /
+  wh/readers.py via tf.train.string_input_producer(shuffle=True) + shuffle_batch_join(capacity=5*batch_size)): the file
+  list is re-shuffled every epoch and records pass through a shuffle buffer of `shuffle_buffer` (default 5 * batch_size)
+  records.  The order depends only on (seed, file list, record counts), never on record contents, so every data-parallel
+  rank that runs this generator with the same seed sees the same batches and can parse just its own rows.
+  drop_remainder: the reference's shuffle_batch_join (allow_smaller_final_batch=False) never emits a short final batch."""
+  rng = random.Random(seed)
+  cap = (5 * batch_size if shuffle_buffer is None else shuffle_buffer) if shuffle else 0
+  pool, batch = [], []
+  for _ in range(num_epochs):
+    files = _files(data_pattern)
+    if shuffle:
+      rng.shuffle(files)
+    for path in files:
+      for rec in tfrecord_iterator(path, verify_crc):
+        if cap:
+          if len(pool) < cap:
+            pool.append(rec)
+            continue
+          j = rng.randrange(cap)
+          rec, pool[j] = pool[j], rec
+        batch.append(rec)
+        if len(batch) == batch_size:
+          yield batch
+          batch = []
+  rng.shuffle(pool)
+  for rec in pool:
+    batch.append(rec)
+    if len(batch) == batch_size:
+      yield batch
+      batch = []
+  if batch and not drop_remainder:
+    yield batch
+
+
+def shard_range(n_rows, shard):
+  """Rows [lo, hi) of a batch owned by rank r of w (balanced: sizes differ by at most one)."""
+  if shard is None:
+    return 0, n_rows
+  r, w = shard
+  base, extra = divmod(n_rows, w)
+  lo = r * base + min(r, extra)
+  return lo, lo + base + (1 if r < extra else 0)
+
+
+def prefetch(generator, depth=2):
+  """Runs `generator` in a background thread, `depth` batches ahead of the consumer -- the stand-in for the reference's
+  queue-runner threads (wh/train.py:199-209): TFRecord parsing overlaps the GPU step."""
+  import queue
+  import threading
+  q = queue.Queue(maxsize=max(depth, 1))
+  end = object()
+
+  def work():
+    try:
+      for item in generator:
+        q.put(item)
+      q.put(end)
+    except BaseException as e:                         # surfaces in the consumer
+      q.put(e)
+
+  threading.Thread(target=work, daemon=True).start()
+  while True:
+    item = q.get()
+    if item is end:
+      return
+    if isinstance(item, BaseException):
+      raise item
+    yield item
+
+
 class YT8MAggregatedFeatureReader(BaseReader):
   """Video-level Examples (wh/readers.py:66-125)."""
 
@@ -249,23 +333,24 @@ class YT8MAggregatedFeatureReader(BaseReader):
         "length of feature_names (={}) != length of feature_sizes (={})".format(len(feature_names), len(feature_sizes))
     self.num_classes, self.feature_sizes, self.feature_names = num_classes, list(feature_sizes), list(feature_names)
 
-  def prepare_reader(self, data_pattern, batch_size=1024, num_epochs=1, verify_crc=False):
-    """Generator of (video_ids [B], features fp32 [B, sum(sizes)], labels bool [B, C], num_frames ones [B])."""
-    ids, feats, labels = [], [], []
-    for _ in range(num_epochs):
-      for path in _files(data_pattern):
-        for rec in tfrecord_iterator(path, verify_crc):
-          ex = parse_example(rec)
-          ids.append(ex["video_id"][1][0])
-          feats.append(np.concatenate([ex[n][1][:s] for n, s in zip(self.feature_names, self.feature_sizes)]))
-          lab = np.zeros(self.num_classes, dtype=bool)
-          lab[ex["labels"][1][ex["labels"][1] < self.num_classes]] = True
-          labels.append(lab)
-          if len(ids) == batch_size:
-            yield ids, torch.from_numpy(np.stack(feats)), torch.from_numpy(np.stack(labels)), torch.ones(len(ids), dtype=torch.int32)
-            ids, feats, labels = [], [], []
-    if ids:
-      yield ids, torch.from_numpy(np.stack(feats)), torch.from_numpy(np.stack(labels)), torch.ones(len(ids), dtype=torch.int32)
+  def prepare_reader(self, data_pattern, batch_size=1024, num_epochs=1, verify_crc=False, shuffle=False, seed=0, shard=None,
+                     drop_remainder=False, shuffle_buffer=None):
+    """Generator of (video_ids [B], features fp32 [B, sum(sizes)], labels bool [B, C], num_frames ones [B]).
+    shard=(rank, world): only this rank's rows of every batch are parsed and returned, and a 5th element carries the
+    GLOBAL row count of the batch."""
+    for recs in record_batches(data_pattern, batch_size, num_epochs, verify_crc, shuffle, seed, shuffle_buffer, drop_remainder):
+      lo, hi = shard_range(len(recs), shard)
+      ids, feats, labels = [], [], []
+      for rec in recs[lo:hi]:
+        ex = parse_example(rec)
+        ids.append(ex["video_id"][1][0])
+        feats.append(np.concatenate([ex[n][1][:s] for n, s in zip(self.feature_names, self.feature_sizes)]))
+        labels.append(_label_vector(ex.get("labels"), self.num_classes))
+      d = sum(self.feature_sizes)
+      out = (ids, torch.from_numpy(np.stack(feats)) if feats else torch.zeros((0, d)),
+             torch.from_numpy(np.stack(labels)) if labels else torch.zeros((0, self.num_classes), dtype=torch.bool),
+             torch.ones(len(ids), dtype=torch.int32))
+      yield out if shard is None else out + (len(recs),)
 
 
 class PackedFrames(object):
@@ -358,39 +443,34 @@ class YT8MFrameFeatureReader(BaseReader):
     out[:n] = mat[:n]
     return out, n
 
-  def prepare_reader(self, data_pattern, batch_size=1024, num_epochs=1, verify_crc=False, packed=False):
+  def prepare_reader(self, data_pattern, batch_size=1024, num_epochs=1, verify_crc=False, packed=False, shuffle=False, seed=0,
+                     shard=None, drop_remainder=False, shuffle_buffer=None):
     """Generator of (video_ids, features uint8 [B, max_frames, D], labels bool [B, C], num_frames int32 [B]).
-    packed=True: the features come as a PackedFrames (real frames only; same .shape) instead of the padded tensor."""
-    ids, mats, labels, nfs = [], [], [], []
-
-    def flush():
-      nf = torch.tensor(nfs, dtype=torch.int32)
+    packed=True: the features come as a PackedFrames (real frames only; same .shape) instead of the padded tensor.
+    shuffle / seed / shard / drop_remainder: see record_batches and YT8MAggregatedFeatureReader.prepare_reader."""
+    d = sum(self.feature_sizes)
+    for recs in record_batches(data_pattern, batch_size, num_epochs, verify_crc, shuffle, seed, shuffle_buffer, drop_remainder):
+      lo, hi = shard_range(len(recs), shard)
+      ids, mats, labels, nfs = [], [], [], []
+      for rec in recs[lo:hi]:
+        ctx, lists = parse_sequence_example(rec)
+        parts, nf = [], -1
+        for name, size in zip(self.feature_names, self.feature_sizes):
+          m, n = self.get_video_matrix([f[1][0] for f in lists[name]], size)
+          if nf != -1 and n != nf:
+            raise ValueError("feature %s has %d frames, expected %d" % (name, n, nf))
+          nf = n
+          parts.append(m)
+        ids.append(ctx["video_id"][1][0])
+        mats.append(np.concatenate(parts, axis=1))
+        labels.append(_label_vector(ctx.get("labels"), self.num_classes))
+        nfs.append(nf)
+      nft = torch.tensor(nfs, dtype=torch.int32)
       if packed:
-        feats = PackedFrames(torch.from_numpy(np.concatenate([m[:n] for m, n in zip(mats, nfs)], axis=0)), nf, self.max_frames)
+        data = np.concatenate([m[:n] for m, n in zip(mats, nfs)], axis=0) if mats else np.zeros((0, d), dtype=np.uint8)
+        feats = PackedFrames(torch.from_numpy(data), nft, self.max_frames)
       else:
-        feats = torch.from_numpy(np.stack(mats))
-      return ids, feats, torch.from_numpy(np.stack(labels)), nf
-
-    for _ in range(num_epochs):
-      for path in _files(data_pattern):
-        for rec in tfrecord_iterator(path, verify_crc):
-          ctx, lists = parse_sequence_example(rec)
-          parts, nf = [], -1
-          for name, size in zip(self.feature_names, self.feature_sizes):
-            m, n = self.get_video_matrix([f[1][0] for f in lists[name]], size)
-            if nf != -1 and n != nf:
-              raise ValueError("feature %s has %d frames, expected %d" % (name, n, nf))
-            nf = n
-            parts.append(m)
-          ids.append(ctx["video_id"][1][0])
-          mats.append(np.concatenate(parts, axis=1))
-          lab = np.zeros(self.num_classes, dtype=bool)
-          idx = ctx["labels"][1]
-          lab[idx[idx < self.num_classes]] = True
-          labels.append(lab)
-          nfs.append(nf)
-          if len(ids) == batch_size:
-            yield flush()
-            ids, mats, labels, nfs = [], [], [], []
-    if ids:
-      yield flush()
+        feats = torch.from_numpy(np.stack(mats)) if mats else torch.zeros((0, self.max_frames, d), dtype=torch.uint8)
+      lab = torch.from_numpy(np.stack(labels)) if labels else torch.zeros((0, self.num_classes), dtype=torch.bool)
+      out = (ids, feats, lab, nft)
+      yield out if shard is None else out + (len(recs),)

@@ -48,7 +48,11 @@ if __name__ == "__main__":
   flags.DEFINE_integer("max_steps", None, "The maximum number of iterations of the training loop.")
   flags.DEFINE_float("keep_checkpoint_every_n_hours", 1.0, "How many hours before saving a new checkpoint")
   flags.DEFINE_integer("keep_checkpoint_interval", 15, "How many minutes to wait before saving a new checkpoint")
-  flags.DEFINE_integer("num_readers", 8, "How many threads to use for reading input files. (accepted, unused)")
+  flags.DEFINE_integer("num_readers", 8, "How many batches the background input thread may run ahead of the training step "
+                       "(the reference's queue-runner thread count, wh/train.py:199-209); 0 = read synchronously.")
+  flags.DEFINE_integer("shuffle_seed", 0, "Seed of the input shuffle (file order per epoch + a 5*batch_size record buffer, "
+                       "as string_input_producer(shuffle=True) + shuffle_batch_join do in the reference).")
+  flags.DEFINE_bool("shuffle_input", True, "Shuffle the training input like the reference does; False replays the files in sorted order.")
   flags.DEFINE_string("optimizer", "AdamOptimizer", "What optimizer class to use.")
   flags.DEFINE_float("clip_gradient_norm", 1.0, "Norm to clip gradients to.")
   flags.DEFINE_bool("log_device_placement", False, "Whether to write the device on which every op will run into the logs on startup.")
@@ -186,20 +190,30 @@ class Trainer(object):
     steps, last_save = 0, time.time()
     # frame-level batches travel as readers.PackedFrames: only the real frames cross PCIe (the padding is made on the GPU)
     packed = {"packed": True} if FLAGS.frame_features else {}
-    for video_ids, feats, labels, num_frames in self.reader.prepare_reader(FLAGS.train_data_pattern, FLAGS.batch_size, FLAGS.num_epochs,
-                                                                           **packed):
+    # Input pipeline (wh/train.py:199-209): the file order is re-shuffled every epoch and records pass through a shuffle
+    # buffer of 5 * batch_size; every rank derives the SAME record order from --shuffle_seed and parses only its own rows of
+    # each global batch; a background thread keeps --num_readers batches ahead of the step.  Like the reference's
+    # shuffle_batch_join (allow_smaller_final_batch=False) a final batch with fewer videos than ranks is dropped -- every
+    # rank sees the same global row count, so they all skip it together and nobody waits alone in the all-reduce.
+    batches = self.reader.prepare_reader(FLAGS.train_data_pattern, FLAGS.batch_size, FLAGS.num_epochs, shuffle=FLAGS.shuffle_input,
+                                         seed=FLAGS.shuffle_seed, shard=(rank, world), **packed)
+    if FLAGS.num_readers > 0:
+      batches = readers.prefetch(batches, depth=min(FLAGS.num_readers, 4))
+    for video_ids, feats, labels, num_frames, n_global in batches:
+      if n_global < world:
+        logging.info("dropping a final batch of %d videos (fewer than the %d ranks)", n_global, world)
+        continue
       steps += 1
       t0 = time.time()
-      lo, hi = yt8m_dp.shard_rows(feats.shape[0])
-      x, nf = transformer.transform(feats[lo:hi].cuda(non_blocking=True), num_frames[lo:hi])
-      y = labels[lo:hi].cuda(non_blocking=True).float()
+      x, nf = transformer.transform(feats.cuda(non_blocking=True), num_frames)
+      y = labels.cuda(non_blocking=True).float()
       frame_args = (nf.to("cuda", torch.int32),) if FLAGS.frame_features else ()
       p = trainer.step(x, *frame_args, y, FLAGS.base_learning_rate, FLAGS.learning_rate_decay, FLAGS.learning_rate_decay_examples,
-                       FLAGS.clip_gradient_norm, FLAGS.regularization_penalty, global_batch=feats.shape[0])
+                       FLAGS.clip_gradient_norm, FLAGS.regularization_penalty, global_batch=n_global)
       if self.is_master:
         # the log line's metrics (wh/train.py:578-591) from the per-video top-32 extracted on the GPU: 64 numbers per video
         # cross PCIe instead of 4716, and the host loop is O(B * 32)
-        lv = labels[lo:hi].numpy().astype("float32")
+        lv = labels.numpy().astype("float32")
         kk = min(32, p.shape[1])
         ti, tv = nat.topk_rows(p, kk)
         hit1, perr, gap = eval_util.step_metrics_from_topk(tv.cpu().numpy(), ti.cpu().numpy(), lv, top_k=min(20, kk))
@@ -210,7 +224,7 @@ class Trainer(object):
         logging.info("training step " + str(trainer.global_step) + "| Hit@1: " + ("%.2f" % hit1) +
                      " PERR: " + ("%.2f" % perr) + " GAP: " +
                      ("%.2f" % gap) + " Recall@%d: " % FLAGS.recall_at_n + "N/A" + " Loss: " + str(loss_val) +
-                     " Examples/sec: %.1f" % (feats.shape[0] / max(seconds, 1e-9)))
+                     " Examples/sec: %.1f" % (n_global / max(seconds, 1e-9)))
         if time.time() - last_save > FLAGS.keep_checkpoint_interval * 60:
           self.save(trainer)
           last_save = time.time()
@@ -240,6 +254,11 @@ def main(unused_argv=None):
   off = [n for n in ("reweight", "distillation_features", "distillation_as_input", "distillation_as_boosting") if getattr(FLAGS, n)]
   if off or FLAGS.distillation_percent > 0 or FLAGS.distillation_type != 0:
     raise NotImplementedError("train.py: the boosting / distillation pipeline (--reweight, --distillation_*) is outside the hot path")
+  if FLAGS.dropout or FLAGS.keep_prob != 1.0 or FLAGS.noise_level != 0.0:
+    # accepted for command-line compatibility, but never silently ignored: a run that asks for them would train a different,
+    # unregularised model
+    raise NotImplementedError("train.py: --dropout / --keep_prob / --noise_level (training-time regularisers of models outside "
+                              "SURVEY.md §8) are not built; leave them at their defaults")
   if not torch.cuda.is_available():
     raise SystemExit("train.py: no CUDA device; the yt8m_b200 path has no CPU fallback")
   rank, world, local_rank = yt8m_dp.init_from_env()

@@ -43,6 +43,6 @@ def shard_rows(n_rows, group=None):
   """Contiguous row range [lo, hi) of the global batch owned by this rank (rank r owns rows
   [r*B/W, (r+1)*B/W) -- SURVEY.md §8e)."""
   w, r = world_size(group), rank(group)
-  per = (n_rows + w - 1) // w
-  lo = min(r * per, n_rows)
-  return lo, min(lo + per, n_rows)
+  base, extra = divmod(n_rows, w)                # balanced: shard sizes differ by at most one row; a rank is empty only
+  lo = r * base + min(r, extra)                  # when n_rows < world (callers drop such a batch on every rank together)
+  return lo, lo + base + (1 if r < extra else 0)

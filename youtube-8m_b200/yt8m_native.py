@@ -134,6 +134,30 @@ def kernel_timer_read(pairs):
   return [a.elapsed_time(b) for a, b in pairs]
 
 
+class region(object):
+  """``with nat.region("attention_pool"):`` -- a named group of library calls.  A no-op unless bench.py's kernel timer is
+  armed with exactly this tag, in which case ONE CUDA-event pair brackets the whole group (e.g. the logits GEMM + the
+  pooling kernel of the attention pooler)."""
+
+  def __init__(self, tag):
+    self.tag, self.e1 = tag, None
+
+  def __enter__(self):
+    global _KT
+    if _KT is not None and _KT["tag"] == self.tag:
+      ext = torch.cuda.is_current_stream_capturing()
+      e0 = torch.cuda.Event(enable_timing=True, external=ext)
+      self.e1 = torch.cuda.Event(enable_timing=True, external=ext)
+      e0.record()
+      _KT["ev"].append((e0, self.e1))
+    return self
+
+  def __exit__(self, *exc):
+    if self.e1 is not None:
+      self.e1.record()
+    return False
+
+
 def _call(name, *args):
   fn = getattr(_lib, name)
   if _KT is not None and _KT["tag"] in name:
@@ -246,6 +270,7 @@ def _workspace(nbytes, device):
 
 
 FMT_BF16, FMT_F16 = 0, 1
+SUMS_FLOATS = 4104                 # include/yt8m_b200.h: YT8M_SUMS_FLOATS
 
 
 def _fmt(t):
@@ -349,8 +374,8 @@ def lstm_fwd(x, num_frames, w_packed, b_packed, hidden, forget_bias=1.0, want_se
   ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
   wp = (c_void_p * layers)(*[w.data_ptr() for w in w_packed])
   bp = (c_void_p * layers)(*[v.data_ptr() for v in b_packed])
-  _check(_lib.yt8m_lstm_fwd(_p(x), _p(num_frames), b, t, d, hidden, layers, ctypes.cast(wp, c_void_p), ctypes.cast(bp, c_void_p),
-                            float(forget_bias), _p(state), _p(seq), _p(seq_bf), _p(ws), ws_bytes, _stream()), "yt8m_lstm_fwd")
+  _call("yt8m_lstm_fwd", _p(x), _p(num_frames), b, t, d, hidden, layers, ctypes.cast(wp, c_void_p), ctypes.cast(bp, c_void_p),
+        float(forget_bias), _p(state), _p(seq), _p(seq_bf), _p(ws), ws_bytes, _stream())
   return state, seq, seq_bf
 
 
@@ -610,7 +635,7 @@ def moe_bwd_dlogits(x_hi, x_lo, w_packed, bias_packed, dp, vocab, num_mixtures, 
 
 def grad_reg_sumsq(grad, param, l2, moe_per=0, moe_nmix=0):
   rows, row_len = (param.shape[0], param.shape[1]) if param.dim() == 2 else (1, param.numel())
-  sums = _f32((4,), param.device)
+  sums = _f32((SUMS_FLOATS,), param.device)     # [0..3] results, the rest: scratch of the deterministic reduction
   _check(_lib.yt8m_grad_reg_sumsq(_p(grad), _p(param), rows, row_len, float(l2), moe_per, moe_nmix, _p(sums), _stream()),
          "yt8m_grad_reg_sumsq")
   return sums

@@ -167,6 +167,11 @@ class VariableStore(object):
     return {k: v.value.detach().cpu() for k, v in self.vars.items()}
 
   def load_state_dict(self, sd, strict=True):
+    if strict:
+      # both directions: a model variable that the checkpoint lacks would silently keep its random initialisation
+      missing = sorted(k for k in self.vars if k not in sd)
+      if missing:
+        raise KeyError("model variables missing from the checkpoint: %s" % ", ".join(missing))
     for k, t in sd.items():
       if k in self.vars:
         self.vars[k].assign(t)
