@@ -81,7 +81,7 @@ def rnd(rs, shape, scale=1.0):
 def case_inputs(case):
   """Returns (inputs dict, weights dict by TF variable name, flags dict) for a named case."""
   rs = np.random.RandomState({"moe": 1, "logistic": 2, "chain": 3, "deep_chain": 4, "xent": 5, "lstm_att_max": 6, "lstm_multi_att": 7,
-                              "dequantize": 8, "lstm": 9, "lstm_memory": 10, "zt_attention": 11, "dbof_bn": 12, "dbof_bias": 13, "video_matrix": 14, "format_lines": 15, "log_lines": 16}[case])
+                              "dequantize": 8, "lstm": 9, "lstm_memory": 10, "zt_attention": 11, "dbof_bn": 12, "dbof_bias": 13, "video_matrix": 14, "format_lines": 15, "log_lines": 16, "multitask_xent": 17}[case])
   b, d, v, m = 4, 8, 6, 2
   if case == "moe":
     return ({"x": rnd(rs, (b, d))}, {"gates/weights": rnd(rs, (d, v * (m + 1))), "experts/weights": rnd(rs, (d, v * m)),
@@ -115,6 +115,13 @@ def case_inputs(case):
     p = 1.0 / (1.0 + np.exp(-rnd(rs, (b, v), 2.0)))
     p[0, 0], p[1, 1] = 0.0, 1.0                     # the epsilon inside the logs matters exactly here
     return ({"p": p.astype(np.float32), "labels": rs.random_sample((b, v)) < 0.4}, {}, {"label_smoothing": False})
+  if case == "multitask_xent":
+    # wh/losses.py:271-279 with --support_type="label,label" (the chain scripts, training_scripts/run-cascade-75-chaining-video.sh:17-20)
+    # and with --support_type="frequent"
+    sig = lambda a: (1.0 / (1.0 + np.exp(-a))).astype(np.float32)
+    return ({"p": sig(rnd(rs, (b, v), 2.0)), "support_ll": sig(rnd(rs, (b, 2 * v), 2.0)), "support_freq": sig(rnd(rs, (b, 3), 2.0)),
+             "labels": rs.random_sample((b, v)) < 0.4}, {},
+            {"label_smoothing": False, "support_loss_percent": 0.3, "num_frequents": 3, "num_classes": v})
   if case in ("lstm", "lstm_memory"):
     bb, t, dd, h, layers = 3, 6, 4, 5, 2
     x = rnd(rs, (bb, t, dd))
@@ -219,6 +226,14 @@ def run_reference(case):
     losses = load("losses.py", "ref_losses")
     out = losses.CrossEntropyLoss().calculate_loss(shim.t(inputs["p"]), inputs["labels"])
     return {"loss": float(out)}
+  elif case == "multitask_xent":
+    losses = load("losses.py", "ref_losses")
+    res = {}
+    for st, key in (("label,label", "support_ll"), ("frequent", "support_freq")):
+      fv.support_type = st
+      res[st] = float(losses.MultiTaskCrossEntropyLoss().calculate_loss(shim.t(inputs["p"]), shim.t(inputs[key]), inputs["labels"]))
+      res["support_labels:" + st] = np.asarray(losses.MultiTaskCrossEntropyLoss().get_support(inputs["labels"]), dtype=np.float32).tolist()
+    return res
   elif case == "lstm_att_max":
     mod = load("all_frame_models/lstm_attention_max_pooling_model.py", "ref_lstm_att_max")
     out = mod.LstmAttentionMaxPoolingModel().create_model(shim.t(inputs["x"]), v, inputs["num_frames"])["predictions"]
@@ -284,7 +299,7 @@ def run_reference(case):
   return {"predictions": np.asarray(out, dtype=np.float64).tolist()}
 
 
-CASES = ["moe", "logistic", "chain", "deep_chain", "xent", "lstm", "lstm_memory", "lstm_att_max", "lstm_multi_att", "zt_attention",
+CASES = ["moe", "logistic", "chain", "deep_chain", "xent", "multitask_xent", "lstm", "lstm_memory", "lstm_att_max", "lstm_multi_att", "zt_attention",
          "dbof_bn", "dbof_bias", "video_matrix", "format_lines", "log_lines", "dequantize"]
 
 

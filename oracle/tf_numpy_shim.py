@@ -220,7 +220,9 @@ def install(flag_values):
   tf.convert_to_tensor = lambda x, **kw: t(x)
   tf.unstack = lambda x, **kw: [int(v) for v in x]
   tf.zeros_like = lambda x, **kw: np.zeros_like(np.asarray(x))
-  tf.slice = lambda x, begin, size, name=None: t(np.asarray(x)[tuple(slice(int(b_), int(b_) + int(n_)) for b_, n_ in zip(begin, size))])
+  # tf.slice: size -1 = "everything from begin to the end of that dimension"
+  tf.slice = lambda x, begin, size, name=None: t(np.asarray(x)[tuple(slice(int(b_), None if int(n_) < 0 else int(b_) + int(n_))
+                                                                        for b_, n_ in zip(begin, size))])
   tf.fill = lambda dims, value, name=None: t(np.full([int(d_) for d_ in dims], value, dtype=np.float32))
   contrib = types.ModuleType("tensorflow.contrib")
   rnn = types.ModuleType("tensorflow.contrib.rnn")

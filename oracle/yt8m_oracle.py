@@ -341,6 +341,28 @@ def cross_entropy_loss(predictions, labels, epsilon=10e-6):
   return (-ce).sum(dim=1).mean()
 
 
+def support_labels(labels, support_type, num_frequents=200, vertical_mapping=None):
+  """wh/losses.py:222-258 (MultiTaskLoss.get_support): "label" = the labels themselves, "frequent" = the first
+  num_frequents label columns, "vertical" = (labels . mapping) > 0.2 with a [V, num_verticals] 0/1 mapping, a comma list =
+  the column concatenation of its parts."""
+  y = labels.to(DT)
+  if "," in support_type:
+    return torch.cat([support_labels(labels, st, num_frequents, vertical_mapping) for st in support_type.split(",")], dim=1)
+  if support_type == "label":
+    return y
+  if support_type == "frequent":
+    return y[:, :num_frequents]
+  if support_type == "vertical":
+    return ((y @ vertical_mapping.to(DT)) > 0.2).to(DT)
+  raise NotImplementedError(support_type)
+
+
+def multitask_cross_entropy_loss(predictions, support_predictions, labels, sup_labels, support_loss_percent):
+  """wh/losses.py:271-279: CE(predictions, labels) * (1 - p) + CE(support_predictions, support_labels) * p."""
+  return (cross_entropy_loss(predictions, labels) * (1.0 - support_loss_percent) +
+          cross_entropy_loss(support_predictions, sup_labels) * support_loss_percent)
+
+
 def exponential_decay(base_lr, global_step, batch_size, decay_examples, decay):
   """wh/train.py:303-308, staircase=True: lr * decay ** floor(step*B / decay_examples)."""
   return base_lr * decay ** math.floor(global_step * batch_size / decay_examples)

@@ -158,3 +158,41 @@ def test_epoch_log_line_against_reference_code():
   import utils
   inp, _, _ = G.case_inputs("log_lines")
   assert utils.FormatEpochInfo(inp["epoch"]) == GOLDEN["log_lines"]["epoch"]
+
+
+def test_multitask_loss_and_support_labels_match_the_reference():
+  """wh/losses.py:222-279 executed from the reference source (oracle/make_model_golden.py case multitask_xent): the oracle's
+  MultiTaskCrossEntropyLoss and the product's host-side support-label construction."""
+  import torch
+  import losses
+  from yt8m_flags import FLAGS
+  inp, _, fl = G.case_inputs("multitask_xent")
+  gold = GOLDEN["multitask_xent"]
+  labels = torch.from_numpy(inp["labels"])
+  for st, key in (("label,label", "support_ll"), ("frequent", "support_freq")):
+    want_sup = np.asarray(gold["support_labels:" + st], dtype=np.float32)
+    sup = O.support_labels(labels, st, num_frequents=fl["num_frequents"])
+    assert np.array_equal(sup.numpy(), want_sup)
+    got = O.multitask_cross_entropy_loss(torch.from_numpy(inp["p"]), torch.from_numpy(inp[key]), labels, sup, fl["support_loss_percent"])
+    assert abs(float(got) - gold[st]) < 2e-5 * gold[st]
+    with FLAGS.override(support_type=st, num_frequents=fl["num_frequents"]):
+      assert np.array_equal(losses.MultiTaskCrossEntropyLoss().get_support(labels), want_sup)
+
+
+def test_vertical_support_labels(tmp_path):
+  """support_type="vertical" (wh/losses.py:231-247): (labels . mapping) > 0.2 with the 0/1 table read from --vertical_file."""
+  import torch
+  import losses
+  from yt8m_flags import FLAGS
+  f = tmp_path / "vertical.tsv"
+  f.write_text("0 1\n1 1\n2 0\n3 2\n7\n")
+  labels = torch.tensor([[1, 0, 0, 0, 0], [0, 0, 1, 1, 0], [0, 0, 0, 0, 1]], dtype=torch.bool)
+  vm = torch.zeros(5, 3)
+  for a, b in ((0, 1), (1, 1), (2, 0), (3, 2)):
+    vm[a, b] = 1
+  want = O.support_labels(labels, "vertical", vertical_mapping=vm).numpy()
+  losses.MultiTaskLoss._vertical = None
+  with FLAGS.override(support_type="vertical", num_classes=5, num_verticals=3, vertical_file=str(f)):
+    got = losses.MultiTaskCrossEntropyLoss().get_support(labels)
+  losses.MultiTaskLoss._vertical = None
+  assert np.array_equal(got, want) and got.tolist() == [[0, 1, 0], [1, 0, 1], [0, 0, 0]]

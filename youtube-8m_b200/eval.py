@@ -75,9 +75,13 @@ def evaluation_loop(reader, model, checkpoint, last_global_step_val):
         logging.info("skip this checkpoint global_step_val=%s (same as the previous one).", global_step_val)
         return global_step_val
     kw = {"num_frames": nf} if nf is not None else {}
-    p = model.create_model(x, vocab_size=reader.num_classes, is_training=False, **kw)["predictions"]
+    result = model.create_model(x, vocab_size=reader.num_classes, is_training=False, **kw)
+    p = result["predictions"]
     y = labels.cuda(non_blocking=True).float()
-    loss = float(loss_fn.calculate_loss(p, y))
+    if FLAGS.multitask:                            # wh/eval.py:188-190: the loss also sees the support predictions
+      loss = float(loss_fn.calculate_loss(p, result["support_predictions"], labels))
+    else:
+      loss = float(loss_fn.calculate_loss(p, y))
     it = evl_metrics.accumulate(p.cpu().numpy(), labels.numpy().astype("float32"), loss)
     examples_processed += labels.shape[0]
     logging.info("examples_processed: %d | global_step %s | Batch Hit@1: %.3f | Batch PERR: %.3f | Batch Loss: %.3f | "

@@ -100,8 +100,18 @@ class Trainer(object):
     model_cls = utils.find_class_by_name(self.model_name, [frame_level_models, video_level_models])
     if FLAGS.optimizer != "AdamOptimizer":
       raise NotImplementedError("only --optimizer=AdamOptimizer (the reference default) is built")
-    if FLAGS.label_loss != "CrossEntropyLoss":
-      raise NotImplementedError("only --label_loss=CrossEntropyLoss (the reference default) is built")
+    self.multitask = None
+    if FLAGS.multitask:
+      # wh/train.py:394-413: the loss takes (predictions, support_predictions, labels); built for the two chain models, whose
+      # training scripts are the ones that pass --multitask=True --label_loss=MultiTaskCrossEntropyLoss
+      if FLAGS.label_loss != "MultiTaskCrossEntropyLoss" or model_cls not in (video_level_models.ChainMoeModel,
+                                                                              video_level_models.DeepCombineChainModel):
+        raise NotImplementedError("--multitask is built for --label_loss=MultiTaskCrossEntropyLoss with ChainMoeModel / "
+                                  "DeepCombineChainModel")
+      self.multitask = losses.MultiTaskCrossEntropyLoss()
+    elif FLAGS.label_loss != "CrossEntropyLoss":
+      raise NotImplementedError("only --label_loss=CrossEntropyLoss (the reference default; MultiTaskCrossEntropyLoss with "
+                                "--multitask) is built")
     if model_cls in (frame_level_models.NetVLADModel, frame_level_models.GatedNetVLADModel):
       if FLAGS.netvlad_add_batch_norm or FLAGS.video_level_classifier_model != "MoeModel":
         raise NotImplementedError("train.py --model=%s: the CUDA training step is built for "
@@ -138,13 +148,11 @@ class Trainer(object):
       return yt8m_trainer.AttentionTrainer(in_dim, heads=FLAGS.moe_num_extend, vocab=self.reader.num_classes,
                                            mixtures=FLAGS.moe_num_mixtures)
     if model_cls is video_level_models.ChainMoeModel:
-      if FLAGS.multitask:
-        raise NotImplementedError("train.py --model=ChainMoeModel: --multitask (a separate loss on the support predictions) is not built")
       return yt8m_trainer.ChainMoeTrainer(in_dim, vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures,
                                           num_supports=FLAGS.num_supports)
     if model_cls is video_level_models.DeepCombineChainModel:
-      if FLAGS.multitask or FLAGS.deep_chain_relu_type != "relu":
-        raise NotImplementedError("train.py --model=DeepCombineChainModel: built without --multitask and with --deep_chain_relu_type=relu")
+      if FLAGS.deep_chain_relu_type != "relu":
+        raise NotImplementedError("train.py --model=DeepCombineChainModel: built with --deep_chain_relu_type=relu")
       return yt8m_trainer.DeepCombineChainTrainer(in_dim, vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures,
                                                   layers=FLAGS.deep_chain_layers, relu_cells=FLAGS.deep_chain_relu_cells)
     if model_cls is video_level_models.LogisticModel:
@@ -208,8 +216,12 @@ class Trainer(object):
       x, nf = transformer.transform(feats.cuda(non_blocking=True), num_frames)
       y = labels.cuda(non_blocking=True).float()
       frame_args = (nf.to("cuda", torch.int32),) if FLAGS.frame_features else ()
+      extra = {}
+      if self.multitask is not None:
+        extra = {"support_labels": torch.from_numpy(self.multitask.get_support(labels)).cuda(non_blocking=True),
+                 "support_loss_percent": FLAGS.support_loss_percent}
       p = trainer.step(x, *frame_args, y, FLAGS.base_learning_rate, FLAGS.learning_rate_decay, FLAGS.learning_rate_decay_examples,
-                       FLAGS.clip_gradient_norm, FLAGS.regularization_penalty, global_batch=n_global)
+                       FLAGS.clip_gradient_norm, FLAGS.regularization_penalty, global_batch=n_global, **extra)
       if self.is_master:
         # the log line's metrics (wh/train.py:578-591) from the per-video top-32 extracted on the GPU: 64 numbers per video
         # cross PCIe instead of 4716, and the host loop is O(B * 32)

@@ -31,6 +31,19 @@ def adam_lr_t(lr, step, beta1=0.9, beta2=0.999):
   return lr * math.sqrt(1.0 - beta2 ** step) / (1.0 - beta1 ** step)
 
 
+class _mix_loss(object):
+  """The --multitask label loss main * (1 - p) + sum(support parts) * p, kept as 1-element device tensors until someone asks
+  for the number (float()) -- no synchronisation inside the step."""
+
+  def __init__(self, parts, pct):
+    self.parts, self.pct = parts, pct
+
+  def __float__(self):
+    main = float(self.parts["main"])
+    sup = sum(float(v) for k, v in self.parts.items() if k != "main")
+    return main * (1.0 - self.pct) + sup * self.pct
+
+
 def _moe_row_index(vocab, mixtures):
   """Packed-row index of every reference column: gates [V*(M+1)], experts [V*M] (class-major, mixture-minor)."""
   per = 2 * mixtures + 1
@@ -126,12 +139,13 @@ class HeadTrainer(object):
       return nat.linear(hi, self.w_bf16, a_lo=lo, n=self.v, k=self.d, shift=self.b, act="sigmoid")["f32"], (hi, lo)
     return nat.moe_fwd(hi, self.w_bf16, self.b, self.v, self.m, x_lo=lo, d=self.d), (hi, lo)
 
-  def backward(self, p, hi, lo, labels, global_batch, want_dx=False):
+  def backward(self, p, hi, lo, labels, global_batch, want_dx=False, loss_weight=1.0):
     """Loss + gradients of this rank's shard into self.gw / self.gb (NOT yet all-reduced).  Returns (loss, dx):
-    dx [B_local, D] fp32 = dLoss/dx when want_dx (the head sits on top of a trainable frame-level model)."""
+    dx [B_local, D] fp32 = dLoss/dx when want_dx (the head sits on top of a trainable frame-level model).
+    loss_weight scales the gradient only (--multitask: 1 - support_loss_percent, wh/losses.py:279)."""
     b_local = p.shape[0]
     # d(mean over the GLOBAL batch)/dp: xent divides by the local batch, so rescale by B_local / B_global
-    loss, dp = nat.xent(p, labels, want_grad=True, grad_scale=b_local / float(global_batch))
+    loss, dp = nat.xent(p, labels, want_grad=True, grad_scale=loss_weight * b_local / float(global_batch))
     return loss, self.backward_from_dp(dp, p, hi, lo, want_dx)
 
   def backward_from_dp(self, dp, p, hi, lo, want_dx=False):
@@ -636,14 +650,22 @@ class ChainMoeTrainer(object):
     return self._tf_layout(flat)
 
   def step(self, x, labels, base_lr=0.01, lr_decay=0.95, lr_decay_examples=4000000, clip_gradient_norm=1.0,
-           regularization_penalty=1.0, global_batch=None):
+           regularization_penalty=1.0, global_batch=None, support_labels=None, support_loss_percent=0.1):
+    """support_labels [B, num_supports] (--multitask, wh/train.py:394-413 + wh/losses.py:271-279): the label loss becomes
+    CE(main) * (1 - support_loss_percent) + CE(support predictions, support labels) * support_loss_percent."""
     b = x.shape[0]
     global_batch = global_batch or b * self.world
+    pct = support_loss_percent if support_labels is not None else 0.0
     sp, (s_hi, s_lo) = self.support.forward(x)                                        # [B, S] support predictions
     main_in = torch.cat([x.float()[:, :self.d], sp[:, :self.s]], dim=1)               # tf.concat (device copy)
     p, (m_hi, m_lo) = self.main.forward(main_in)
-    loss, d_in = self.main.backward(p, m_hi, m_lo, labels, global_batch, want_dx=True)
+    loss, d_in = self.main.backward(p, m_hi, m_lo, labels, global_batch, want_dx=True, loss_weight=1.0 - pct)
     d_sp = d_in[:, self.d:self.d + self.s].contiguous()                               # the columns that came from the support head
+    loss_parts = {"main": loss}
+    if support_labels is not None:
+      sup_loss, d_sup = nat.xent(sp, support_labels, want_grad=True, grad_scale=pct * b / float(global_batch))
+      nat.add_inplace(d_sp, d_sup)
+      loss_parts["support"] = sup_loss
     self.support.backward_from_dp(d_sp, sp, s_hi, s_lo)
     yt8m_dp.all_reduce_sum_(self.grad, self.group)                                    # the ONE collective of the step
     if self.keep_grads:
@@ -653,7 +675,7 @@ class ChainMoeTrainer(object):
     self.support.apply(lr_t, clip_gradient_norm, regularization_penalty)
     self.main.apply(lr_t, clip_gradient_norm, regularization_penalty)
     self.global_step += 1
-    self.last = {"label_loss_local": loss, "lr": lr}
+    self.last = {"label_loss_local": _mix_loss(loss_parts, pct), "lr": lr, "support_predictions": sp}
     return p
 
 
@@ -897,9 +919,15 @@ class DeepCombineChainTrainer(object):
 
   # ---- step ------------------------------------------------------------------------------------------
   def step(self, x, labels, base_lr=0.01, lr_decay=0.95, lr_decay_examples=4000000, clip_gradient_norm=1.0,
-           regularization_penalty=1.0, global_batch=None):
+           regularization_penalty=1.0, global_batch=None, support_labels=None, support_loss_percent=0.1):
+    """support_labels [B, layers * V] (--multitask; the reference's chain scripts pass --support_type="label,label,..."): adds
+    CE(concat of the sub-predictions, support labels) * support_loss_percent and weighs the main loss by the rest
+    (wh/losses.py:271-279)."""
     b = x.shape[0]
     global_batch = global_batch or b * self.world
+    pct = support_loss_percent if support_labels is not None else 0.0
+    if support_labels is not None and support_labels.shape[1] != self.nl * self.v:
+      raise ValueError("support labels have %d columns, the model emits %d support predictions" % (support_labels.shape[1], self.nl * self.v))
     cur = x.float()[:, :self.d].contiguous()
     saved = []
     for i in range(self.nl):
@@ -910,7 +938,8 @@ class DeepCombineChainTrainer(object):
       saved.append((sub, s_hi, s_lo, p_hi, z))
       cur = torch.cat([cur, n32], dim=1)                                               # tf.concat (device copy)
     p, (m_hi, m_lo) = self.heads[self.nl].forward(cur)
-    loss, dcur = self.heads[self.nl].backward(p, m_hi, m_lo, labels, global_batch, want_dx=True)
+    loss, dcur = self.heads[self.nl].backward(p, m_hi, m_lo, labels, global_batch, want_dx=True, loss_weight=1.0 - pct)
+    loss_parts = {"main": loss}
     for i in range(self.nl - 1, -1, -1):
       sub, s_hi, s_lo, p_hi, z = saved[i]
       dn = dcur[:, self.dims[i]:self.dims[i] + self.r].contiguous()                    # the columns that came from this layer
@@ -919,8 +948,13 @@ class DeepCombineChainTrainer(object):
       nat.wgrad(dzr_hi, dzr_lo, p_hi, self.r, self.v, out=self.g["wr%d" % i])          # dWr^T [relu_cells, V]
       nat.colsum_bf16(dzr_hi, dzr_lo, self.r, out=self.g["br%d" % i].view(-1))
       wr_t = nat.pack_transpose(self.p["wr%d" % i])                                    # bf16 [V(pad), relu_cells]: dgrad operand
-      dsub = nat.linear(dzr_hi, wr_t, a_lo=dzr_lo, n=self.v, k=self.r)["f32"]          # dL/d sub-prediction [B, V]
-      dx_i = self.heads[i].backward_from_dp(dsub.contiguous(), sub, s_hi, s_lo, want_dx=(i > 0))
+      dsub = nat.linear(dzr_hi, wr_t, a_lo=dzr_lo, n=self.v, k=self.r)["f32"].contiguous()   # dL/d sub-prediction [B, V]
+      if support_labels is not None:                                                   # this layer's share of the support loss
+        sl_i = support_labels[:, i * self.v:(i + 1) * self.v].contiguous()
+        sup_loss, d_sup = nat.xent(sub, sl_i, want_grad=True, grad_scale=pct * b / float(global_batch))
+        nat.add_inplace(dsub, d_sup)
+        loss_parts["support%d" % i] = sup_loss
+      dx_i = self.heads[i].backward_from_dp(dsub, sub, s_hi, s_lo, want_dx=(i > 0))
       if i > 0:
         dnext = dcur[:, :self.dims[i]].contiguous()                                    # what continues down the chain ...
         nat.add_inplace(dnext, dx_i[:, :self.dims[i]].contiguous())                    # ... + the path through this layer's MoE
@@ -939,7 +973,7 @@ class DeepCombineChainTrainer(object):
     for head in self.heads:
       head.apply(lr_t, clip_gradient_norm, regularization_penalty)
     self.global_step += 1
-    self.last = {"label_loss_local": loss, "lr": lr}
+    self.last = {"label_loss_local": _mix_loss(loss_parts, pct), "lr": lr}
     return p
 
 
