@@ -22,6 +22,10 @@
 using namespace yt8m;
 
 namespace yt8m {
+int launch_netvlad_v5(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K, const yt8m_bf16* cw_packed,
+                      const float* scale, const float* shift, const float* cw2, yt8m_bf16* out, int out_f16, float* stats,
+                      cudaStream_t stream);
+bool netvlad_v5_supported(int T, int D, int K);
 int launch_netvlad_v4(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, const yt8m_bf16* cw_packed,
                       const float* scale, const float* shift, const float* cw2, yt8m_bf16* out, int out_f16, float* stats,
                       cudaStream_t stream);
@@ -1131,7 +1135,10 @@ extern "C" int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B
   YT8M_REQUIRE(out_fmt == YT8M_FMT_BF16 || (out_fmt == YT8M_FMT_F16 && !out_lo), YT8M_E_UNSUPPORTED,
                "yt8m_netvlad_fwd: out_fmt must be YT8M_FMT_BF16, or YT8M_FMT_F16 without a lo tensor");
   const int out_f16 = out_fmt == YT8M_FMT_F16;
-  // K = 64, a single 16-bit output tensor, at least three 32-frame tiles: the one-pass cluster kernel (yt8m_netvlad_v4.cu)
+  // K = 64, a single 16-bit output tensor: the one-pass four-CTA-cluster kernel (yt8m_netvlad_v5.cu)
+  if (!out_lo && !out_f32 && ld_out == static_cast<long long>(D) * K && netvlad_v5_supported(T, D, K) && !(host_debug_flags() & (4096 | 2048)))
+    return launch_netvlad_v5(x, num_frames, B, T, D, K, cw_packed, scale, shift, cw2, out_hi, out_f16, stats, stream);
+  // (debug flag 2048: the two-CTA predecessor, yt8m_netvlad_v4.cu: K = 64, at least three 32-frame tiles)
   if (K == 64 && !out_lo && !out_f32 && ld_out == static_cast<long long>(D) * K && D / 128 <= 9 && T > 64 &&
       !(host_debug_flags() & 4096))
     return launch_netvlad_v4(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_hi, out_f16, stats, stream);
