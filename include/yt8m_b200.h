@@ -196,6 +196,19 @@ int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, in
                      const yt8m_bf16* cw2_hi, const yt8m_bf16* cw2_lo, float* out_f32, yt8m_bf16* out_hi,
                      yt8m_bf16* out_lo, long long ld_out, int out_fmt, float* stats, yt8m_stream_t stream);
 
+/* The same layer with BLOCKED ("tiled") layouts for the two tensors its epilogue touches element by element, so that every
+ * global access of the kernel is a contiguous 512-byte warp access straight from the accumulator registers (csrc/
+ * yt8m_netvlad_v5.cu: four-CTA cluster per video, every frame read from HBM once):
+ *   descriptor  element (d, k) of a video at  ((d / 32) * (K / 8) + k / 8) * 256 + (d % 32) * 8 + k % 8      [16-bit values]
+ *   cw2_tiled   element (d, k)             at  ((d / 32) * (K / 4) + k / 4) * 128 + (d % 32) * 4 + k % 4      [fp32]
+ * The descriptor is a permutation of the row-major [D, K] flattening: the layer that consumes it (the hidden FC) applies the
+ * same permutation to its weight ROWS once, at packing time (the flatten order of a VLAD descriptor is a free choice).
+ * K = 64, D % 64 == 0, 256 <= D <= 1280; out_fmt: YT8M_FMT_BF16 (hi only) or YT8M_FMT_F16; stats as for yt8m_netvlad_fwd. */
+int yt8m_netvlad_tiled_supported(int T, int D, int K);
+int yt8m_netvlad_fwd_tiled(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K, const yt8m_bf16* cw_packed,
+                           const float* scale, const float* shift, const float* cw2_tiled, yt8m_bf16* out_tiled, int out_fmt,
+                           float* stats, yt8m_stream_t stream);
+
 /* debug only: device buffer (>= 128 u64, or NULL to disable) that receives globaltimer stamps of the
  * NetVLAD kernel's phases for CTA 0 (tools/netvlad_timeline.py decodes them) */
 int yt8m_debug_set_timeline(unsigned long long* dev_buf);

@@ -37,7 +37,22 @@ def run(flags):
   nat.debug_set_flags(0)
   return out[0].float().cpu(), out[3].cpu()
 
-v5, st5 = run(0)
+idx8 = nat.netvlad_tiled_index(D, K, 8, dev)
+idx4 = nat.netvlad_tiled_index(D, K, 4, dev)
+c2t = cw2.to(dev).reshape(-1)[idx4].contiguous()
+targs = (xb, nf.to(dev), cwp, scale.to(dev), shift.to(dev), c2t)
+
+def run_tiled():
+  out, st = nat.netvlad_fwd_tiled(*targs, out_f16=f16, want_stats=True)
+  torch.cuda.synchronize()
+  std = torch.empty_like(out)
+  std[:, idx8] = out                          # tiled position p holds row-major element idx8[p]
+  return std.float().cpu(), st.cpu()
+
+v5, st5 = run_tiled()
+if B <= 8:
+  u5, _ = run(1 << 20)                        # the same kernel with row-major epilogue accesses
+  print("  tiled vs row-major epilogue: max %.3e" % float((v5 - u5).abs().max()))
 print("v5 ran: B=%d T=%d D=%d K=%d fmt=%s finite=%s" % (B, T, D, K, fmt, bool(torch.isfinite(v5).all())), flush=True)
 if B * T * D <= 40 * 300 * 1152:
   want = O.netvlad_pool(x, nf, cw, scale, shift, cw2)
@@ -47,20 +62,19 @@ if B * T * D <= 40 * 300 * 1152:
   bad = (v5 - want).abs().reshape(B, D, K)
   print("  worst videos", bad.amax(dim=(1, 2)).topk(min(4, B)).indices.tolist(), "worst d", bad.amax(dim=(0, 2)).topk(4).indices.tolist(),
         "worst k", bad.amax(dim=(0, 1)).topk(4).indices.tolist())
-old, sto = run(2048)                          # the previous kernel for this shape (v4 / generic)
+old, sto = run(0)                             # the previous kernel for this shape (v4 / generic)
 print("  vs previous kernel: l2 %.3e  max %.3e   stats: asum %.3e ssq %.3e" % (
     float((v5 - old).norm() / old.norm()), float((v5 - old).abs().max()), float((st5[:, :K] - sto[:, :K]).abs().max()),
     float(((st5[:, K:] - sto[:, K:]).abs() / sto[:, K:].abs().clamp_min(1e-6)).max())))
 if do_time:
   real = int(nf.clamp(0, T).sum())
-  for name, flag in (("v5", 0), ("previous", 2048)):
-    nat.debug_set_flags(flag)
+  for name, fn in (("v5 tiled", lambda: nat.netvlad_fwd_tiled(*targs, out_f16=f16)), ("previous", lambda: nat.netvlad_fwd(*args, out_f16=f16))):
     for _ in range(3):
-      nat.netvlad_fwd(*args, out_f16=f16)
+      fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(20):
-      nat.netvlad_fwd(*args, out_f16=f16)
+      fn()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) * 50

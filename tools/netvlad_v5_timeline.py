@@ -12,14 +12,17 @@ nf = torch.full((B,), T, dtype=torch.int32, device=dev)
 cw = (torch.randn(K, D, device=dev) / math.sqrt(D)).to(torch.bfloat16)
 cw2 = torch.randn(D, K, device=dev) / math.sqrt(D)
 for _ in range(3):
-  nat.netvlad_fwd(x, nf, cw, None, None, cw2, out_f16=True)
+  nat.netvlad_fwd_tiled(x, nf, cw, None, None, cw2, out_f16=True)
 buf = torch.zeros(384, dtype=torch.int64, device=dev)
 nat.debug_set_timeline(buf)
-nat.netvlad_fwd(x, nf, cw, None, None, cw2, out_f16=True)
+nat.netvlad_fwd_tiled(x, nf, cw, None, None, cw2, out_f16=True)
 torch.cuda.synchronize()
 nat.debug_set_timeline(None)
 t = buf.cpu().tolist()
-t0 = min(v for v in t if v > 0)
+pos = [v for v in t if v > 0]
+if not pos:
+  raise SystemExit("no stamps: build with YT8M_NVCC_EXTRA=-DYT8M_V5_TIMELINE")
+t0 = min(pos)
 names = {}
 for i in range(8):
   names[i] = "mma0: tile %d landed" % i
@@ -29,6 +32,7 @@ for i in range(8):
   names[32 + i] = "mma1: tile %d assignment landed" % i
   names[40 + i] = "mma1: tile %d issued" % i
   names[56 + i] = "prod: tile %d slot free" % i
+names.update({52: "epi : V in registers", 53: "epi : a_sum ready", 54: "epi : residual done", 55: "epi : ssq reduced", 64: "epi : peers' norms landed"})
 names.update({48: "epi : video complete", 49: "epi : pass 1 done", 50: "epi : norms exchanged", 51: "epi : pass 2 done"})
 for it in range(3):
   ev = [(t[it * 128 + s] - t0, names[s]) for s in names if t[it * 128 + s] > 0]

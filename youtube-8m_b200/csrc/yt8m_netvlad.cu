@@ -1135,10 +1135,11 @@ extern "C" int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B
   YT8M_REQUIRE(out_fmt == YT8M_FMT_BF16 || (out_fmt == YT8M_FMT_F16 && !out_lo), YT8M_E_UNSUPPORTED,
                "yt8m_netvlad_fwd: out_fmt must be YT8M_FMT_BF16, or YT8M_FMT_F16 without a lo tensor");
   const int out_f16 = out_fmt == YT8M_FMT_F16;
-  // K = 64, a single 16-bit output tensor: the one-pass four-CTA-cluster kernel (yt8m_netvlad_v5.cu)
-  if (!out_lo && !out_f32 && ld_out == static_cast<long long>(D) * K && netvlad_v5_supported(T, D, K) && !(host_debug_flags() & (4096 | 2048)))
+  // (debug flag 1 << 20: the four-CTA-cluster kernel of yt8m_netvlad_fwd_tiled with ROW-MAJOR epilogue accesses -- slower than
+  //  its tiled form, kept to check the kernel against this entry point's layout)
+  if ((host_debug_flags() & (1 << 20)) && !out_lo && !out_f32 && ld_out == static_cast<long long>(D) * K && netvlad_v5_supported(T, D, K))
     return launch_netvlad_v5(x, num_frames, B, T, D, K, cw_packed, scale, shift, cw2, out_hi, out_f16, stats, stream);
-  // (debug flag 2048: the two-CTA predecessor, yt8m_netvlad_v4.cu: K = 64, at least three 32-frame tiles)
+  // K = 64, a single 16-bit output tensor, at least three 32-frame tiles: the one-pass two-CTA-cluster kernel (yt8m_netvlad_v4.cu)
   if (K == 64 && !out_lo && !out_f32 && ld_out == static_cast<long long>(D) * K && D / 128 <= 9 && T > 64 &&
       !(host_debug_flags() & 4096))
     return launch_netvlad_v4(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out_hi, out_f16, stats, stream);

@@ -52,7 +52,7 @@ template <int KC>
 struct Cfg {
   static constexpr int kSlots = KC == 64 ? 3 : 2;        // X tiles in flight
   static constexpr int kSB = KC == 64 ? 2 : 1;           // S (logits) accumulators in TMEM
-  static constexpr int kVB = KC == 64 ? 2 : 1;           // V accumulators in TMEM
+  static constexpr int kVB = 1;                          // V accumulators in TMEM (the other 3 x KC columns hold this CTA's cw2 slice)
   static constexpr int kAT = KC == 64 ? 2 : 1;           // assignment tiles in shared memory
   static constexpr int kRB = KC == 64 ? 2 : 1;           // receive buffers for partial logits
   static constexpr int kCwSubBytes = KC * 128;           // one 64-feature block of the centres: KC rows x 128 B
@@ -63,7 +63,8 @@ struct Cfg {
   static constexpr int kSCol = 0;
   static constexpr int kVCol = kSB * KC;                 // 128
   static constexpr int kVStride = kMaxMb * KC;           // columns of one V accumulator
-  static_assert(kVCol + kVB * kVStride <= 512, "TMEM budget");
+  static constexpr int kC2Col = kVCol + kVB * kVStride;  // fp32 cw2[d0 .. d0 + DH, :] resident for the whole kernel (KC = 64)
+  static_assert(kC2Col + (KC == 64 ? kVStride : 0) <= 512, "TMEM budget");
   static constexpr int kOffCw = 0;
   static constexpr int kOffX = kOffCw + kMaxKb * kCwSubBytes;
   static constexpr int kOffA = kOffX + kSlots * kXSlotBytes;
@@ -82,10 +83,14 @@ struct Cfg {
 // [0,8) mma0: tile landed   [8,16) exch: S ready   [16,24) owner: partials landed   [24,32) owner: assignment sent
 // [32,40) mma1: assignment landed   [40,48) mma1: issued   48 epi: video complete   49 pass 1 done   50 norms exchanged
 // 51 pass 2 done   [56,64) producer: slot free
+#ifdef YT8M_V5_TIMELINE
 #define NV5_T(itv, slot)                                                                                          \
   do {                                                                                                            \
     if (timeline && blockIdx.x == 0 && (itv) < 3) timeline[(itv) * 128 + (slot)] = global_timer_ns();              \
   } while (0)
+#else
+#define NV5_T(itv, slot) do { } while (0)
+#endif
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -106,6 +111,21 @@ __device__ __forceinline__ float warp_transpose_reduce32(float* v, int lane) {
   return v[0];
 }
 
+// Code size matters here: sixteen warps in six roles run concurrently out of one instruction cache (the first version's
+// straight-line bodies -- ~3100 hot SASS instructions -- made pure-ALU stretches run at ~15 cycles per instruction).  The
+// bounded-wait loops are therefore a few instructions each, loops stay rolled where registers allow, and the debug timeline
+// is compiled in only with -DYT8M_V5_TIMELINE.
+// compact bounded waits (ptxas cannot allocate registers for real calls in a kernel that uses setmaxnreg, so they are inline;
+// ~100 cycles per probe: a wedged pipeline traps after a few seconds instead of hanging the GPU)
+__device__ __forceinline__ void wait_bar_inl(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) { if (++spins > (1u << 25)) __trap(); }
+}
+__device__ __forceinline__ void wait_bar_cluster_inl(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait_cluster(bar, parity)) { if (++spins > (1u << 25)) __trap(); }
+}
+
 __device__ __forceinline__ uint32_t taddr_of(uint32_t tmem_base, int quadrant) {
   return tmem_base + (static_cast<uint32_t>(quadrant * 32) << 16);
 }
@@ -121,7 +141,10 @@ __device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t ma
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 
-template <int KC>
+// TILED = the blocked descriptor / centre layouts of yt8m_netvlad_fwd_tiled (include/yt8m_b200.h): every global access of the
+// epilogue is then a 512-byte contiguous warp access straight from / to the registers that tcgen05.ld filled (lane = feature
+// row), with no shared-memory transposition.
+template <int KC, bool TILED>
 __global__ void __cluster_dims__(kC, 1, 1) __launch_bounds__(kThreads, 1)
 netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_constant__ CUtensorMap tm_xb,
                   const __grid_constant__ CUtensorMap tm_cw, uint16_t* __restrict__ out, const int* __restrict__ num_frames, int B,
@@ -290,31 +313,44 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
     }
     __syncwarp();
     const CUtensorMap* tmx = (static_cast<int>(rank) < kb_extra) ? &tm_xa : &tm_xb;     // box = this CTA's nkb feature blocks
+    // L2 prefetch cursor: a load issued when its slot frees pays the full HBM latency (~0.9 us) inside a three-slot ring whose
+    // slots live ~3.5 us; every load therefore also asks L2 for the tile kAhead tiles further down this CTA's stream.
+    constexpr int kAhead = 3;
+    const bool do_pf = !(dbg_flags & 65536);
+    int itp = 0, ip = 0, ntp = n_iter > 0 ? vnt(0) : 0;
+    auto prefetch_next = [&]() {
+      if (itp >= n_iter) return;
+      if (do_pf && elect_one()) tma_prefetch_4d(tmx, 0, ip * kF, kb0, vid(itp));
+      __syncwarp();
+      if (++ip == ntp) { ++itp; ip = 0; ntp = itp < n_iter ? vnt(itp) : 0; }
+    };
+    for (int j = 0; j < C::kSlots + kAhead; ++j) prefetch_next();
     int G = 0;
     for (int it = 0; it < n_iter; ++it) {
       const int b = vid(it);
       const int ntv = vnt(it);
       for (int i = 0; i < ntv; ++i, ++G) {
         const int slot = G % C::kSlots, u = G / C::kSlots;
-        mbar_wait(&x_empty[slot], (u & 1) ^ 1u);
+        wait_bar_inl(&x_empty[slot], (u & 1) ^ 1u);
         if (lane == 0 && i < 8) NV5_T(it, 56 + i);
         if (elect_one()) {
           mbar_arrive_expect_tx(&x_full[slot], nkb * kSubBytes);
           tma_load_4d(xs + slot * kXSlotBytes, tmx, &x_full[slot], 0, i * kF, kb0, b, kEvictFirst);
         }
         __syncwarp();
+        prefetch_next();
       }
     }
   } else if (warp == 1) {
     // =================================== MMA issuer, phase 0 =============================
     // S[f, k] = X . Cw^T (K-major x K-major), M = 64 frames: frame 16 j + i lands in TMEM lane 32 j + i
     constexpr uint32_t idesc0 = make_idesc_bf16(64, KC, 0, 0);
-    mbar_wait(cw_full, 0);
+    wait_bar_inl(cw_full, 0);
     int it0 = 0, i0 = 0, nt0 = n_iter > 0 ? vnt(0) : 0;       // (video, tile) of G, for the debug timeline only
     for (int G = 0; G < total_tiles; ++G) {
       const int sb = G % C::kSB, us = G / C::kSB, slot = G % C::kSlots;
-      mbar_wait(&s_free[sb], (us & 1) ^ 1u);
-      mbar_wait(&x_full[slot], (G / C::kSlots) & 1);
+      wait_bar_inl(&s_free[sb], (us & 1) ^ 1u);
+      wait_bar_inl(&x_full[slot], (G / C::kSlots) & 1);
       tc_fence_after();
       if (lane == 0 && i0 < 8) NV5_T(it0, i0);
       if (elect_one()) {
@@ -344,13 +380,13 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
         const int ab = G % C::kAT, ua = G / C::kAT, slot = G % C::kSlots;
         if (elect_one()) mbar_arrive_expect_tx(&a_full[ab], C::kATileBytes);      // 64 rows from the four owners
         __syncwarp();
-        mbar_wait_cluster(&a_full[ab], ua & 1);
-        mbar_wait(&x_full[slot], (G / C::kSlots) & 1);               // (long complete: phase 0 of this tile ran on it)
+        wait_bar_cluster_inl(&a_full[ab], ua & 1);
+        wait_bar_inl(&x_full[slot], (G / C::kSlots) & 1);               // (long complete: phase 0 of this tile ran on it)
         fence_proxy_async();                                         // st.async rows -> tcgen05 operand reads
         tc_fence_after();
         if (lane == 0 && i < 8) NV5_T(it, 32 + i);
         if (i == 0) {                                                // the epilogue has drained this accumulator (video it - kVB)
-          mbar_wait(&v_free[vb], (uv & 1) ^ 1u);
+          wait_bar_inl(&v_free[vb], (uv & 1) ^ 1u);
           tc_fence_after();
         }
         if (elect_one()) {
@@ -368,7 +404,7 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
         }
         __syncwarp();
         if (lane == 0 && i < 8) NV5_T(it, 40 + i);
-        mbar_wait(&a_sumdone[ab], ua & 1);                           // the a_sum warp has read the tile too
+        wait_bar_inl(&a_sumdone[ab], ua & 1);                           // the a_sum warp has read the tile too
         if (elect_one()) {
           umma_commit(&x_empty[slot]);
           umma_commit_multicast(&a_credit[ab], 0xF);                 // every owner may overwrite tile ab in this CTA
@@ -389,9 +425,9 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
       const int p = it & 1;
       for (int i = 0; i < ntv; ++i, ++G) {
         const int ab = G % C::kAT, ua = G / C::kAT;
-        mbar_wait_cluster(&a_full[ab], ua & 1);
+        wait_bar_cluster_inl(&a_full[ab], ua & 1);
         const uint8_t* at = atile + ab * C::kATileBytes;
-#pragma unroll 8
+#pragma unroll 4
         for (int f = 0; f < kF; ++f) {
 #pragma unroll
           for (int a = 0; a < KC / 64; ++a) {
@@ -403,7 +439,7 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_sumdone[ab]);
       }
-      mbar_wait(&asum_free[p], ((it >> 1) & 1) ^ 1u);                // the epilogue has consumed a_sum of video it-2
+      wait_bar_inl(&asum_free[p], ((it >> 1) & 1) ^ 1u);                // the epilogue has consumed a_sum of video it-2
 #pragma unroll
       for (int a = 0; a < KC / 64; ++a) {
         asum_s[p * KC + a * 64 + 2 * lane] = acc[2 * a];
@@ -445,7 +481,7 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
     for (int G = 0; G < total_tiles; ++G) {
       const int sb = G % C::kSB, us = G / C::kSB, rb = G % C::kRB, ur = G / C::kRB, ab = G % C::kAT, ua = G / C::kAT;
       if (lane == 0) mbar_arrive_expect_tx(&recv_full[q * 2 + rb], (kC - 1) * 4 * C::kRecvRow);
-      mbar_wait(&s_full[sb], us & 1);
+      wait_bar_inl(&s_full[sb], us & 1);
       tc_fence_after();
       if (warp == 4 && lane == 0 && i < 8) NV5_T(it, 8 + i);
       float r[KC];
@@ -456,7 +492,7 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[sb]);
       // the three owners are done with what this warp pushed NRB tiles ago
-      mbar_wait(&send_credit[q * 2 + rb], (ur & 1) ^ 1u);
+      wait_bar_inl(&send_credit[q * 2 + rb], (ur & 1) ^ 1u);
       if (sender) {
 #pragma unroll
         for (int c = 0; c < KC / 4; ++c)
@@ -468,7 +504,7 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
         for (int c = 0; c < KC / 4; ++c) row[c] = make_float4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
       }
       __syncwarp();
-      mbar_wait_cluster(&recv_full[q * 2 + rb], ur & 1);
+      wait_bar_cluster_inl(&recv_full[q * 2 + rb], ur & 1);
       if (warp == 4 && lane == 0 && i < 8) NV5_T(it, 16 + i);
       // ---- owner role: sum the four partials of my 8 clusters, masked softmax over the frame's 8 threads ----
       float l[8];
@@ -512,7 +548,7 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
       for (int j = 0; j < 4; ++j)
         pk[j] = pack_bf16x2(__float2bfloat16_rn(valid ? l[2 * j] * inv : 0.0f), __float2bfloat16_rn(valid ? l[2 * j + 1] * inv : 0.0f));
       // every CTA's phase 1 is done with assignment tile ab of NAT tiles ago
-      mbar_wait(&a_credit[ab], (ua & 1) ^ 1u);
+      wait_bar_inl(&a_credit[ab], (ua & 1) ^ 1u);
 #pragma unroll
       for (int d = 0; d < kC; ++d)
         st_async_v4_b32(a_tile_remote[d] + ab * C::kATileBytes + a_off, a_full_remote[d] + ab * 8, pk[0], pk[1], pk[2], pk[3]);
@@ -535,49 +571,71 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
     const int et = e * 32 + lane;                             // 0..255
     // accumulator blocks in which this warp's 32 rows exist (a prefix: only the last block can be half valid)
     const int nmb_w = (DH - q * 32 + 127) / 128 > 0 ? (DH - q * 32 + 127) / 128 : 0;
+    const uint32_t tv = taddr_of(tmem_base, q) + C::kVCol + h * 32;        // this warp's V columns: + m * KC per block
+    const uint32_t tc2 = taddr_of(tmem_base, q) + C::kC2Col + h * 32;      // and the matching block of cw2
+    // ---- once: this warp's share of cw2 into TMEM (the residual then never touches global memory; loops below are ROLLED on
+    //      purpose: sixteen warps in six roles share one instruction cache, straight-line unrolled bodies thrashed it) ----
+#pragma unroll 1
+    for (int m = 0; m < nmb_w; ++m) {
+      // row-major cw2 [D, K]: lane = row, 8 chunks of 4 floats;  tiled: [D/32][K/4 chunks][32 rows][4 floats]
+      const long long g32 = (d0 + m * 128 + q * 32) >> 5;
+      const float4* c2 = TILED ? reinterpret_cast<const float4*>(cw2) + (g32 * (KC / 4) + h * 8) * 32 + lane
+                               : reinterpret_cast<const float4*>(cw2 + (static_cast<long long>(d0) + m * 128 + q * 32 + lane) * KC + h * 32);
+      constexpr int kCs = TILED ? 32 : 1;                     // float4 stride between consecutive chunks
+      float c[32];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 t4 = __ldg(c2 + j * kCs);
+        c[4 * j] = t4.x; c[4 * j + 1] = t4.y; c[4 * j + 2] = t4.z; c[4 * j + 3] = t4.w;
+      }
+      tmem_st32(tc2 + m * KC, reinterpret_cast<const uint32_t*>(c));
+    }
+    tmem_st_wait();
     for (int it = 0; it < n_iter; ++it) {
       const int b = vid(it);
       const int p = it & 1;
-      const int vb = it % C::kVB, uv = it / C::kVB;
-      const uint32_t tlane = taddr_of(tmem_base, q) + C::kVCol + vb * C::kVStride + h * 32;
       if (et == 0) mbar_arrive_expect_tx(&ssq_full[p], (kC - 1) * KC * 4);   // this video's partial sums from the three peers
-      mbar_wait(&v_full[vb], uv & 1);
+      wait_bar_inl(&v_full[0], it & 1);
       tc_fence_after();
       if (et == 0) NV5_T(it, 48);
+      // the accumulator leaves TMEM at once (3 x 32 columns per lane) and goes back to phase 1: the next video's aggregation
+      // never waits for this epilogue
       float v[kMaxMb][32];
 #pragma unroll
       for (int m = 0; m < kMaxMb; ++m)
-        if (m < nmb_w) tmem_ld32(tlane + m * KC, reinterpret_cast<uint32_t*>(v[m]));
+        if (m < nmb_w) tmem_ld32(tv + m * KC, reinterpret_cast<uint32_t*>(v[m]));
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&v_free[vb]);                // phase 1 of video it + kVB may overwrite the accumulator
-      mbar_wait(&asum_ready[p], (it >> 1) & 1);
+      if (lane == 0) mbar_arrive(&v_free[0]);
+      if (et == 0) NV5_T(it, 52);
+      wait_bar_inl(&asum_ready[p], (it >> 1) & 1);
       const float* asum = asum_s + p * KC + h * 32;
-      // ---- pass 1 (registers): V -= a_sum * cw2 in fp32, per-cluster sum of squares ----
       float ssq[32];
 #pragma unroll
       for (int j = 0; j < 32; ++j) ssq[j] = 0.0f;
+      // ---- pass 1 (registers): V -= a_sum * cw2 in fp32 (cw2 from TMEM, 16 columns at a time), per-cluster sum of squares ----
 #pragma unroll
       for (int m = 0; m < kMaxMb; ++m) {
         if (m < nmb_w) {
-          const float4* c2 = reinterpret_cast<const float4*>(cw2 + (static_cast<long long>(d0) + m * 128 + q * 32 + lane) * KC + h * 32);
 #pragma unroll
-          for (int g4 = 0; g4 < 2; ++g4) {
-            float4 cc[4];
+          for (int g = 0; g < 2; ++g) {
+            float c[16];
+            tmem_ld16(tc2 + m * KC + g * 16, reinterpret_cast<uint32_t*>(c));
+            tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 4; ++c) cc[c] = __ldg(c2 + g4 * 4 + c);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float4 as4 = *reinterpret_cast<const float4*>(asum + g4 * 16 + c * 4);     // broadcast read
-              const int j = g4 * 16 + c * 4;
-              v[m][j] -= as4.x * cc[c].x; v[m][j + 1] -= as4.y * cc[c].y; v[m][j + 2] -= as4.z * cc[c].z; v[m][j + 3] -= as4.w * cc[c].w;
+            for (int j4 = 0; j4 < 4; ++j4) {
+              const float4 as4 = *reinterpret_cast<const float4*>(asum + g * 16 + j4 * 4);     // broadcast read
+              const int j = g * 16 + j4 * 4;
+              v[m][j] -= as4.x * c[j4 * 4]; v[m][j + 1] -= as4.y * c[j4 * 4 + 1];
+              v[m][j + 2] -= as4.z * c[j4 * 4 + 2]; v[m][j + 3] -= as4.w * c[j4 * 4 + 3];
               ssq[j] += v[m][j] * v[m][j]; ssq[j + 1] += v[m][j + 1] * v[m][j + 1];
               ssq[j + 2] += v[m][j + 2] * v[m][j + 2]; ssq[j + 3] += v[m][j + 3] * v[m][j + 3];
             }
           }
         }
       }
+      if (et == 0) NV5_T(it, 54);
       ssq_w[e * 32 + lane] = warp_transpose_reduce32(ssq, lane);      // lane L: sum over this warp's rows of cluster 32 h + L
       named_bar_sync(1, 256);                                 // this CTA's partial sums are complete
       if (et == 0) NV5_T(it, 49);
@@ -592,7 +650,8 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
           st_async_f32(mapa_u32(smem_u32(&ssq_part[(p * kC + rank) * KC + et]), dst), mapa_u32(smem_u32(&ssq_full[p]), dst), mine);
         }
       }
-      mbar_wait_cluster(&ssq_full[p], (it >> 1) & 1);
+      wait_bar_cluster_inl(&ssq_full[p], (it >> 1) & 1);
+      if (et == 0) NV5_T(it, 64);
       named_bar_sync(1, 256);                                 // (the own slot was written by threads of other warps)
       if (et < KC) {
         const float* sp = ssq_part + p * kC * KC + et;
@@ -612,24 +671,26 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
       const float gs = rsqrtf(fmaxf(total, 1e-12f));
       if (stats && rank == 0 && et == 0) stats[static_cast<long long>(b) * (2 * KC + 1) + 2 * KC] = total;
       if (et == 0) NV5_T(it, 50);
-      // ---- pass 2 (registers): rescale (intra-norm x final L2 norm), convert, store: every lane writes the 64 contiguous
-      //      bytes of its row that hold clusters 32 h .. + 31 ----
+      // ---- pass 2 (registers): rescale (intra-norm x final L2 norm), convert, store ----
 #pragma unroll
       for (int m = 0; m < kMaxMb; ++m) {
         if (m < nmb_w) {
-          uint16_t* dst = out + (static_cast<long long>(b) * D + d0 + m * 128 + q * 32 + lane) * KC + h * 32;
+          // row-major [D, K]: 64 contiguous bytes per lane;  tiled: [D/32][K/8 chunks][32 rows][8 values]
+          const long long g32 = (d0 + m * 128 + q * 32) >> 5;
+          uint16_t* dst = TILED ? out + static_cast<long long>(b) * D * KC + ((g32 * (KC / 8) + h * 4) * 32 + lane) * 8
+                                : out + (static_cast<long long>(b) * D + d0 + m * 128 + q * 32 + lane) * KC + h * 32;
+          constexpr int kOs = TILED ? 256 : 8;                // element stride between consecutive 16-byte chunks
 #pragma unroll
           for (int j8 = 0; j8 < 4; ++j8) {
             float w8[8];
             const float4 f0 = *reinterpret_cast<const float4*>(fscale_s + h * 32 + j8 * 8), f1 = *reinterpret_cast<const float4*>(fscale_s + h * 32 + j8 * 8 + 4);
-            w8[0] = v[m][j8 * 8 + 0] * (f0.x * gs); w8[1] = v[m][j8 * 8 + 1] * (f0.y * gs);
-            w8[2] = v[m][j8 * 8 + 2] * (f0.z * gs); w8[3] = v[m][j8 * 8 + 3] * (f0.w * gs);
-            w8[4] = v[m][j8 * 8 + 4] * (f1.x * gs); w8[5] = v[m][j8 * 8 + 5] * (f1.y * gs);
-            w8[6] = v[m][j8 * 8 + 6] * (f1.z * gs); w8[7] = v[m][j8 * 8 + 7] * (f1.w * gs);
+            const float fs8[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};          // broadcast reads
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w8[j] = v[m][j8 * 8 + j] * (fs8[j] * gs);
             uint4 hi, lo;
             if (out_f16) hi = pack8_f16(w8);
             else pack8_hi_lo(w8, hi, lo);
-            *reinterpret_cast<uint4*>(dst + j8 * 8) = hi;
+            *reinterpret_cast<uint4*>(dst + j8 * kOs) = hi;
           }
         }
       }
@@ -645,7 +706,7 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
   }
 }
 
-template <int KC>
+template <int KC, bool TILED>
 int launch_v5(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, const yt8m_bf16* cw_packed, const float* scale,
               const float* shift, const float* cw2, yt8m_bf16* out, int out_f16, float* stats, cudaStream_t stream) {
   using C = Cfg<KC>;
@@ -669,18 +730,18 @@ int launch_v5(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, co
   }
   static int max_clusters = -1;
   if (max_clusters < 0) {
-    YT8M_CUDA(cudaFuncSetAttribute(netvlad_v5_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemTotal));
+    YT8M_CUDA(cudaFuncSetAttribute(netvlad_v5_kernel<KC, TILED>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemTotal));
     cudaLaunchConfig_t qc{};
     qc.gridDim = dim3(kC * 37, 1, 1);
     qc.blockDim = dim3(kThreads, 1, 1);
     qc.dynamicSmemBytes = C::kSmemTotal;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, netvlad_v5_kernel<KC>, &qc) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
+    if (cudaOccupancyMaxActiveClusters(&n, netvlad_v5_kernel<KC, TILED>, &qc) != cudaSuccess) { (void)cudaGetLastError(); n = 0; }
     max_clusters = n > 0 ? n : 32;              // (the query can fail under a profiler: 32 clusters always fit 148 SMs)
     if (max_clusters > 37) max_clusters = 37;
   }
   const int clusters = B < max_clusters ? B : max_clusters;
-  netvlad_v5_kernel<KC><<<kC * clusters, kThreads, C::kSmemTotal, stream>>>(tm_xa, tm_xb, tm_cw, reinterpret_cast<uint16_t*>(out), num_frames, B, T,
+  netvlad_v5_kernel<KC, TILED><<<kC * clusters, kThreads, C::kSmemTotal, stream>>>(tm_xa, tm_xb, tm_cw, reinterpret_cast<uint16_t*>(out), num_frames, B, T,
                                                                             D, scale, shift, cw2, out_f16, stats, host_debug_timeline(),
                                                                             host_debug_flags());
   return check_launch("netvlad_v5_kernel");
@@ -696,5 +757,20 @@ int yt8m::launch_netvlad_v5(const yt8m_bf16* x, const int* num_frames, int B, in
                             const float* scale, const float* shift, const float* cw2, yt8m_bf16* out, int out_f16, float* stats,
                             cudaStream_t stream) {
   YT8M_REQUIRE(netvlad_v5_supported(T, D, K), YT8M_E_BADSHAPE, "netvlad v5: T=%d D=%d K=%d", T, D, K);
-  return launch_v5<64>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out, out_f16, stats, stream);
+  return launch_v5<64, false>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out, out_f16, stats, stream);
+}
+
+extern "C" int yt8m_netvlad_tiled_supported(int T, int D, int K) { return yt8m::netvlad_v5_supported(T, D, K) && D % 32 == 0 ? 1 : 0; }
+
+extern "C" int yt8m_netvlad_fwd_tiled(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K, const yt8m_bf16* cw_packed,
+                                      const float* scale, const float* shift, const float* cw2_tiled, yt8m_bf16* out_tiled,
+                                      int out_fmt, float* stats, yt8m_stream_t stream_) {
+  YT8M_REQUIRE(x && num_frames && cw_packed && cw2_tiled && out_tiled, YT8M_E_BADPTR, "yt8m_netvlad_fwd_tiled: null pointer");
+  YT8M_REQUIRE(B > 0 && T > 0, YT8M_E_BADSHAPE, "yt8m_netvlad_fwd_tiled: B=%d T=%d", B, T);
+  YT8M_REQUIRE(yt8m_netvlad_tiled_supported(T, D, K), YT8M_E_UNSUPPORTED,
+               "yt8m_netvlad_fwd_tiled: needs K = 64 and D %% 64 == 0 with 256 <= D <= 1280 (D=%d K=%d)", D, K);
+  YT8M_REQUIRE(out_fmt == YT8M_FMT_BF16 || out_fmt == YT8M_FMT_F16, YT8M_E_UNSUPPORTED, "yt8m_netvlad_fwd_tiled: out_fmt");
+  YT8M_REQUIRE(aligned16(out_tiled) && aligned16(cw2_tiled), YT8M_E_BADPTR, "yt8m_netvlad_fwd_tiled: out / cw2 must be 16-byte aligned");
+  return launch_v5<64, true>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2_tiled, out_tiled, out_fmt == YT8M_FMT_F16, stats,
+                             static_cast<cudaStream_t>(stream_));
 }

@@ -361,10 +361,20 @@ class NetVLADModel(models.BaseModel):
     if FLAGS.netvlad_operand_format not in ("f16", "bf16x2"):
       raise ValueError("--netvlad_operand_format must be 'f16' or 'bf16x2'")
     f16 = FLAGS.netvlad_operand_format == "f16"
-    vlad_hi, vlad_lo, _ = nat.netvlad_fwd(x, nf, cwp, scale, shift, cw2.value, want_lo=not f16, cw2_split=c2split, out_f16=f16)
-
     hw = st.get("hidden1_weights", (cluster_size * d, hidden1_size), ops.random_normal(1 / math.sqrt(cluster_size)))
-    if f16:   # the fp16 conversion of the packed weights (a dtype conversion: bf16 values >= 2^-17 are exact in fp16)
+    tiled = f16 and nat.netvlad_tiled_supported(t, d, cluster_size)
+    if tiled:
+      # the one-pass four-CTA-cluster kernel writes the descriptor in a blocked order (include/yt8m_b200.h); the hidden layer's
+      # weight ROWS are gathered into the same order once, at packing time -- the product v . W is unchanged
+      c2t = st.packed(cw2, "tiled", lambda: cw2.value.reshape(-1)[nat.netvlad_tiled_index(d, cluster_size, 4, cw2.value.device)].contiguous())
+      vlad_hi, vlad_lo = nat.netvlad_fwd_tiled(x, nf, cwp, scale, shift, c2t, out_f16=True), None
+      hwp = st.packed(hw, "kmajor_f16_tiled", lambda: nat.pack_transpose(
+          hw.value[nat.netvlad_tiled_index(d, cluster_size, 8, hw.value.device)]).to(torch.float16))
+    else:
+      vlad_hi, vlad_lo, _ = nat.netvlad_fwd(x, nf, cwp, scale, shift, cw2.value, want_lo=not f16, cw2_split=c2split, out_f16=f16)
+    if tiled:
+      pass
+    elif f16:   # the fp16 conversion of the packed weights (a dtype conversion: bf16 values >= 2^-17 are exact in fp16)
       hwp = st.packed(hw, "kmajor_f16", lambda: nat.pack_transpose(hw.value).to(torch.float16))
     else:
       hwp = st.packed(hw, "kmajor", lambda: nat.pack_transpose(hw.value))

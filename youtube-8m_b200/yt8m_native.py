@@ -65,6 +65,9 @@ _SIGS = {
                                    c_void_p, c_void_p]),
     "yt8m_netvlad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
+    "yt8m_netvlad_tiled_supported": (c_int, [c_int, c_int, c_int]),
+    "yt8m_netvlad_fwd_tiled": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_int, c_void_p, c_void_p]),
     "yt8m_netvlad_bwd_norm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
     "yt8m_netvlad_bwd_assign": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
@@ -505,6 +508,40 @@ def netvlad_fwd(x, num_frames, cw_packed, scale, shift, cw2, want_f32=False, wan
   if want_stats:
     return oh, (ol if want_lo else None), of, stats
   return oh, (ol if want_lo else None), of
+
+
+def netvlad_tiled_supported(t, d, k):
+  return bool(_lib.yt8m_netvlad_tiled_supported(t, d, k))
+
+
+_tiled_index_cache = {}
+
+
+def netvlad_tiled_index(d, k, width, device):
+  """int64 [D*K]: idx[tiled position] = row-major position d*K + k for the blocked layouts of yt8m_netvlad_fwd_tiled
+  (width 8: the 16-bit descriptor; width 4: fp32 cw2).  `tensor.reshape(-1)[idx]` (or `rows[idx]` for the next layer's
+  weight) produces the tiled order -- an index gather, no arithmetic."""
+  key = (d, k, width, str(device))
+  if key not in _tiled_index_cache:
+    dd = torch.arange(d).unsqueeze(1)
+    kk = torch.arange(k).unsqueeze(0)
+    pos = ((dd // 32) * (k // width) + kk // width) * (32 * width) + (dd % 32) * width + kk % width
+    idx = torch.empty(d * k, dtype=torch.int64)
+    idx[pos.reshape(-1)] = (dd * k + kk).reshape(-1)
+    _tiled_index_cache[key] = idx.to(device)
+  return _tiled_index_cache[key]
+
+
+def netvlad_fwd_tiled(x, num_frames, cw_packed, scale, shift, cw2_tiled, out_f16=True, want_stats=False):
+  """One-pass NetVLAD with the blocked layouts (see include/yt8m_b200.h): returns the TILED descriptor [B, D*K] (fp16 or bf16)
+  (+ stats)."""
+  b, t, d = x.shape
+  k = cw_packed.shape[0]
+  out = torch.empty((b, d * k), dtype=torch.float16 if out_f16 else torch.bfloat16, device=x.device)
+  stats = _f32((b, 2 * k + 1), x.device) if want_stats else None
+  _call("yt8m_netvlad_fwd_tiled", _p(x), _p(num_frames), b, t, d, k, _p(cw_packed), _p(scale), _p(shift), _p(cw2_tiled), _p(out),
+        FMT_F16 if out_f16 else FMT_BF16, _p(stats), _stream())
+  return (out, stats) if want_stats else out
 
 
 def netvlad_bwd_norm(dy, y, stats, cw2, want_dcw2=True):
