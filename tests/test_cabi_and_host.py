@@ -157,3 +157,17 @@ def test_cli_and_model_flags_match_the_reference():
       k2, d2 = scope[name]
       assert k2 == kind.replace("boolean", "bool"), (fname, name, kind, k2)
       assert d2 == default and type(d2) == type(default), "%s: --%s default %r != reference %r" % (fname, name, d2, default)
+
+
+def test_netvlad_tiled_index_is_the_documented_permutation():
+  """include/yt8m_b200.h (yt8m_netvlad_fwd_tiled): element (d, k) sits at ((d/32)*(K/w) + k/w)*(32*w) + (d%32)*w + k%w with
+  w = 8 (16-bit descriptor) or 4 (fp32 cw2); the helper returns the gather index tiled position -> row-major position."""
+  import torch
+  import yt8m_native as nat
+  for d, k, w in ((320, 64, 8), (1152, 64, 4), (256, 64, 8)):
+    idx = nat.netvlad_tiled_index(d, k, w, "cpu")
+    assert sorted(idx.tolist()) == list(range(d * k))
+    dd = torch.randint(0, d, (50,))
+    kk = torch.randint(0, k, (50,))
+    pos = ((dd // 32) * (k // w) + kk // w) * (32 * w) + (dd % 32) * w + kk % w
+    assert torch.equal(idx[pos], dd * k + kk)

@@ -165,3 +165,42 @@ def test_netvlad_one_pass_kernel_short_and_empty_videos(nat, b, t, d):
   assert float(got[0].abs().max()) == 0.0 and float(got[5].abs().max()) == 0.0          # no frames -> zero descriptor
   err = (got - want).norm(dim=1) / want.norm(dim=1).clamp_min(1e-6)
   assert float(err.max()) < 4e-3, (int(err.argmax()), float(err.max()), int(nf[int(err.argmax())]))
+
+
+@pytest.mark.parametrize("b,t,d,fmt", [(200, 96, 256, "f16"), (1100, 70, 256, "f16"), (90, 300, 1152, "f16"), (41, 300, 1024, "bf16"),
+                                       (3, 64, 320, "f16"), (150, 129, 1280, "f16")])
+def test_netvlad_tiled_kernel_short_and_empty_videos(nat, b, t, d, fmt):
+  """yt8m_netvlad_fwd_tiled (yt8m_netvlad_v5.cu: a cluster of FOUR CTAs per video, 64-frame tiles, blocked descriptor / cw2
+  layouts): only ceil(num_frames / 64) tiles per video are streamed, videos are scheduled longest first by a counting sort
+  (several videos per cluster, more clusters than videos, uneven feature splits 5,5,4,4 / 4,4,4,4 / 2,1,1,1 / 5,5,5,5).  Empty,
+  one-frame, tile-boundary and full-length videos in one batch: every descriptor, un-tiled, against the oracle; the saved
+  statistics against their definitions."""
+  g = torch.Generator().manual_seed(b + d)
+  k = 64
+  assert nat.netvlad_tiled_supported(t, d, k)
+  x = synth.bf16r(torch.randn(b, t, d, generator=g))
+  x = x * torch.rsqrt((x * x).sum(dim=2, keepdim=True))
+  nf = torch.randint(0, t + 1, (b,), generator=g, dtype=torch.int32)
+  nf[:3] = torch.tensor([0, 1, t], dtype=torch.int32)
+  if b > 8:
+    nf[3:8] = torch.tensor([min(64, t), min(65, t), 0, min(63, t), min(128, t)], dtype=torch.int32)
+  x = synth.bf16r(x * (torch.arange(t).unsqueeze(0) < nf.unsqueeze(1)).float().unsqueeze(2))
+  cw, cw2 = synth.normal((d, k), g, 4.0), torch.randn(d, k, generator=g) / math.sqrt(d)          # cw2 is NOT bf16-representable
+  scale, shift = 1.0 + 0.1 * torch.randn(k, generator=g), 0.1 * torch.randn(k, generator=g)
+  want = O.netvlad_pool(x, nf, cw, scale, shift, cw2)
+  idx8, idx4 = nat.netvlad_tiled_index(d, k, 8, DEV), nat.netvlad_tiled_index(d, k, 4, DEV)
+  c2t = cw2.to(DEV).reshape(-1)[idx4].contiguous()
+  out, stats = nat.netvlad_fwd_tiled(bf(x), nf.to(DEV), nat.pack_transpose(cw.to(DEV)), scale.to(DEV), shift.to(DEV), c2t,
+                                     out_f16=(fmt == "f16"), want_stats=True)
+  got = torch.empty_like(out)
+  got[:, idx8] = out                                      # tiled position p holds row-major element idx8[p]
+  got = got.float().cpu()
+  assert bool(torch.isfinite(got).all())
+  assert float(got[0].abs().max()) == 0.0                 # no frames -> zero descriptor
+  err = (got - want).norm(dim=1) / want.norm(dim=1).clamp_min(1e-6)
+  tol = 4e-3 if fmt == "f16" else 8e-3                    # one fp16 / bf16 rounding of the output on top of the bf16 assignment
+  assert float(err.max()) < tol, (int(err.argmax()), float(err.max()), int(nf[int(err.argmax())]))
+  # stats = {a_sum[K], ||V[:, k]||^2 [K], sum_k ||V_k||^2 / max(||V_k||^2, eps)}: a_sum adds up to the number of frames
+  st = stats.cpu()
+  assert float((st[:, :k].sum(dim=1) - nf.clamp(0, t).float()).abs().max()) < 0.05 * max(t, 1) ** 0.5 + 0.6
+  assert bool((st[:, k:2 * k] >= 0).all())
