@@ -203,11 +203,16 @@ int yt8m_netvlad_fwd(const yt8m_bf16* x, const int* num_frames, int B, int T, in
  *   cw2_tiled   element (d, k)             at  ((d / 32) * (K / 4) + k / 4) * 128 + (d % 32) * 4 + k % 4      [fp32]
  * The descriptor is a permutation of the row-major [D, K] flattening: the layer that consumes it (the hidden FC) applies the
  * same permutation to its weight ROWS once, at packing time (the flatten order of a VLAD descriptor is a free choice).
- * K = 64, D % 64 == 0, 256 <= D <= 1280; out_fmt: YT8M_FMT_BF16 (hi only) or YT8M_FMT_F16; stats as for yt8m_netvlad_fwd. */
+ * K = 64, D % 64 == 0, 256 <= D <= 1280; out_fmt: YT8M_FMT_BF16 (hi only) or YT8M_FMT_F16; stats as for yt8m_netvlad_fwd.
+ * workspace (>= yt8m_netvlad_tiled_workspace_bytes, may be NULL): scratch for the bf16 assignment [B, T, K].  With it (and
+ * D <= 1152) the layer runs as TWO streaming kernels (csrc/yt8m_netvlad_v6.cu: assignment GEMM + softmax with the centres
+ * resident in shared memory, then aggregation + normalisation by a four-CTA cluster per video); without it, as the one-pass
+ * cluster kernel (csrc/yt8m_netvlad_v5.cu), whose per-tile chain of dependent steps is ~2x slower. */
 int yt8m_netvlad_tiled_supported(int T, int D, int K);
+size_t yt8m_netvlad_tiled_workspace_bytes(int B, int T, int D, int K);
 int yt8m_netvlad_fwd_tiled(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K, const yt8m_bf16* cw_packed,
                            const float* scale, const float* shift, const float* cw2_tiled, yt8m_bf16* out_tiled, int out_fmt,
-                           float* stats, yt8m_stream_t stream);
+                           float* stats, void* workspace, size_t workspace_bytes, yt8m_stream_t stream);
 
 /* debug only: device buffer (>= 128 u64, or NULL to disable) that receives globaltimer stamps of the
  * NetVLAD kernel's phases for CTA 0 (tools/netvlad_timeline.py decodes them) */

@@ -167,14 +167,16 @@ def test_netvlad_one_pass_kernel_short_and_empty_videos(nat, b, t, d):
   assert float(err.max()) < 4e-3, (int(err.argmax()), float(err.max()), int(nf[int(err.argmax())]))
 
 
+@pytest.mark.parametrize("two_kernels", [False, True])
 @pytest.mark.parametrize("b,t,d,fmt", [(200, 96, 256, "f16"), (1100, 70, 256, "f16"), (90, 300, 1152, "f16"), (41, 300, 1024, "bf16"),
                                        (3, 64, 320, "f16"), (150, 129, 1280, "f16")])
-def test_netvlad_tiled_kernel_short_and_empty_videos(nat, b, t, d, fmt):
+def test_netvlad_tiled_kernel_short_and_empty_videos(nat, b, t, d, fmt, two_kernels):
   """yt8m_netvlad_fwd_tiled (yt8m_netvlad_v5.cu: a cluster of FOUR CTAs per video, 64-frame tiles, blocked descriptor / cw2
   layouts): only ceil(num_frames / 64) tiles per video are streamed, videos are scheduled longest first by a counting sort
   (several videos per cluster, more clusters than videos, uneven feature splits 5,5,4,4 / 4,4,4,4 / 2,1,1,1 / 5,5,5,5).  Empty,
   one-frame, tile-boundary and full-length videos in one batch: every descriptor, un-tiled, against the oracle; the saved
-  statistics against their definitions."""
+  statistics against their definitions.  two_kernels: the assignment + aggregation pair (yt8m_netvlad_v6.cu; D <= 1152, else the
+  entry point falls back to the one-pass kernel)."""
   g = torch.Generator().manual_seed(b + d)
   k = 64
   assert nat.netvlad_tiled_supported(t, d, k)
@@ -191,7 +193,7 @@ def test_netvlad_tiled_kernel_short_and_empty_videos(nat, b, t, d, fmt):
   idx8, idx4 = nat.netvlad_tiled_index(d, k, 8, DEV), nat.netvlad_tiled_index(d, k, 4, DEV)
   c2t = cw2.to(DEV).reshape(-1)[idx4].contiguous()
   out, stats = nat.netvlad_fwd_tiled(bf(x), nf.to(DEV), nat.pack_transpose(cw.to(DEV)), scale.to(DEV), shift.to(DEV), c2t,
-                                     out_f16=(fmt == "f16"), want_stats=True)
+                                     out_f16=(fmt == "f16"), want_stats=True, two_kernels=two_kernels)
   got = torch.empty_like(out)
   got[:, idx8] = out                                      # tiled position p holds row-major element idx8[p]
   got = got.float().cpu()

@@ -42,14 +42,16 @@ idx4 = nat.netvlad_tiled_index(D, K, 4, dev)
 c2t = cw2.to(dev).reshape(-1)[idx4].contiguous()
 targs = (xb, nf.to(dev), cwp, scale.to(dev), shift.to(dev), c2t)
 
-def run_tiled():
-  out, st = nat.netvlad_fwd_tiled(*targs, out_f16=f16, want_stats=True)
+def run_tiled(two=True):
+  out, st = nat.netvlad_fwd_tiled(*targs, out_f16=f16, want_stats=True, two_kernels=two)
   torch.cuda.synchronize()
   std = torch.empty_like(out)
   std[:, idx8] = out                          # tiled position p holds row-major element idx8[p]
   return std.float().cpu(), st.cpu()
 
 v5, st5 = run_tiled()
+one, st1 = run_tiled(False)
+print("  two-kernel vs one-pass: max %.3e  stats %.3e" % (float((v5 - one).abs().max()), float((st5 - st1).abs().max())))
 if B <= 8:
   u5, _ = run(1 << 20)                        # the same kernel with row-major epilogue accesses
   print("  tiled vs row-major epilogue: max %.3e" % float((v5 - u5).abs().max()))
@@ -68,7 +70,8 @@ print("  vs previous kernel: l2 %.3e  max %.3e   stats: asum %.3e ssq %.3e" % (
     float(((st5[:, K:] - sto[:, K:]).abs() / sto[:, K:].abs().clamp_min(1e-6)).max())))
 if do_time:
   real = int(nf.clamp(0, T).sum())
-  for name, fn in (("v5 tiled", lambda: nat.netvlad_fwd_tiled(*targs, out_f16=f16)), ("previous", lambda: nat.netvlad_fwd(*args, out_f16=f16))):
+  for name, fn in (("two kernels (v6)", lambda: nat.netvlad_fwd_tiled(*targs, out_f16=f16)),
+                   ("one pass (v5)", lambda: nat.netvlad_fwd_tiled(*targs, out_f16=f16, two_kernels=False)), ("previous", lambda: nat.netvlad_fwd(*args, out_f16=f16))):
     for _ in range(3):
       fn()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

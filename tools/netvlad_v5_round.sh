@@ -9,6 +9,8 @@ for s in "1 64 256 f16" "2 128 256 f16" "2 300 1152 f16" "4 100 256 f16" "7 300 
 done 2>&1 | tee gpurun_out/v5_check.txt
 echo "=== timing"
 timeout 200 python tools/netvlad_v5_check.py 256 300 1152 f16 time 2>&1 | tail -6 | tee -a gpurun_out/v5_check.txt
+echo "=== scan"
+timeout 200 python tools/netvlad_v5_scan.py 2>&1 | tail -18 | tee gpurun_out/v6_scan.txt
 echo "=== timeline"
 timeout 120 python tools/netvlad_v5_timeline.py 256 2>&1 | tail -150 > gpurun_out/v5_timeline.txt
 head -70 gpurun_out/v5_timeline.txt

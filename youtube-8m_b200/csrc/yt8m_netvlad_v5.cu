@@ -762,15 +762,33 @@ int yt8m::launch_netvlad_v5(const yt8m_bf16* x, const int* num_frames, int B, in
 
 extern "C" int yt8m_netvlad_tiled_supported(int T, int D, int K) { return yt8m::netvlad_v5_supported(T, D, K) && D % 32 == 0 ? 1 : 0; }
 
+namespace yt8m {
+int launch_netvlad_v6(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K, const yt8m_bf16* cw_packed,
+                      const float* scale, const float* shift, const float* cw2_tiled, yt8m_bf16* out_tiled, int out_f16, float* stats,
+                      void* workspace, size_t workspace_bytes, cudaStream_t stream);
+bool netvlad_v6_supported(int T, int D, int K);
+size_t netvlad_v6_workspace_bytes(int B, int T, int K);
+}
+
+extern "C" size_t yt8m_netvlad_tiled_workspace_bytes(int B, int T, int D, int K) {
+  return yt8m::netvlad_v6_supported(T, D, K) ? yt8m::netvlad_v6_workspace_bytes(B, T, K) : 0;
+}
+
 extern "C" int yt8m_netvlad_fwd_tiled(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K, const yt8m_bf16* cw_packed,
                                       const float* scale, const float* shift, const float* cw2_tiled, yt8m_bf16* out_tiled,
-                                      int out_fmt, float* stats, yt8m_stream_t stream_) {
+                                      int out_fmt, float* stats, void* workspace, size_t workspace_bytes, yt8m_stream_t stream_) {
   YT8M_REQUIRE(x && num_frames && cw_packed && cw2_tiled && out_tiled, YT8M_E_BADPTR, "yt8m_netvlad_fwd_tiled: null pointer");
   YT8M_REQUIRE(B > 0 && T > 0, YT8M_E_BADSHAPE, "yt8m_netvlad_fwd_tiled: B=%d T=%d", B, T);
   YT8M_REQUIRE(yt8m_netvlad_tiled_supported(T, D, K), YT8M_E_UNSUPPORTED,
                "yt8m_netvlad_fwd_tiled: needs K = 64 and D %% 64 == 0 with 256 <= D <= 1280 (D=%d K=%d)", D, K);
   YT8M_REQUIRE(out_fmt == YT8M_FMT_BF16 || out_fmt == YT8M_FMT_F16, YT8M_E_UNSUPPORTED, "yt8m_netvlad_fwd_tiled: out_fmt");
   YT8M_REQUIRE(aligned16(out_tiled) && aligned16(cw2_tiled), YT8M_E_BADPTR, "yt8m_netvlad_fwd_tiled: out / cw2 must be 16-byte aligned");
-  return launch_v5<64, true>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2_tiled, out_tiled, out_fmt == YT8M_FMT_F16, stats,
-                             static_cast<cudaStream_t>(stream_));
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  // two streaming kernels (assignment, then aggregation: yt8m_netvlad_v6.cu) when the caller provides the scratch for the
+  // assignment; the one-pass four-CTA-cluster kernel otherwise (and for D > 1152, or with debug flag 1 << 21)
+  if (workspace && yt8m::netvlad_v6_supported(T, D, K) && workspace_bytes >= yt8m::netvlad_v6_workspace_bytes(B, T, K) &&
+      !(host_debug_flags() & (1 << 21)))
+    return yt8m::launch_netvlad_v6(x, num_frames, B, T, D, K, cw_packed, scale, shift, cw2_tiled, out_tiled, out_fmt == YT8M_FMT_F16, stats,
+                                   workspace, workspace_bytes, stream);
+  return launch_v5<64, true>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2_tiled, out_tiled, out_fmt == YT8M_FMT_F16, stats, stream);
 }

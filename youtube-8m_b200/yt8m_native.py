@@ -66,8 +66,9 @@ _SIGS = {
     "yt8m_netvlad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "yt8m_netvlad_tiled_supported": (c_int, [c_int, c_int, c_int]),
+    "yt8m_netvlad_tiled_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "yt8m_netvlad_fwd_tiled": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                       c_int, c_void_p, c_void_p]),
+                                       c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "yt8m_netvlad_bwd_norm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                       c_void_p]),
     "yt8m_netvlad_bwd_assign": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
@@ -532,15 +533,18 @@ def netvlad_tiled_index(d, k, width, device):
   return _tiled_index_cache[key]
 
 
-def netvlad_fwd_tiled(x, num_frames, cw_packed, scale, shift, cw2_tiled, out_f16=True, want_stats=False):
-  """One-pass NetVLAD with the blocked layouts (see include/yt8m_b200.h): returns the TILED descriptor [B, D*K] (fp16 or bf16)
-  (+ stats)."""
+def netvlad_fwd_tiled(x, num_frames, cw_packed, scale, shift, cw2_tiled, out_f16=True, want_stats=False, two_kernels=False):
+  """NetVLAD with the blocked layouts (see include/yt8m_b200.h): returns the TILED descriptor [B, D*K] (fp16 or bf16)
+  (+ stats).  two_kernels: pass the assignment scratch, which selects the assignment + aggregation kernel pair (measured
+  slower than the one-pass kernel as soon as the batch's frames outgrow L2: it reads them twice)."""
   b, t, d = x.shape
   k = cw_packed.shape[0]
   out = torch.empty((b, d * k), dtype=torch.float16 if out_f16 else torch.bfloat16, device=x.device)
   stats = _f32((b, 2 * k + 1), x.device) if want_stats else None
+  ws_bytes = _lib.yt8m_netvlad_tiled_workspace_bytes(b, t, d, k) if two_kernels else 0
+  ws = _workspace(ws_bytes, x.device) if ws_bytes else None
   _call("yt8m_netvlad_fwd_tiled", _p(x), _p(num_frames), b, t, d, k, _p(cw_packed), _p(scale), _p(shift), _p(cw2_tiled), _p(out),
-        FMT_F16 if out_f16 else FMT_BF16, _p(stats), _stream())
+        FMT_F16 if out_f16 else FMT_BF16, _p(stats), _p(ws), ws.numel() if ws is not None else 0, _stream())
   return (out, stats) if want_stats else out
 
 
