@@ -300,6 +300,24 @@ int yt8m_netvlad_bwd_assign(const yt8m_bf16* x, const int* num_frames, const flo
 int yt8m_act_bwd(const float* dy, const float* y, long long rows, int cols, int act, const float* col_scale,
                  yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out, yt8m_stream_t stream);
 
+/* ---- training-mode batch normalisation (slim.batch_norm(is_training=True); wh/all_frame_models/dbof_model.py:64-108,
+ * update ops wh/train.py:449-456).  x: fp32 or bf16 [rows, ld >= cols].
+ * yt8m_bn_stats: mean[c], var[c] = mean / BIASED variance of every column over the rows (tf.nn.moments).
+ * yt8m_bn_fold:  scale = gamma * rsqrt(var + eps), shift = beta - mean * scale (gamma / beta NULL = 1 / 0); when moving_mean /
+ *   moving_var are given they are updated in place: moving <- decay * moving + (1 - decay) * batch (slim decay 0.999).
+ * yt8m_col_affine_act: out = act(x * scale + shift) as fp32 and/or bf16 hi (+lo), row stride ld_out.
+ * yt8m_bn_bwd: backward of y = act(gamma * (x - mean) * rsqrt(var + eps) + beta) THROUGH the batch statistics, given dy = dL/dy
+ *   and y (NULL when act = none):  g = dy * act'(y);  dbeta = sum_r g;  dgamma = sum_r g * xhat;
+ *   dx = gamma * rstd * (g - dbeta / rows - xhat * dgamma / rows) as fp32 and/or bf16 hi (+lo) (all nullable). */
+int yt8m_bn_stats(const void* x, int src_dtype, long long rows, int cols, long long ld, float* mean, float* var, yt8m_stream_t stream);
+int yt8m_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int cols, float* scale,
+                 float* shift, float* moving_mean, float* moving_var, float decay, yt8m_stream_t stream);
+int yt8m_col_affine_act(const void* x, int src_dtype, long long rows, int cols, long long ld, const float* scale, const float* shift,
+                        int act, float* out_f32, yt8m_bf16* out_hi, yt8m_bf16* out_lo, long long ld_out, yt8m_stream_t stream);
+int yt8m_bn_bwd(const float* dy, long long ld_dy, const float* y, long long ld_y, const void* x, int src_dtype, long long ld_x,
+                const float* mean, const float* var, float eps, const float* gamma, int act, long long rows, int cols,
+                float* dgamma, float* dbeta, float* dx_f32, yt8m_bf16* dx_hi, yt8m_bf16* dx_lo, long long ld_dx, yt8m_stream_t stream);
+
 /* top-k per row, descending (wh/inference.py:76-87 format_lines; wh/eval_util.py:164 top_k_triplets).
  * k <= 32.  idx_out: int32 [rows, k]; val_out: fp32 [rows, k]. */
 int yt8m_topk_rows(const float* x, long long rows, int cols, int k, int* idx_out, float* val_out,

@@ -224,3 +224,39 @@ def test_captured_step_replay_matches_eager(env):
   assert float((got1 - got2).abs().max()) > 1e-5          # the refilled inputs were seen
   ms = step.kernel_ms()
   assert len(ms) == 1 and 0.0 < ms[0] < 50.0
+
+
+def test_dbof_model_training_mode_batch_norm(env):
+  """DbofModel.create_model(is_training=True) with the reference's default flags: slim.batch_norm with BATCH statistics in all
+  three layers (wh/all_frame_models/dbof_model.py:64-108) against the oracle, and the moving averages it leaves behind."""
+  flm, vlm, FLAGS, ops = env
+  b = 8
+  x, nf, _ = synth.model_input(b, seed=17)
+  g = torch.Generator().manual_seed(18)
+  fi = (torch.rand(b, 30, generator=g) * nf.unsqueeze(1)).to(torch.int64)
+  kw = dict(model_input=x.to(DEV).to(torch.bfloat16), vocab_size=V, num_frames=nf.to(DEV), frame_index=fi)
+  with FLAGS.override(dbof_cluster_size=2048, dbof_hidden_size=1024, moe_num_mixtures=2, iterations=30):
+    st = ops.get_store()
+    st.reset(seed=9)
+    model = flm.DbofModel()
+    model.create_model(**kw)                                   # creates the variables (inference form)
+    for name, v in st.vars.items():
+      if name.endswith("/weights"):
+        v.assign(synth.bf16r(v.value.cpu() * 3.0))
+    sd0 = {k: t.clone() for k, t in st.state_dict().items()}
+    out = model.create_model(is_training=True, **kw)
+    torch.cuda.synchronize()
+    sd1 = st.state_dict()
+
+  def bn(scope):
+    return {"gamma": sd0[scope + "/gamma"], "beta": sd0[scope + "/beta"], "mean": sd0[scope + "/moving_mean"], "var": sd0[scope + "/moving_variance"]}
+  p = {"cluster_w": sd0["cluster_weights"], "hidden_w": sd0["hidden1_weights"], "input_bn": bn("input_bn"), "cluster_bn": bn("cluster_bn"),
+       "hidden1_bn": bn("hidden1_bn")}
+  from oracle import yt8m_oracle as O
+  h = O.dbof_pool(x, fi, p, is_training=True, add_batch_norm=True, pooling="max")
+  want = O.moe_model(h, sd0["gates/weights"], sd0["experts/weights"], sd0["experts/biases"], V, 2)
+  check(out["predictions"], want)
+  rows = x[torch.arange(b).unsqueeze(1), fi].reshape(b * 30, -1)
+  _, mm, mv = O.batch_norm(rows, sd0["input_bn/gamma"], sd0["input_bn/beta"], sd0["input_bn/moving_mean"], sd0["input_bn/moving_variance"], True)
+  assert float((sd1["input_bn/moving_mean"] - mm).abs().max()) < 1e-6 and float((sd1["input_bn/moving_variance"] - mv).abs().max()) < 1e-6
+  assert float((sd1["hidden1_bn/moving_mean"] - sd0["hidden1_bn/moving_mean"]).abs().max()) > 0

@@ -99,6 +99,21 @@ def _bn_affine(scope, channels, is_training):
   return st.packed(gamma, "bn_affine", build, version=ver)
 
 
+def _bn_train(scope, x, act, want_bf16=True):
+  """slim.batch_norm(is_training=True) (+ activation) on a [rows, channels] activation: batch statistics, and the moving
+  averages of the scope's variables updated in place like the reference's UPDATE_OPS (wh/train.py:449-456)."""
+  st = ops.get_store()
+  c = x.shape[1]
+  gamma = st.get(scope + "/gamma", (c,), ops.ones_init, round_bf16=False)
+  beta = st.get(scope + "/beta", (c,), ops.zeros_init, round_bf16=False)
+  mean = st.get(scope + "/moving_mean", (c,), ops.zeros_init, trainable=False, round_bf16=False)
+  var = st.get(scope + "/moving_variance", (c,), ops.ones_init, trainable=False, round_bf16=False)
+  out, _ = nat.bn_train_fwd(x, gamma.value, beta.value, mean.value, var.value, act=act, want_bf16=want_bf16)
+  mean.version += 1
+  var.version += 1
+  return out
+
+
 def _lstm_stack(model_input, num_frames, want_seq=False, want_seq_bf16=False):
   """MultiRNNCell[BasicLSTMCell(lstm_cells, forget_bias=1.0)] x lstm_layers under
   dynamic_rnn(sequence_length=num_frames) (wh/all_frame_models/lstm_model.py:30-47).
@@ -290,6 +305,21 @@ class DbofModel(models.BaseModel):
     st = ops.get_store()
     cw = st.get("cluster_weights", (d, cluster_size), ops.random_normal(1 / math.sqrt(d)))
     hw = st.get("hidden1_weights", (cluster_size, hidden1_size), ops.random_normal(1 / math.sqrt(cluster_size)))
+    if add_batch_norm and is_training:
+      # batch statistics (dbof_model.py:64-108 with is_training=True): the statistics sit between the GEMMs, so the layers run
+      # un-fused here; the moving averages of the three scopes are updated in place
+      if method != "max":
+        raise NotImplementedError("is_training=True is built for --dbof_pooling_method=max")
+      cwp = st.packed(cw, "kmajor", lambda: nat.pack_transpose(cw.value))
+      hwp = st.packed(hw, "kmajor", lambda: nat.pack_transpose(hw.value))
+      r = _bn_train("input_bn", rows.contiguous(), None)
+      z = nat.linear(r["hi"], cwp, a_lo=r["lo"], n=cluster_size, k=d)["f32"]
+      act = _bn_train("cluster_bn", z, "relu6", want_bf16=False)["f32"]
+      hi, lo = nat.split_bf16(nat.group_max_rows(act, iterations))
+      z3 = nat.linear(hi, hwp, a_lo=lo, n=hidden1_size, k=cluster_size)["f32"]
+      hidden = _bn_train("hidden1_bn", z3, "relu6")
+      act = ops.Act(f32=hidden["f32"], hi=hidden["hi"], lo=hidden["lo"], cols=hidden1_size)
+      return _classifier().create_model(model_input=act, original_input=model_input, vocab_size=vocab_size, **unused_params)
     rows_lo = None
     if add_batch_norm:
       s_in, t_in = _bn_affine("input_bn", d, is_training)

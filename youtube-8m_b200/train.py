@@ -134,11 +134,12 @@ class Trainer(object):
                                                vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures,
                                                kind="multi" if multi else "max_pooling")
     if model_cls is frame_level_models.DbofModel:
-      if FLAGS.dbof_add_batch_norm or FLAGS.dbof_pooling_method != "max" or FLAGS.video_level_classifier_model != "MoeModel":
-        raise NotImplementedError("train.py --model=DbofModel: the CUDA training step is built for --dbof_add_batch_norm=False, "
+      if FLAGS.dbof_pooling_method != "max" or FLAGS.video_level_classifier_model != "MoeModel":
+        raise NotImplementedError("train.py --model=DbofModel: the CUDA training step is built for "
                                   "--dbof_pooling_method=max and --video_level_classifier_model=MoeModel")
       t = yt8m_trainer.DbofTrainer(in_dim, cluster_size=FLAGS.dbof_cluster_size, hidden=FLAGS.dbof_hidden_size,
-                                   iterations=FLAGS.iterations, vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures)
+                                   iterations=FLAGS.iterations, vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures,
+                                   batch_norm=FLAGS.dbof_add_batch_norm)
       t.sample_random_frames = FLAGS.sample_random_frames
       return t
     if model_cls is frame_level_models.AttentionModel:

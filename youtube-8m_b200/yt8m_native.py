@@ -89,6 +89,11 @@ _SIGS = {
     "yt8m_grad_reg_sumsq": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_float, c_int, c_int, c_void_p, c_void_p]),
     "yt8m_clip_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_float, c_float, c_float,
                                     c_float, c_float, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "yt8m_bn_stats": (c_int, [c_void_p, c_int, c_ll, c_int, c_ll, c_void_p, c_void_p, c_void_p]),
+    "yt8m_bn_fold": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+    "yt8m_col_affine_act": (c_int, [c_void_p, c_int, c_ll, c_int, c_ll, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
+    "yt8m_bn_bwd": (c_int, [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_int, c_ll, c_void_p, c_void_p, c_float, c_void_p, c_int, c_ll, c_int,
+                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
     "yt8m_topk_rows": (c_int, [c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 for _name, (_res, _args) in _SIGS.items():
@@ -583,6 +588,63 @@ def act_bwd(dy, y, act=None, col_scale=None):
   _check(_lib.yt8m_act_bwd(_p(dy.contiguous()), _p(y.contiguous()), rows, cols, ACT[act], _p(col_scale), _p(hi), _p(lo), ld,
                            _stream()), "yt8m_act_bwd")
   return hi[:, :cols], lo[:, :cols]
+
+
+BN_EPS, BN_DECAY = 1e-3, 0.999       # slim.batch_norm defaults
+
+
+def _src(t):
+  return {torch.float32: SRC_F32, torch.bfloat16: SRC_BF16}[t.dtype]
+
+
+def bn_train_fwd(x, gamma, beta, moving_mean=None, moving_var=None, act=None, want_f32=True, want_bf16=False):
+  """slim.batch_norm(is_training=True) on x [rows, cols] (fp32 or bf16, row stride >= cols) followed by `act`: batch statistics,
+  folded affine + activation, and the in-place moving-average update.  Returns (out dict f32 / hi / lo, (mean, var))."""
+  rows, cols = x.shape
+  dev = x.device
+  mean, var = _f32((cols,), dev), _f32((cols,), dev)
+  _call("yt8m_bn_stats", _p(x), _src(x), rows, cols, x.stride(0), _p(mean), _p(var), _stream())
+  scale, shift = _f32((cols,), dev), _f32((cols,), dev)
+  _call("yt8m_bn_fold", _p(gamma), _p(beta), _p(mean), _p(var), BN_EPS, cols, _p(scale), _p(shift), _p(moving_mean), _p(moving_var), BN_DECAY,
+        _stream())
+  ld = pad8(cols)
+  of = _f32((rows, ld), dev) if want_f32 else None
+  oh = torch.zeros((rows, ld), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+  ol = torch.zeros((rows, ld), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+  _call("yt8m_col_affine_act", _p(x), _src(x), rows, cols, x.stride(0), _p(scale), _p(shift), ACT[act], _p(of), _p(oh), _p(ol), ld, _stream())
+  out = {}
+  if of is not None:
+    out["f32"] = of[:, :cols]
+  if oh is not None:
+    out["hi"], out["lo"] = oh[:, :cols], ol[:, :cols]
+  return out, (mean, var)
+
+
+def bn_moving_update(moving_mean, moving_var, mean, var):
+  """moving <- decay * moving + (1 - decay) * batch, in place (the UPDATE_OPS of slim.batch_norm)."""
+  cols = mean.shape[0]
+  scratch = _f32((2, cols), mean.device)
+  _call("yt8m_bn_fold", None, None, _p(mean), _p(var), BN_EPS, cols, _p(scratch[0]), _p(scratch[1]), _p(moving_mean), _p(moving_var),
+        BN_DECAY, _stream())
+
+
+def bn_train_bwd(dy, y, x, stats, gamma, act=None, want_dx=True):
+  """Backward of bn_train_fwd: dy, y fp32 [rows, cols] (y = the forward's fp32 output; ignored when act is None), x = the forward's
+  input.  Returns (dgamma, dbeta, dx_hi, dx_lo, dx_f32) -- dx as bf16 hi/lo operands AND fp32 (None when not wanted)."""
+  rows, cols = x.shape
+  dev = x.device
+  mean, var = stats
+  dgamma, dbeta = _f32((cols,), dev), _f32((cols,), dev)
+  ld = pad8(cols)
+  dxf = _f32((rows, ld), dev) if want_dx else None
+  dh = torch.zeros((rows, ld), dtype=torch.bfloat16, device=dev) if want_dx else None
+  dl = torch.zeros((rows, ld), dtype=torch.bfloat16, device=dev) if want_dx else None
+  yy = y if ACT[act] != 0 else None
+  _call("yt8m_bn_bwd", _p(dy), dy.stride(0), _p(yy), yy.stride(0) if yy is not None else 0, _p(x), _src(x), x.stride(0), _p(mean), _p(var),
+        BN_EPS, _p(gamma), ACT[act], rows, cols, _p(dgamma), _p(dbeta), _p(dxf), _p(dh), _p(dl), ld, _stream())
+  if not want_dx:
+    return dgamma, dbeta, None, None, None
+  return dgamma, dbeta, dh[:, :cols], dl[:, :cols], dxf[:, :cols]
 
 
 def debug_set_timeline(buf):

@@ -978,21 +978,40 @@ class DeepCombineChainTrainer(object):
 
 
 class DbofTrainer(object):
-  """The training step for DbofModel (wh/all_frame_models/dbof_model.py:62-123) in its bias form
-  (--dbof_add_batch_norm=False, --dbof_pooling_method=max) + MoeModel: sample `iterations` frames per video, cluster
-  projection D -> cluster_size + bias + ReLU6, max over the sampled frames, hidden FC + bias + ReLU6, MoE head; the
-  backward routes the pooled gradient to the arg-max frame of every (video, cluster) (yt8m_group_max_rows_bwd) and
+  """The training step for DbofModel (wh/all_frame_models/dbof_model.py:62-123, --dbof_pooling_method=max) + MoeModel: sample
+  `iterations` frames per video, cluster projection D -> cluster_size, ReLU6, max over the sampled frames, hidden FC, ReLU6, MoE
+  head; the backward routes the pooled gradient to the arg-max frame of every (video, cluster) (yt8m_group_max_rows_bwd) and
   computes the cluster-weight gradient as one MN-major GEMM over all B*iterations sampled rows.
-  The batch-norm form needs batch statistics and their backward, which are not built."""
+
+  batch_norm=True (the reference default, --dbof_add_batch_norm=True): slim.batch_norm(is_training=True) on the sampled input
+  rows, after the cluster projection and after the hidden FC (dbof_model.py:64-108) -- batch statistics (biased variance),
+  backward THROUGH the statistics (yt8m_bn_bwd), and the moving averages (decay 0.999) that wh/train.py:449-456 runs as
+  update ops.  Data parallel: every rank normalises with the statistics of ITS shard (no collective in the forward pass); the
+  batch moments ride at the tail of the flat gradient buffer, so the ONE all-reduce also averages them and every replica
+  applies the same moving-average update.
+  batch_norm=False: the bias form (cluster_biases / hidden1_biases)."""
+
+  BN = (("input_bn", "d"), ("cluster_bn", "c"), ("hidden1_bn", "h"))
 
   def __init__(self, feature_dim, cluster_size=8192, hidden=1024, iterations=30, vocab=4716, mixtures=2, l2_penalty=1e-8,
-               device=None, group=None):
+               device=None, group=None, batch_norm=False):
     self.d, self.c, self.h, self.n, self.v, self.m = feature_dim, cluster_size, hidden, iterations, vocab, mixtures
+    self.bn = batch_norm
     self.dev = device or torch.device("cuda", torch.cuda.current_device())
     self.group = group
     self.world = yt8m_dp.world_size(group)
-    sizes = [("cw", cluster_size * feature_dim), ("cb", cluster_size), ("wh", hidden * cluster_size), ("bh", hidden),
-             ("head", HeadTrainer.flat_size("moe", hidden, vocab, mixtures))]
+    dims = {"d": feature_dim, "c": cluster_size, "h": hidden}
+    if batch_norm:
+      sizes = [("cw", cluster_size * feature_dim), ("wh", hidden * cluster_size)]
+      for scope, k in self.BN:
+        sizes += [(scope + "/gamma", dims[k]), (scope + "/beta", dims[k])]
+    else:
+      sizes = [("cw", cluster_size * feature_dim), ("cb", cluster_size), ("wh", hidden * cluster_size), ("bh", hidden)]
+    sizes.append(("head", HeadTrainer.flat_size("moe", hidden, vocab, mixtures)))
+    self._param_names = [n for n, _ in sizes if n != "head"]
+    if batch_norm:                                   # batch moments: all-reduced with the gradients, never optimised
+      for scope, k in self.BN:
+        sizes += [(scope + "/mean", dims[k]), (scope + "/var", dims[k])]
     total = sum(n for _, n in sizes)
     self.param = torch.zeros(total, dtype=torch.float32, device=self.dev)
     self.grad = torch.zeros_like(self.param)
@@ -1002,10 +1021,13 @@ class DbofTrainer(object):
     for name, n in sizes:
       self._off[name] = (off, off + n)
       off += n
-    shapes = {"cw": (cluster_size, feature_dim), "cb": (cluster_size, 1), "wh": (hidden, cluster_size), "bh": (hidden, 1)}
+    shapes = {"cw": (cluster_size, feature_dim), "wh": (hidden, cluster_size), "cb": (cluster_size, 1), "bh": (hidden, 1)}
     self.p, self.g, self.am, self.av = {}, {}, {}, {}
-    for name, shp in shapes.items():
+    for name, n in sizes:
+      if name == "head":
+        continue
       a, b = self._off[name]
+      shp = shapes.get(name, (n, 1))
       self.p[name], self.g[name] = self.param[a:b].view(shp), self.grad[a:b].view(shp)
       self.am[name], self.av[name] = self.adam_m[a:b].view(shp), self.adam_v[a:b].view(shp)
     a, b = self._off["head"]
@@ -1013,6 +1035,12 @@ class DbofTrainer(object):
                             storage=(self.param[a:b], self.grad[a:b], self.adam_m[a:b], self.adam_v[a:b]))
     self.cw_bf16 = torch.zeros((cluster_size, feature_dim), dtype=torch.bfloat16, device=self.dev)
     self.wh_bf16 = torch.zeros((hidden, cluster_size), dtype=torch.bfloat16, device=self.dev)
+    # moving statistics (non-trainable variables of the reference graph)
+    self.moving = {}
+    if batch_norm:
+      for scope, k in self.BN:
+        self.moving[scope + "/moving_mean"] = torch.zeros(dims[k], device=self.dev)
+        self.moving[scope + "/moving_variance"] = torch.ones(dims[k], device=self.dev)
     self.sample_random_frames = True
     self.global_step = 0
     self.keep_grads = False
@@ -1021,29 +1049,52 @@ class DbofTrainer(object):
   def import_state(self, sd):
     dev = self.dev
     self.p["cw"].copy_(sd["cluster_weights"].t().to(dev))
-    self.p["cb"].copy_(sd["cluster_biases"].view(-1, 1).to(dev))
     self.p["wh"].copy_(sd["hidden1_weights"].t().to(dev))
-    self.p["bh"].copy_(sd["hidden1_biases"].view(-1, 1).to(dev))
+    if self.bn:
+      for scope, _ in self.BN:
+        self.p[scope + "/gamma"].copy_(sd[scope + "/gamma"].view(-1, 1).to(dev))
+        self.p[scope + "/beta"].copy_(sd[scope + "/beta"].view(-1, 1).to(dev))
+        self.moving[scope + "/moving_mean"].copy_(sd[scope + "/moving_mean"].to(dev))
+        self.moving[scope + "/moving_variance"].copy_(sd[scope + "/moving_variance"].to(dev))
+    else:
+      self.p["cb"].copy_(sd["cluster_biases"].view(-1, 1).to(dev))
+      self.p["bh"].copy_(sd["hidden1_biases"].view(-1, 1).to(dev))
     self.cw_bf16.copy_(self.p["cw"])
     self.wh_bf16.copy_(self.p["wh"])
     self.head.import_state({k: sd[k] for k in ("gates/weights", "experts/weights", "experts/biases")})
 
-  def _tf_layout(self, flat):
+  def _tf_layout(self, flat, with_moving=False):
     v = {}
-    for name in ("cw", "cb", "wh", "bh"):
+    for name in self._param_names:
       a, b = self._off[name]
       v[name] = flat[a:b].view(self.p[name].shape)
-    out = {"cluster_weights": v["cw"].t().contiguous().cpu(), "cluster_biases": v["cb"].reshape(-1).cpu().clone(),
-           "hidden1_weights": v["wh"].t().contiguous().cpu(), "hidden1_biases": v["bh"].reshape(-1).cpu().clone()}
+    out = {"cluster_weights": v["cw"].t().contiguous().cpu(), "hidden1_weights": v["wh"].t().contiguous().cpu()}
+    if self.bn:
+      for scope, _ in self.BN:
+        out[scope + "/gamma"] = v[scope + "/gamma"].reshape(-1).cpu().clone()
+        out[scope + "/beta"] = v[scope + "/beta"].reshape(-1).cpu().clone()
+        if with_moving:
+          out[scope + "/moving_mean"] = self.moving[scope + "/moving_mean"].cpu().clone()
+          out[scope + "/moving_variance"] = self.moving[scope + "/moving_variance"].cpu().clone()
+    else:
+      out["cluster_biases"] = v["cb"].reshape(-1).cpu().clone()
+      out["hidden1_biases"] = v["bh"].reshape(-1).cpu().clone()
     a, b = self._off["head"]
     out.update(self.head.grads_tf_layout(flat[a:b]))
     return out
 
   def export_state(self):
-    return self._tf_layout(self.param)
+    return self._tf_layout(self.param, with_moving=True)
 
   def grads_tf_layout(self, flat):
     return self._tf_layout(flat)
+
+  def _bn_forward(self, scope, x, act, want_bf16):
+    out, stats = nat.bn_train_fwd(x, self.p[scope + "/gamma"].view(-1), self.p[scope + "/beta"].view(-1), act=act, want_bf16=want_bf16)
+    # this rank's batch moments, pre-divided by the world size: the all-reduce turns them into the cross-rank average
+    self.g[scope + "/mean"].view(-1).copy_(stats[0]).div_(self.world) if self.world > 1 else self.g[scope + "/mean"].view(-1).copy_(stats[0])
+    self.g[scope + "/var"].view(-1).copy_(stats[1]).div_(self.world) if self.world > 1 else self.g[scope + "/var"].view(-1).copy_(stats[1])
+    return out, stats
 
   def step(self, x, num_frames, labels, base_lr=0.01, lr_decay=0.95, lr_decay_examples=4000000, clip_gradient_norm=1.0,
            regularization_penalty=1.0, global_batch=None, frame_index=None):
@@ -1056,33 +1107,70 @@ class DbofTrainer(object):
     if frame_index is None:
       frame_index = frame_level_models.sample_frames(num_frames, n, self.sample_random_frames)
     rows = x[torch.arange(b, device=x.device).unsqueeze(1), frame_index.to(x.device)].reshape(b * n, d).contiguous()   # gather_nd
-    act = nat.linear(rows, self.cw_bf16, n=self.c, k=d, shift=self.p["cb"].view(-1), act="relu6")["f32"]               # [B*n, C]
+    if self.bn:
+      r, st1 = self._bn_forward("input_bn", rows, None, True)                                                          # hi + lo operand
+      z2 = nat.linear(r["hi"], self.cw_bf16, a_lo=r["lo"], n=self.c, k=d)["f32"]                                       # [B*n, C]
+      a2, st2 = self._bn_forward("cluster_bn", z2, "relu6", False)
+      act = a2["f32"]
+      rows_op = r["hi"]
+    else:
+      act = nat.linear(rows, self.cw_bf16, n=self.c, k=d, shift=self.p["cb"].view(-1), act="relu6")["f32"]             # [B*n, C]
+      rows_op = rows
     pooled = nat.group_max_rows(act, n)                                                                                # [B, C]
     q_hi, q_lo = nat.split_bf16(pooled)
-    hid = nat.linear(q_hi, self.wh_bf16, a_lo=q_lo, n=self.h, k=self.c, shift=self.p["bh"].view(-1), act="relu6", out_f32=True,
-                     out_bf16=True, out_lo=True)
+    if self.bn:
+      z3 = nat.linear(q_hi, self.wh_bf16, a_lo=q_lo, n=self.h, k=self.c)["f32"]
+      hid, st3 = self._bn_forward("hidden1_bn", z3, "relu6", True)
+    else:
+      hid = nat.linear(q_hi, self.wh_bf16, a_lo=q_lo, n=self.h, k=self.c, shift=self.p["bh"].view(-1), act="relu6", out_f32=True,
+                       out_bf16=True, out_lo=True)
     p = nat.moe_fwd(hid["hi"], self.head.w_bf16, self.head.b, self.v, self.m, x_lo=hid["lo"], d=self.h)
     # ---- backward
     loss, dhid = self.head.backward(p, hid["hi"], hid["lo"], labels, global_batch, want_dx=True)
-    dpre_hi, dpre_lo = nat.act_bwd(dhid[:, :self.h].contiguous(), hid["f32"], act="relu6")
+    dhid = dhid[:, :self.h].contiguous()
+    if self.bn:
+      dg, db, dpre_hi, dpre_lo, _ = nat.bn_train_bwd(dhid, hid["f32"], z3, st3, self.p["hidden1_bn/gamma"].view(-1), act="relu6")
+      self.g["hidden1_bn/gamma"].view(-1).copy_(dg)
+      self.g["hidden1_bn/beta"].view(-1).copy_(db)
+    else:
+      dpre_hi, dpre_lo = nat.act_bwd(dhid, hid["f32"], act="relu6")
+      nat.colsum_bf16(dpre_hi, dpre_lo, self.h, out=self.g["bh"].view(-1))
     nat.wgrad(dpre_hi, dpre_lo, q_hi, self.h, self.c, out=self.g["wh"])                  # d hidden1_weights^T [H, C]
-    nat.colsum_bf16(dpre_hi, dpre_lo, self.h, out=self.g["bh"].view(-1))
     wh_t = nat.pack_transpose(self.p["wh"])                                              # bf16 [C, H]: the dgrad operand
     dpooled = nat.linear(dpre_hi, wh_t, a_lo=dpre_lo, n=self.c, k=self.h)["f32"]
     del wh_t
     dact = nat.group_max_rows_bwd(act, dpooled.contiguous(), n)                          # to the arg-max frame of every (video, cluster)
-    dz_hi, dz_lo = nat.act_bwd(dact, act, act="relu6")
-    nat.wgrad(dz_hi, dz_lo, rows, self.c, d, out=self.g["cw"])                           # d cluster_weights^T [C, D]
-    nat.colsum_bf16(dz_hi, dz_lo, self.c, out=self.g["cb"].view(-1))
+    if self.bn:
+      dg, db, dz_hi, dz_lo, _ = nat.bn_train_bwd(dact, act, z2, st2, self.p["cluster_bn/gamma"].view(-1), act="relu6")
+      self.g["cluster_bn/gamma"].view(-1).copy_(dg)
+      self.g["cluster_bn/beta"].view(-1).copy_(db)
+    else:
+      dz_hi, dz_lo = nat.act_bwd(dact, act, act="relu6")
+      nat.colsum_bf16(dz_hi, dz_lo, self.c, out=self.g["cb"].view(-1))
+    nat.wgrad(dz_hi, dz_lo, rows_op, self.c, d, out=self.g["cw"])                        # d cluster_weights^T [C, D]
+    if self.bn:
+      # input_bn has trainable gamma / beta: the cluster projection's input gradient, then the statistics' backward (no dx:
+      # the frames themselves are data)
+      cw_t = nat.pack_transpose(self.p["cw"])                                            # bf16 [D, C]
+      drows = nat.linear(dz_hi, cw_t, a_lo=dz_lo, n=d, k=self.c)["f32"]
+      del cw_t
+      dg, db, _, _, _ = nat.bn_train_bwd(drows, None, rows, st1, self.p["input_bn/gamma"].view(-1), act=None, want_dx=False)
+      self.g["input_bn/gamma"].view(-1).copy_(dg)
+      self.g["input_bn/beta"].view(-1).copy_(db)
     yt8m_dp.all_reduce_sum_(self.grad, self.group)                                       # the ONE collective of the step
     if self.keep_grads:
       self.last_grad = self.grad.clone()
     lr = exponential_decay(base_lr, self.global_step, global_batch, lr_decay_examples, lr_decay)
     lr_t = adam_lr_t(lr, self.global_step + 1)
-    for name, bf in (("cw", self.cw_bf16), ("cb", None), ("wh", self.wh_bf16), ("bh", None)):
+    bf = {"cw": self.cw_bf16, "wh": self.wh_bf16}
+    for name in self._param_names:
       sums = nat.grad_reg_sumsq(self.g[name], self.p[name], 0.0)
-      nat.clip_adam_step(self.p[name], self.g[name], self.am[name], self.av[name], sums, clip_gradient_norm, lr_t, param_bf16=bf)
+      nat.clip_adam_step(self.p[name], self.g[name], self.am[name], self.av[name], sums, clip_gradient_norm, lr_t, param_bf16=bf.get(name))
     self.head.apply(lr_t, clip_gradient_norm, regularization_penalty)
+    if self.bn:                                                                          # update ops (wh/train.py:449-456)
+      for scope, _ in self.BN:
+        nat.bn_moving_update(self.moving[scope + "/moving_mean"], self.moving[scope + "/moving_variance"],
+                             self.g[scope + "/mean"].view(-1), self.g[scope + "/var"].view(-1))
     self.global_step += 1
     self.head.global_step = self.global_step
     self.last = {"label_loss_local": loss, "lr": lr}
