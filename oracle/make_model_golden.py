@@ -42,6 +42,7 @@ def load(rel, name, extra=None):
   """exec one reference file as module `name` (stubs for its project-local imports come from sys.modules)."""
   mod = types.ModuleType(name)
   mod.__dict__["xrange"] = range
+  mod.__dict__["map"] = lambda f, *a: list(map(f, *a))       # py2: map returns a list (lstm_parallel_finaloutput_model.py:34,56)
   mod.__dict__["print"] = lambda *a, **k: None
   if extra:
     mod.__dict__.update(extra)
@@ -81,7 +82,7 @@ def rnd(rs, shape, scale=1.0):
 def case_inputs(case):
   """Returns (inputs dict, weights dict by TF variable name, flags dict) for a named case."""
   rs = np.random.RandomState({"moe": 1, "logistic": 2, "chain": 3, "deep_chain": 4, "xent": 5, "lstm_att_max": 6, "lstm_multi_att": 7,
-                              "dequantize": 8, "lstm": 9, "lstm_memory": 10, "zt_attention": 11, "dbof_bn": 12, "dbof_bias": 13, "video_matrix": 14, "format_lines": 15, "log_lines": 16, "multitask_xent": 17}[case])
+                              "dequantize": 8, "lstm": 9, "lstm_memory": 10, "zt_attention": 11, "dbof_bn": 12, "dbof_bias": 13, "video_matrix": 14, "format_lines": 15, "log_lines": 16, "multitask_xent": 17, "cnn_deep_chain": 18, "lstm_parallel": 19}[case])
   b, d, v, m = 4, 8, 6, 2
   if case == "moe":
     return ({"x": rnd(rs, (b, d))}, {"gates/weights": rnd(rs, (d, v * (m + 1))), "experts/weights": rnd(rs, (d, v * m)),
@@ -115,6 +116,47 @@ def case_inputs(case):
     p = 1.0 / (1.0 + np.exp(-rnd(rs, (b, v), 2.0)))
     p[0, 0], p[1, 1] = 0.0, 1.0                     # the epsilon inside the logs matters exactly here
     return ({"p": p.astype(np.float32), "labels": rs.random_sample((b, v)) < 0.4}, {}, {"label_smoothing": False})
+  if case == "cnn_deep_chain":
+    # wh/all_frame_models/cnn_deep_combine_chain_model.py: 3 videos x 6 frames x 4 features, relu_cells = 3, 2 chain layers
+    bb, t, dd, rc, layers = 3, 6, 4, 3, 2
+    x = rnd(rs, (bb, t, dd))
+    nf = np.array([6, 3, 1], dtype=np.int32)
+    x = x * (np.arange(t)[None, :] < nf[:, None])[:, :, None]
+    w = {"mean-relu/weights": rnd(rs, (dd, rc)), "mean-relu/biases": rnd(rs, (rc,), 0.3)}
+    for l in range(layers + 1):
+      for fs, nfil in ((1, rc), (2, rc), (3, 2 * rc)):
+        w["cnn%dcnn-filter-len%d" % (l, fs)] = rnd(rs, (dd * fs, nfil), 0.7)
+    din = 4 * rc
+    for l in range(layers + 1):
+      sc = "prediction-%d" % l if l < layers else "-main"
+      w["gates-%s/weights" % sc] = rnd(rs, (din, v * (m + 1)))
+      w["experts-%s/weights" % sc] = rnd(rs, (din, v * m))
+      w["experts-%s/biases" % sc] = rnd(rs, (v * m,), 0.3)
+      if l < layers:
+        w["relu-%d/weights" % l] = rnd(rs, (v, rc))
+        w["relu-%d/biases" % l] = rnd(rs, (rc,), 0.3)
+      din = dd + 4 * rc + (l + 2) * rc              # mean_input + cnn descriptor + the relu layers so far
+    return ({"x": x.astype(np.float32), "num_frames": nf}, w,
+            {"moe_num_mixtures": m, "num_supports": 25, "deep_chain_layers": layers, "deep_chain_relu_cells": rc, "vocab": v})
+  if case == "lstm_parallel":
+    # wh/all_frame_models/lstm_parallel_finaloutput_model.py: two modalities (5 + 3 features), LSTM sizes 4 and 2, 2 layers each
+    bb, t, sizes, hs, layers = 3, 5, (5, 3), (4, 2), 2
+    x = rnd(rs, (bb, t, sum(sizes)))
+    nf = np.array([5, 2, 4], dtype=np.int32)
+    x = x * (np.arange(t)[None, :] < nf[:, None])[:, :, None]
+    w = {}
+    for i, (dsz, h) in enumerate(zip(sizes, hs)):
+      for l in range(layers):
+        din = dsz if l == 0 else h
+        w["RNN%d/multi_rnn_cell/cell_%d/basic_lstm_cell/weights" % (i, l)] = rnd(rs, (din + h, 4 * h), 0.5)
+        w["RNN%d/multi_rnn_cell/cell_%d/basic_lstm_cell/biases" % (i, l)] = rnd(rs, (4 * h,), 0.2)
+    feat = layers * sum(hs)
+    w["gates/weights"], w["experts/weights"] = rnd(rs, (feat, v * (m + 1)), 0.5), rnd(rs, (feat, v * m), 0.5)
+    w["experts/biases"] = rnd(rs, (v * m,), 0.3)
+    return ({"x": x.astype(np.float32), "num_frames": nf}, w,
+            {"lstm_cells": ",".join(str(h) for h in hs), "lstm_layers": layers, "feature_names": "rgb,audio",
+             "feature_sizes": ",".join(str(d_) for d_ in sizes), "moe_num_mixtures": m, "rnn_swap_memory": False,
+             "video_level_classifier_model": "MoeModel", "vocab": v})
   if case == "multitask_xent":
     # wh/losses.py:271-279 with --support_type="label,label" (the chain scripts, training_scripts/run-cascade-75-chaining-video.sh:17-20)
     # and with --support_type="frequent"
@@ -226,6 +268,18 @@ def run_reference(case):
     losses = load("losses.py", "ref_losses")
     out = losses.CrossEntropyLoss().calculate_loss(shim.t(inputs["p"]), inputs["labels"])
     return {"loss": float(out)}
+  elif case == "cnn_deep_chain":
+    mod = load("all_frame_models/cnn_deep_combine_chain_model.py", "ref_cnn_deep_chain")
+    res = mod.CnnDeepCombineChainModel().create_model(shim.t(inputs["x"]), v, inputs["num_frames"])
+    return {"predictions": np.asarray(res["predictions"]).tolist(), "support_predictions": np.asarray(res["support_predictions"]).tolist()}
+  elif case == "lstm_parallel":
+    vlm = types.ModuleType("video_level_models")
+    vlm.MoeModel = load("all_video_models/moe_model.py", "ref_moe").MoeModel
+    sys.modules["video_level_models"] = vlm
+    sys.modules["utils"].GetListOfFeatureNamesAndSizes = load_function(os.path.join(REF, "utils.py"), "GetListOfFeatureNamesAndSizes",
+                                                                        {"logging": types.SimpleNamespace(error=lambda *a, **k: None)})
+    mod = load("all_frame_models/lstm_parallel_finaloutput_model.py", "ref_lstm_parallel")
+    out = mod.LstmParallelFinaloutputModel().create_model(shim.t(inputs["x"]), v, inputs["num_frames"])["predictions"]
   elif case == "multitask_xent":
     losses = load("losses.py", "ref_losses")
     res = {}
@@ -299,7 +353,7 @@ def run_reference(case):
   return {"predictions": np.asarray(out, dtype=np.float64).tolist()}
 
 
-CASES = ["moe", "logistic", "chain", "deep_chain", "xent", "multitask_xent", "lstm", "lstm_memory", "lstm_att_max", "lstm_multi_att", "zt_attention",
+CASES = ["moe", "logistic", "chain", "deep_chain", "xent", "multitask_xent", "cnn_deep_chain", "lstm_parallel", "lstm", "lstm_memory", "lstm_att_max", "lstm_multi_att", "zt_attention",
          "dbof_bn", "dbof_bias", "video_matrix", "format_lines", "log_lines", "dequantize"]
 
 

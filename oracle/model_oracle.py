@@ -99,6 +99,24 @@ def attention_chain(sd, x, nf, vocab, mixtures, heads, layers):
   return p.reshape(-1, heads, vocab).max(dim=1).values
 
 
+def cnn_deep_combine_chain(sd, x, nf, vocab, mixtures, layers, filter_sizes=(1, 2, 3)):
+  """wh/all_frame_models/cnn_deep_combine_chain_model.py:43-88 (variables by the reference's names)."""
+  def moe_p(scope):
+    return {"gate_w": sd["gates-%s/weights" % scope], "expert_w": sd["experts-%s/weights" % scope], "expert_b": sd["experts-%s/biases" % scope]}
+  p = {"mean_relu_w": sd["mean-relu/weights"], "mean_relu_b": sd["mean-relu/biases"],
+       "cnn": [[(fs, sd["cnn%dcnn-filter-len%d" % (l, fs)]) for fs in filter_sizes] for l in range(layers + 1)],
+       "layers": [dict(moe_p("prediction-%d" % l), relu_w=sd["relu-%d/weights" % l], relu_b=sd["relu-%d/biases" % l]) for l in range(layers)],
+       "main": moe_p("-main")}
+  return O.cnn_deep_combine_chain_model(x, nf, p, vocab, mixtures, layers)
+
+
+def lstm_parallel_finaloutput(sd, x, nf, vocab, mixtures, feature_sizes, layers=2):
+  """wh/all_frame_models/lstm_parallel_finaloutput_model.py:32-73 + MoeModel."""
+  stacks = [[(sd["RNN%d/multi_rnn_cell/cell_%d/basic_lstm_cell/weights" % (i, l)], sd["RNN%d/multi_rnn_cell/cell_%d/basic_lstm_cell/biases" % (i, l)])
+             for l in range(layers)] for i in range(len(feature_sizes))]
+  return _moe(sd, O.lstm_parallel_finaloutput_state(x, nf, feature_sizes, stacks), vocab, mixtures)
+
+
 def dbof(sd, x, frame_index, vocab, mixtures, pooling="max"):
   """wh/all_frame_models/dbof_model.py:62-123 (inference-mode batch norm) + MoeModel."""
   def bn(scope):

@@ -178,12 +178,26 @@ def install(flag_values):
   tf.negative = lambda x, name=None: t(-np.asarray(x, dtype=np.float32))
   tf.square = lambda x, name=None: t(np.square(np.asarray(x, dtype=np.float32)))
   tf.maximum = lambda a, b, name=None: (max(a, b) if isinstance(a, int) and isinstance(b, int) else t(np.maximum(a, b)))
-  tf.expand_dims = lambda x, axis, name=None: np.expand_dims(np.asarray(x), axis).view(T)
+  tf.expand_dims = lambda x, axis=None, name=None, dim=None: np.expand_dims(np.asarray(x), axis if axis is not None else dim).view(T)   # TF 1.0 also takes dim=
   tf.einsum = lambda eq, *ops: t(np.einsum(eq, *[np.asarray(o, dtype=np.float32) for o in ops]))
   tf.sequence_mask = _sequence_mask
   tf.name_scope, tf.variable_scope = _name_scope, _scope
   tf.constant_initializer = lambda value, **kw: np.asarray(value, dtype=np.float32)
-  tf.get_variable = lambda name, shape=None, dtype=None, trainable=True, initializer=None, **kw: t(np.reshape(initializer, shape))
+  # tf.get_variable: a constant initialiser IS the value (lookup tables); a random initialiser means "trainable variable": the
+  # harness supplies its value under scope/name
+  def _get_variable(name, shape=None, dtype=None, trainable=True, initializer=None, **kw):
+    if isinstance(initializer, tuple) and initializer and initializer[0] == "initial value":
+      v = _var(name)
+      assert tuple(v.shape) == tuple(shape), (name, v.shape, shape)
+      return t(v)
+    return t(np.reshape(initializer, shape))
+  tf.get_variable = _get_variable
+  tf.truncated_normal_initializer = lambda mean=0.0, stddev=1.0, **kw: ("initial value", None)
+  # ops used by CnnDeepCombineChainModel / LstmParallelFinaloutputModel (wh/all_frame_models/cnn_deep_combine_chain_model.py:24-41,
+  # :105-116; lstm_parallel_finaloutput_model.py:36)
+  tf.pad = lambda x, paddings, name=None: t(np.pad(np.asarray(x, dtype=np.float32), [tuple(int(v) for v in p_) for p_ in paddings]))
+  tf.split = lambda x, sizes, axis=0, name=None: [t(a) for a in np.split(np.asarray(x, dtype=np.float32), np.cumsum(sizes)[:-1], axis=axis)]
+  nn.embedding_lookup = lambda params, ids, name=None: t(np.asarray(params)[np.asarray(ids).astype(np.int64)])
   # ops used by zt's AttentionModel (zt/frame_level_models.py:4372-4398)
   tf.abs = lambda x, name=None: t(np.abs(np.asarray(x, dtype=np.float32)))
   tf.shape = lambda x, name=None: tuple(np.asarray(x).shape)
@@ -244,6 +258,7 @@ def install(flag_values):
     return t(y)
   slim.batch_norm = _batch_norm
   contrib.rnn, contrib.slim = rnn, slim
+  contrib.layers = types.SimpleNamespace(l2_regularizer=lambda scale: ("l2", scale))     # cnn_deep_combine_chain_model.py:36
   tf.contrib = contrib
   flags = types.ModuleType("tensorflow.flags")
   flags.FLAGS = flag_values

@@ -265,6 +265,55 @@ def attention_model_pool(x, num_frames, w, b):
   return state.reshape(-1, d)
 
 
+def shifted_concat_cnn(x, filters):
+  """wh/all_frame_models/cnn_deep_combine_chain_model.py:13-41 (CnnDeepCombineChainModel.cnn): for every filter
+  (length fs, matrix [D*fs, nf]) the input is concatenated with its copies shifted DOWN by 1 .. fs-1 frames (zero rows shifted
+  in at the front, tf.pad + slice, :24-29) and contracted over the D*fs axis ("ijk,kl->ijl", :38); the outputs are concatenated
+  along the channel axis.  x: [B, T, D]; filters: list of (fs, W)."""
+  bsz, t_max, d = x.shape
+  shifts = [x] + [torch.cat([torch.zeros(bsz, i, d, dtype=x.dtype), x[:, :t_max - i]], dim=1) for i in range(1, max(f for f, _ in filters))]
+  return torch.cat([torch.cat(shifts[:fs], dim=2) @ w for fs, w in filters], dim=2)
+
+
+def cnn_deep_combine_chain_model(x, num_frames, p, vocab_size, num_mixtures, num_layers):
+  """wh/all_frame_models/cnn_deep_combine_chain_model.py:43-88.  p: mean_relu_w/b; cnn[l] = list of (fs, W) for l = 0..num_layers;
+  layers[l] = MoE (gate_w, expert_w, expert_b) + relu_w / relu_b; main = MoE.  The max over time runs over ALL max_frames rows
+  (:67, :83: tf.reduce_max without a mask -- padded rows contribute their shifted neighbours and zeros).
+  Returns (predictions [B, V], support_predictions [B, V * num_layers])."""
+  bsz, t_max, d = x.shape
+  mask = sequence_mask(num_frames, t_max, x.dtype)
+  mean_input = torch.einsum("ijk,ij->ik", x, mask) / num_frames.to(x.dtype).unsqueeze(1)
+  relu_layers = [l2_normalize(torch.relu(mean_input @ p["mean_relu_w"] + p["mean_relu_b"]), dim=1)]
+
+  def pooled_cnn(l):
+    return l2_normalize(shifted_concat_cnn(x, p["cnn"][l]).max(dim=1).values, dim=1)
+
+  next_input = pooled_cnn(0)
+  supports = []
+  for l in range(num_layers):
+    lyr = p["layers"][l]
+    sub = moe_model(next_input, lyr["gate_w"], lyr["expert_w"], lyr["expert_b"], vocab_size, num_mixtures)
+    supports.append(sub)
+    relu_layers.append(l2_normalize(torch.relu(sub @ lyr["relu_w"] + lyr["relu_b"]), dim=1))
+    next_input = torch.cat([mean_input, pooled_cnn(l + 1)] + relu_layers, dim=1)
+  main = moe_model(next_input, p["main"]["gate_w"], p["main"]["expert_w"], p["main"]["expert_b"], vocab_size, num_mixtures)
+  return main, torch.cat(supports, dim=1)
+
+
+def lstm_parallel_finaloutput_state(x, num_frames, feature_sizes, stacks):
+  """wh/all_frame_models/lstm_parallel_finaloutput_model.py:32-64: the input is split by modality (:36), every slice is
+  L2-normalised per frame (:36), run through its own MultiRNNCell stack (tuple state), and the h states of every layer of every
+  stack are concatenated (:58-61).  stacks[i]: list of (W, b) per layer of modality i."""
+  hs = []
+  off = 0
+  for size, layers in zip(feature_sizes, stacks):
+    sub = l2_normalize(x[:, :, off:off + size], dim=2)
+    off += size
+    _, states = dynamic_rnn_lstm(sub, num_frames, layers)
+    hs.extend(h for _, h in states)
+  return torch.cat(hs, dim=1)
+
+
 # ----------------------------------------------------------------------------------------
 # DBoF (wh/all_frame_models/dbof_model.py) and NetVLAD (not in the reference)
 # ----------------------------------------------------------------------------------------

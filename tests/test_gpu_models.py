@@ -260,3 +260,39 @@ def test_dbof_model_training_mode_batch_norm(env):
   _, mm, mv = O.batch_norm(rows, sd0["input_bn/gamma"], sd0["input_bn/beta"], sd0["input_bn/moving_mean"], sd0["input_bn/moving_variance"], True)
   assert float((sd1["input_bn/moving_mean"] - mm).abs().max()) < 1e-6 and float((sd1["input_bn/moving_variance"] - mv).abs().max()) < 1e-6
   assert float((sd1["hidden1_bn/moving_mean"] - sd0["hidden1_bn/moving_mean"]).abs().max()) > 0
+
+
+def test_cnn_deep_combine_chain_model(env):
+  """CnnDeepCombineChainModel (wh/all_frame_models/cnn_deep_combine_chain_model.py): the temporal CNN as three
+  tensor-core GEMMs over the shifted-concat operand + max over time + the chain of MoE stages, against the oracle (itself held
+  to the reference source by tests/test_oracle_golden_models.py)."""
+  flm, vlm, FLAGS, ops = env
+  b = 12
+  x, nf, _ = synth.model_input(b, frames=120, seed=31)
+  nf[0], nf[1] = 120, 1
+  x = x * (torch.arange(120).unsqueeze(0) < nf.unsqueeze(1)).float().unsqueeze(2)
+  y = synth.labels(b, V)
+  with FLAGS.override(moe_num_mixtures=2, deep_chain_layers=2, deep_chain_relu_cells=64):
+    out, sd = build_and_run(ops, flm.CnnDeepCombineChainModel(), {"gates": 30.0, "experts": 30.0, "relu-": 3.0, "cnn": 1.0},
+                            model_input=x.to(DEV).to(torch.bfloat16), vocab_size=V, num_frames=nf.to(DEV))
+  want, want_sup = model_oracle.cnn_deep_combine_chain(sd, x, nf, V, 2, 2)
+  check(out["predictions"], want, y)
+  check(out["support_predictions"], want_sup)
+
+
+def test_lstm_parallel_finaloutput_model(env):
+  """LstmParallelFinaloutputModel (wh/all_frame_models/lstm_parallel_finaloutput_model.py) with the reference's
+  modalities: rgb 1024 -> LSTM-1024 x 2, audio 128 -> LSTM-128 x 2, h states concatenated (2304-d) -> MoE."""
+  flm, vlm, FLAGS, ops = env
+  import yt8m_flags as flags
+  for name, default in (("feature_names", "mean_rgb"), ("feature_sizes", "1024")):
+    if name not in FLAGS:
+      flags.DEFINE_string(name, default, "defined by the command-line front ends (train.py / eval.py / inference.py)")
+  b = 5
+  x, nf, _ = synth.model_input(b, frames=40, seed=32, min_frames=5)
+  with FLAGS.override(lstm_cells="1024,128", lstm_layers=2, moe_num_mixtures=2, feature_names="rgb,audio", feature_sizes="1024,128",
+                      video_level_classifier_model="MoeModel"):
+    out, sd = build_and_run(ops, flm.LstmParallelFinaloutputModel(), {"basic_lstm_cell": 1.0, "gates": 10.0, "experts": 10.0},
+                            model_input=x.to(DEV).to(torch.bfloat16), vocab_size=V, num_frames=nf.to(DEV))
+  want = model_oracle.lstm_parallel_finaloutput(sd, x, nf, V, 2, [1024, 128], 2)
+  check(out["predictions"], want)

@@ -196,3 +196,25 @@ def test_vertical_support_labels(tmp_path):
     got = losses.MultiTaskCrossEntropyLoss().get_support(labels)
   losses.MultiTaskLoss._vertical = None
   assert np.array_equal(got, want) and got.tolist() == [[0, 1, 0], [1, 0, 1], [0, 0, 0]]
+
+
+def test_cnn_deep_combine_chain_matches_the_reference():
+  """wh/all_frame_models/cnn_deep_combine_chain_model.py:10-124 executed from the reference source (shifted-concat temporal CNN,
+  unmasked max over time, chain of MoE stages): predictions and support predictions."""
+  inp, w, fl = G.case_inputs("cnn_deep_chain")
+  sd = {k: torch.from_numpy(v) for k, v in w.items()}
+  got, sup = MO.cnn_deep_combine_chain(sd, torch.from_numpy(inp["x"]), torch.from_numpy(inp["num_frames"]), fl["vocab"],
+                                       fl["moe_num_mixtures"], fl["deep_chain_layers"])
+  want, want_sup = np.asarray(GOLDEN["cnn_deep_chain"]["predictions"]), np.asarray(GOLDEN["cnn_deep_chain"]["support_predictions"])
+  assert np.abs(got.numpy() - want).max() < 3e-6 and np.abs(sup.numpy() - want_sup).max() < 3e-6
+
+
+def test_lstm_parallel_finaloutput_matches_the_reference():
+  """wh/all_frame_models/lstm_parallel_finaloutput_model.py:13-73 executed from the reference source: per-modality L2
+  normalisation, one LSTM stack per modality under RNN<i>, concatenation of every layer's h state."""
+  inp, w, fl = G.case_inputs("lstm_parallel")
+  sd = {k: torch.from_numpy(v) for k, v in w.items()}
+  sizes = [int(s) for s in fl["feature_sizes"].split(",")]
+  got = MO.lstm_parallel_finaloutput(sd, torch.from_numpy(inp["x"]), torch.from_numpy(inp["num_frames"]), fl["vocab"],
+                                     fl["moe_num_mixtures"], sizes, fl["lstm_layers"])
+  assert np.abs(got.numpy() - np.asarray(GOLDEN["lstm_parallel"]["predictions"])).max() < 3e-6

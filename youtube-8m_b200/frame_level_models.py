@@ -114,11 +114,11 @@ def _bn_train(scope, x, act, want_bf16=True):
   return out
 
 
-def _lstm_stack(model_input, num_frames, want_seq=False, want_seq_bf16=False):
+def _lstm_stack(model_input, num_frames, want_seq=False, want_seq_bf16=False, hidden=None, scope="RNN"):
   """MultiRNNCell[BasicLSTMCell(lstm_cells, forget_bias=1.0)] x lstm_layers under
   dynamic_rnn(sequence_length=num_frames) (wh/all_frame_models/lstm_model.py:30-47).
   Returns (state [B, L*2*H] = [c0, h0, c1, h1, ...], outputs fp32, outputs bf16)."""
-  hidden = int(FLAGS.lstm_cells)
+  hidden = int(FLAGS.lstm_cells) if hidden is None else hidden
   layers = FLAGS.lstm_layers
   x = ops.frames_operand(model_input)
   d = x.shape[2]
@@ -126,9 +126,9 @@ def _lstm_stack(model_input, num_frames, want_seq=False, want_seq_bf16=False):
   wps, bps = [], []
   for l in range(layers):
     in_dim = d if l == 0 else hidden
-    scope = "RNN/multi_rnn_cell/cell_%d/basic_lstm_cell" % l
-    w = st.get(scope + "/weights", (in_dim + hidden, 4 * hidden), ops.xavier_uniform)
-    b = st.get(scope + "/biases", (4 * hidden,), ops.zeros_init, round_bf16=False)
+    cell = scope + "/multi_rnn_cell/cell_%d/basic_lstm_cell" % l
+    w = st.get(cell + "/weights", (in_dim + hidden, 4 * hidden), ops.xavier_uniform)
+    b = st.get(cell + "/biases", (4 * hidden,), ops.zeros_init, round_bf16=False)
     wp, bp = st.packed(w, "lstm", lambda w=w, b=b, in_dim=in_dim: nat.lstm_pack(w.value, b.value, in_dim, hidden),
                        version=(w.version, b.version))
     wps.append(wp)
@@ -182,6 +182,97 @@ class LstmMemoryModel(models.BaseModel):
     final_state = torch.cat([c for c, _ in _split_state(state, layers, hidden)], dim=1)   # device copy
     return _classifier().create_model(model_input=final_state, original_input=model_input, vocab_size=vocab_size,
                                       num_frames=num_frames, **unused_params)
+
+
+class LstmParallelFinaloutputModel(models.BaseModel):
+  """wh/all_frame_models/lstm_parallel_finaloutput_model.py:13-73: one LSTM stack PER MODALITY (--feature_names / --feature_sizes,
+  --lstm_cells="1024,128"): every slice of the frame features is L2-normalised per frame (:36), runs through its own
+  MultiRNNCell under variable scope RNN<i> (:45-56), and the classifier sees the concatenation of the h states of every layer of
+  every stack (:58-61)."""
+
+  def create_model(self, model_input, vocab_size, num_frames, **unused_params):
+    import utils
+    lstm_sizes = [int(v) for v in str(FLAGS.lstm_cells).split(",")]
+    _, feature_sizes = utils.GetListOfFeatureNamesAndSizes(FLAGS.feature_names, FLAGS.feature_sizes)
+    assert len(lstm_sizes) == len(feature_sizes), \
+        "length of lstm_sizes (={}) != length of feature_sizes (={})".format(len(lstm_sizes), len(feature_sizes))
+    x = ops.frames_operand(model_input)
+    b, t, d = x.shape
+    if sum(feature_sizes) != d:
+      raise ValueError("--feature_sizes add up to %d, the input has %d features" % (sum(feature_sizes), d))
+    nf = num_frames.to(x.device, torch.int32)
+    layers = FLAGS.lstm_layers
+    hs, off = [], 0
+    for i, (size, hidden) in enumerate(zip(feature_sizes, lstm_sizes)):
+      sub = nat.l2norm_rows(x[:, :, off:off + size].contiguous())          # tf.split (device copy) + tf.nn.l2_normalize(dim=2)
+      off += size
+      state, _, _ = _lstm_stack(sub, nf, hidden=hidden, scope="RNN%d" % i)
+      hs.extend(h for _, h in _split_state(state, layers, hidden))
+    final_state = torch.cat(hs, dim=1)                                     # tf.concat (device copy)
+    return _classifier().create_model(model_input=final_state, original_input=model_input, vocab_size=vocab_size,
+                                      **unused_params)
+
+
+class CnnDeepCombineChainModel(models.BaseModel):
+  """wh/all_frame_models/cnn_deep_combine_chain_model.py:10-88: a temporal CNN (filters over 1, 2 and 3 consecutive frames, max
+  over time) feeds a chain of MoE sub-predictions; every stage sees the mean-pooled input, a FRESH CNN descriptor and the
+  ReLU-projected, L2-normalised predictions of all earlier stages.
+
+  The convolution is a dense GEMM: the operand row of frame t is [x_t, x_{t-1}, x_{t-2}] (zero rows shifted in at the front,
+  :24-29), built once and shared by every filter length (its first D*fs columns) and by all deep_chain_layers + 1 CNN stages --
+  their filters of one length are stacked along the output axis, so the whole model runs THREE tensor-core GEMMs over the
+  B*T frame rows, followed by the max over time (over all max_frames rows, as the reference's unmasked tf.reduce_max does)."""
+
+  FILTER_SIZES = (1, 2, 3)
+
+  def create_model(self, model_input, vocab_size, num_frames, num_mixtures=None, l2_penalty=1e-8, sub_scope="",
+                   original_input=None, **unused_params):
+    num_layers = FLAGS.deep_chain_layers
+    relu_cells = FLAGS.deep_chain_relu_cells
+    num_filters = (relu_cells, relu_cells, relu_cells * 2)
+    x = ops.frames_operand(model_input)
+    b, t, d = x.shape
+    nf = num_frames.to(x.device, torch.int32)
+    st = ops.get_store()
+    # mean over the valid frames == attention pooling with equal logits (einsum("ijk,ij->ik") / num_frames, :55-57)
+    pooled, _, _ = nat.attn_pool(torch.zeros((b, t, 1), device=x.device), x, nf, 1, 0, want_bf16=False)
+    mean_input = ops.Act(f32=pooled.reshape(b, d))
+    mean_relu = ops.fully_connected(mean_input, relu_cells, sub_scope + "mean-relu", activation_fn="relu", l2_penalty=l2_penalty,
+                                    want_bf16=False)
+    relu_layers = [ops.l2_normalize_rows(mean_relu)]
+    # shifted-concat operand [B, T, 3D]: columns [i*D, (i+1)*D) hold the frames shifted down by i (device copies, no arithmetic)
+    fs_max = max(self.FILTER_SIZES)
+    xcat = torch.zeros((b, t, fs_max * d), dtype=x.dtype, device=x.device)
+    for i in range(fs_max):
+      xcat[:, i:, i * d:(i + 1) * d] = x[:, :t - i]
+    rows = xcat.reshape(b * t, fs_max * d)
+    # every CNN stage's filters of one length, stacked along the output axis: [D*fs, (L+1)*nf]
+    pooled_cnn = []
+    for fs, nfil in zip(self.FILTER_SIZES, num_filters):
+      ws = [st.get(sub_scope + "cnn%dcnn-filter-len%d" % (l, fs), (d * fs, nfil), ops.truncated_normal(0.1), l2=l2_penalty)
+            for l in range(num_layers + 1)]
+      wp = st.packed(ws[0], "cnn_stack_len%d" % fs, lambda ws=ws: nat.pack_transpose(torch.cat([w.value for w in ws], dim=1)),
+                     version=tuple(w.version for w in ws))
+      out = nat.linear(rows, wp, n=(num_layers + 1) * nfil, k=d * fs)["f32"]            # [B*T, (L+1)*nf]
+      pooled_cnn.append(nat.group_max_rows(out, t).reshape(b, num_layers + 1, nfil))     # max over time
+    def cnn_descriptor(l):
+      cat = torch.cat([pc[:, l] for pc in pooled_cnn], dim=1).contiguous()               # tf.concat over filter lengths
+      return ops.l2_normalize_rows(cat)
+    next_input = cnn_descriptor(0)
+    support_predictions = []
+    for layer in range(num_layers):
+      sub_prediction = self.sub_model(next_input, vocab_size, sub_scope=sub_scope + "prediction-%d" % layer)
+      support_predictions.append(sub_prediction)
+      sub_relu = ops.fully_connected(sub_prediction, relu_cells, sub_scope + "relu-%d" % layer, activation_fn="relu",
+                                     l2_penalty=l2_penalty, want_bf16=False)
+      relu_layers.append(ops.l2_normalize_rows(sub_relu))
+      next_input = ops.concat([mean_input, cnn_descriptor(layer + 1)] + relu_layers)
+    main = self.sub_model(next_input, vocab_size, sub_scope=sub_scope + "-main")
+    return {"predictions": main, "support_predictions": torch.cat(support_predictions, dim=1)}
+
+  def sub_model(self, model_input, vocab_size, num_mixtures=None, l2_penalty=1e-8, sub_scope="", **unused_params):
+    num_mixtures = num_mixtures or FLAGS.moe_num_mixtures
+    return ops.moe_head(model_input, vocab_size, num_mixtures, "gates-" + sub_scope, "experts-" + sub_scope, l2_penalty)
 
 
 class LstmAttentionMaxPoolingModel(models.BaseModel):
