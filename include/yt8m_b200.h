@@ -170,6 +170,14 @@ int yt8m_attn_pool_fwd(const float* logits, long long ld_logits, const yt8m_bf16
                        int B, int T, int A, int F, int mode, float* out, yt8m_bf16* out_hi, yt8m_bf16* out_lo,
                        yt8m_stream_t stream);
 
+/* The LSTM-free attention pooler of zt/frame_level_models.py:4372-4398 in ONE kernel (BASELINE.json configs[4]): logits
+ * x[b, t, :] . W[:, a] (w_packed: bf16 [A, ldw >= D], K-major as from yt8m_pack_transpose_bf16 of W[:D]; the mean-pooled half of
+ * Attention/W and Attention/b shift every frame of a video alike and cancel in the softmax over t), masked softmax over the
+ * frames (t < num_frames[b], or -- num_frames NULL -- "frame row has a non-zero entry"), weighted sum of the frames.  The frames
+ * leave HBM once (the pooling pass re-reads them from L2).  A = 8 heads; D % 8 == 0.  out: fp32 [B, A, D] (+ bf16 hi / lo). */
+int yt8m_attn_pool_fused(const yt8m_bf16* x, const yt8m_bf16* w_packed, long long ldw, const int* num_frames, int B, int T, int D,
+                         int A, float* out, yt8m_bf16* out_hi, yt8m_bf16* out_lo, yt8m_stream_t stream);
+
 /* backward of yt8m_attn_pool_fwd (same logits / feats / mask / mode): dout fp32 [B, A, F] ->
  * dlogits fp32 [B, T, ld_dl >= A] (zero for masked frames) and, when dfeats != NULL, dfeats fp32 [B, T, F]
  * (needed when feats are LSTM outputs: lstm_attention_max_pooling_model.py:63). */

@@ -1,0 +1,148 @@
+// yt8m_b200 -- fused multi-head attention pooling over the raw frames (zt/frame_level_models.py:4372-4398; BASELINE.json configs[4]):
+//   logits[t, a] = x[t, :] . W[:, a]   (the mean-pooled half of W and the bias add a per-video constant: softmax over t ignores it)
+//   w[t, a] = softmax_t(logits)[t, a] * mask[t], renormalised over t        (mask: t < num_frames, or "frame row is non-zero")
+//   out[a, :] = sum_t w[t, a] * x[t, :]
+// ONE kernel, one CTA per video, the frames leave HBM once: phase A (a warp per frame) computes the A logits of every frame and
+// keeps them in shared memory (T x A floats); phase B streams the same frames again -- out of L2, they were read microseconds
+// ago by the same SM -- and accumulates the A weighted sums, every thread owning four feature columns.  SURVEY.md §8(d): HBM
+// bound, 691,200 B per 300-frame video.  The predecessor ran a tensor-core GEMM over all B*T rows (N = 8 of a 32-wide tile),
+// wrote B*T x 8 logits to HBM and read the frames a second time in a separate kernel: 0.50 ms at B = 256 (profiles/
+// r02a_bench_c5.json); the arithmetic here is 11 MFLOP per video -- CUDA cores are plenty.
+#include "yt8m_common.cuh"
+#include "yt8m_host.h"
+
+using namespace yt8m;
+
+namespace {
+
+constexpr int kMaxA = 8;
+
+template <int A>
+__global__ void __launch_bounds__(1024)
+attn_pool_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, long long ldw,
+                       const int* __restrict__ num_frames, int T, int D, float* __restrict__ out,
+                       __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  float* wl = reinterpret_cast<float*>(smem_raw);               // [T][A] logits -> weights
+  float* inv_s = wl + static_cast<size_t>(T) * A;               // [A] 1 / sum (+ A floats of padding: 16-byte alignment below)
+  // W^T staged as [D][A] bf16: one 16-byte vector per feature (A = 8)
+  __nv_bfloat16* wt = reinterpret_cast<__nv_bfloat16*>(inv_s + 2 * A);
+  static_assert(A == 8, "one uint4 of weights per feature");
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
+  const __nv_bfloat16* xb = x + static_cast<long long>(b) * T * D;
+  const int nf = num_frames ? min(max(__ldg(num_frames + b), 0), T) : T;
+  for (int i = tid; i < D * A; i += blockDim.x) {
+    const int d = i / A, a = i - d * A;
+    wt[i] = w[static_cast<long long>(a) * ldw + d];             // K-major packed [A, ldw] -> [D][A]
+  }
+  __syncthreads();
+  // ---- phase A: a warp per frame; lane owns feature pairs 2 * (lane + 32 j) ----
+  const int npairs = D / 2;
+  for (int t = warp; t < nf; t += nwarps) {
+    const uint32_t* row = reinterpret_cast<const uint32_t*>(xb + static_cast<long long>(t) * D);
+    float acc[A];
+#pragma unroll
+    for (int a = 0; a < A; ++a) acc[a] = 0.0f;
+    bool nz = false;
+    for (int pidx = lane; pidx < npairs; pidx += 32) {
+      const uint32_t u = __ldg(row + pidx);
+      nz |= (u & 0x7FFF7FFFu) != 0u;
+      const float x0 = __uint_as_float(u << 16), x1 = __uint_as_float(u & 0xFFFF0000u);
+      const uint4 wa = *reinterpret_cast<const uint4*>(wt + (2 * pidx) * A);          // feature 2 pidx: heads 0..7
+      const uint4 wb = *reinterpret_cast<const uint4*>(wt + (2 * pidx + 1) * A);      // feature 2 pidx + 1
+      const uint32_t wa4[4] = {wa.x, wa.y, wa.z, wa.w}, wb4[4] = {wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[2 * j] += x0 * __uint_as_float(wa4[j] << 16) + x1 * __uint_as_float(wb4[j] << 16);
+        acc[2 * j + 1] += x0 * __uint_as_float(wa4[j] & 0xFFFF0000u) + x1 * __uint_as_float(wb4[j] & 0xFFFF0000u);
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) acc[a] = warp_sum(acc[a]);
+    nz = __any_sync(0xffffffffu, nz);
+    if (lane < A) {
+      float v = acc[0];
+#pragma unroll
+      for (int a = 1; a < A; ++a) v = (lane == a) ? acc[a] : v;
+      wl[t * A + lane] = (num_frames || nz) ? v : -INFINITY;     // non-zero-frame mask (zt/frame_level_models.py:4372-4375)
+    }
+  }
+  __syncthreads();
+  // ---- softmax over the valid frames: warp a handles head a ----
+  if (warp < A) {
+    const int a = warp;
+    float mx = -INFINITY;
+    for (int t = lane; t < nf; t += 32) mx = fmaxf(mx, wl[t * A + a]);
+    mx = warp_max(mx);
+    float sum = 0.0f;
+    for (int t = lane; t < nf; t += 32) {
+      const float l = wl[t * A + a];
+      const float e = (l != -INFINITY) ? __expf(l - mx) : 0.0f;
+      wl[t * A + a] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    if (lane == 0) inv_s[a] = 1.0f / sum;                        // sum == 0 only for an all-masked video: NaN like 0/0 in TF
+  }
+  __syncthreads();
+  // ---- phase B: thread owns feature columns 4 tid .. 4 tid + 3 ----
+  const int c0 = 4 * tid;
+  if (c0 < D) {
+    float acc[A][4];
+#pragma unroll
+    for (int a = 0; a < A; ++a) { acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.0f; }
+#pragma unroll 4
+    for (int t = 0; t < nf; ++t) {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<long long>(t) * D + c0));
+      const float x0 = __uint_as_float(u.x << 16), x1 = __uint_as_float(u.x & 0xFFFF0000u);
+      const float x2 = __uint_as_float(u.y << 16), x3 = __uint_as_float(u.y & 0xFFFF0000u);
+      const float4 p0 = *reinterpret_cast<const float4*>(wl + t * A), p1 = *reinterpret_cast<const float4*>(wl + t * A + 4);   // broadcast reads
+      const float p[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        const float pa = p[a];
+        acc[a][0] += pa * x0; acc[a][1] += pa * x1; acc[a][2] += pa * x2; acc[a][3] += pa * x3;
+      }
+    }
+#pragma unroll
+    for (int a = 0; a < A; ++a) {
+      const float s = inv_s[a];
+      const float v0 = acc[a][0] * s, v1 = acc[a][1] * s, v2 = acc[a][2] * s, v3 = acc[a][3] * s;
+      const long long o = (static_cast<long long>(b) * A + a) * D + c0;
+      if (out) *reinterpret_cast<float4*>(out + o) = make_float4(v0, v1, v2, v3);
+      if (out_hi) {
+        __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+        split_bf16(v0, h0, l0); split_bf16(v1, h1, l1); split_bf16(v2, h2, l2); split_bf16(v3, h3, l3);
+        *reinterpret_cast<uint2*>(out_hi + o) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+        if (out_lo) *reinterpret_cast<uint2*>(out_lo + o) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+      }
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int yt8m_attn_pool_fused(const yt8m_bf16* x, const yt8m_bf16* w_packed, long long ldw, const int* num_frames, int B, int T,
+                                    int D, int A, float* out, yt8m_bf16* out_hi, yt8m_bf16* out_lo, yt8m_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  YT8M_REQUIRE(x && w_packed && (out || out_hi), YT8M_E_BADPTR, "yt8m_attn_pool_fused: null pointer");
+  YT8M_REQUIRE(B > 0 && T > 0 && D > 0 && D % 8 == 0 && D <= 4096 && ldw >= D, YT8M_E_BADSHAPE,
+               "yt8m_attn_pool_fused: bad shape B=%d T=%d D=%d", B, T, D);
+  YT8M_REQUIRE(A == kMaxA, YT8M_E_UNSUPPORTED, "yt8m_attn_pool_fused: built for %d heads (moe_num_extend / lstm_attentions default), got %d",
+               kMaxA, A);
+  const size_t smem = (static_cast<size_t>(T) * A + 2 * A + 4) * sizeof(float) + static_cast<size_t>(D) * A * 2 + 16;
+  YT8M_REQUIRE(smem <= 200 * 1024, YT8M_E_UNSUPPORTED, "yt8m_attn_pool_fused: T * A + D * A too large for shared memory");
+  auto kern = attn_pool_fused_kernel<kMaxA>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    YT8M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done = true;
+  }
+  int threads = ((D / 4 + 31) / 32) * 32;              // phase B: four columns per thread
+  if (threads < 8 * 32) threads = 8 * 32;              // the softmax step wants a warp per head
+  kern<<<B, threads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(w_packed), ldw,
+                                     num_frames, T, D, out, reinterpret_cast<__nv_bfloat16*>(out_hi),
+                                     reinterpret_cast<__nv_bfloat16*>(out_lo));
+  return check_launch("attn_pool_fused_kernel");
+}

@@ -351,9 +351,13 @@ class AttentionModel(models.BaseModel):
     st.get("Attention/b", (num_extend,), ops.constant_init(0.1), l2=l2_penalty, round_bf16=False)
     wp = st.packed(w, "kmajor_top", lambda: nat.pack_transpose(w.value[:d].contiguous()))
     with nat.region("attention_pool"):
-      logits = nat.linear(x.reshape(b * t, d), wp, n=num_extend, k=d)["f32"]
-      logits3 = logits.as_strided((b, t, num_extend), (t * logits.stride(0), logits.stride(0), 1))
-      pooled, hi, lo = nat.attn_pool(logits3, x, None, num_extend, 0)
+      if num_extend == 8 and d % 8 == 0 and d <= 4096:
+        # one kernel: logits, masked softmax over the frames, weighted sum -- the frames leave HBM once
+        pooled, hi, lo = nat.attn_pool_fused(x, wp, None, num_extend)
+      else:
+        logits = nat.linear(x.reshape(b * t, d), wp, n=num_extend, k=d)["f32"]
+        logits3 = logits.as_strided((b, t, num_extend), (t * logits.stride(0), logits.stride(0), 1))
+        pooled, hi, lo = nat.attn_pool(logits3, x, None, num_extend, 0)
     act = ops.Act(f32=pooled.reshape(b * num_extend, d), hi=hi.reshape(b * num_extend, d),
                   lo=lo.reshape(b * num_extend, d))
     out = _classifier().create_model(model_input=act, vocab_size=vocab_size, **unused_params)

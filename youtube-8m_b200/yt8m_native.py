@@ -63,6 +63,7 @@ _SIGS = {
     "yt8m_group_max_rows_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p]),
     "yt8m_attn_pool_fwd": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_void_p, c_void_p]),
+    "yt8m_attn_pool_fused": (c_int, [c_void_p, c_void_p, c_ll, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "yt8m_netvlad_fwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "yt8m_netvlad_tiled_supported": (c_int, [c_int, c_int, c_int]),
@@ -487,6 +488,17 @@ def attn_pool(logits, feats, num_frames, heads, mode, want_bf16=True):
   ol = _bf16((b, heads, f), feats.device) if want_bf16 else None
   _check(_lib.yt8m_attn_pool_fwd(_p(logits), logits.stride(1), _p(feats), _p(num_frames), b, t, heads, f, mode, _p(out), _p(oh),
                                  _p(ol), _stream()), "yt8m_attn_pool_fwd")
+  return out, oh, ol
+
+
+def attn_pool_fused(x, w_packed, num_frames, heads, want_bf16=True):
+  """x bf16 [B, T, D]; w_packed bf16 [A, >= D] (K-major attention weights) -> fp32 [B, A, D] (+ bf16 hi / lo): logits, masked
+  softmax over the frames and the weighted sum in one kernel (num_frames None = the non-zero-frame mask)."""
+  b, t, d = x.shape
+  out = _f32((b, heads, d), x.device)
+  oh = _bf16((b, heads, d), x.device) if want_bf16 else None
+  ol = _bf16((b, heads, d), x.device) if want_bf16 else None
+  _call("yt8m_attn_pool_fused", _p(x), _p(w_packed), w_packed.stride(0), _p(num_frames), b, t, d, heads, _p(out), _p(oh), _p(ol), _stream())
   return out, oh, ol
 
 
