@@ -18,7 +18,7 @@ namespace {
 constexpr int kMaxA = 8;
 
 template <int A>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(1024, 1)
 attn_pool_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, long long ldw,
                        const int* __restrict__ num_frames, int T, int D, float* __restrict__ out,
                        __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
@@ -34,28 +34,49 @@ attn_pool_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
   const int nf = num_frames ? min(max(__ldg(num_frames + b), 0), T) : T;
   for (int i = tid; i < D * A; i += blockDim.x) {
     const int d = i / A, a = i - d * A;
-    wt[i] = w[static_cast<long long>(a) * ldw + d];             // K-major packed [A, ldw] -> [D][A]
+    // K-major packed [A, ldw] -> [D][A]; the 16-byte slot of feature d inside its 128-byte chunk (8 features) is XOR-swizzled
+    // with the chunk index: consecutive lanes read consecutive chunks in phase A, without bank conflicts
+    const int c = d >> 3, slot = (d & 7) ^ (c & 7);
+    wt[(c * 8 + slot) * A + a] = w[static_cast<long long>(a) * ldw + d];
   }
   __syncthreads();
-  // ---- phase A: a warp per frame; lane owns feature pairs 2 * (lane + 32 j) ----
-  const int npairs = D / 2;
+  // ---- phase A: a warp per frame; lane owns the 16-byte chunks (8 features) lane, lane + 32, ...; the chunks of a frame are
+  //      requested in batches of kBatch BEFORE any of them is used: the pass is latency bound (one warp, one frame at a time),
+  //      so the number of loads in flight is what sets its speed (a load-use-load loop ran at ~12 us per frame) ----
+  constexpr int kBatch = 5;                                      // 5 x 32 lanes x 8 features = 1280 >= 1152
+  const int nchunks = D / 8;
   for (int t = warp; t < nf; t += nwarps) {
-    const uint32_t* row = reinterpret_cast<const uint32_t*>(xb + static_cast<long long>(t) * D);
+    const uint4* row = reinterpret_cast<const uint4*>(xb + static_cast<long long>(t) * D);
     float acc[A];
 #pragma unroll
     for (int a = 0; a < A; ++a) acc[a] = 0.0f;
     bool nz = false;
-    for (int pidx = lane; pidx < npairs; pidx += 32) {
-      const uint32_t u = __ldg(row + pidx);
-      nz |= (u & 0x7FFF7FFFu) != 0u;
-      const float x0 = __uint_as_float(u << 16), x1 = __uint_as_float(u & 0xFFFF0000u);
-      const uint4 wa = *reinterpret_cast<const uint4*>(wt + (2 * pidx) * A);          // feature 2 pidx: heads 0..7
-      const uint4 wb = *reinterpret_cast<const uint4*>(wt + (2 * pidx + 1) * A);      // feature 2 pidx + 1
-      const uint32_t wa4[4] = {wa.x, wa.y, wa.z, wa.w}, wb4[4] = {wb.x, wb.y, wb.z, wb.w};
+    for (int c0 = 0; c0 < nchunks; c0 += 32 * kBatch) {
+      uint4 u[kBatch];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[2 * j] += x0 * __uint_as_float(wa4[j] << 16) + x1 * __uint_as_float(wb4[j] << 16);
-        acc[2 * j + 1] += x0 * __uint_as_float(wa4[j] & 0xFFFF0000u) + x1 * __uint_as_float(wb4[j] & 0xFFFF0000u);
+      for (int j = 0; j < kBatch; ++j) {
+        const int c = c0 + lane + 32 * j;
+        u[j] = c < nchunks ? __ldg(row + c) : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int j = 0; j < kBatch; ++j) {
+        const int c = c0 + lane + 32 * j;
+        if (c < nchunks) {
+          const uint32_t xw[4] = {u[j].x, u[j].y, u[j].z, u[j].w};
+          nz |= ((xw[0] | xw[1] | xw[2] | xw[3]) & 0x7FFF7FFFu) != 0u;
+          const uint4* wrow = reinterpret_cast<const uint4*>(wt + static_cast<size_t>(c) * 8 * A);     // 8 features x 8 heads
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float x0 = __uint_as_float(xw[i] << 16), x1 = __uint_as_float(xw[i] & 0xFFFF0000u);
+            const uint4 wa = wrow[(2 * i) ^ (c & 7)], wb = wrow[(2 * i + 1) ^ (c & 7)];
+            const uint32_t wa4[4] = {wa.x, wa.y, wa.z, wa.w}, wb4[4] = {wb.x, wb.y, wb.z, wb.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              acc[2 * k] += x0 * __uint_as_float(wa4[k] << 16) + x1 * __uint_as_float(wb4[k] << 16);
+              acc[2 * k + 1] += x0 * __uint_as_float(wa4[k] & 0xFFFF0000u) + x1 * __uint_as_float(wb4[k] & 0xFFFF0000u);
+            }
+          }
+        }
       }
     }
 #pragma unroll
@@ -92,7 +113,7 @@ attn_pool_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
     float acc[A][4];
 #pragma unroll
     for (int a = 0; a < A; ++a) { acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.0f; }
-#pragma unroll 4
+#pragma unroll 8
     for (int t = 0; t < nf; ++t) {
       const uint2 u = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<long long>(t) * D + c0));
       const float x0 = __uint_as_float(u.x << 16), x1 = __uint_as_float(u.x & 0xFFFF0000u);
