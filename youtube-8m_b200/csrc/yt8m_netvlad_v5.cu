@@ -464,10 +464,10 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
     const int src_slot = static_cast<int>((rank - dst_cta - 1) & 3u); // my slot in the owner's buffer (0..2)
     const uint32_t recv_remote = mapa_u32(smem_u32(myrecv), dst_cta & 3) + (src_slot * 4 + (lane & 3)) * C::kRecvRow;
     const uint32_t recv_full_remote = mapa_u32(smem_u32(&recv_full[q * 2]), dst_cta & 3);
-    static_assert(KC == 64, "the exchange warps' thread mapping assumes 64 clusters (8 threads x 8 clusters per frame)");
-    float sc[8], sh[8];
+    constexpr int kPer = KC / 8;                                      // clusters per softmax thread (8 threads per frame)
+    float sc[kPer], sh[kPer];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { sc[j] = scale_s[8 * part + j]; sh[j] = shift_s[8 * part + j]; }
+    for (int j = 0; j < kPer; ++j) { sc[j] = scale_s[kPer * part + j]; sh[j] = shift_s[kPer * part + j]; }
     uint32_t a_tile_remote[kC], a_full_remote[kC];
 #pragma unroll
     for (int d = 0; d < kC; ++d) {
@@ -475,7 +475,6 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
       a_full_remote[d] = mapa_u32(smem_u32(a_full), d);
     }
     const int f = q * 16 + static_cast<int>(rank) * 4 + jj;           // the frame (inside a tile) this thread helps to softmax
-    const uint32_t a_off = sw128_offset(f, part);
     int it = 0, i = 0, ntv = n_iter > 0 ? vnt(0) : 0;
     int nf = n_iter > 0 ? min(max(__ldg(num_frames + vid(0)), 0), T) : 0;
     for (int G = 0; G < total_tiles; ++G) {
@@ -484,43 +483,51 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
       wait_bar_inl(&s_full[sb], us & 1);
       tc_fence_after();
       if (warp == 4 && lane == 0 && i < 8) NV5_T(it, 8 + i);
-      float r[KC];
+      // the three owners are done with what this warp pushed NRB tiles ago
+      wait_bar_inl(&send_credit[q * 2 + rb], (ur & 1) ^ 1u);
+      // 64 logit columns at a time: TMEM -> registers -> the frame's owner (own frames: source slot 3 of my buffer)
+#pragma unroll 1
+      for (int hc = 0; hc < KC / 64; ++hc) {
+        float r[64];
+        tmem_ld32(taddr_of(tmem_base, q) + C::kSCol + sb * KC + hc * 64, reinterpret_cast<uint32_t*>(r));
+        tmem_ld32(taddr_of(tmem_base, q) + C::kSCol + sb * KC + hc * 64 + 32, reinterpret_cast<uint32_t*>(r) + 32);
+        tmem_ld_wait();
+        if (sender) {
 #pragma unroll
-      for (int c = 0; c < KC / 32; ++c) tmem_ld32(taddr_of(tmem_base, q) + C::kSCol + sb * KC + c * 32, reinterpret_cast<uint32_t*>(r) + c * 32);
-      tmem_ld_wait();
+          for (int c = 0; c < 16; ++c)
+            st_async_v4(recv_remote + rb * C::kRecvBytes + hc * 256 + c * 16, recv_full_remote + rb * 8, r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+        } else if (lane < 16) {
+          float4* row = reinterpret_cast<float4*>(myrecv + rb * C::kRecvBytes + (3 * 4 + (lane & 3)) * C::kRecvRow + hc * 256);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) row[c] = make_float4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+        }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[sb]);
-      // the three owners are done with what this warp pushed NRB tiles ago
-      wait_bar_inl(&send_credit[q * 2 + rb], (ur & 1) ^ 1u);
-      if (sender) {
-#pragma unroll
-        for (int c = 0; c < KC / 4; ++c)
-          st_async_v4(recv_remote + rb * C::kRecvBytes + c * 16, recv_full_remote + rb * 8, r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
-      } else if (lane < 16) {
-        // my own four frames: into source slot 3 of my buffer (plain shared-memory stores)
-        float4* row = reinterpret_cast<float4*>(myrecv + rb * C::kRecvBytes + (3 * 4 + (lane & 3)) * C::kRecvRow);
-#pragma unroll
-        for (int c = 0; c < KC / 4; ++c) row[c] = make_float4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
-      }
-      __syncwarp();
       wait_bar_cluster_inl(&recv_full[q * 2 + rb], ur & 1);
       if (warp == 4 && lane == 0 && i < 8) NV5_T(it, 16 + i);
-      // ---- owner role: sum the four partials of my 8 clusters, masked softmax over the frame's 8 threads ----
-      float l[8];
+      // ---- owner role: sum the four partials of my kPer clusters, masked softmax over the frame's 8 threads ----
+      float l[kPer];
       {
-        const uint8_t* base = myrecv + rb * C::kRecvBytes + jj * C::kRecvRow + part * 32;
-        const float4 a0 = *reinterpret_cast<const float4*>(base), a1 = *reinterpret_cast<const float4*>(base + 16);
-        l[0] = a0.x; l[1] = a0.y; l[2] = a0.z; l[3] = a0.w; l[4] = a1.x; l[5] = a1.y; l[6] = a1.z; l[7] = a1.w;
+        const uint8_t* base = myrecv + rb * C::kRecvBytes + jj * C::kRecvRow + part * kPer * 4;
 #pragma unroll
-        for (int s = 1; s < kC; ++s) {
-          const float4 b0 = *reinterpret_cast<const float4*>(base + s * 4 * C::kRecvRow), b1 = *reinterpret_cast<const float4*>(base + s * 4 * C::kRecvRow + 16);
-          l[0] += b0.x; l[1] += b0.y; l[2] += b0.z; l[3] += b0.w; l[4] += b1.x; l[5] += b1.y; l[6] += b1.z; l[7] += b1.w;
+        for (int g4 = 0; g4 < kPer / 4; ++g4) {
+          const float4 a0 = *reinterpret_cast<const float4*>(base + g4 * 16);
+          l[4 * g4] = a0.x; l[4 * g4 + 1] = a0.y; l[4 * g4 + 2] = a0.z; l[4 * g4 + 3] = a0.w;
+        }
+#pragma unroll
+        for (int sidx = 1; sidx < kC; ++sidx) {
+#pragma unroll
+          for (int g4 = 0; g4 < kPer / 4; ++g4) {
+            const float4 b0 = *reinterpret_cast<const float4*>(base + sidx * 4 * C::kRecvRow + g4 * 16);
+            l[4 * g4] += b0.x; l[4 * g4 + 1] += b0.y; l[4 * g4 + 2] += b0.z; l[4 * g4 + 3] += b0.w;
+          }
         }
       }
       float mx = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < kPer; ++j) {
         l[j] = l[j] * sc[j] + sh[j];
         mx = fmaxf(mx, l[j]);
       }
@@ -533,7 +540,7 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
       if (lane < kC - 1) mbar_arrive_cluster_relaxed(mapa_u32(smem_u32(&send_credit[q * 2 + rb]), (rank + 1 + lane) & 3u));
       float sum = 0.0f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < kPer; ++j) {
         l[j] = __expf(l[j] - mx);
         sum += l[j];
       }
@@ -543,15 +550,20 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
       const float inv = 1.0f / sum;
       const bool valid = (i * kF + f) < nf;
       // select, not multiply: rows of frames >= num_frames may hold non-finite garbage
-      uint32_t pk[4];
+      uint32_t pk[kPer / 2];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
+      for (int j = 0; j < kPer / 2; ++j)
         pk[j] = pack_bf16x2(__float2bfloat16_rn(valid ? l[2 * j] * inv : 0.0f), __float2bfloat16_rn(valid ? l[2 * j + 1] * inv : 0.0f));
       // every CTA's phase 1 is done with assignment tile ab of NAT tiles ago
       wait_bar_inl(&a_credit[ab], (ua & 1) ^ 1u);
 #pragma unroll
-      for (int d = 0; d < kC; ++d)
-        st_async_v4_b32(a_tile_remote[d] + ab * C::kATileBytes + a_off, a_full_remote[d] + ab * 8, pk[0], pk[1], pk[2], pk[3]);
+      for (int e8 = 0; e8 < kPer / 8; ++e8) {                         // my 16-byte chunks of the row: clusters 8 c .. 8 c + 7
+        const int c = part * (kPer / 8) + e8;
+        const uint32_t off = ab * C::kATileBytes + (c >> 3) * kSubBytes + sw128_offset(f, c & 7);
+#pragma unroll
+        for (int d = 0; d < kC; ++d)
+          st_async_v4_b32(a_tile_remote[d] + off, a_full_remote[d] + ab * 8, pk[4 * e8], pk[4 * e8 + 1], pk[4 * e8 + 2], pk[4 * e8 + 3]);
+      }
       if (warp == 4 && lane == 0 && i < 8) NV5_T(it, 24 + i);
       if (++i == ntv) {
         ++it; i = 0;
@@ -565,7 +577,7 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
     // warp e = (lane quadrant q, cluster half h): rows q*32 .. +31 of every 128-row accumulator block, clusters 32 h .. + 31.
     // The accumulator is read from TMEM once (and handed back to phase 1 right away); the corrected values stay in registers
     // across the exchange of the per-cluster norms.
-    static_assert(KC == 64, "the epilogue's warp mapping assumes 64 clusters (two 32-cluster halves)");
+    if constexpr (KC == 64) {
     const int e = warp - 8;
     const int q = e & 3, h = e >> 2;
     const int et = e * 32 + lane;                             // 0..255
@@ -696,6 +708,124 @@ netvlad_v5_kernel(const __grid_constant__ CUtensorMap tm_xa, const __grid_consta
       }
       if (et == 0) NV5_T(it, 51);
     }
+    } else {
+      // ---- K = 128: the accumulator (384 columns) and the logits fill TMEM, so cw2 comes from global memory (tiled: coalesced)
+      //      and the corrected accumulator is written back to TMEM between the two passes.  warp e = (lane quadrant q, parity h):
+      //      32-cluster column quarters h and h + 2. ----
+      const int e = warp - 8;
+      const int q = e & 3, h = e >> 2;
+      const int et = e * 32 + lane;                           // 0..255
+      const int nmb_w = (DH - q * 32 + 127) / 128 > 0 ? (DH - q * 32 + 127) / 128 : 0;
+      const uint32_t tv = taddr_of(tmem_base, q) + C::kVCol;
+      for (int it = 0; it < n_iter; ++it) {
+        const int b = vid(it);
+        const int p = it & 1;
+        if (et == 0) mbar_arrive_expect_tx(&ssq_full[p], (kC - 1) * KC * 4);
+        wait_bar_inl(&asum_ready[p], (it >> 1) & 1);
+        wait_bar_inl(&v_full[0], it & 1);
+        tc_fence_after();
+        // ---- pass 1: V -= a_sum * cw2 (fp32), write back, per-cluster sum of squares ----
+#pragma unroll 1
+        for (int cq = h; cq < KC / 32; cq += 2) {
+          float as[32], ssq[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t4 = *reinterpret_cast<const float4*>(asum_s + p * KC + cq * 32 + 4 * j);
+            as[4 * j] = t4.x; as[4 * j + 1] = t4.y; as[4 * j + 2] = t4.z; as[4 * j + 3] = t4.w;
+            ssq[4 * j] = 0.0f; ssq[4 * j + 1] = 0.0f; ssq[4 * j + 2] = 0.0f; ssq[4 * j + 3] = 0.0f;
+          }
+#pragma unroll 1
+          for (int m = 0; m < nmb_w; ++m) {
+            const long long g32 = (d0 + m * 128 + q * 32) >> 5;
+            const float4* c2 = TILED ? reinterpret_cast<const float4*>(cw2) + (g32 * (KC / 4) + cq * 8) * 32 + lane
+                                     : reinterpret_cast<const float4*>(cw2 + (static_cast<long long>(d0) + m * 128 + q * 32 + lane) * KC + cq * 32);
+            constexpr int kCs = TILED ? 32 : 1;
+            float4 cc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cc[j] = __ldg(c2 + j * kCs);
+            float v[32];
+            tmem_ld32(tv + m * KC + cq * 32, reinterpret_cast<uint32_t*>(v));
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              v[4 * j] -= as[4 * j] * cc[j].x; v[4 * j + 1] -= as[4 * j + 1] * cc[j].y;
+              v[4 * j + 2] -= as[4 * j + 2] * cc[j].z; v[4 * j + 3] -= as[4 * j + 3] * cc[j].w;
+              ssq[4 * j] += v[4 * j] * v[4 * j]; ssq[4 * j + 1] += v[4 * j + 1] * v[4 * j + 1];
+              ssq[4 * j + 2] += v[4 * j + 2] * v[4 * j + 2]; ssq[4 * j + 3] += v[4 * j + 3] * v[4 * j + 3];
+            }
+            tmem_st32(tv + m * KC + cq * 32, reinterpret_cast<const uint32_t*>(v));
+          }
+          ssq_w[(e * 2 + (cq >> 1)) * 32 + lane] = warp_transpose_reduce32(ssq, lane);
+        }
+        tmem_st_wait();
+        named_bar_sync(1, 256);
+        if (et < KC) {
+          const int cq = et >> 5, kk = et & 31;                 // quarter cq lives in the warps of parity cq & 1, slot cq >> 1
+          float mine = 0.0f;
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) mine += ssq_w[((((cq & 1) * 4 + qq) * 2) + (cq >> 1)) * 32 + kk];
+          ssq_part[(p * kC + rank) * KC + et] = mine;
+#pragma unroll
+          for (int sidx = 1; sidx < kC; ++sidx) {
+            const uint32_t dst = (rank + sidx) & 3u;
+            st_async_f32(mapa_u32(smem_u32(&ssq_part[(p * kC + rank) * KC + et]), dst), mapa_u32(smem_u32(&ssq_full[p]), dst), mine);
+          }
+        }
+        wait_bar_cluster_inl(&ssq_full[p], (it >> 1) & 1);
+        named_bar_sync(1, 256);
+        if (et < KC) {
+          const float* sp = ssq_part + p * kC * KC + et;
+          const float ss = (sp[0] + sp[KC]) + (sp[2 * KC] + sp[3 * KC]);
+          const float rs = rsqrtf(fmaxf(ss, 1e-12f));
+          fscale_s[et] = rs;
+          contrib_s[et] = ss * rs * rs;
+          if (stats && rank == 0) {
+            stats[static_cast<long long>(b) * (2 * KC + 1) + et] = asum_s[p * KC + et];
+            stats[static_cast<long long>(b) * (2 * KC + 1) + KC + et] = ss;
+          }
+        }
+        named_bar_sync(1, 256);
+        if (et == 0) mbar_arrive(&asum_free[p]);
+        float tsum = 0.0f;
+#pragma unroll
+        for (int j = 0; j < KC / 32; ++j) tsum += contrib_s[j * 32 + lane];
+        const float total = warp_sum(tsum);
+        const float gs = rsqrtf(fmaxf(total, 1e-12f));
+        if (stats && rank == 0 && et == 0) stats[static_cast<long long>(b) * (2 * KC + 1) + 2 * KC] = total;
+        // ---- pass 2: rescale, convert, store ----
+#pragma unroll 1
+        for (int cq = h; cq < KC / 32; cq += 2) {
+          float fs[32];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 t4 = *reinterpret_cast<const float4*>(fscale_s + cq * 32 + 4 * j);
+            fs[4 * j] = t4.x * gs; fs[4 * j + 1] = t4.y * gs; fs[4 * j + 2] = t4.z * gs; fs[4 * j + 3] = t4.w * gs;
+          }
+#pragma unroll 1
+          for (int m = 0; m < nmb_w; ++m) {
+            float v[32];
+            tmem_ld32(tv + m * KC + cq * 32, reinterpret_cast<uint32_t*>(v));
+            tmem_ld_wait();
+            const long long g32 = (d0 + m * 128 + q * 32) >> 5;
+            uint16_t* dst = TILED ? out + static_cast<long long>(b) * D * KC + ((g32 * (KC / 8) + cq * 4) * 32 + lane) * 8
+                                  : out + (static_cast<long long>(b) * D + d0 + m * 128 + q * 32 + lane) * KC + cq * 32;
+            constexpr int kOs = TILED ? 256 : 8;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= fs[j];
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              uint4 hi, lo;
+              if (out_f16) hi = pack8_f16(v + 8 * j8);
+              else pack8_hi_lo(v + 8 * j8, hi, lo);
+              *reinterpret_cast<uint4*>(dst + j8 * kOs) = hi;
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&v_free[0]);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -750,13 +880,14 @@ int launch_v5(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, co
 }  // namespace
 
 bool yt8m::netvlad_v5_supported(int T, int D, int K) {
-  return (K == 64) && D % 64 == 0 && D / 64 >= kC && (D / 64 + kC - 1) / kC <= kMaxKb && T >= 1;
+  return (K == 64 || K == 128) && D % 64 == 0 && D / 64 >= kC && (D / 64 + kC - 1) / kC <= kMaxKb && T >= 1;
 }
 
 int yt8m::launch_netvlad_v5(const yt8m_bf16* x, const int* num_frames, int B, int T, int D, int K, const yt8m_bf16* cw_packed,
                             const float* scale, const float* shift, const float* cw2, yt8m_bf16* out, int out_f16, float* stats,
                             cudaStream_t stream) {
   YT8M_REQUIRE(netvlad_v5_supported(T, D, K), YT8M_E_BADSHAPE, "netvlad v5: T=%d D=%d K=%d", T, D, K);
+  if (K == 128) return launch_v5<128, false>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out, out_f16, stats, stream);
   return launch_v5<64, false>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2, out, out_f16, stats, stream);
 }
 
@@ -780,7 +911,7 @@ extern "C" int yt8m_netvlad_fwd_tiled(const yt8m_bf16* x, const int* num_frames,
   YT8M_REQUIRE(x && num_frames && cw_packed && cw2_tiled && out_tiled, YT8M_E_BADPTR, "yt8m_netvlad_fwd_tiled: null pointer");
   YT8M_REQUIRE(B > 0 && T > 0, YT8M_E_BADSHAPE, "yt8m_netvlad_fwd_tiled: B=%d T=%d", B, T);
   YT8M_REQUIRE(yt8m_netvlad_tiled_supported(T, D, K), YT8M_E_UNSUPPORTED,
-               "yt8m_netvlad_fwd_tiled: needs K = 64 and D %% 64 == 0 with 256 <= D <= 1280 (D=%d K=%d)", D, K);
+               "yt8m_netvlad_fwd_tiled: needs K in {64, 128} and D %% 64 == 0 with 256 <= D <= 1280 (D=%d K=%d)", D, K);
   YT8M_REQUIRE(out_fmt == YT8M_FMT_BF16 || out_fmt == YT8M_FMT_F16, YT8M_E_UNSUPPORTED, "yt8m_netvlad_fwd_tiled: out_fmt");
   YT8M_REQUIRE(aligned16(out_tiled) && aligned16(cw2_tiled), YT8M_E_BADPTR, "yt8m_netvlad_fwd_tiled: out / cw2 must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -790,5 +921,7 @@ extern "C" int yt8m_netvlad_fwd_tiled(const yt8m_bf16* x, const int* num_frames,
       !(host_debug_flags() & (1 << 21)))
     return yt8m::launch_netvlad_v6(x, num_frames, B, T, D, K, cw_packed, scale, shift, cw2_tiled, out_tiled, out_fmt == YT8M_FMT_F16, stats,
                                    workspace, workspace_bytes, stream);
+  if (K == 128)
+    return launch_v5<128, true>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2_tiled, out_tiled, out_fmt == YT8M_FMT_F16, stats, stream);
   return launch_v5<64, true>(x, num_frames, B, T, D, cw_packed, scale, shift, cw2_tiled, out_tiled, out_fmt == YT8M_FMT_F16, stats, stream);
 }
