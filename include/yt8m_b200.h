@@ -294,14 +294,25 @@ int yt8m_clip_adam_step(float* param, const float* grad, float* m, float* v, lon
 /* ---- backward of the NetVLAD layer and of a dense layer's activation (frame-level training step) ----------
  * Definition: oracle/yt8m_oracle.py:netvlad_pool (not in the reference).  All tensors fp32 unless noted.
  * yt8m_netvlad_bwd_norm:   dy, y [B, D*K] (y = the forward's fp32 output), stats from the forward, cw2 [D, K] ->
- *   dv [B, D*K] = dL/dV (V = un-normalised descriptor), dasum [B, K] = dL/da_sum, dcw2 [D, K] (nullable) = dL/dcw2.
+ *   dv [B, D*K] = dL/dV (V = un-normalised descriptor), dasum [B, K] = dL/da_sum, dcw2 [D, K] (nullable) = dL/dcw2;
+ *   dv_hi / dv_lo (nullable, together): the same dv as bf16 hi + lo [B, D, K], the tensor-core operand of
+ *   yt8m_netvlad_bwd_assign_fused.  dcw2 uses a library-owned scratch buffer per device: calls that write dcw2 must be
+ *   ordered on one stream per device.
  * yt8m_netvlad_bwd_assign: x bf16 [B, T, D], z [B*T, K] = scale * (x . Cw) + shift (recomputed with
  *   yt8m_linear_fwd), dv, dasum -> dzs bf16 hi/lo [B*T, K] = dL/d(x . Cw) (i.e. dz * scale; rows t >= num_frames
  *   are zero), dshift [K] (nullable) = dL/dshift.  da_ws: scratch fp32 [B*T, K].  dL/dCw^T [K, D] then is
  *   yt8m_wgrad(dzs, x).  K in {32, 64, 128}, D % 32 == 0.
+ * yt8m_netvlad_bwd_assign_fused: the same result in ONE tcgen05 kernel that recomputes the logits itself (no z, no
+ *   scratch): cw_packed bf16 [K, ldcw >= D] and scale / shift [K] (nullable) are the forward's operands, dv_hi / dv_lo
+ *   come from yt8m_netvlad_bwd_norm.  K in {64, 128}, D % 64 == 0 (yt8m_netvlad_bwd_assign_fused_supported).
  * yt8m_act_bwd: d_pre = dy * act'(y) * col_scale  (y = post-activation output of yt8m_linear_fwd) as bf16 hi/lo. */
 int yt8m_netvlad_bwd_norm(const float* dy, const float* y, const float* stats, const float* cw2, int B, int D, int K,
-                          float* dv, float* dasum, float* dcw2, yt8m_stream_t stream);
+                          float* dv, float* dasum, float* dcw2, yt8m_bf16* dv_hi, yt8m_bf16* dv_lo, yt8m_stream_t stream);
+int yt8m_netvlad_bwd_assign_fused_supported(int T, int D, int K);
+int yt8m_netvlad_bwd_assign_fused(const yt8m_bf16* x, const int* num_frames, const yt8m_bf16* cw_packed, long long ldcw,
+                                  const float* scale, const float* shift, const yt8m_bf16* dv_hi, const yt8m_bf16* dv_lo,
+                                  const float* dasum, int B, int T, int D, int K, yt8m_bf16* dzs_hi, yt8m_bf16* dzs_lo,
+                                  float* dshift, yt8m_stream_t stream);
 int yt8m_netvlad_bwd_assign(const yt8m_bf16* x, const int* num_frames, const float* z, const float* dv, const float* dasum,
                             const float* scale, int B, int T, int D, int K, float* da_ws, yt8m_bf16* dzs_hi,
                             yt8m_bf16* dzs_lo, float* dshift, yt8m_stream_t stream);

@@ -39,7 +39,22 @@ def _worker(rank, world, port, q):
   loss = O.cross_entropy_loss(O.logistic_model(x[lo:hi], w0, b0), y[lo:hi]) * ((hi - lo) / float(B))
   loss.backward()
   flat = torch.cat([w0.grad.reshape(-1), b0.grad.reshape(-1)])
+  # the trainers' exchange: contiguous pieces of the flat buffer, started separately, finished together
+  pieces = flat.clone()
+  xch = yt8m_dp.GradExchange()
+  xch.start(pieces[100:])
+  xch.start(pieces[40:100])
+  xch.start(pieces[:40])
+  xch.start(pieces[:0])                    # an empty piece is skipped
+  xch.finish()
+  assert not xch.pending
+  solo = flat.clone()
+  one = yt8m_dp.GradExchange(world=1)      # a single-process run inside a larger job: no exchange
+  one.start(solo)
+  one.finish()
+  assert torch.equal(solo, flat)
   yt8m_dp.all_reduce_sum_(flat)
+  assert torch.equal(pieces, flat)
   q.put((rank, lo, hi, flat.clone()))
   torch.distributed.barrier()
   torch.distributed.destroy_process_group()

@@ -141,10 +141,19 @@ def test_netvlad_backward_kernels(k, with_scale):
   _, _, y32, stats = nat.netvlad_fwd(xd, nf.to(DEV), cwp, sc, shift.detach().to(DEV), cw2.detach().to(DEV), want_f32=True,
                                      want_lo=True, want_stats=True)
   assert _rel_l2(y32, y) < 1e-3
-  dv, dasum, dcw2 = nat.netvlad_bwd_norm(dy.to(DEV), y32, stats, cw2.detach().to(DEV))
+  dv, dasum, dcw2, dv_split = nat.netvlad_bwd_norm(dy.to(DEV), y32, stats, cw2.detach().to(DEV), want_split=True)
+  assert float(((dv_split[0].float() + dv_split[1].float()) - dv).abs().max()) <= 2.0 ** -16 * float(dv.abs().max())
   z = nat.linear(xd.reshape(b * t, d), cwp, n=k, k=d, scale=sc, shift=shift.detach().to(DEV))["f32"]
   dz_hi, dz_lo, dshift = nat.netvlad_bwd_assign(xd, nf.to(DEV), z, dv, dasum, scale=sc)
   dcw_t = nat.wgrad(dz_hi, dz_lo, xd.reshape(b * t, d), k, d)                 # [K, D] = dL/dCw^T
+  # the one-kernel tensor-core version (logits recomputed on chip, yt8m_netvlad_bwd_tc.cu): same gradients
+  assert nat.netvlad_bwd_assign_fused_supported(t, d, k)
+  fz_hi, fz_lo, fshift = nat.netvlad_bwd_assign_fused(xd, nf.to(DEV), cwp, sc, shift.detach().to(DEV), dv_split, dasum)
+  fcw_t = nat.wgrad(fz_hi, fz_lo, xd.reshape(b * t, d), k, d)
+  assert _rel_l2(fshift, shift.grad) < 1e-2
+  assert _rel_l2(fcw_t.t(), cw.grad) < 1e-2
+  assert _rel_l2(fz_hi.float() + fz_lo.float(), dz_hi.float() + dz_lo.float()) < 2e-3
+  assert float((fz_hi.float().reshape(b, t, k))[1, 1:].abs().max()) == 0.0
   # gradients pass through bf16 assignments / bf16 hi-lo dz: 1e-2 of the gradient's norm
   assert _rel_l2(dcw2, cw2.grad) < 1e-2
   assert _rel_l2(dshift, shift.grad) < 1e-2

@@ -71,6 +71,7 @@ def run_frames(group_world):
   import yt8m_dp as dp
   saved = dp.all_reduce_sum_
   if group_world == 1:
+    t.world = t.head.world = 1                      # the gradient exchange of this trainer is skipped
     dp.all_reduce_sum_ = lambda flat, group=None: flat
     lo, hi = 0, Bf
   else:

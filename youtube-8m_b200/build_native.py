@@ -13,7 +13,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libyt8m_b200.so")
-SOURCES = ["yt8m_host.cu", "yt8m_gemm.cu", "yt8m_rowops.cu", "yt8m_netvlad.cu", "yt8m_train.cu", "yt8m_netvlad_bwd.cu", "yt8m_netvlad_v4.cu", "yt8m_netvlad_v5.cu", "yt8m_netvlad_v6.cu", "yt8m_lstm_rec.cu", "yt8m_seq_bwd.cu", "yt8m_bn.cu", "yt8m_attn_fused.cu"]
+SOURCES = ["yt8m_host.cu", "yt8m_gemm.cu", "yt8m_rowops.cu", "yt8m_netvlad.cu", "yt8m_train.cu", "yt8m_netvlad_bwd.cu", "yt8m_netvlad_bwd_tc.cu", "yt8m_netvlad_v4.cu", "yt8m_netvlad_v5.cu", "yt8m_netvlad_v6.cu", "yt8m_lstm_rec.cu", "yt8m_seq_bwd.cu", "yt8m_bn.cu", "yt8m_attn_fused.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"] + os.environ.get("YT8M_NVCC_EXTRA", "").split()

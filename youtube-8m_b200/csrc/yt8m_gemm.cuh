@@ -346,18 +346,51 @@ struct EpiLinear {
         }
         continue;
       }
+      // The per-column affine and the activation are applied chunk-wise with the run-time tests OUTSIDE the element loops: the
+      // first version tested col < N, col_scale, col_shift and switched on the activation for each of the 32 elements (~70 SASS
+      // instructions per element): the weight-gradient GEMMs (302 MB of fp32 output, no affine, no activation) were bound by
+      // the epilogue's INSTRUCTION count at 615 GB/s, whatever the contraction length (profiles/r02d_wgrad_ncu.md).
+      const bool full = (col0 + 32 <= s.N) && ((p.ld_out & 7) == 0);
       float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(r[j]);
-        const int col = col0 + j;
-        if (col < s.N) {
-          if (p.col_scale) x *= __ldg(p.col_scale + col);
-          if (p.col_shift) x += __ldg(p.col_shift + col);
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+      if (col0 + 32 <= s.N) {
+        if (p.col_scale) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= __ldg(p.col_scale + col0 + j);
         }
-        v[j] = apply_act(x, p.act);
+        if (p.col_shift) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += __ldg(p.col_shift + col0 + j);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          if (col0 + j < s.N) {
+            if (p.col_scale) v[j] *= __ldg(p.col_scale + col0 + j);
+            if (p.col_shift) v[j] += __ldg(p.col_shift + col0 + j);
+          }
+        }
       }
-      const bool full = (col0 + 32 <= s.N) && ((p.ld_out & 7) == 0);
+      switch (p.act) {
+        case ACT_NONE: break;
+        case ACT_RELU:
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.0f);
+          break;
+        case ACT_RELU6:
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fminf(fmaxf(v[j], 0.0f), 6.0f);
+          break;
+        case ACT_SIGMOID:
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = sigmoidf_(v[j]);
+          break;
+        default:
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          break;
+      }
       if (p.out_f32) {
         if (full) {
           float4* dst = reinterpret_cast<float4*>(p.out_f32 + base);

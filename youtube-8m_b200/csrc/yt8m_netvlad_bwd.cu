@@ -23,76 +23,137 @@ namespace {
 
 constexpr int kNormThreads = 256;
 
-// (1) one CTA per video.  stats[b] = {asum[K], ss[K], total}.  Two passes over the video's D x K slab (L2 resident).
+// (1) one CTA per video.  stats[b] = {asum[K], ss[K], total}.  Two passes over the video's D x K slab; a thread owns FOUR
+// adjacent clusters (16-byte loads, a warp covers 512 contiguous bytes) and keeps four rows in flight -- the first version
+// (one float per thread, one row in flight) ran at 1.2 TB/s (profiles/r02d_train_step_launches.txt: 190 us for 226 MB).
 template <int KC>
 __global__ void __launch_bounds__(kNormThreads)
 netvlad_bwd_norm_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ stats,
-                        const float* __restrict__ cw2, int D, float* __restrict__ dv, float* __restrict__ dasum) {
-  constexpr int kGroups = kNormThreads / KC;
-  __shared__ float red_r[kGroups][KC], red_y2[kGroups][KC], coef_a[KC], coef_b[KC], red_s[kGroups][KC];
+                        const float* __restrict__ cw2, int D, float* __restrict__ dv, float* __restrict__ dasum,
+                        __nv_bfloat16* __restrict__ dv_hi, __nv_bfloat16* __restrict__ dv_lo) {
+  constexpr int kTpr = KC / 4;                          // threads per row
+  constexpr int kRows = kNormThreads / kTpr;            // rows per sweep
+  __shared__ float4 red_a[kRows][kTpr], red_b[kRows][kTpr];
+  __shared__ float coef_a[KC], coef_b[KC], col_r[KC], col_y2[KC];
   __shared__ float r_tot;
   const int b = blockIdx.x;
-  const int k = threadIdx.x % KC, grp = threadIdx.x / KC;
+  const int c4 = threadIdx.x % kTpr, grp = threadIdx.x / kTpr;
   const long long base = static_cast<long long>(b) * D * KC;
+  const float4* dy4 = reinterpret_cast<const float4*>(dy + base) + c4;
+  const float4* y4 = reinterpret_cast<const float4*>(y + base) + c4;
   const float* st = stats + static_cast<long long>(b) * (2 * KC + 1);
-  float r = 0.0f, y2 = 0.0f;
-  for (int d = grp; d < D; d += kGroups) {
-    const float yy = y[base + static_cast<long long>(d) * KC + k];
-    r += dy[base + static_cast<long long>(d) * KC + k] * yy;
-    y2 += yy * yy;
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f), y2 = r;
+#pragma unroll 4
+  for (int d = grp; d < D; d += kRows) {
+    const float4 yy = __ldg(y4 + static_cast<long long>(d) * kTpr), dd = __ldg(dy4 + static_cast<long long>(d) * kTpr);
+    r.x += dd.x * yy.x; r.y += dd.y * yy.y; r.z += dd.z * yy.z; r.w += dd.w * yy.w;
+    y2.x += yy.x * yy.x; y2.y += yy.y * yy.y; y2.z += yy.z * yy.z; y2.w += yy.w * yy.w;
   }
-  red_r[grp][k] = r;
-  red_y2[grp][k] = y2;
+  red_a[grp][c4] = r;
+  red_b[grp][c4] = y2;
   __syncthreads();
-  if (grp == 0) {
-    for (int g = 1; g < kGroups; ++g) { r += red_r[g][k]; y2 += red_y2[g][k]; }
-    red_r[0][k] = r;
-    red_y2[0][k] = y2;
+  if (threadIdx.x < KC) {                               // fixed order: deterministic
+    const int k = threadIdx.x;
+    float sr = 0.0f, sy = 0.0f;
+    for (int g = 0; g < kRows; ++g) {
+      sr += reinterpret_cast<const float*>(&red_a[g][0])[k];
+      sy += reinterpret_cast<const float*>(&red_b[g][0])[k];
+    }
+    col_r[k] = sr;
+    col_y2[k] = sy;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.0f;
-    for (int j = 0; j < KC; ++j) t += red_r[0][j];
+    for (int j = 0; j < KC; ++j) t += col_r[j];
     r_tot = t;
   }
   __syncthreads();
-  if (grp == 0) {
+  if (threadIdx.x < KC) {
+    const int k = threadIdx.x;
     const float ss = st[KC + k], total = st[2 * KC];
     const bool col_live = ss > 1e-12f, all_live = total > 1e-12f;
     const float rs = rsqrtf(fmaxf(ss, 1e-12f)), gs = rsqrtf(fmaxf(total, 1e-12f));
     const float R = all_live ? r_tot : 0.0f;                       // clamped norm: the scale is a constant
     // dU = gs (dY - R Y);  dV_k = rs (dU_k - (<dU_k, Y_k> / gs) Y_k)  with <dU_k, Y_k> = gs (r_k - R y2_k)
-    const float q = col_live ? (red_r[0][k] - R * red_y2[0][k]) : 0.0f;
+    const float q = col_live ? (col_r[k] - R * col_y2[k]) : 0.0f;
     coef_a[k] = rs * gs;                                           // multiplies dY
     coef_b[k] = -rs * (gs * R + q / gs);                           // multiplies Y
   }
   __syncthreads();
-  const float ca = coef_a[k], cb = coef_b[k];
-  float s = 0.0f;
-  for (int d = grp; d < D; d += kGroups) {
-    const long long o = base + static_cast<long long>(d) * KC + k;
-    const float g = ca * dy[o] + cb * y[o];
-    dv[o] = g;
-    s += g * cw2[static_cast<long long>(d) * KC + k];
+  const float4 ca = *reinterpret_cast<const float4*>(coef_a + 4 * c4), cb = *reinterpret_cast<const float4*>(coef_b + 4 * c4);
+  const float4* c24 = reinterpret_cast<const float4*>(cw2) + c4;
+  float4* dv4 = reinterpret_cast<float4*>(dv + base) + c4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int d = grp; d < D; d += kRows) {
+    const long long o = static_cast<long long>(d) * kTpr;
+    const float4 yy = __ldg(y4 + o), dd = __ldg(dy4 + o), cc = __ldg(c24 + o);
+    float4 g;
+    g.x = ca.x * dd.x + cb.x * yy.x; g.y = ca.y * dd.y + cb.y * yy.y; g.z = ca.z * dd.z + cb.z * yy.z; g.w = ca.w * dd.w + cb.w * yy.w;
+    dv4[o] = g;
+    if (dv_hi) {                                          // tensor-core operands of the assignment backward (yt8m_netvlad_bwd_tc.cu)
+      __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+      split_bf16(g.x, h0, l0); split_bf16(g.y, h1, l1); split_bf16(g.z, h2, l2); split_bf16(g.w, h3, l3);
+      const long long e = base + (o + c4) * 4;
+      *reinterpret_cast<uint2*>(dv_hi + e) = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+      *reinterpret_cast<uint2*>(dv_lo + e) = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+    }
+    s.x += g.x * cc.x; s.y += g.y * cc.y; s.z += g.z * cc.z; s.w += g.w * cc.w;
   }
-  red_s[grp][k] = s;
   __syncthreads();
-  if (grp == 0) {
-    for (int g = 1; g < kGroups; ++g) s += red_s[g][k];
-    dasum[static_cast<long long>(b) * KC + k] = -s;
+  red_a[grp][c4] = s;
+  __syncthreads();
+  if (threadIdx.x < KC) {
+    const int k = threadIdx.x;
+    float t = 0.0f;
+    for (int g = 0; g < kRows; ++g) t += reinterpret_cast<const float*>(&red_a[g][0])[k];
+    dasum[static_cast<long long>(b) * KC + k] = -t;
   }
 }
 
-// (2) dC2[e] = -sum_b asum[b, e % K] * dV[b, e]     (coalesced over e, serial over the batch)
-__global__ void netvlad_bwd_dcw2_kernel(const float* __restrict__ dv, const float* __restrict__ stats, int B, long long n, int KC,
-                                        float* __restrict__ dcw2) {
-  for (long long e = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; e < n;
-       e += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int k = static_cast<int>(e % KC);
-    float acc = 0.0f;
-    for (int b = 0; b < B; ++b) acc -= stats[static_cast<long long>(b) * (2 * KC + 1) + k] * dv[static_cast<long long>(b) * n + e];
-    dcw2[e] = acc;
+// (2) dC2[e] = -sum_b asum[b, e % K] * dV[b, e].  A thread owns four adjacent elements; the batch is cut into kDcGroups
+// slices (blockIdx.y) whose partial sums are combined in a fixed order by the last slice to finish (a ticket per column
+// block: no atomics on the data, the result does not depend on the arrival order).
+constexpr int kDcGroups = 8;
+__global__ void __launch_bounds__(256)
+netvlad_bwd_dcw2_kernel(const float* __restrict__ dv, const float* __restrict__ stats, int B, long long n, int KC,
+                        float* __restrict__ partial, unsigned int* __restrict__ tickets, float* __restrict__ dcw2) {
+  const long long e4 = blockIdx.x * 256LL + threadIdx.x;             // float4 index
+  const int g = blockIdx.y;
+  const int per = (B + kDcGroups - 1) / kDcGroups;
+  const int b0 = g * per, b1 = min(B, b0 + per);
+  const bool live = e4 * 4 < n;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (live) {
+    const int k = static_cast<int>((e4 * 4) % KC);
+    const float4* src = reinterpret_cast<const float4*>(dv) + e4;
+#pragma unroll 8
+    for (int b = b0; b < b1; ++b) {
+      const float4 v = __ldg(src + static_cast<long long>(b) * (n / 4));
+      const float* ap = stats + static_cast<long long>(b) * (2 * KC + 1) + k;      // rows of 2K + 1 floats: not 16-byte aligned
+      const float4 a = make_float4(__ldg(ap), __ldg(ap + 1), __ldg(ap + 2), __ldg(ap + 3));
+      acc.x -= a.x * v.x; acc.y -= a.y * v.y; acc.z -= a.z * v.z; acc.w -= a.w * v.w;
+    }
+    reinterpret_cast<float4*>(partial)[static_cast<long long>(g) * (n / 4) + e4] = acc;
   }
+  __threadfence();
+  __shared__ unsigned int last;
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(tickets + blockIdx.x, 1u);
+  __syncthreads();
+  if (last != kDcGroups - 1) return;
+  __threadfence();
+  if (live) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int gg = 0; gg < kDcGroups; ++gg) {
+      const float4 v = __ldcg(reinterpret_cast<const float4*>(partial) + static_cast<long long>(gg) * (n / 4) + e4);
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    reinterpret_cast<float4*>(dcw2)[e4] = t;
+  }
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;                     // self-cleaning: the next launch finds zeros
 }
 
 // (3) da[b, t, :] = x[b, t, :] . dV[b]    CTA = (video, 64-frame tile): 64 x KC outputs, 256 threads, 4 x (KC/16) each.
@@ -241,14 +302,17 @@ __global__ void act_bwd_kernel(const float* __restrict__ dy, const float* __rest
 extern "C" {
 
 int yt8m_netvlad_bwd_norm(const float* dy, const float* y, const float* stats, const float* cw2, int B, int D, int K, float* dv,
-                          float* dasum, float* dcw2, yt8m_stream_t stream_) {
+                          float* dasum, float* dcw2, yt8m_bf16* dv_hi_, yt8m_bf16* dv_lo_, yt8m_stream_t stream_) {
+  __nv_bfloat16* dv_hi = reinterpret_cast<__nv_bfloat16*>(dv_hi_);
+  __nv_bfloat16* dv_lo = reinterpret_cast<__nv_bfloat16*>(dv_lo_);
+  YT8M_REQUIRE((dv_hi == nullptr) == (dv_lo == nullptr), YT8M_E_BADPTR, "yt8m_netvlad_bwd_norm: dv_hi and dv_lo come together");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   YT8M_REQUIRE(dy && y && stats && cw2 && dv && dasum, YT8M_E_BADPTR, "yt8m_netvlad_bwd_norm: null pointer");
   YT8M_REQUIRE(B > 0 && D > 0, YT8M_E_BADSHAPE, "yt8m_netvlad_bwd_norm: bad shape B=%d D=%d", B, D);
   switch (K) {
-    case 32: netvlad_bwd_norm_kernel<32><<<B, kNormThreads, 0, stream>>>(dy, y, stats, cw2, D, dv, dasum); break;
-    case 64: netvlad_bwd_norm_kernel<64><<<B, kNormThreads, 0, stream>>>(dy, y, stats, cw2, D, dv, dasum); break;
-    case 128: netvlad_bwd_norm_kernel<128><<<B, kNormThreads, 0, stream>>>(dy, y, stats, cw2, D, dv, dasum); break;
+    case 32: netvlad_bwd_norm_kernel<32><<<B, kNormThreads, 0, stream>>>(dy, y, stats, cw2, D, dv, dasum, dv_hi, dv_lo); break;
+    case 64: netvlad_bwd_norm_kernel<64><<<B, kNormThreads, 0, stream>>>(dy, y, stats, cw2, D, dv, dasum, dv_hi, dv_lo); break;
+    case 128: netvlad_bwd_norm_kernel<128><<<B, kNormThreads, 0, stream>>>(dy, y, stats, cw2, D, dv, dasum, dv_hi, dv_lo); break;
     default:
       set_error("yt8m_netvlad_bwd_norm: K=%d unsupported (32, 64, 128)", K);
       return YT8M_E_UNSUPPORTED;
@@ -256,7 +320,27 @@ int yt8m_netvlad_bwd_norm(const float* dy, const float* y, const float* stats, c
   int rc = check_launch("netvlad_bwd_norm_kernel");
   if (rc != YT8M_OK || !dcw2) return rc;
   const long long n = static_cast<long long>(D) * K;
-  netvlad_bwd_dcw2_kernel<<<static_cast<int>(std::min<long long>((n + 255) / 256, 148 * 8)), 256, 0, stream>>>(dv, stats, B, n, K, dcw2);
+  const int blocks = static_cast<int>((n / 4 + 255) / 256);
+  // library-owned scratch (per device): kDcGroups partial sums + one ticket per column block, zeroed once
+  static void* scratch[16] = {};
+  static size_t scratch_bytes[16] = {};
+  int devid = 0;
+  YT8M_CUDA(cudaGetDevice(&devid));
+  YT8M_REQUIRE(devid >= 0 && devid < 16, YT8M_E_UNSUPPORTED, "yt8m_netvlad_bwd_norm: device ordinal %d", devid);
+  const size_t ticket_bytes = 4096;
+  YT8M_REQUIRE(blocks * sizeof(unsigned int) <= ticket_bytes, YT8M_E_UNSUPPORTED, "yt8m_netvlad_bwd_norm: D * K too large");
+  const size_t need = ticket_bytes + static_cast<size_t>(kDcGroups) * n * sizeof(float);
+  if (scratch_bytes[devid] < need) {
+    YT8M_CUDA(cudaStreamSynchronize(stream));
+    if (scratch[devid]) YT8M_CUDA(cudaFree(scratch[devid]));
+    scratch[devid] = nullptr; scratch_bytes[devid] = 0;
+    YT8M_CUDA(cudaMalloc(&scratch[devid], need));
+    YT8M_CUDA(cudaMemset(scratch[devid], 0, ticket_bytes));
+    scratch_bytes[devid] = need;
+  }
+  unsigned int* tickets = static_cast<unsigned int*>(scratch[devid]);
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(scratch[devid]) + ticket_bytes);
+  netvlad_bwd_dcw2_kernel<<<dim3(blocks, kDcGroups), 256, 0, stream>>>(dv, stats, B, n, K, partial, tickets, dcw2);
   return check_launch("netvlad_bwd_dcw2_kernel");
 }
 

@@ -35,17 +35,38 @@ __global__ void logistic_bwd_dz_kernel(const float* __restrict__ dp, const float
   }
 }
 
-// column sums over the batch of a bf16 hi(+lo) matrix: out[n] = sum_b (hi + lo)[b, n]
-__global__ void colsum_bf16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, long long ld,
-                                   int rows, int cols, float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
-  float acc = 0.0f;
-  for (int r = 0; r < rows; ++r) {
-    acc += __bfloat162float(hi[(long long)r * ld + c]);
-    if (lo) acc += __bfloat162float(lo[(long long)r * ld + c]);
+// column sums over the batch of a bf16 hi(+lo) matrix: out[n] = sum_b (hi + lo)[b, n].  A CTA owns 64 columns: 32 lanes x 2
+// columns, 8 row groups (the first version gave a column to a thread and walked the rows serially: 4 CTAs for the hidden
+// layer's 1024 columns, 40 us for 1 MB).  Fixed summation order.
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, long long ld, int rows, int cols,
+                   float* __restrict__ out) {
+  __shared__ float red[8][64];
+  const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 64 + 2 * lane;
+  float a0 = 0.0f, a1 = 0.0f;
+  if (c < cols) {                                        // cols and ld are even (bf16 pairs): c + 1 < cols too
+#pragma unroll 4
+    for (int r = grp; r < rows; r += 8) {
+      const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(hi + static_cast<long long>(r) * ld + c));
+      a0 += __uint_as_float(h << 16);
+      a1 += __uint_as_float(h & 0xFFFF0000u);
+      if (lo) {
+        const uint32_t l = __ldg(reinterpret_cast<const uint32_t*>(lo + static_cast<long long>(r) * ld + c));
+        a0 += __uint_as_float(l << 16);
+        a1 += __uint_as_float(l & 0xFFFF0000u);
+      }
+    }
   }
-  out[c] = acc;
+  red[grp][2 * lane] = a0;
+  red[grp][2 * lane + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < cols) {
+    float t = 0.0f;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) t += red[g][threadIdx.x];
+    out[blockIdx.x * 64 + threadIdx.x] = t;
+  }
 }
 
 // segment of a packed row: 0 = plain tensor / MoE gate rows, 1 = MoE expert rows, -1 = padding row
@@ -315,8 +336,9 @@ int yt8m_colsum_bf16(const yt8m_bf16* hi, const yt8m_bf16* lo, long long ld, int
                      yt8m_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   YT8M_REQUIRE(hi && out, YT8M_E_BADPTR, "yt8m_colsum_bf16: null pointer");
-  YT8M_REQUIRE(rows > 0 && cols > 0 && ld >= cols, YT8M_E_BADSHAPE, "yt8m_colsum_bf16: bad shape");
-  colsum_bf16_kernel<<<(cols + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hi),
+  YT8M_REQUIRE(rows > 0 && cols > 0 && ld >= cols && cols % 2 == 0 && ld % 2 == 0, YT8M_E_BADSHAPE,
+               "yt8m_colsum_bf16: bad shape (cols and ld even) rows=%d cols=%d ld=%lld", rows, cols, ld);
+  colsum_bf16_kernel<<<(cols + 63) / 64, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hi),
                                                             reinterpret_cast<const __nv_bfloat16*>(lo), ld, rows, cols, out);
   return check_launch("colsum_bf16_kernel");
 }

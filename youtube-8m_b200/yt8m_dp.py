@@ -39,6 +39,30 @@ def all_reduce_sum_(flat, group=None):
   return flat
 
 
+class GradExchange:
+  """The gradient exchange of one training step.  The flat fp32 gradient buffer is summed over the ranks in a few
+  CONTIGUOUS pieces, each handed to the collective library as soon as the backward has written its last element:
+  NCCL runs on its own stream, so the 300 MB weight gradient of the hidden layer travels over NVLink while the
+  pooling layer's backward still computes.  (Round 1 issued one all-reduce after the whole backward: 1.07 ms of a
+  4.14 ms step were a fully exposed collective at 8 ranks -- VERDICT r01 item 6.)  start() orders the piece after
+  everything already enqueued on the current stream; finish() makes the current stream wait for every piece (the
+  host is not blocked with NCCL; gloo, used by the CPU tests, blocks).  A single process: both are no-ops."""
+
+  def __init__(self, group=None, world=None):
+    self.group = group
+    self.pending = []
+    self.world = world_size(group) if world is None else world      # world=1: a single-process run inside a larger job
+
+  def start(self, piece):
+    if self.world > 1 and piece.numel() > 0:
+      self.pending.append(dist.all_reduce(piece, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+  def finish(self):
+    for work in self.pending:
+      work.wait()
+    self.pending = []
+
+
 def shard_rows(n_rows, group=None):
   """Contiguous row range [lo, hi) of the global batch owned by this rank (rank r owns rows
   [r*B/W, (r+1)*B/W) -- SURVEY.md §8e)."""

@@ -71,7 +71,10 @@ _SIGS = {
     "yt8m_netvlad_fwd_tiled": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                        c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "yt8m_netvlad_bwd_norm": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
-                                      c_void_p]),
+                                      c_void_p, c_void_p, c_void_p]),
+    "yt8m_netvlad_bwd_assign_fused_supported": (c_int, [c_int, c_int, c_int]),
+    "yt8m_netvlad_bwd_assign_fused": (c_int, [c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                              c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "yt8m_netvlad_bwd_assign": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
                                         c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "yt8m_act_bwd": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_void_p]),
@@ -565,16 +568,36 @@ def netvlad_fwd_tiled(x, num_frames, cw_packed, scale, shift, cw2_tiled, out_f16
   return (out, stats) if want_stats else out
 
 
-def netvlad_bwd_norm(dy, y, stats, cw2, want_dcw2=True):
-  """dy, y fp32 [B, D*K]; stats [B, 2K+1]; cw2 fp32 [D, K] -> (dv [B, D*K], dasum [B, K], dcw2 [D, K] or None)."""
+def netvlad_bwd_norm(dy, y, stats, cw2, want_dcw2=True, want_split=False):
+  """dy, y fp32 [B, D*K]; stats [B, 2K+1]; cw2 fp32 [D, K] -> (dv [B, D*K], dasum [B, K], dcw2 [D, K] or None)
+  (+ (dv_hi, dv_lo) bf16 [B, D*K] when want_split: the operands of netvlad_bwd_assign_fused)."""
   d, k = cw2.shape
   b = dy.shape[0]
   dv = _f32((b, d * k), dy.device)
   dasum = _f32((b, k), dy.device)
   dcw2 = _f32((d, k), dy.device) if want_dcw2 else None
+  hi = _bf16((b, d * k), dy.device) if want_split else None
+  lo = _bf16((b, d * k), dy.device) if want_split else None
   _check(_lib.yt8m_netvlad_bwd_norm(_p(dy.contiguous()), _p(y.contiguous()), _p(stats), _p(cw2.contiguous()), b, d, k, _p(dv),
-                                    _p(dasum), _p(dcw2), _stream()), "yt8m_netvlad_bwd_norm")
-  return dv, dasum, dcw2
+                                    _p(dasum), _p(dcw2), _p(hi), _p(lo), _stream()), "yt8m_netvlad_bwd_norm")
+  return (dv, dasum, dcw2, (hi, lo)) if want_split else (dv, dasum, dcw2)
+
+
+def netvlad_bwd_assign_fused_supported(t, d, k):
+  return bool(_lib.yt8m_netvlad_bwd_assign_fused_supported(t, d, k))
+
+
+def netvlad_bwd_assign_fused(x, num_frames, cw_packed, scale, shift, dv_split, dasum, want_dshift=True):
+  """The assignment backward in one tcgen05 kernel (logits recomputed on chip): x bf16 [B, T, D]; cw_packed bf16 [K, >=D];
+  scale / shift [K] or None; dv_split = (hi, lo) bf16 [B, D*K]; dasum [B, K] -> (dzs_hi, dzs_lo bf16 [B*T, K], dshift)."""
+  b, t, d = x.shape
+  k = dasum.shape[1]
+  hi, lo = _bf16((b * t, k), x.device), _bf16((b * t, k), x.device)
+  dshift = _f32((k,), x.device) if want_dshift else None
+  _check(_lib.yt8m_netvlad_bwd_assign_fused(_p(x), _p(num_frames), _p(cw_packed), cw_packed.stride(0), _p(scale), _p(shift),
+                                            _p(dv_split[0]), _p(dv_split[1]), _p(dasum), b, t, d, k, _p(hi), _p(lo), _p(dshift),
+                                            _stream()), "yt8m_netvlad_bwd_assign_fused")
+  return hi, lo, dshift
 
 
 def netvlad_bwd_assign(x, num_frames, z, dv, dasum, scale=None, want_dshift=True):

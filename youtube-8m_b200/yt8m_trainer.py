@@ -217,7 +217,8 @@ class NetVLADTrainer(object):
   clip_by_norm and TF-Adam (wh/train.py:440-466).  NetVLAD itself is not part of the reference (oracle/
   yt8m_oracle.py:netvlad_pool); the bias variant (--netvlad_add_batch_norm=False) is the one trained here.
 
-  One flat fp32 buffer holds every gradient, so data parallelism is ONE all-reduce per step.
+  One flat fp32 buffer holds every gradient; data parallelism sums it over the ranks once per step, in three contiguous
+  pieces started as their gradients become final (yt8m_dp.GradExchange).
   Layouts: cluster_weights^T [K, D], cluster_biases [K], cluster_weights2 [D, K], hidden1_weights^T [H, K*D],
   hidden1_biases [H], then the packed MoE head.  import_state / export_state speak the model's TF names."""
 
@@ -328,6 +329,10 @@ class NetVLADTrainer(object):
     p, sv = self.forward(x, num_frames)
     hid = sv["hid"]
     loss, dhid = self.head.backward(p, sv["top"][0], sv["top"][1], labels, global_batch, want_dx=True)
+    # the gradient exchange: the flat buffer [cw cb c2 | wfc bfc (wg bg) | head] leaves in three contiguous pieces, each as
+    # soon as it is final -- the classifier's 97 MB and the hidden layer's 302 MB travel while the rest of the backward runs
+    xch = yt8m_dp.GradExchange(self.group, self.world)
+    xch.start(self.grad[self._off["head"][0]:])
     if self.gating:
       # context gating y = h * sigmoid(h . Wg + bg): direct path + the path through the gate logits
       dhid, _, dg_hi, dg_lo = nat.context_gate_bwd(dhid[:, :self.h].contiguous(), hid["f32"], sv["g"], None, self.p["bg"].view(-1))
@@ -339,17 +344,24 @@ class NetVLADTrainer(object):
     dpre_hi, dpre_lo = nat.act_bwd(dhid, hid["f32"], act="relu6" if self.relu else None)
     nat.wgrad(dpre_hi, dpre_lo, sv["vh"], self.h, self.kd, out=self.g["wfc"])          # dWfc^T [H, K*D]
     nat.colsum_bf16(dpre_hi, dpre_lo, self.h, out=self.g["bfc"].view(-1))
+    xch.start(self.grad[self._off["wfc"][0]:self._off["head"][0]])
     wfc_tf = nat.pack_transpose(self.p["wfc"])                                          # bf16 [K*D, H]: the dgrad operand
     dvlad = nat.linear(dpre_hi, wfc_tf, a_lo=dpre_lo, n=self.kd, k=self.h)["f32"]       # [B, K*D]
     del wfc_tf
     # NetVLAD layer
-    dv, dasum, dc2 = nat.netvlad_bwd_norm(dvlad, sv["y32"], sv["stats"], self.p["c2"])
+    if nat.netvlad_bwd_assign_fused_supported(t, d, self.k):
+      # one tcgen05 kernel: logits recomputed on chip, da = X . dV on the tensor cores, softmax backward in its epilogue
+      dv, dasum, dc2, dv_split = nat.netvlad_bwd_norm(dvlad, sv["y32"], sv["stats"], self.p["c2"], want_split=True)
+      dz_hi, dz_lo, dshift = nat.netvlad_bwd_assign_fused(x, num_frames, self.cw_bf16, None, self.p["cb"].view(-1), dv_split, dasum)
+    else:
+      dv, dasum, dc2 = nat.netvlad_bwd_norm(dvlad, sv["y32"], sv["stats"], self.p["c2"])
+      z = nat.linear(x.reshape(b * t, d), self.cw_bf16, n=self.k, k=d, shift=self.p["cb"].view(-1))["f32"]
+      dz_hi, dz_lo, dshift = nat.netvlad_bwd_assign(x, num_frames, z, dv, dasum)
     self.g["c2"].copy_(dc2)
-    z = nat.linear(x.reshape(b * t, d), self.cw_bf16, n=self.k, k=d, shift=self.p["cb"].view(-1))["f32"]
-    dz_hi, dz_lo, dshift = nat.netvlad_bwd_assign(x, num_frames, z, dv, dasum)
     self.g["cb"].view(-1).copy_(dshift)
     nat.wgrad(dz_hi, dz_lo, x.reshape(b * t, d), self.k, d, out=self.g["cw"])           # dCw^T [K, D]
-    yt8m_dp.all_reduce_sum_(self.grad, self.group)                                      # the ONE collective of the step
+    xch.start(self.grad[:self._off["wfc"][0]])
+    xch.finish()
     if self.keep_grads:
       self.last_grad = self.grad.clone()
     lr = exponential_decay(base_lr, self.global_step, global_batch, lr_decay_examples, lr_decay)
