@@ -76,6 +76,8 @@ def parse():
   ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
   ap.add_argument("--cpu-sample", type=int, default=0, help="videos per CPU-baseline forward (0 = the config's own)")
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--dp-gradient-dtype", default="float32", choices=["float32", "bfloat16"],
+                  help="wire format of the train step's gradient exchange (train.py --dp_gradient_dtype); float32 = the reference's arithmetic")
   ap.add_argument("--train-steps", type=int, default=8, help="timed steps of the training-step measurement (0 = skip)")
   ap.add_argument("--graphs", type=int, default=4, help="captured copies of the step, each with ITS OWN input batch, rotated through the timed region")
   ap.add_argument("--operand-format", default="f16", choices=["f16", "bf16x2"],
@@ -513,8 +515,8 @@ def main():
       del xs
   clocks = sampler.stop() if rank == 0 else None
 
-  # ---- the training step of the same workload: forward + full backward + per-tensor clip + Adam; under torchrun ONE NCCL
-  # all-reduce of the flat gradient per step; inputs resident.  This is the part of the path that communicates.
+  # ---- the training step of the same workload: forward + full backward + per-tensor clip + Adam; under torchrun the flat
+  # gradient is summed over the ranks once per step (NCCL); inputs resident.  This is the part of the path that communicates.
   ms_train, train_what, grad_floats = None, None, None
   if args.train_steps > 0:
     bn_flag = FLAGS.netvlad_add_batch_norm
@@ -527,6 +529,8 @@ def main():
     ops.get_store().reset(seed=9)
     FLAGS.netvlad_add_batch_norm = bn_flag
     grad_floats = int(tr.grad.numel())
+    if args.dp_gradient_dtype == "bfloat16":
+      tr.wire_dtype = torch.bfloat16
     y_dev = synth.labels(B, V, seed=8 + rank).to(dev)
     x_d, nf_d, _ = resident[0]
     ms_train = timed(lambda: tr.step(x_d, nf_d, y_dev, global_batch=world * B), args.train_steps, 3)
@@ -603,8 +607,9 @@ def main():
       "gpu_launches": int(launches),
       "train_step": None if ms_train is None else {
           "value": world * B / (ms_train * 1e-3), "unit": "videos/s", "ms_per_step": ms_train, "steps": args.train_steps,
+          "gradient_wire_dtype": args.dp_gradient_dtype,
           "n_gpus": world, "global_batch": world * B,
-          "what": "%s; resident inputs; one all-reduce of the flat gradient (%.1f M floats) per step when n_gpus > 1" %
+          "what": "%s; resident inputs; when n_gpus > 1 the flat fp32 gradient (%.1f M floats) is summed over the ranks once per step (NetVLAD models: in three contiguous pieces started as the backward finishes them)" %
                   (train_what, grad_floats / 1e6)},
       "roofline": roof,
       "clocks": clocks,

@@ -42,10 +42,14 @@ def _worker(rank, world, port, q):
   # the trainers' exchange: contiguous pieces of the flat buffer, started separately, finished together
   pieces = flat.clone()
   xch = yt8m_dp.GradExchange()
-  xch.start(pieces[100:])
-  xch.start(pieces[40:100])
-  xch.start(pieces[:40])
-  xch.start(pieces[:0])                    # an empty piece is skipped
+  xch.start(pieces[100:], "a")
+  xch.start(pieces[40:100], "b")
+  xch.start(pieces[:40], "c")
+  xch.start(pieces[:0], "empty")           # an empty piece is skipped
+  assert len(xch.pending) == 3
+  xch.wait("b")                            # pieces complete in issue order: waiting for b covers a
+  assert [n for n, _ in xch.pending] == ["c"]
+  xch.wait("empty")                        # unknown / skipped name: nothing to wait for
   xch.finish()
   assert not xch.pending
   solo = flat.clone()

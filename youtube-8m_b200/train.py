@@ -52,6 +52,9 @@ if __name__ == "__main__":
                        "(the reference's queue-runner thread count, wh/train.py:199-209); 0 = read synchronously.")
   flags.DEFINE_integer("shuffle_seed", 0, "Seed of the input shuffle (file order per epoch + a 5*batch_size record buffer, "
                        "as string_input_producer(shuffle=True) + shuffle_batch_join do in the reference).")
+  flags.DEFINE_string("dp_gradient_dtype", "float32", "Wire format of the data-parallel gradient exchange of the NetVLAD trainers: "
+                      "float32 (the reference's arithmetic: towers sum fp32 gradients, wh/train.py:461-466) or bfloat16 (half the "
+                      "bytes on NVLink, every rank's gradient rounded to 8 significant bits before the sum).")
   flags.DEFINE_bool("shuffle_input", True, "Shuffle the training input like the reference does; False replays the files in sorted order.")
   flags.DEFINE_string("optimizer", "AdamOptimizer", "What optimizer class to use.")
   flags.DEFINE_float("clip_gradient_norm", 1.0, "Norm to clip gradients to.")
@@ -116,9 +119,13 @@ class Trainer(object):
       if FLAGS.netvlad_add_batch_norm or FLAGS.video_level_classifier_model != "MoeModel":
         raise NotImplementedError("train.py --model=%s: the CUDA training step is built for "
                                   "--netvlad_add_batch_norm=False with --video_level_classifier_model=MoeModel" % self.model_name)
-      return yt8m_trainer.NetVLADTrainer(in_dim, clusters=FLAGS.netvlad_cluster_size, hidden=FLAGS.netvlad_hidden_size,
-                                         vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures, relu=FLAGS.netvlad_relu,
-                                         gating=model_cls is frame_level_models.GatedNetVLADModel)
+      if FLAGS.dp_gradient_dtype not in ("float32", "bfloat16"):
+        raise ValueError("--dp_gradient_dtype must be float32 or bfloat16")
+      t = yt8m_trainer.NetVLADTrainer(in_dim, clusters=FLAGS.netvlad_cluster_size, hidden=FLAGS.netvlad_hidden_size,
+                                      vocab=self.reader.num_classes, mixtures=FLAGS.moe_num_mixtures, relu=FLAGS.netvlad_relu,
+                                      gating=model_cls is frame_level_models.GatedNetVLADModel)
+      t.wire_dtype = torch.bfloat16 if FLAGS.dp_gradient_dtype == "bfloat16" else None
+      return t
     if model_cls in (frame_level_models.LstmModel, frame_level_models.LstmMemoryModel):
       if FLAGS.video_level_classifier_model != "MoeModel":
         raise NotImplementedError("train.py --model=%s: the CUDA training step is built for "

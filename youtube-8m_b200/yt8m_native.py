@@ -753,6 +753,25 @@ def wgrad(a_hi, a_lo, b, m, n, out=None):
   return out
 
 
+def dgrad(dz_hi, dz_lo, w_rows, n):
+  """dx[B, n] fp32 = dz[B, rows] . W[rows, :n] with W in the layout the FORWARD uses (bf16 [rows, ld >= n], the output
+  features of the layer as rows).  The contraction runs over the rows of both stored operands once dz is transposed (a few
+  MB), so this is the MN-major GEMM of yt8m_wgrad -- no transposed copy of the weight matrix (the first version rebuilt a
+  bf16 W^T from the fp32 master every step: 160 us for the 302 MB hidden layer of BASELINE config 2)."""
+  b, rows = dz_hi.shape[0], w_rows.shape[0]
+  bp = pad8(b)
+
+  def tr(z):
+    if z is None:
+      return None
+    t = torch.zeros((rows, bp), dtype=torch.bfloat16, device=z.device) if bp != b else torch.empty((rows, bp), dtype=torch.bfloat16,
+                                                                                                    device=z.device)
+    t[:, :b] = z[:, :rows].t()
+    return t
+
+  return wgrad(tr(dz_hi), tr(dz_lo), w_rows, b, n)
+
+
 def colsum_bf16(hi, lo, cols, out=None):
   if out is None:
     out = _f32((cols,), hi.device)

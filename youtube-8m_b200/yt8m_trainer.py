@@ -159,10 +159,8 @@ class HeadTrainer(object):
     nat.colsum_bf16(dz_hi, dz_lo, self.rows, out=self.gb)
     dx = None
     if want_dx:
-      # dX[B, D] = dZ[B, rows] . W[rows, D]: the K-major operand is W^T [D, rows] -- a bf16 transpose of the master
-      # (same rounding as the forward's operand copy)
-      wt = nat.pack_transpose(self.w)
-      dx = nat.linear(dz_hi, wt, a_lo=dz_lo, n=self.d, k=self.rows)["f32"]
+      # dX[B, D] = dZ[B, rows] . W[rows, D]: contraction over the rows of the forward's own bf16 operand copy
+      dx = nat.dgrad(dz_hi, dz_lo, self.w_bf16, self.d)
     return dx
 
   def apply(self, lr_t, clip_gradient_norm=1.0, regularization_penalty=1.0):
@@ -331,23 +329,20 @@ class NetVLADTrainer(object):
     loss, dhid = self.head.backward(p, sv["top"][0], sv["top"][1], labels, global_batch, want_dx=True)
     # the gradient exchange: the flat buffer [cw cb c2 | wfc bfc (wg bg) | head] leaves in three contiguous pieces, each as
     # soon as it is final -- the classifier's 97 MB and the hidden layer's 302 MB travel while the rest of the backward runs
-    xch = yt8m_dp.GradExchange(self.group, self.world)
-    xch.start(self.grad[self._off["head"][0]:])
+    xch = yt8m_dp.GradExchange(self.group, self.world, getattr(self, "wire_dtype", None))
+    xch.start(self.grad[self._off["head"][0]:], "head")
     if self.gating:
       # context gating y = h * sigmoid(h . Wg + bg): direct path + the path through the gate logits
       dhid, _, dg_hi, dg_lo = nat.context_gate_bwd(dhid[:, :self.h].contiguous(), hid["f32"], sv["g"], None, self.p["bg"].view(-1))
       nat.wgrad(dg_hi, dg_lo, hid["hi"], self.h, self.h, out=self.g["wg"])             # dWg^T [out, in]
       nat.colsum_bf16(dg_hi, dg_lo, self.h, out=self.g["bg"].view(-1))
-      wg_t = nat.pack_transpose(self.p["wg"])                                           # bf16 [in, out]: the dgrad operand
-      nat.add_inplace(dhid, nat.linear(dg_hi, wg_t, a_lo=dg_lo, n=self.h, k=self.h)["f32"])
+      nat.add_inplace(dhid, nat.dgrad(dg_hi, dg_lo, self.wg_bf16, self.h))              # through the forward's bf16 Wg^T [out, in]
     # hidden FC: h = act(vlad . Wfc + b)
     dpre_hi, dpre_lo = nat.act_bwd(dhid, hid["f32"], act="relu6" if self.relu else None)
     nat.wgrad(dpre_hi, dpre_lo, sv["vh"], self.h, self.kd, out=self.g["wfc"])          # dWfc^T [H, K*D]
     nat.colsum_bf16(dpre_hi, dpre_lo, self.h, out=self.g["bfc"].view(-1))
-    xch.start(self.grad[self._off["wfc"][0]:self._off["head"][0]])
-    wfc_tf = nat.pack_transpose(self.p["wfc"])                                          # bf16 [K*D, H]: the dgrad operand
-    dvlad = nat.linear(dpre_hi, wfc_tf, a_lo=dpre_lo, n=self.kd, k=self.h)["f32"]       # [B, K*D]
-    del wfc_tf
+    xch.start(self.grad[self._off["wfc"][0]:self._off["head"][0]], "fc")
+    dvlad = nat.dgrad(dpre_hi, dpre_lo, self.wfc_bf16, self.kd)                         # [B, K*D] through the forward's bf16 Wfc^T [H, K*D]
     # NetVLAD layer
     if nat.netvlad_bwd_assign_fused_supported(t, d, self.k):
       # one tcgen05 kernel: logits recomputed on chip, da = X . dV on the tensor cores, softmax backward in its epilogue
@@ -360,19 +355,25 @@ class NetVLADTrainer(object):
     self.g["c2"].copy_(dc2)
     self.g["cb"].view(-1).copy_(dshift)
     nat.wgrad(dz_hi, dz_lo, x.reshape(b * t, d), self.k, d, out=self.g["cw"])           # dCw^T [K, D]
-    xch.start(self.grad[:self._off["wfc"][0]])
-    xch.finish()
+    xch.start(self.grad[:self._off["wfc"][0]], "pool")
     if self.keep_grads:
+      xch.finish()
       self.last_grad = self.grad.clone()
     lr = exponential_decay(base_lr, self.global_step, global_batch, lr_decay_examples, lr_decay)
     lr_t = adam_lr_t(lr, self.global_step + 1)
-    tensors = [("cw", self.cw_bf16), ("cb", None), ("c2", None), ("wfc", self.wfc_bf16), ("bfc", None)]
-    if self.gating:
-      tensors += [("wg", self.wg_bf16), ("bg", None)]
-    for name, bf in tensors:
-      sums = nat.grad_reg_sumsq(self.g[name], self.p[name], 0.0)
-      nat.clip_adam_step(self.p[name], self.g[name], self.am[name], self.av[name], sums, clip_gradient_norm, lr_t, param_bf16=bf)
+
+    def update(tensors):
+      for name, bf in tensors:
+        sums = nat.grad_reg_sumsq(self.g[name], self.p[name], 0.0)
+        nat.clip_adam_step(self.p[name], self.g[name], self.am[name], self.av[name], sums, clip_gradient_norm, lr_t, param_bf16=bf)
+
+    # each piece is updated as it arrives: the classifier's Adam runs while the hidden layer's 302 MB are still on the wire
+    xch.wait("head")
     self.head.apply(lr_t, clip_gradient_norm, regularization_penalty)
+    xch.wait("fc")
+    update([("wfc", self.wfc_bf16), ("bfc", None)] + ([("wg", self.wg_bf16), ("bg", None)] if self.gating else []))
+    xch.wait("pool")
+    update([("cw", self.cw_bf16), ("cb", None), ("c2", None)])
     self.global_step += 1
     self.head.global_step = self.global_step
     self.last = {"label_loss_local": loss, "lr": lr}
