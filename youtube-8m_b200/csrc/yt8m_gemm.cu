@@ -208,6 +208,31 @@ int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda,
   return YT8M_OK;
 }
 
+}  // extern "C"
+
+// acc[M, N] (fp32, row stride ld_acc) += A[M, K] . W[N, K]^T, the contraction split over CTAs and reduced with fp32 vector
+// atomics straight into acc: no workspace, no memset, no finalize pass.  The reverse LSTM recurrence calls it once per frame
+// (dh_{t-1} += dG_t . Wh: M = batch, N = H, K = 4H): with yt8m_linear_fwd's split-K that was a memset + GEMM + finalize
+// triple per step (profiles/r02f_lstm_train_profile.txt: 598 x (1.7 + 7.9 + 2.4) us).
+int yt8m::linear_accumulate(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, const yt8m_bf16* w, long long ldw, int M,
+                            int N, int K, float* acc, long long ld_acc, cudaStream_t stream) {
+  YT8M_REQUIRE(a_hi && w && acc, YT8M_E_BADPTR, "linear_accumulate: null pointer");
+  YT8M_REQUIRE(M > 0 && N > 0 && K > 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K && ld_acc >= N, YT8M_E_BADSHAPE,
+               "linear_accumulate: bad shape M=%d N=%d K=%d", M, N, K);
+  const int tiles = ((M + kBlockM - 1) / kBlockM) * ((N + 127) / 128);
+  const int num_kb = (K + kBlockK - 1) / kBlockK;
+  const int split_k = std::max(1, std::min(kNumSms / std::max(tiles, 1), num_kb / 4));
+  EpiLinear::Params ep{};
+  ep.act = ACT_NONE;
+  ep.split_k = std::max(split_k, 2);                    // > 1 selects the atomic epilogue, also for a single split
+  ep.out_f32 = acc;
+  ep.ld_out = ld_acc;
+  return a_lo ? launch_gemm<128, 2, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream)
+              : launch_gemm<128, 1, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream);
+}
+
+extern "C" {
+
 int yt8m_pack_transpose_bf16(const float* w_kn, int K, int N, yt8m_bf16* w_packed, long long ldw, yt8m_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   YT8M_REQUIRE(w_kn && w_packed, YT8M_E_BADPTR, "yt8m_pack_transpose_bf16: null pointer");

@@ -20,6 +20,31 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+void* lib_scratch(int slot, size_t bytes, size_t ticket_bytes, cudaStream_t stream) {
+  constexpr int kMaxDev = 16;
+  static void* buf[kMaxDev][kScratchSlots] = {};
+  static size_t cap[kMaxDev][kScratchSlots] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev || slot < 0 || slot >= kScratchSlots) {
+    set_error("lib_scratch: device ordinal %d / slot %d out of range", dev, slot);
+    return nullptr;
+  }
+  if (cap[dev][slot] < bytes) {
+    cudaStreamSynchronize(stream);
+    if (buf[dev][slot]) cudaFree(buf[dev][slot]);
+    buf[dev][slot] = nullptr;
+    cap[dev][slot] = 0;
+    const size_t want = bytes + bytes / 2;                 // head-room: shapes grow a few times, not every call
+    if (cudaMalloc(&buf[dev][slot], want) != cudaSuccess || cudaMemset(buf[dev][slot], 0, ticket_bytes) != cudaSuccess) {
+      set_error("lib_scratch: cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(cudaGetLastError()));
+      buf[dev][slot] = nullptr;
+      return nullptr;
+    }
+    cap[dev][slot] = want;
+  }
+  return buf[dev][slot];
+}
+
 int& host_debug_flags() {
   static int flags = 0;
   return flags;

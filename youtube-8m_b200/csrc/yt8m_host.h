@@ -25,6 +25,17 @@ int make_tmap_bf16_nd(CUtensorMap* out, const void* ptr, int rank, const uint64_
 
 int check_launch(const char* what);
 
+// acc += A . W^T with split-K atomics straight into acc (yt8m_gemm.cu)
+int linear_accumulate(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, const yt8m_bf16* w, long long ldw, int M, int N,
+                      int K, float* acc, long long ld_acc, cudaStream_t stream);
+
+// Library-owned device scratch, one buffer per (device, slot), grown on demand (the growth synchronises `stream` and frees the
+// old buffer).  The first `ticket_bytes` are zero after allocation and are kept zero by their users (self-cleaning tickets of
+// last-block reductions).  Users of one slot must be ordered on one stream per device.  Returns nullptr on failure
+// (yt8m_last_error is set).
+enum ScratchSlot : int { kScratchDcw2 = 0, kScratchColsum = 1, kScratchSlots = 2 };
+void* lib_scratch(int slot, size_t bytes, size_t ticket_bytes, cudaStream_t stream);
+
 // debug / experiment switches set through yt8m_debug_set_flags (host copy; 0 in normal operation)
 int& host_debug_flags();
 

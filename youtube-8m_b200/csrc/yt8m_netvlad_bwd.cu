@@ -321,25 +321,13 @@ int yt8m_netvlad_bwd_norm(const float* dy, const float* y, const float* stats, c
   if (rc != YT8M_OK || !dcw2) return rc;
   const long long n = static_cast<long long>(D) * K;
   const int blocks = static_cast<int>((n / 4 + 255) / 256);
-  // library-owned scratch (per device): kDcGroups partial sums + one ticket per column block, zeroed once
-  static void* scratch[16] = {};
-  static size_t scratch_bytes[16] = {};
-  int devid = 0;
-  YT8M_CUDA(cudaGetDevice(&devid));
-  YT8M_REQUIRE(devid >= 0 && devid < 16, YT8M_E_UNSUPPORTED, "yt8m_netvlad_bwd_norm: device ordinal %d", devid);
+  // library-owned scratch (per device): kDcGroups partial sums + one ticket per column block
   const size_t ticket_bytes = 4096;
   YT8M_REQUIRE(blocks * sizeof(unsigned int) <= ticket_bytes, YT8M_E_UNSUPPORTED, "yt8m_netvlad_bwd_norm: D * K too large");
-  const size_t need = ticket_bytes + static_cast<size_t>(kDcGroups) * n * sizeof(float);
-  if (scratch_bytes[devid] < need) {
-    YT8M_CUDA(cudaStreamSynchronize(stream));
-    if (scratch[devid]) YT8M_CUDA(cudaFree(scratch[devid]));
-    scratch[devid] = nullptr; scratch_bytes[devid] = 0;
-    YT8M_CUDA(cudaMalloc(&scratch[devid], need));
-    YT8M_CUDA(cudaMemset(scratch[devid], 0, ticket_bytes));
-    scratch_bytes[devid] = need;
-  }
-  unsigned int* tickets = static_cast<unsigned int*>(scratch[devid]);
-  float* partial = reinterpret_cast<float*>(static_cast<char*>(scratch[devid]) + ticket_bytes);
+  void* scratch = lib_scratch(kScratchDcw2, ticket_bytes + static_cast<size_t>(kDcGroups) * n * sizeof(float), ticket_bytes, stream);
+  if (!scratch) return YT8M_E_CUDA;
+  unsigned int* tickets = static_cast<unsigned int*>(scratch);
+  float* partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + ticket_bytes);
   netvlad_bwd_dcw2_kernel<<<dim3(blocks, kDcGroups), 256, 0, stream>>>(dv, stats, B, n, K, partial, tickets, dcw2);
   return check_launch("netvlad_bwd_dcw2_kernel");
 }

@@ -53,7 +53,7 @@ __global__ void lstm_bwd_scan_kernel(float* __restrict__ G, float* __restrict__ 
 struct LstmBwdStep {
   const float* acts;        // [B, T, 4H] gate activations (unit-major)
   const float* c_seq;       // [B, T, H]
-  const float* dh_acc;      // [B, H]: dG_{t+1} . Wh
+  float* dh_acc;            // [B, H]: dG_{t+1} . Wh, accumulated by split-K atomics; the reader zeroes what it consumed
   const float* dstate_c;    // [B] rows of stride ld_state: dL/dc_final of this layer
   const float* dstate_h;
   long long ld_state;
@@ -75,6 +75,9 @@ __global__ void lstm_bwd_step_kernel(const LstmBwdStep p) {
   const bool last_live = (t + 1 >= nf);      // the step above is frozen or does not exist: take dL/dstate
   const long long so = static_cast<long long>(b) * p.ld_state + u;
   float dh = last_live ? (p.dstate_h ? p.dstate_h[so] : 0.0f) : p.dh_acc[idx];
+  // the next frame's product accumulates into this buffer: leave zeros behind (rows that are frozen or take dL/dstate never
+  // received anything but zeros: their dG above is zero)
+  if (!last_live) p.dh_acc[idx] = 0.0f;
   const float dc_in = last_live ? (p.dstate_c ? p.dstate_c[so] : 0.0f) : p.dc[idx];
   const long long row = static_cast<long long>(b) * p.T + t;
   if (p.dout) dh += p.dout[row * p.H + u];
@@ -449,6 +452,7 @@ int yt8m_lstm_bwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D
     // 3. reverse recurrence
     YT8M_CUDA(cudaMemsetAsync(ws.dg_hi, 0, static_cast<size_t>(rows) * 4 * H * 2, stream));
     YT8M_CUDA(cudaMemsetAsync(ws.dg_lo, 0, static_cast<size_t>(rows) * 4 * H * 2, stream));
+    YT8M_CUDA(cudaMemsetAsync(ws.dh_acc, 0, static_cast<size_t>(B) * H * sizeof(float), stream));
     LstmBwdStep sp{};
     sp.acts = ws.G; sp.c_seq = ws.c_seq; sp.dh_acc = ws.dh_acc;
     sp.dstate_c = dstate ? dstate + static_cast<long long>(l) * 2 * H : nullptr;
@@ -463,10 +467,9 @@ int yt8m_lstm_bwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D
       lstm_bwd_step_kernel<<<cell_blocks, 256, 0, stream>>>(sp);
       if ((rc = check_launch("lstm_bwd_step_kernel")) != YT8M_OK) return rc;
       if (t == 0) break;
-      rc = yt8m_linear_fwd(reinterpret_cast<const yt8m_bf16*>(ws.dg_hi) + static_cast<long long>(t) * 4 * H,
-                           reinterpret_cast<const yt8m_bf16*>(ws.dg_lo) + static_cast<long long>(t) * 4 * H,
-                           static_cast<long long>(T) * 4 * H, wt_rec, 4 * H, B, H, 4 * H, nullptr, nullptr, YT8M_ACT_NONE,
-                           YT8M_FMT_BF16, YT8M_FMT_BF16, ws.dh_acc, nullptr, nullptr, H, ws.splitk, ws.splitk_bytes, stream_);
+      rc = linear_accumulate(reinterpret_cast<const yt8m_bf16*>(ws.dg_hi) + static_cast<long long>(t) * 4 * H,
+                             reinterpret_cast<const yt8m_bf16*>(ws.dg_lo) + static_cast<long long>(t) * 4 * H,
+                             static_cast<long long>(T) * 4 * H, wt_rec, 4 * H, B, H, 4 * H, ws.dh_acc, H, stream);
       if (rc != YT8M_OK) return rc;
     }
     // 4. parameter gradients over all frames, and the gradient of the layer below

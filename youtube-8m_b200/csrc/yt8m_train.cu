@@ -35,19 +35,25 @@ __global__ void logistic_bwd_dz_kernel(const float* __restrict__ dp, const float
   }
 }
 
-// column sums over the batch of a bf16 hi(+lo) matrix: out[n] = sum_b (hi + lo)[b, n].  A CTA owns 64 columns: 32 lanes x 2
-// columns, 8 row groups (the first version gave a column to a thread and walked the rows serially: 4 CTAs for the hidden
-// layer's 1024 columns, 40 us for 1 MB).  Fixed summation order.
+// column sums over the rows of a bf16 hi(+lo) matrix: out[n] = sum_b (hi + lo)[b, n].  A CTA owns 64 columns (32 lanes x 2
+// columns, 8 row groups) of one row SLICE (blockIdx.y); with more than one slice the partial sums go to scratch and the last
+// slice of a column block to finish adds them in slice order (a self-cleaning ticket: no atomics on the data, the result does
+// not depend on arrival order).  The first version gave a column to a thread and walked ALL rows serially: 4 CTAs for the hidden
+// layer's 1024 columns (40 us for 1 MB), 16 CTAs x 19,200 rows for the LSTM bias gradient.
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __restrict__ lo, long long ld, int rows, int cols,
-                   float* __restrict__ out) {
+                   float* __restrict__ partial, unsigned int* __restrict__ tickets, float* __restrict__ out) {
   __shared__ float red[8][64];
+  __shared__ unsigned int last;
   const int lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
   const int c = blockIdx.x * 64 + 2 * lane;
+  const int slices = gridDim.y;
+  const int per = (rows + slices - 1) / slices;
+  const int r0 = blockIdx.y * per, r1 = min(rows, r0 + per);
   float a0 = 0.0f, a1 = 0.0f;
   if (c < cols) {                                        // cols and ld are even (bf16 pairs): c + 1 < cols too
 #pragma unroll 4
-    for (int r = grp; r < rows; r += 8) {
+    for (int r = r0 + grp; r < r1; r += 8) {
       const uint32_t h = __ldg(reinterpret_cast<const uint32_t*>(hi + static_cast<long long>(r) * ld + c));
       a0 += __uint_as_float(h << 16);
       a1 += __uint_as_float(h & 0xFFFF0000u);
@@ -61,12 +67,29 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ hi, const __nv_bfloat16* __
   red[grp][2 * lane] = a0;
   red[grp][2 * lane + 1] = a1;
   __syncthreads();
-  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < cols) {
-    float t = 0.0f;
+  const int col = blockIdx.x * 64 + threadIdx.x;
+  float t = 0.0f;
+  if (threadIdx.x < 64) {
 #pragma unroll
     for (int g = 0; g < 8; ++g) t += red[g][threadIdx.x];
-    out[blockIdx.x * 64 + threadIdx.x] = t;
   }
+  if (slices == 1) {
+    if (threadIdx.x < 64 && col < cols) out[col] = t;
+    return;
+  }
+  if (threadIdx.x < 64 && col < cols) partial[static_cast<long long>(blockIdx.y) * cols + col] = t;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(tickets + blockIdx.x, 1u);
+  __syncthreads();
+  if (last != static_cast<unsigned int>(slices - 1)) return;
+  __threadfence();
+  if (threadIdx.x < 64 && col < cols) {
+    float s = 0.0f;
+    for (int y = 0; y < slices; ++y) s += __ldcg(partial + static_cast<long long>(y) * cols + col);
+    out[col] = s;
+  }
+  if (threadIdx.x == 0) tickets[blockIdx.x] = 0u;
 }
 
 // segment of a packed row: 0 = plain tensor / MoE gate rows, 1 = MoE expert rows, -1 = padding row
@@ -338,8 +361,21 @@ int yt8m_colsum_bf16(const yt8m_bf16* hi, const yt8m_bf16* lo, long long ld, int
   YT8M_REQUIRE(hi && out, YT8M_E_BADPTR, "yt8m_colsum_bf16: null pointer");
   YT8M_REQUIRE(rows > 0 && cols > 0 && ld >= cols && cols % 2 == 0 && ld % 2 == 0, YT8M_E_BADSHAPE,
                "yt8m_colsum_bf16: bad shape (cols and ld even) rows=%d cols=%d ld=%lld", rows, cols, ld);
-  colsum_bf16_kernel<<<(cols + 63) / 64, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hi),
-                                                            reinterpret_cast<const __nv_bfloat16*>(lo), ld, rows, cols, out);
+  const int col_blocks = (cols + 63) / 64;
+  const int slices = std::max(1, std::min(32, rows / 128));
+  float* partial = nullptr;
+  unsigned int* tickets = nullptr;
+  if (slices > 1) {
+    const size_t ticket_bytes = (static_cast<size_t>(col_blocks) * sizeof(unsigned int) + 255) & ~size_t(255);
+    void* scratch = lib_scratch(kScratchColsum, 65536 + static_cast<size_t>(slices) * cols * sizeof(float), 65536, stream);
+    YT8M_REQUIRE(ticket_bytes <= 65536, YT8M_E_UNSUPPORTED, "yt8m_colsum_bf16: too many columns (%d)", cols);
+    if (!scratch) return YT8M_E_CUDA;
+    tickets = static_cast<unsigned int*>(scratch);
+    partial = reinterpret_cast<float*>(static_cast<char*>(scratch) + 65536);
+  }
+  colsum_bf16_kernel<<<dim3(col_blocks, slices), 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(hi),
+                                                                  reinterpret_cast<const __nv_bfloat16*>(lo), ld, rows, cols, partial,
+                                                                  tickets, out);
   return check_launch("colsum_bf16_kernel");
 }
 
