@@ -62,3 +62,37 @@ if which in ("all", "lstm"):
   torch.cuda.synchronize()
   _, st = O.dynamic_rnn_lstm(x, nf, ws)
   print("lstm (persistent recurrence): rel %.2e" % rel(state.cpu(), O.lstm_model_state(st)))
+
+if which in ("all", "train"):
+  # the training step's new kernels: tensor-core assignment backward, vectorised norm backward, ticketed dcw2 / column sums,
+  # in-place split-K accumulation of the reverse LSTM recurrence -- through the trainers (two steps: the self-cleaning
+  # tickets and the zero-on-read accumulator are exercised on their second use)
+  import yt8m_trainer
+  Bf, T, Df, K, H, Vf, M = 6, 140, 256, 64, 128, 200, 2
+  xf, nff, _ = synth.model_input(Bf, T, Df, seed=5, min_frames=1)
+  nff[0] = 0
+  yf = synth.labels(Bf, Vf, seed=5, per_video=3.4)
+  sdf = {"cluster_weights": synth.normal((Df, K), g, 4.0), "cluster_biases": 0.1 * torch.randn(K, generator=g),
+         "cluster_weights2": synth.normal((Df, K), g, 1 / math.sqrt(Df)), "hidden1_weights": synth.normal((K * Df, H), g, 12.0 / math.sqrt(K)),
+         "hidden1_biases": 0.1 * torch.randn(H, generator=g), "gates/weights": synth.xavier((H, Vf * (M + 1)), g, 2.0),
+         "experts/weights": synth.xavier((H, Vf * M), g, 2.0), "experts/biases": 0.1 * torch.randn(Vf * M, generator=g)}
+  t = yt8m_trainer.NetVLADTrainer(Df, clusters=K, hidden=H, vocab=Vf, mixtures=M, device=torch.device(dev))
+  t.import_state(sdf)
+  for _ in range(2):
+    t.step(xf.to(dev).to(torch.bfloat16), nff.to(dev), yf.to(dev))
+  torch.cuda.synchronize()
+  print("NetVLAD trainer: 2 steps, params finite %s" % bool(torch.isfinite(t.param).all()))
+  Bl, Tl, Dl, Hl, Ll = 4, 200, 64, 256, 2
+  xl, nfl, _ = synth.model_input(Bl, Tl, Dl, seed=6, min_frames=2)
+  yl = synth.labels(Bl, Vf, seed=6, per_video=3.4)
+  sdl = {"gates/weights": synth.xavier((Ll * 2 * Hl, Vf * (M + 1)), g, 2.0), "experts/weights": synth.xavier((Ll * 2 * Hl, Vf * M), g, 2.0),
+         "experts/biases": 0.1 * torch.randn(Vf * M, generator=g)}
+  for l in range(Ll):
+    sdl[yt8m_trainer.LstmTrainer.SCOPE % l + "/weights"] = synth.xavier(((Dl if l == 0 else Hl) + Hl, 4 * Hl), g, 2.0)
+    sdl[yt8m_trainer.LstmTrainer.SCOPE % l + "/biases"] = synth.bf16r(0.1 * torch.randn(4 * Hl, generator=g))
+  tl = yt8m_trainer.LstmTrainer(Dl, hidden=Hl, layers=Ll, vocab=Vf, mixtures=M, device=torch.device(dev))
+  tl.import_state(sdl)
+  for _ in range(2):
+    tl.step(xl.to(dev).to(torch.bfloat16), nfl.to(dev), yl.to(dev))
+  torch.cuda.synchronize()
+  print("LSTM trainer: 2 steps, params finite %s" % bool(torch.isfinite(tl.param).all()))
