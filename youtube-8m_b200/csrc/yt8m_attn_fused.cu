@@ -11,6 +11,8 @@
 #include "yt8m_common.cuh"
 #include "yt8m_host.h"
 
+#include <algorithm>
+
 using namespace yt8m;
 
 namespace {
@@ -20,7 +22,7 @@ constexpr int kMaxA = 8;
 template <int A>
 __global__ void __launch_bounds__(1024, 1)
 attn_pool_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w, long long ldw,
-                       const int* __restrict__ num_frames, int T, int D, float* __restrict__ out,
+                       const int* __restrict__ num_frames, int T, int D, int G, float* __restrict__ out,
                        __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   float* wl = reinterpret_cast<float*>(smem_raw);               // [T][A] logits -> weights
@@ -28,6 +30,7 @@ attn_pool_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
   // W^T staged as [D][A] bf16: one 16-byte vector per feature (A = 8)
   __nv_bfloat16* wt = reinterpret_cast<__nv_bfloat16*>(inv_s + 2 * A);
   static_assert(A == 8, "one uint4 of weights per feature");
+  uint8_t* fold_raw = reinterpret_cast<uint8_t*>(wt + static_cast<size_t>(D) * A);     // [A][D] floats: phase B's group fold (16-byte aligned: D % 8 == 0)
   const int b = blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nwarps = blockDim.x >> 5;
   const __nv_bfloat16* xb = x + static_cast<long long>(b) * T * D;
@@ -107,14 +110,18 @@ attn_pool_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
     if (lane == 0) inv_s[a] = 1.0f / sum;                        // sum == 0 only for an all-masked video: NaN like 0/0 in TF
   }
   __syncthreads();
-  // ---- phase B: thread owns feature columns 4 tid .. 4 tid + 3 ----
-  const int c0 = 4 * tid;
-  if (c0 < D) {
-    float acc[A][4];
+  // ---- phase B: a thread owns feature columns 4 j .. 4 j + 3 of every G-th frame (G = thread groups of D / 4 threads: 3 for
+  //      1024 threads at D = 1152); the groups' partial sums are folded into group 0 through shared memory, in group order ----
+  const int tpg = D / 4;                                   // threads per group
+  const int grp = tid / tpg, j = tid - grp * tpg;
+  const int c0 = 4 * j;
+  const bool active = grp < G;
+  float acc[A][4];
 #pragma unroll
-    for (int a = 0; a < A; ++a) { acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.0f; }
-#pragma unroll 8
-    for (int t = 0; t < nf; ++t) {
+  for (int a = 0; a < A; ++a) { acc[a][0] = acc[a][1] = acc[a][2] = acc[a][3] = 0.0f; }
+  if (active) {
+#pragma unroll 4
+    for (int t = grp; t < nf; t += G) {
       const uint2 u = __ldg(reinterpret_cast<const uint2*>(xb + static_cast<long long>(t) * D + c0));
       const float x0 = __uint_as_float(u.x << 16), x1 = __uint_as_float(u.x & 0xFFFF0000u);
       const float x2 = __uint_as_float(u.y << 16), x3 = __uint_as_float(u.y & 0xFFFF0000u);
@@ -126,6 +133,24 @@ attn_pool_fused_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
         acc[a][0] += pa * x0; acc[a][1] += pa * x1; acc[a][2] += pa * x2; acc[a][3] += pa * x3;
       }
     }
+  }
+  float4* fold = reinterpret_cast<float4*>(fold_raw);      // [A][D / 4] float4
+  for (int g = 1; g < G; ++g) {
+    __syncthreads();
+    if (grp == g) {
+#pragma unroll
+      for (int a = 0; a < A; ++a) fold[a * tpg + j] = make_float4(acc[a][0], acc[a][1], acc[a][2], acc[a][3]);
+    }
+    __syncthreads();
+    if (grp == 0) {
+#pragma unroll
+      for (int a = 0; a < A; ++a) {
+        const float4 v = fold[a * tpg + j];
+        acc[a][0] += v.x; acc[a][1] += v.y; acc[a][2] += v.z; acc[a][3] += v.w;
+      }
+    }
+  }
+  if (grp == 0) {
 #pragma unroll
     for (int a = 0; a < A; ++a) {
       const float s = inv_s[a];
@@ -152,7 +177,14 @@ extern "C" int yt8m_attn_pool_fused(const yt8m_bf16* x, const yt8m_bf16* w_packe
                "yt8m_attn_pool_fused: bad shape B=%d T=%d D=%d", B, T, D);
   YT8M_REQUIRE(A == kMaxA, YT8M_E_UNSUPPORTED, "yt8m_attn_pool_fused: built for %d heads (moe_num_extend / lstm_attentions default), got %d",
                kMaxA, A);
-  const size_t smem = (static_cast<size_t>(T) * A + 2 * A + 4) * sizeof(float) + static_cast<size_t>(D) * A * 2 + 16;
+  // phase A wants many warps (a frame each); phase B folds G groups of D / 4 threads (G = 3 at D = 1152): as many threads as
+  // the kernel may have (1024), but at least one full group; the fold buffer only when it fits
+  int threads = 1024;
+  if (D / 4 > threads) threads = ((D / 4 + 31) / 32) * 32;
+  int G = std::max(1, std::min(threads / (D / 4), 4));
+  const size_t base = (static_cast<size_t>(T) * A + 2 * A + 4) * sizeof(float) + static_cast<size_t>(D) * A * 2 + 16;
+  if (G > 1 && base + static_cast<size_t>(D) * A * sizeof(float) > 200 * 1024) G = 1;
+  const size_t smem = base + (G > 1 ? static_cast<size_t>(D) * A * sizeof(float) : 0);
   YT8M_REQUIRE(smem <= 200 * 1024, YT8M_E_UNSUPPORTED, "yt8m_attn_pool_fused: T * A + D * A too large for shared memory");
   auto kern = attn_pool_fused_kernel<kMaxA>;
   static bool attr_done = false;
@@ -160,10 +192,8 @@ extern "C" int yt8m_attn_pool_fused(const yt8m_bf16* x, const yt8m_bf16* w_packe
     YT8M_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done = true;
   }
-  int threads = ((D / 4 + 31) / 32) * 32;              // phase B: four columns per thread
-  if (threads < 8 * 32) threads = 8 * 32;              // the softmax step wants a warp per head
   kern<<<B, threads, smem, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), reinterpret_cast<const __nv_bfloat16*>(w_packed), ldw,
-                                     num_frames, T, D, out, reinterpret_cast<__nv_bfloat16*>(out_hi),
+                                     num_frames, T, D, G, out, reinterpret_cast<__nv_bfloat16*>(out_hi),
                                      reinterpret_cast<__nv_bfloat16*>(out_lo));
   return check_launch("attn_pool_fused_kernel");
 }
