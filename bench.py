@@ -602,6 +602,9 @@ def main():
                        % (n_graphs, int(real_rows * D * 2 / 1e6))},
       "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "videos/s", "ms_per_step": ms_e2e,
               "h2d_bytes_per_step": packed_host.nbytes(), "d2h_bytes_per_step": pred_host.numel() * 4,
+              # per rank; a PCIe 5.0 x16 link moves ~55 GB/s of pinned host memory: when this figure sits there, e2e is bound
+              # by the host link, not by the kernels (compare ms_per_step of the resident `value`)
+              "h2d_gb_per_s_per_gpu": packed_host.nbytes() / (ms_e2e * 1e-3) / 1e9,
               "host_batch": "readers.PackedFrames: uint8 real frames only (%d of %d frame rows; num_frames ~ U{30..300}), padded on "
                             "the GPU" % (packed_host.data.shape[0], B * T)},
       "gpu_launches": int(launches),

@@ -186,6 +186,36 @@ def test_act_bwd_and_wgrad_split():
   assert float((got.cpu() - a.t() @ bm).abs().max()) < 1e-3 * float((a.t() @ bm).abs().max())
 
 
+def test_dgrad_through_forward_weights_and_sliced_colsum():
+  """nat.dgrad (dx = dz . W with W in the FORWARD's [out, in] bf16 layout: the MN-major GEMM on dz^T, no transposed weight
+  copy) against fp32 matmul, for a batch that is not a multiple of 8 and for the split-K shape of the MoE head; and the
+  column sums over a tall matrix (row slices + ticketed fold): exact against a float64 sum, identical run to run."""
+  if not torch.cuda.is_available():
+    pytest.skip("no CUDA device")
+  import yt8m_native as nat
+  g = torch.Generator().manual_seed(11)
+  for b, rows, n in ((37, 256, 1000), (64, 2432, 128)):
+    dz = torch.randn(b, rows, generator=g)
+    w = synth.bf16r(torch.randn(rows, n, generator=g) / math.sqrt(rows))
+    hi, lo = nat.split_bf16(dz.to(DEV))
+    wb = torch.zeros((rows, nat.pad8(n)), dtype=torch.bfloat16, device=DEV)
+    wb[:, :n] = w.to(DEV)
+    got = nat.dgrad(hi, lo, wb, n)
+    want = (hi.float() + lo.float()).cpu() @ w
+    assert got.shape == (b, n)
+    assert float((got.cpu() - want).abs().max()) < 2e-5 * float(want.abs().max()) + 1e-6
+  rows, cols = 5000, 200
+  m = torch.randn(rows, cols, generator=g)
+  hi, lo = nat.split_bf16(m.to(DEV))
+  want = (hi.double() + lo.double()).sum(dim=0).cpu()
+  first = nat.colsum_bf16(hi, lo, cols).cpu()
+  assert float((first.double() - want).abs().max()) < 1e-5 * float(want.abs().max()) + 1e-4
+  for _ in range(3):                                       # the tickets clean up after themselves; fixed summation order
+    assert torch.equal(nat.colsum_bf16(hi, lo, cols).cpu(), first)
+  small = nat.colsum_bf16(hi[:100], lo[:100], cols).cpu()   # single-slice path
+  assert float((small.double() - (hi[:100].double() + lo[:100].double()).sum(dim=0).cpu()).abs().max()) < 1e-4
+
+
 # ------------------------------------------------------------------------------------------------
 # the whole frame-level training step: NetVLAD + hidden FC + MoE head (BASELINE config 2, reduced sizes)
 # ------------------------------------------------------------------------------------------------
