@@ -404,6 +404,12 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
   }
 }
 
+// ---- programmatic dependent launch (no-ops unless the grid was launched with cudaLaunchAttributeProgrammaticStreamSerialization) ----
+// launch_dependents: the NEXT kernel on the stream may start its prologue once every CTA of this grid has issued this (or exited);
+// wait: blocks until the PREVIOUS grid has completed and its global writes are visible.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- descriptors (bit layouts: cute/arch/mma_sm100_desc.hpp in the vendored CUTLASS headers) ----
 // Instruction descriptor, kind::f16, A/B = bf16, D = fp32.
 //   [4,6) c_format=1(F32)  [7,10) a_format=1(BF16)  [10,13) b_format=1(BF16)

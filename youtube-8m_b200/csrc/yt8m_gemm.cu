@@ -13,7 +13,7 @@ constexpr int kNumSms = 148;
 template <int BLOCK_N, int A_SPLIT, class Epi, int MT = 1, int CTAS = 1>
 int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, const yt8m_bf16* w, long long ldw, int M,
                 int N_rows_w, int N, int K, int split_k, const typename Epi::Params& ep, cudaStream_t stream,
-                int a_f16 = 0, unsigned long long hint_a = kEvictNormal, unsigned long long hint_w = kEvictNormal) {
+                int a_f16 = 0, unsigned long long hint_a = kEvictNormal, unsigned long long hint_w = kEvictNormal, bool pdl = false) {
   using S = GemmSmem<BLOCK_N, A_SPLIT, false, MT, CTAS>;
   CUtensorMap tm_a_hi, tm_a_lo, tm_b;
   int rc;
@@ -39,7 +39,18 @@ int launch_gemm(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, con
   const int splits = (num_kb + shape.kb_per_split - 1) / shape.kb_per_split;
   const long long tiles = static_cast<long long>((N + BLOCK_N - 1) / BLOCK_N) * ((M + MT * kBlockM - 1) / (MT * kBlockM)) * splits;
   const int grid = static_cast<int>(std::min<long long>(tiles, kNumSms * CTAS));       // persistent CTAs walk the tiles
-  kern<<<grid, kGemmThreads, S::kTotal + Epi::kSmemBytes, stream>>>(tm_a_hi, tm_a_lo, tm_b, shape, ep);
+  if (pdl) {
+    // the kernel's prologue overlaps the tail of the previous kernel on the stream (griddepcontrol.wait inside)
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kGemmThreads); cfg.dynamicSmemBytes = S::kTotal + Epi::kSmemBytes; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    YT8M_CUDA(cudaLaunchKernelEx(&cfg, kern, tm_a_hi, tm_a_lo, tm_b, shape, ep));
+  } else {
+    kern<<<grid, kGemmThreads, S::kTotal + Epi::kSmemBytes, stream>>>(tm_a_hi, tm_a_lo, tm_b, shape, ep);
+  }
   return check_launch("gemm_tcgen05_kernel");
 }
 
@@ -215,7 +226,7 @@ int yt8m_linear_fwd(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda,
 // (dh_{t-1} += dG_t . Wh: M = batch, N = H, K = 4H): with yt8m_linear_fwd's split-K that was a memset + GEMM + finalize
 // triple per step (profiles/r02f_lstm_train_profile.txt: 598 x (1.7 + 7.9 + 2.4) us).
 int yt8m::linear_accumulate(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, const yt8m_bf16* w, long long ldw, int M,
-                            int N, int K, float* acc, long long ld_acc, cudaStream_t stream) {
+                            int N, int K, float* acc, long long ld_acc, cudaStream_t stream, bool pdl) {
   YT8M_REQUIRE(a_hi && w && acc, YT8M_E_BADPTR, "linear_accumulate: null pointer");
   YT8M_REQUIRE(M > 0 && N > 0 && K > 0 && lda % 8 == 0 && ldw % 8 == 0 && lda >= K && ldw >= K && ld_acc >= N, YT8M_E_BADSHAPE,
                "linear_accumulate: bad shape M=%d N=%d K=%d", M, N, K);
@@ -227,8 +238,8 @@ int yt8m::linear_accumulate(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long l
   ep.split_k = std::max(split_k, 2);                    // > 1 selects the atomic epilogue, also for a single split
   ep.out_f32 = acc;
   ep.ld_out = ld_acc;
-  return a_lo ? launch_gemm<128, 2, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream)
-              : launch_gemm<128, 1, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream);
+  return a_lo ? launch_gemm<128, 2, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream, 0, kEvictNormal, kEvictNormal, pdl)
+              : launch_gemm<128, 1, EpiLinear, 1>(a_hi, a_lo, lda, w, ldw, M, N, N, K, split_k, ep, stream, 0, kEvictNormal, kEvictNormal, pdl);
 }
 
 extern "C" {

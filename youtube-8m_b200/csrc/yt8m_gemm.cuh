@@ -130,6 +130,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  // programmatic dependent launch (used by the per-frame GEMMs of the reverse LSTM recurrence): everything above -- barrier
+  // init, TMEM allocation, descriptor prefetch -- ran while the previous kernel was still executing; nothing below touches
+  // global memory before the previous grid has completed.  Plain launches: both are no-ops.
+  griddep_launch_dependents();
+  griddep_wait();
 
   if (warp == 0) {
     // ------------------------------- TMA producer: A (hi [+ lo]) -------------------------------

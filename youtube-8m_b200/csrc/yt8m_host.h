@@ -25,9 +25,10 @@ int make_tmap_bf16_nd(CUtensorMap* out, const void* ptr, int rank, const uint64_
 
 int check_launch(const char* what);
 
-// acc += A . W^T with split-K atomics straight into acc (yt8m_gemm.cu)
+// acc += A . W^T with split-K atomics straight into acc (yt8m_gemm.cu).  pdl: launch with programmatic stream serialization (the
+// kernel's prologue overlaps the previous kernel on the stream; it waits for that kernel's completion before touching memory)
 int linear_accumulate(const yt8m_bf16* a_hi, const yt8m_bf16* a_lo, long long lda, const yt8m_bf16* w, long long ldw, int M, int N,
-                      int K, float* acc, long long ld_acc, cudaStream_t stream);
+                      int K, float* acc, long long ld_acc, cudaStream_t stream, bool pdl = false);
 
 // Library-owned device scratch, one buffer per (device, slot), grown on demand (the growth synchronises `stream` and frees the
 // old buffer).  The first `ticket_bytes` are zero after allocation and are kept zero by their users (self-cleaning tickets of

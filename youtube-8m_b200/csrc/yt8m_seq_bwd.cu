@@ -66,6 +66,10 @@ struct LstmBwdStep {
 };
 
 __global__ void lstm_bwd_step_kernel(const LstmBwdStep p) {
+  // chained with the per-frame GEMM by programmatic dependent launch: let the GEMM of this frame set itself up now, and do not
+  // read dh_acc before the GEMM of the frame above has completed (no-ops for a plain launch)
+  griddep_launch_dependents();
+  griddep_wait();
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= static_cast<long long>(p.B) * p.H) return;
   const int b = static_cast<int>(idx / p.H), u = static_cast<int>(idx % p.H);
@@ -464,12 +468,22 @@ int yt8m_lstm_bwd(const yt8m_bf16* x, const int* num_frames, int B, int T, int D
     const yt8m_bf16* wt_rec = wt_packed[l] + static_cast<long long>(in) * 4 * H;      // rows [in, in+H) of W^T: Wh
     for (int t = T - 1; t >= 0; --t) {
       sp.t = t;
-      lstm_bwd_step_kernel<<<cell_blocks, 256, 0, stream>>>(sp);
+      if (t == T - 1) {
+        lstm_bwd_step_kernel<<<cell_blocks, 256, 0, stream>>>(sp);         // follows memsets: a plain launch
+      } else {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cell_blocks); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        YT8M_CUDA(cudaLaunchKernelEx(&cfg, lstm_bwd_step_kernel, sp));
+      }
       if ((rc = check_launch("lstm_bwd_step_kernel")) != YT8M_OK) return rc;
       if (t == 0) break;
       rc = linear_accumulate(reinterpret_cast<const yt8m_bf16*>(ws.dg_hi) + static_cast<long long>(t) * 4 * H,
                              reinterpret_cast<const yt8m_bf16*>(ws.dg_lo) + static_cast<long long>(t) * 4 * H,
-                             static_cast<long long>(T) * 4 * H, wt_rec, 4 * H, B, H, 4 * H, ws.dh_acc, H, stream);
+                             static_cast<long long>(T) * 4 * H, wt_rec, 4 * H, B, H, 4 * H, ws.dh_acc, H, stream, /*pdl=*/true);
       if (rc != YT8M_OK) return rc;
     }
     // 4. parameter gradients over all frames, and the gradient of the layer below
