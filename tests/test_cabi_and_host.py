@@ -26,6 +26,40 @@ def test_library_exports_every_declared_symbol():
   assert yt8m_native.moe_packed_rows(4716, 64) == -1
 
 
+def test_ctypes_signatures_match_the_header_prototypes():
+  """Every binding in yt8m_native._SIGS has the argument COUNT and, per argument, the KIND (pointer / 32-bit int / 64-bit
+  int / size_t / float) of the prototype in include/yt8m_b200.h -- a drift between the header and the ctypes table (an
+  argument added on one side only) corrupts the call frame silently; this catches it without a GPU."""
+  import ctypes
+  import yt8m_native
+  header = open(os.path.join(ROOT, "include", "yt8m_b200.h")).read()
+  header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+  header = re.sub(r"//[^\n]*", " ", header)
+  protos = dict((m.group(2), (m.group(1), m.group(3))) for m in
+                re.finditer(r"\b([A-Za-z_][A-Za-z0-9_ ]*?[\s\*]+)(yt8m_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", header))
+
+  def kind_of_c(decl):
+    decl = decl.strip()
+    if "*" in decl or decl.startswith("yt8m_stream_t"):
+      return "ptr"
+    base = re.sub(r"\b(const|unsigned)\b", "", decl).split()
+    t = " ".join(base[:-1]) if len(base) > 1 else base[0]
+    return {"int": "i32", "long long": "i64", "size_t": "size", "float": "f32"}.get(t, t)
+
+  def kind_of_ctypes(t):
+    return {ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr", ctypes.c_int: "i32", ctypes.c_longlong: "i64",
+            ctypes.c_size_t: "size", ctypes.c_float: "f32"}.get(t, str(t))
+
+  assert set(protos) == set(yt8m_native._SIGS)
+  for name, (res, args) in yt8m_native._SIGS.items():
+    ret_decl, arg_decl = protos[name]
+    c_args = [a for a in (x.strip() for x in arg_decl.split(",")) if a and a != "void"]
+    assert len(c_args) == len(args), (name, len(c_args), len(args))
+    assert [kind_of_c(a) for a in c_args] == [kind_of_ctypes(t) for t in args], (name, c_args)
+    want_ret = "ptr" if "*" in ret_decl else kind_of_c(ret_decl + " x")
+    assert kind_of_ctypes(res) == want_ret, (name, ret_decl)
+
+
 def test_sass_contains_tcgen05_and_tma():
   import build_native
   sass = subprocess.run(["cuobjdump", "-sass", build_native.build()], capture_output=True, text=True).stdout
