@@ -10,8 +10,11 @@
 //   (3) yt8m_netvlad_bwd_da:     da[t,k] = sum_d x[t,d] dV[d,k]                     (batched [T x D] . [D x K])
 //   (4) yt8m_netvlad_bwd_softmax: g = da + dasum; dz = a * (g - sum_k a g), masked; dshift; dz * scale as bf16 hi/lo
 //   (5) dCw^T[K, D] = (dz*scale)^T . X  through yt8m_wgrad (tcgen05, split over the B*T contraction rows)
-// Round 1: (3) is a SIMT tile kernel (11 GFLOP at B = 256 -- small next to the FC / MoE backward GEMMs); the
-// tensor-core version (batched tcgen05 with the recompute of z fused in) is listed in DESIGN.md as next.
+// (3) + (4) here are the generic path (K = 32, or D not a multiple of 64): a SIMT tile kernel for da and a row kernel for the
+// softmax backward, fed with z recomputed by yt8m_linear_fwd.  For K in {64, 128} the trainers use
+// yt8m_netvlad_bwd_assign_fused (yt8m_netvlad_bwd_tc.cu): one tcgen05 kernel that recomputes the logits on chip, forms da on the
+// tensor cores from dV as bf16 hi + lo (emitted by (1)) and does the softmax backward in its epilogue -- 498 us -> 56 us at
+// BASELINE config 2 shapes.
 #include "yt8m_common.cuh"
 #include "yt8m_host.h"
 
