@@ -1,8 +1,9 @@
 """Data-parallel plumbing: one process per GPU, torch.distributed for the rendezvous and the collective.
 
 The path shards by video: forward / inference needs no collective at all; the training
-step has exactly one exchange -- an all-reduce(sum) of the flat fp32 gradient buffer (NCCL over
-NVLink/NVSwitch on the GPU box; gloo for the CPU tests of this host logic)."""
+step has exactly one exchange -- the sum over ranks of the flat fp32 gradient buffer (NCCL over NVLink/NVSwitch on
+the GPU box; gloo for the CPU tests of this host logic), issued as one all-reduce or as a few contiguous pieces
+that overlap the backward (GradExchange)."""
 import os
 
 import torch

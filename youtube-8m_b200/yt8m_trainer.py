@@ -3,9 +3,10 @@ through the C ABI: forward, CrossEntropyLoss + its gradient, backward (fused MoE
 tcgen05 wgrad), L2 regulariser, per-tensor clip_by_norm, TF-1.0 Adam, exponential-decay learning rate.
 
 Data parallel: one process per GPU; every rank computes gradients of ITS shard of the batch
-with the loss gradient pre-scaled by 1/world, then ONE all-reduce(sum) over a single flat fp32 gradient buffer
-(NCCL over NVLink on the GPU box, gloo in the CPU tests) gives every rank the gradient of the mean loss over
-the global batch -- the single-process large-batch semantics of the reference's build_graph (its own multi-
+with the loss gradient pre-scaled by B_local / B_global, then the single flat fp32 gradient buffer is summed over the
+ranks once per step (NCCL over NVLink on the GPU box, gloo in the CPU tests; one all-reduce, or -- NetVLAD trainers --
+three contiguous pieces started while the backward is still running, yt8m_dp.GradExchange) and every rank holds the
+gradient of the mean loss over the global batch -- the single-process large-batch semantics of the reference's build_graph (its own multi-
 worker mode is asynchronous parameter-server and is not reproduced).  Parameters and Adam state are
 replicated and stay bit-identical across ranks because every rank applies the same update.
 
