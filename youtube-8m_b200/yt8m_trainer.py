@@ -400,7 +400,8 @@ class LstmTrainer(object):
 
   memory=False: classifier input = the non-tuple state [c0, h0, c1, h1, ...] (lstm_model.py:52);
   memory=True : classifier input = concat of the layers' c states (lstm_memory_model.py:61).
-  One flat fp32 buffer holds every gradient: data parallelism is ONE all-reduce per step.
+  One flat fp32 buffer holds every gradient; under data parallelism it is summed over the ranks once per step, the
+  classifier's piece while the back-propagation through time is still running.
   Layouts: per layer the packed kernel [4H, in+H] (rows 4u+g) and bias [4H]; then the packed MoE head.
   import_state / export_state speak the reference's TF variable names and layouts."""
 
@@ -488,6 +489,10 @@ class LstmTrainer(object):
     global_batch = global_batch or b * self.world
     p, sv = self.forward(x, num_frames)
     loss, dfeat = self.head.backward(p, sv["hi"], sv["lo"], labels, global_batch, want_dx=True)
+    # the classifier's gradient (174 M floats with MoE-4 on the 4096-d state: 0.7 GB) is final here and travels under the whole
+    # back-propagation through time; the recurrent layers' piece follows at the end (yt8m_dp.GradExchange)
+    xch = yt8m_dp.GradExchange(self.group, self.world)
+    xch.start(self.grad[self._off["head"][0]:], "head")
     if self.memory:
       dstate = torch.zeros((b, self.l * 2 * self.h), dtype=torch.float32, device=self.dev)
       dstate.index_copy_(1, self.state_cols, dfeat[:, :self.head_in].contiguous())
@@ -497,16 +502,19 @@ class LstmTrainer(object):
     nat.lstm_bwd(x, num_frames, self.w_bf16, sv["bs"], wt, self.h, sv["seq_hi"], sv["seq_lo"], dstate=dstate,
                  dw=[self.g["w%d" % l] for l in range(self.l)], db=[self.g["b%d" % l].view(-1) for l in range(self.l)])
     del wt
-    yt8m_dp.all_reduce_sum_(self.grad, self.group)                                # the ONE collective of the step
+    xch.start(self.grad[:self._off["head"][0]], "rnn")
     if self.keep_grads:
+      xch.finish()
       self.last_grad = self.grad.clone()
     lr = exponential_decay(base_lr, self.global_step, global_batch, lr_decay_examples, lr_decay)
     lr_t = adam_lr_t(lr, self.global_step + 1)
+    xch.wait("head")
+    self.head.apply(lr_t, clip_gradient_norm, regularization_penalty)
+    xch.wait("rnn")
     for l in range(self.l):
       for name, bf in (("w%d" % l, self.w_bf16[l]), ("b%d" % l, None)):
         sums = nat.grad_reg_sumsq(self.g[name], self.p[name], 0.0)               # BasicLSTMCell carries no regulariser
         nat.clip_adam_step(self.p[name], self.g[name], self.am[name], self.av[name], sums, clip_gradient_norm, lr_t, param_bf16=bf)
-    self.head.apply(lr_t, clip_gradient_norm, regularization_penalty)
     self.global_step += 1
     self.head.global_step = self.global_step
     self.last = {"label_loss_local": loss, "lr": lr}
